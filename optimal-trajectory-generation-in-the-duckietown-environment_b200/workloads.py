@@ -1,0 +1,65 @@
+"""Synthetic inputs for the BASELINE.json configurations.
+
+Pure NumPy parameter generators: they produce planner states, lattice parameters and obstacle
+parameters *in Frenet coordinates*.  Mapping obstacles to Cartesian positions is done by the
+consumer - the K3 point-transform kernel on the GPU (bench, product path) or the oracle / the
+reference path classes (tests, golden generation) - so that every consumer starts from the
+same numbers.  All draws come from one seeded generator in a fixed order, hence scenario b is
+the same on every rank of a sharded run.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SPLINE_WX = [0, 2.5, 5, 7.5, -3, 2.7]      # config/config_spline2D.json (jsonpickle dump), SURVEY.md section 2 row 22
+SPLINE_WY = [0.7, -6, 5, -9.5, 0, 5]
+CIRCLE_LHR = (8, 5, 2)                     # config/config_circle2D.json
+ROBOT_RADIUS = 0.7                         # lib/tests/test_obstacle_planner.py:16
+
+# Obstacle field of configs 4 and 5, in Frenet coordinates relative to the robot: uniformly spread
+# over [s0 + clearance, s0 + clearance + span] x [-half_width, half_width].  The clearance keeps the
+# robot's own start point (shared by every candidate) collision free, and the area is sized so that
+# a few percent to a quarter of the lattice survives the collision filter (a scene where every
+# candidate is blocked, or none, would not exercise the masked argmin).  s0 <= 25 keeps every
+# obstacle inside the spline's 54.9 m arc length.
+OBSTACLE_CLEARANCE = 3.0
+OBSTACLE_SPAN = 25.0
+OBSTACLE_HALF_WIDTH = 8.0
+
+# "dense lattice" planner parameters of configs 4 and 5 (V1 semantics, others default)
+DENSE_PARAMS = dict(d_road_width=0.1, dt=0.1, num_sample=3, delta_t=0.02)
+
+
+def config4_scenario():
+    """Single planner on the spline path, dense lattice, 64 static obstacles (all active)."""
+    # seed 66: the first seed >= 64 whose field leaves part of the lattice collision free
+    # (2313 of 9600 candidates survive and the masked argmin differs from the unmasked one)
+    rng = np.random.default_rng(66)
+    s_o = rng.uniform(5 + OBSTACLE_CLEARANCE, 5 + OBSTACLE_CLEARANCE + OBSTACLE_SPAN, 64)
+    d_o = rng.uniform(-OBSTACLE_HALF_WIDTH, OBSTACLE_HALF_WIDTH, 64)
+    return dict(p0=(0.3, 0.1, 0.0), s0=(5.0, 2.5, 0.1), t0=0.1, dd=0.0,
+                obs_s=s_o, obs_d=d_o)
+
+
+def config5_scenarios(n_scenarios: int = 4096, n_obstacles: int = 128, seed: int = 4096):
+    """Batched sweep: independent planner states around the low-speed threshold, 128 moving
+    obstacles per scenario spread over the 25 m x 16 m field ahead of each robot."""
+    rng = np.random.default_rng(seed)
+    B, O = n_scenarios, n_obstacles
+    p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.5, .5, B), rng.uniform(-.5, .5, B)], axis=1)
+    s0 = np.stack([rng.uniform(0, 25, B), rng.uniform(0, 4, B), rng.uniform(-.5, .5, B)], axis=1)
+    dd = rng.uniform(-1, 1, B)
+    obs_s = s0[:, 0:1] + rng.uniform(OBSTACLE_CLEARANCE, OBSTACLE_CLEARANCE + OBSTACLE_SPAN, (B, O))
+    obs_d = rng.uniform(-OBSTACLE_HALF_WIDTH, OBSTACLE_HALF_WIDTH, (B, O))
+    obs_speed = rng.uniform(0, 1, (B, O))
+    obs_offset = rng.integers(-1, 1, (B, O)).astype(np.float64)
+    return dict(p0=p0, s0=s0, dd=dd, t0=np.full(B, 0.1), obs_s=obs_s, obs_d=obs_d,
+                obs_speed=obs_speed, obs_offset=obs_offset)
+
+
+def moving_obstacle_frenet(obs_s, obs_d, obs_speed, obs_offset, t):
+    """Frenet position of the synthetic moving obstacles at time t (the reference's time law
+    `t0 + (t * speed) % 50`, lib/sensor/dynamic_obstacle.py:43-44, with t0 := obs_s) and the
+    lateral offset of `ObstacleTrajectory.compute_pt` (:55-56) added to the lateral position."""
+    t = np.asarray(t, dtype=np.float64)
+    return obs_s + (t * obs_speed) % 50, obs_d + obs_offset

@@ -1,0 +1,85 @@
+"""Helpers shared by the oracle and GPU parity tests: golden loading and array packing."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+sys.path.insert(0, ROOT)
+
+FIELDS = ("t", "d", "dot_d", "ddot_d", "dddot_d", "s", "dot_s", "ddot_s", "dddot_s")
+LAT = ("d", "dot_d", "ddot_d", "dddot_d")
+LON = ("s", "dot_s", "ddot_s", "dddot_s")
+RTOL = 1e-5          # north star: coefficients, costs and poses within 1e-5 relative in fp64
+ORACLE_RTOL = 1e-9   # the oracle restates the same NumPy calls; it is held to a much tighter bound
+
+_cache = {}
+
+
+def golden(name):
+    if name not in _cache:
+        _cache[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    return _cache[name]
+
+
+def prefixed(z, prefix):
+    """Sub-dictionary of a golden file: keys starting with `prefix`, prefix removed."""
+    return {k[len(prefix):]: v for k, v in z.items() if k.startswith(prefix)}
+
+
+def pack_lattice(L, t_field=True):
+    """Oracle Lattice -> the golden layout: kept candidates only, [C][Nmax] arrays, NaN padding."""
+    keep = L.keep
+    idx = np.nonzero(keep)[0]
+    rows = L.row_of[idx]
+    out = {"nsteps": L.nsteps[idx].astype(np.int32)}
+    for j, name in enumerate(LAT):
+        out[name] = L.lat[idx, j, :]
+    for j, name in enumerate(LON):
+        out[name] = L.lon[rows, j, :]
+    if t_field:
+        out["t"] = L.t[rows, :]
+    for k in ("cd", "cv", "ct", "ctot"):
+        out[k] = getattr(L, k)[idx]
+    return out
+
+
+def assert_close(a, b, rtol, what="", atol_scale=None):
+    """Relative comparison scaled by the magnitude of the reference array (NaN padding must match)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    na, nb = np.isnan(a), np.isnan(b)
+    assert np.array_equal(na, nb), f"{what}: NaN padding differs"
+    if a.size == 0:
+        return
+    scale = atol_scale if atol_scale is not None else max(1.0, float(np.nanmax(np.abs(b))) if (~nb).any() else 1.0)
+    err = np.abs(np.where(na, 0.0, a - b))
+    tol = rtol * np.maximum(np.abs(np.where(nb, 0.0, b)), scale * 1e-3) if atol_scale is None else rtol * scale
+    bad = err > tol
+    assert not bad.any(), f"{what}: max err {err.max():.3e} at {np.argwhere(bad)[:3].tolist()} (rtol {rtol})"
+
+
+def compare_packed(got, ref, rtol, what="", fields=None):
+    assert np.array_equal(got["nsteps"], ref["nsteps"]), f"{what}: step counts differ"
+    n = ref["nsteps"]
+    nmax = ref[next(k for k in ref if k in FIELDS)].shape[1] if any(k in ref for k in FIELDS) else 0
+    for name in (fields or FIELDS):
+        if name not in ref or name not in got:
+            continue
+        g = got[name][:, :nmax] if got[name].shape[1] >= nmax else np.pad(
+            got[name], ((0, 0), (0, nmax - got[name].shape[1])), constant_values=np.nan)
+        # the oracle pads rows up to its own Nmax with NaN as well; re-mask with the golden's step counts
+        g = np.where(np.arange(nmax)[None, :] < n[:, None], g, np.nan)
+        assert_close(g, ref[name], rtol, f"{what}.{name}")
+    for k in ("cd", "cv", "ct", "ctot"):
+        if k in ref and k in got:
+            assert_close(got[k], ref[k], rtol, f"{what}.{k}")
+
+
+def near_tie(values, idx_a, idx_b, rel=1e-6):
+    """True if the two candidates' costs are within `rel` relative (the north star's tie exception)."""
+    a, b = values[idx_a], values[idx_b]
+    return abs(a - b) <= rel * max(abs(a), abs(b), 1e-300)
