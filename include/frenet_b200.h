@@ -1,0 +1,223 @@
+/*
+ * frenet_b200.h - C ABI of the B200 (sm_100a) Frenet lattice planner hot path.
+ *
+ * The reference (pepes97/Optimal-trajectory-generation-in-the-Duckietown-environment) is pure
+ * Python; it has no FFI layer.  Its boundary for this path is the Python planner API, so every
+ * entry point below names the reference function it replaces (paths relative to the reference
+ * root).  The Python host side (`otg_b200.planner`, `otg_b200.drivers`, `otg_b200.batch`) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would
+ * add to call them from `lib/planner/trajectory_planner.py`.
+ *
+ * Conventions
+ *   - plain C types only; every pointer inside FrenetBuffers / FrenetLattice / FrenetPath is a
+ *     DEVICE pointer owned by the caller (allocate with any CUDA allocator, e.g. torch);
+ *     the structs themselves are HOST PODs read during the call.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no global state
+ *     except the per-thread last-error string; kernels are re-entrant across streams.
+ *   - return value: FRENET_OK or a negative FRENET_ERR_* code; nothing throws across the ABI.
+ *     "No feasible candidate" is not an error of the call: it is reported per scenario in
+ *     FrenetResult.status (the Python wrapper raises ValueError like the reference's `min([])`).
+ *   - there is no CPU fallback: without a CUDA device every launch returns FRENET_ERR_CUDA.
+ *
+ * Indexing: a batch holds n_scen independent planner instances
+ * ("scenarios").  Scenario b owns n_v[b] <= n_v_cap longitudinal targets; row r = i_v * n_t + i_T
+ * owns one longitudinal polynomial, candidate c = r * n_d + i_d one lateral polynomial - the
+ * order in which `generate_range_polynomials` appends (lib/planner/trajectory_planner.py:128-180).
+ * Horizon i_T has n_steps[i_T] samples t_k = k * sample_period (np.arange(0, T + dt, dt)), stored
+ * padded to a multiple of 4 doubles: t_offset[i_T] is the prefix sum of the padded counts.
+ *
+ *   longitudinal field (s, ds, dds, ddds): element (b, r, k)  at  b * row_elems  + i_v * t_offset[n_t] + t_offset[i_T] + k
+ *   lateral field / x / y:                 element (b, c, k)  at  b * cand_elems + (i_v * t_offset[n_t] + t_offset[i_T]) * n_d
+ *                                                                 + i_d * (t_offset[i_T + 1] - t_offset[i_T]) + k
+ *   per-candidate arrays:                  element (b, c)     at  b * n_v_cap * n_t * n_d + c
+ *   per-row arrays:                        element (b, r)     at  b * n_v_cap * n_t + r
+ *
+ * The longitudinal samples are stored once per row: the n_d candidates of a row share them (the
+ * reference deep-copies them into every candidate, lib/planner/trajectory_planner.py:157).
+ */
+#ifndef FRENET_B200_H
+#define FRENET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRENET_B200_ABI_VERSION 1
+
+typedef void* frenet_stream_t; /* cudaStream_t */
+
+enum {
+    FRENET_OK = 0,
+    FRENET_ERR_BAD_ARG = -1, /* null pointer, non-positive size, inconsistent layout */
+    FRENET_ERR_CUDA = -2,    /* launch or runtime error, text in frenet_last_error() */
+    FRENET_ERR_CAPACITY = -3 /* shared-memory demand of the requested shape exceeds 227 KB */
+};
+
+/* FrenetResult.status */
+enum { FRENET_STATUS_OK = 0, FRENET_STATUS_NO_FEASIBLE = 1, FRENET_STATUS_EMPTY = 2 };
+
+/* which lateral parameterisation rule a planner variant uses */
+enum {
+    FRENET_LOWSPEED_OFF = 0,    /* V1DT, V1DTObstacles: `... and False` (trajectory_planner_dt.py:156) */
+    FRENET_LOWSPEED_V1 = 1,     /* ds0 < threshold and |S| > 0 (trajectory_planner.py:159) */
+    FRENET_LOWSPEED_OPTIMAL = 2 /* ds0 < threshold: keep only if signed S > s_thresh (trajectory_planner_optimal.py:155-168) */
+};
+
+/* row_flags bits (K1) */
+enum { FRENET_ROW_EXISTS = 1, FRENET_ROW_LOWSPEED = 2, FRENET_ROW_DROPPED = 4 };
+/* cand_flags bits (K2) */
+enum { FRENET_CAND_VALID = 1, FRENET_CAND_KINEMATIC_OK = 2 };
+
+enum { FRENET_PATH_CIRCLE = 0, FRENET_PATH_SPLINE = 1 };
+
+/* selector for frenet_gather_winner */
+enum { FRENET_SEL_CTOT = 0, FRENET_SEL_CD = 1, FRENET_SEL_CV = 2, FRENET_SEL_CT = 3, FRENET_SEL_MASKED = 4 };
+
+/* Weights and thresholds: the attributes of TrajectoryPlannerParams (lib/planner/trajectory_planner.py:38-67)
+ * that `generate_range_polynomials` reads, plus the collision radius of the drivers and the
+ * (extension, default +inf) kinematic limits. */
+typedef struct FrenetParams {
+    double kj, kt, kd, ks, kdots, klat, klong;
+    double sample_period;       /* delta_t; sampling_t for V1DTObstacles (trajectory_planner_obstacles.py:136) */
+    double low_speed_threshold;
+    double s_thresh;            /* Optimal only */
+    double v_max, a_max, kappa_max; /* EXTENSION: +inf reproduces the reference (no limits) */
+    double radius_sq;           /* robot_radius ** 2, lib/tests/test_obstacle_planner.py:16,48 */
+    int32_t lowspeed_rule;      /* FRENET_LOWSPEED_* */
+    int32_t follow;             /* 1: `s_target` given - quintic longitudinal to the target triples, cost ct */
+} FrenetParams;
+
+/* Lattice geometry shared by every scenario of a batch. */
+typedef struct FrenetLattice {
+    int32_t n_scen;
+    int32_t n_v_cap;
+    int32_t n_t;
+    int32_t n_d;
+    int32_t n_pad_max;       /* max_i (t_offset[i+1] - t_offset[i]) */
+    int32_t reserved;
+    int64_t row_elems;       /* n_v_cap * t_offset[n_t] */
+    int64_t cand_elems;      /* row_elems * n_d */
+    const double* axis_d;    /* [n_d]   np.arange(*di_interval) */
+    const double* axis_t;    /* [n_t]   np.arange(*t_interval) */
+    const int32_t* n_steps;  /* [n_t]   len(np.arange(0, T + dt, dt)) */
+    const int32_t* t_offset; /* [n_t+1] prefix sum of the step counts rounded up to 4 */
+    const double* axis_v;    /* [n_scen][n_v_cap] target speeds (velocity keeping) or target offsets (follow) */
+    const int32_t* n_v;      /* [n_scen] */
+} FrenetLattice;
+
+/* Reference path descriptor (lib/trajectory/circle_trajectory.py:11-72, spline_trajectory.py:9-158). */
+typedef struct FrenetPath {
+    int32_t kind;        /* FRENET_PATH_* */
+    int32_t n_knots;     /* spline only */
+    double circle[16];   /* l, h, r, dt, period, 7 branch boundaries (host-evaluated in the reference's order) */
+    const double* spline_table; /* device [n_knots][9]: knot, ax, bx, cx, dx, ay, by, cy, dy */
+} FrenetPath;
+
+/* Per-scenario result record written by K5 (64 bytes). */
+typedef struct FrenetResult {
+    int32_t argmin_ctot;   /* min(paths, key=ctot), first minimal wins (trajectory_planner.py:101,212); -1 if none */
+    int32_t argmin_cd;     /* key cd  (:99,105) */
+    int32_t argmin_cv;     /* key cv  (:100,106) */
+    int32_t argmin_ct;     /* key ct  (:103) */
+    int32_t argmin_masked; /* key ctot over candidates that pass every enabled filter; -1 if none */
+    int32_t n_valid;       /* candidates the reference would have appended */
+    int32_t n_survivors;   /* of those, how many pass every enabled filter */
+    int32_t status;        /* FRENET_STATUS_* */
+    double min_ctot;
+    double min_masked_ctot;
+    double reserved[2];
+} FrenetResult;
+
+/* Device buffers.  Inputs are read-only for the kernels; outputs may be NULL when the kernel that
+ * writes them is not launched. */
+typedef struct FrenetBuffers {
+    /* inputs */
+    const double* state;       /* [n_scen][6]  p0, dp0, ddp0, s0, ds0, dds0 */
+    const double* scal;        /* [n_scen][3]  dd, desired_speed, t_initial */
+    const double* target;      /* [n_scen][n_t][3] (st, dst, ddst) per horizon, or NULL (params.follow == 0) */
+    const double* obs_xy;      /* [n_scen][n_obs][2] obstacle snapshot, or NULL */
+    const uint8_t* obs_active; /* [n_scen][n_obs] 1 = sensed (tested), or NULL = all */
+    int32_t n_obs;
+    int32_t reserved;
+    /* K1 outputs */
+    double* coef_lon;          /* [n_scen][R][6] a0..a5 (a5 = 0 for the velocity-keeping quartic) */
+    double* coef_lat;          /* [n_scen][C][6] */
+    double* row_S;             /* [n_scen][R] arc length travelled (low-speed horizon) */
+    int32_t* row_flags;        /* [n_scen][R] FRENET_ROW_* */
+    /* K2 outputs */
+    double* lon;               /* 4 fields [4][n_scen][row_elems]:  s, ds, dds, ddds */
+    double* lat;               /* 4 fields [4][n_scen][cand_elems]: d, dd, ddd, dddd */
+    double* cost;              /* 4 arrays [4][n_scen][C]: cd, cv, ct, ctot (unset keys are 0.0 like Frenet()) */
+    uint8_t* cand_flags;       /* [n_scen][C] FRENET_CAND_* */
+    /* K3 outputs */
+    double* xy;                /* 2 fields [2][n_scen][cand_elems]: x, y */
+    uint8_t* curv_ok;          /* [n_scen][C] EXTENSION curvature limit, or NULL (kappa_max = +inf) */
+    /* K4 outputs */
+    uint8_t* coll_free;        /* [n_scen][C] 1 = no collision (check_collisions -> True) */
+    int32_t* first_blocker;    /* [n_scen][C] lowest blocking obstacle index, -1 if none */
+    /* K5 outputs */
+    FrenetResult* result;      /* [n_scen] */
+    /* winner gather */
+    double* winner;            /* [n_scen][11][n_pad_max]: t, d, dd, ddd, dddd, s, ds, dds, ddds, x, y */
+    int32_t* winner_steps;     /* [n_scen] number of valid samples, 0 if no winner */
+} FrenetBuffers;
+
+/* pipeline stage bits for frenet_plan */
+enum {
+    FRENET_STAGE_K1 = 1, FRENET_STAGE_K2 = 2, FRENET_STAGE_K3 = 4, FRENET_STAGE_K4 = 8,
+    FRENET_STAGE_K5 = 16, FRENET_STAGE_GATHER = 32, FRENET_STAGE_CURVATURE = 64
+};
+
+int frenet_abi_version(void);
+const char* frenet_last_error(void);
+
+/* Number of CUDA devices visible to the library (0 when there is no driver). */
+int frenet_device_count(void);
+
+/* K1 - candidate generation: closed-form boundary-value solutions, one thread per lattice cell.
+ * Replaces QuarticPolynomial.__init__ / QuinticPolynomial.__init__ (lib/trajectory/trajectory_1d.py:15-40,
+ * 76-97) as called from generate_range_polynomials (lib/planner/trajectory_planner.py:138,147,160,169). */
+int frenet_k1_coefficients(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, frenet_stream_t stream);
+
+/* K2 - evaluate / cost / feasibility: samples every candidate, accumulates jerk sums and cd/cv/ct/ctot.
+ * Replaces the sampling and cost lines of generate_range_polynomials (trajectory_planner.py:139-176). */
+int frenet_k2_evaluate(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, frenet_stream_t stream);
+
+/* K3 - Frenet -> Cartesian of every candidate against the circle / spline reference path.
+ * Replaces frenet_to_glob + compute_ortogonal_vect (lib/tests/test_obstacle_planner.py:18-25, 53-56). */
+int frenet_k3_cartesian(const FrenetLattice* lat, const FrenetParams* prm, const FrenetPath* path, const FrenetBuffers* buf,
+                        frenet_stream_t stream);
+
+/* EXTENSION - discrete curvature limit on the Cartesian polyline (no reference code). */
+int frenet_k3_curvature(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, frenet_stream_t stream);
+
+/* K4 - candidate x time-step x obstacle collision test.
+ * Replaces check_paths / check_collisions (lib/tests/test_moving_obstacle_planner.py:26-52). */
+int frenet_k4_collision(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, frenet_stream_t stream);
+
+/* K5 - first-wins argmin per cost key, unmasked and masked.
+ * Replaces min(paths, key=attrgetter(...)) (trajectory_planner.py:99-106, 212; test_obstacle_planner.py:90).
+ * use_mask bits: 1 kinematic flags, 2 curv_ok, 4 coll_free. */
+int frenet_k5_argmin(const FrenetLattice* lat, const FrenetBuffers* buf, int32_t use_mask, frenet_stream_t stream);
+
+/* Copies the selected winner's sampled state into buf->winner (what optimal_at_time reads,
+ * trajectory_planner.py:183-195).  sel: FRENET_SEL_*; has_xy: 0 leaves x, y rows untouched. */
+int frenet_gather_winner(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, int32_t sel, int32_t has_xy,
+                         frenet_stream_t stream);
+
+/* The pipeline: launches the stages selected in `stages` in order K1, K2, K3, (curvature), K4, K5, gather. */
+int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetPath* path, const FrenetBuffers* buf,
+                int32_t stages, int32_t use_mask, int32_t gather_sel, frenet_stream_t stream);
+
+/* Point-wise Frenet -> Cartesian (obstacle placement, target point): (x, y) = pt(s) + n(s) * d.
+ * Replaces `trajectory.compute_pt(s) + compute_ortogonal_vect(trajectory, s) * d`
+ * (lib/tests/test_obstacle_planner.py:21; lib/sensor/dynamic_obstacle.py:46-56). */
+int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
+                               frenet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRENET_B200_H */

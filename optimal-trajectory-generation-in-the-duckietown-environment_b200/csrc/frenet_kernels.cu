@@ -1,0 +1,842 @@
+// Frenet lattice planner hot path for B200 (sm_100a): kernels K1..K5 and their C ABI (include/frenet_b200.h).
+//
+// Nothing here is GEMM-shaped: the path is fp64 polynomial evaluation with store-dominated HBM
+// traffic (K2, K3), a candidate x step x obstacle distance test (K4) and a tiny reduction (K5).
+// Design rules used throughout (DESIGN.md has the numbers):
+//   * one CTA per lattice row (scenario, target speed, horizon): the longitudinal samples, the path
+//     frame (point + normal) and the obstacle table are produced / staged once per CTA in shared
+//     memory and reused by the n_d candidates of the row;
+//   * inside a CTA a warp owns a candidate and its lanes own consecutive time steps, so every
+//     global store is a contiguous run of doubles (k fastest, rows padded to 32-byte sectors);
+//   * per-candidate sums (jerk integrals) and maxima are reduced with warp shuffles in a fixed
+//     butterfly order: results are deterministic and sign-symmetric, so the reference's exact
+//     cost ties between mirror candidates (+d / -d) survive and are broken by lowest index;
+//   * K4 culls obstacles per 32-step chunk with a lane-parallel bounding-circle test before the
+//     exact distance test, which keeps the fp64 pipe off the critical path.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "frenet_b200.h"
+
+namespace {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kRowThreads = 256;   // CTA size of the per-row kernels (8 warps)
+constexpr int kMaxSmem = 227 * 1024;
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess)
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else
+        snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+
+#define FRENET_CHECK_LAUNCH(name)                                        \
+    do {                                                                 \
+        cudaError_t e_ = cudaGetLastError();                             \
+        if (e_ != cudaSuccess) return fail(FRENET_ERR_CUDA, name, e_);   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Polynomials
+// ------------------------------------------------------------------------------------------------
+// Closed-form solution of the 3x3 system QuinticPolynomial solves with np.linalg.solve
+// (lib/trajectory/trajectory_1d.py:15-40).
+__device__ __forceinline__ void quintic_bvp(double p0, double dp0, double ddp0, double p1, double dp1, double ddp1, double T,
+                                            double a[6]) {
+    const double a0 = p0, a1 = dp0, a2 = ddp0 / 2.0;
+    const double T2 = T * T, T3 = T2 * T;
+    const double b0 = p1 - a0 - a1 * T - a2 * T2;
+    const double b1 = dp1 - a1 - 2.0 * a2 * T;
+    const double b2 = ddp1 - 2.0 * a2;
+    a[0] = a0;
+    a[1] = a1;
+    a[2] = a2;
+    a[3] = (10.0 * b0 - 4.0 * T * b1 + 0.5 * T2 * b2) / T3;
+    a[4] = (-15.0 * b0 + 7.0 * T * b1 - T2 * b2) / (T3 * T);
+    a[5] = (6.0 * b0 - 3.0 * T * b1 + 0.5 * T2 * b2) / (T3 * T2);
+}
+
+// Closed-form solution of the 2x2 system of QuarticPolynomial (trajectory_1d.py:76-97); end acceleration 0.
+__device__ __forceinline__ void quartic_bvp(double s0, double ds0, double dds0, double ds1, double T, double a[6]) {
+    const double a0 = s0, a1 = ds0, a2 = dds0 / 2.0;
+    const double b1 = ds1 - a1 - 2.0 * a2 * T;
+    const double b2 = 0.0 - 2.0 * a2;
+    const double T2 = T * T;
+    a[0] = a0;
+    a[1] = a1;
+    a[2] = a2;
+    a[3] = (3.0 * b1 - T * b2) / (3.0 * T2);
+    a[4] = (T * b2 - 2.0 * b1) / (4.0 * T2 * T);
+    a[5] = 0.0;
+}
+
+// Value and three derivatives (trajectory_1d.py:42-71, 99-130), Horner form with the integer
+// multiples of the coefficients folded in once per polynomial.
+struct Poly {
+    double a0, a1, a2, a3, a4, a5;  // value
+    double b2, b3, b4, b5;          // 2a2, 3a3, 4a4, 5a5
+    double c3, c4, c5;              // 6a3, 12a4, 20a5
+    double e4, e5;                  // 24a4, 60a5
+
+    __device__ __forceinline__ void load(const double* __restrict__ a) {
+        a0 = a[0]; a1 = a[1]; a2 = a[2]; a3 = a[3]; a4 = a[4]; a5 = a[5];
+        b2 = 2.0 * a2; b3 = 3.0 * a3; b4 = 4.0 * a4; b5 = 5.0 * a5;
+        c3 = 6.0 * a3; c4 = 12.0 * a4; c5 = 20.0 * a5;
+        e4 = 24.0 * a4; e5 = 60.0 * a5;
+    }
+    __device__ __forceinline__ double val(double t) const {
+        return fma(fma(fma(fma(fma(a5, t, a4), t, a3), t, a2), t, a1), t, a0);
+    }
+    __device__ __forceinline__ double d1(double t) const { return fma(fma(fma(fma(b5, t, b4), t, b3), t, b2), t, a1); }
+    __device__ __forceinline__ double d2(double t) const { return fma(fma(fma(c5, t, c4), t, c3), t, b2); }
+    __device__ __forceinline__ double d3(double t) const { return fma(fma(e5, t, e4), t, c3); }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// Row addressing shared by the per-row kernels.
+struct RowAddr {
+    int b, r, iv, iT, N, npad;
+    int64_t lon_off;   // into one longitudinal field
+    int64_t lat_off;   // into one lateral field: first candidate of the row
+    int64_t cand0;     // into per-candidate arrays
+    int64_t lonF, latF, candF;   // field strides
+};
+
+__device__ __forceinline__ RowAddr row_addr(const FrenetLattice& L, int64_t br) {
+    RowAddr A;
+    const int R = L.n_v_cap * L.n_t;
+    A.b = (int)(br / R);
+    A.r = (int)(br % R);
+    A.iv = A.r / L.n_t;
+    A.iT = A.r % L.n_t;
+    A.N = L.n_steps[A.iT];
+    const int off = L.t_offset[A.iT];
+    A.npad = L.t_offset[A.iT + 1] - off;
+    const int64_t sumpad = L.t_offset[L.n_t];
+    const int64_t within = (int64_t)A.iv * sumpad + off;
+    A.lon_off = (int64_t)A.b * L.row_elems + within;
+    A.lat_off = (int64_t)A.b * L.cand_elems + within * L.n_d;
+    A.cand0 = br * L.n_d;
+    A.lonF = (int64_t)L.n_scen * L.row_elems;
+    A.latF = (int64_t)L.n_scen * L.cand_elems;
+    A.candF = (int64_t)L.n_scen * R * L.n_d;
+    return A;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: candidate generation, one thread per lattice cell (scenario, v, T, d)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+    const int64_t C = (int64_t)L.n_v_cap * L.n_t * L.n_d;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= C * L.n_scen) return;
+    const int b = (int)(gid / C);
+    const int c = (int)(gid % C);
+    const int r = c / L.n_d, id = c % L.n_d;
+    const int iv = r / L.n_t, iT = r % L.n_t;
+    const int64_t br = (int64_t)b * L.n_v_cap * L.n_t + r;
+    double* cl = B.coef_lon + br * 6;
+    double* cq = B.coef_lat + gid * 6;
+
+    if (iv >= L.n_v[b]) {   // row beyond this scenario's longitudinal axis
+        if (id == 0) {
+            B.row_flags[br] = 0;
+            B.row_S[br] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) cl[j] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) cq[j] = 0.0;
+        return;
+    }
+    const double* st = B.state + (int64_t)b * 6;
+    const double p0 = st[0], dp0 = st[1], ddp0 = st[2], s0 = st[3], ds0 = st[4], dds0 = st[5];
+    const double T = L.axis_t[iT];
+    const double v = L.axis_v[(int64_t)b * L.n_v_cap + iv];
+
+    double a[6];
+    if (P.follow) {   // trajectory_planner.py:132-138: quintic to (st + offset, dst, ddst)
+        const double* tg = B.target + ((int64_t)b * L.n_t + iT) * 3;
+        quintic_bvp(s0, ds0, dds0, tg[0] + v, tg[1], tg[2], T, a);
+    } else {          // :147 velocity keeping
+        quartic_bvp(s0, ds0, dds0, v, T, a);
+    }
+    // S: arc length at the last sample (:155; signed in the Optimal variant, trajectory_planner_optimal.py:151)
+    Poly pl;
+    pl.load(a);
+    const double t_last = (double)(L.n_steps[iT] - 1) * P.sample_period;
+    const double s_last = pl.val(t_last);
+    const double S = (P.lowspeed_rule == FRENET_LOWSPEED_OPTIMAL) ? (s_last - s0) : fabs(s_last - s0);
+    bool low = false, dropped = false;
+    if (P.lowspeed_rule == FRENET_LOWSPEED_V1) {
+        low = (ds0 < P.low_speed_threshold) && (S > 0.0);
+    } else if (P.lowspeed_rule == FRENET_LOWSPEED_OPTIMAL) {
+        low = ds0 < P.low_speed_threshold;
+        dropped = low && !(S > P.s_thresh);
+    }
+    if (id == 0) {
+        B.row_flags[br] = FRENET_ROW_EXISTS | (low ? FRENET_ROW_LOWSPEED : 0) | (dropped ? FRENET_ROW_DROPPED : 0);
+        B.row_S[br] = S;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) cl[j] = a[j];
+    }
+    double q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (!dropped) quintic_bvp(p0, dp0, ddp0, L.axis_d[id], 0.0, 0.0, low ? S : T, q);   // :160 / :169
+#pragma unroll
+    for (int j = 0; j < 6; ++j) cq[j] = q[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: evaluate / cost / feasibility, one CTA per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+    extern __shared__ double sigma[];   // [n_pad_max] |s_k - s0| (low-speed lateral argument)
+    __shared__ double sh_clong;
+    __shared__ int sh_rowfeas;
+
+    const int64_t br = blockIdx.x;
+    const RowAddr A = row_addr(L, br);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int flags = B.row_flags[br];
+
+    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
+        for (int id = tid; id < L.n_d; id += blockDim.x) {
+            const int64_t c = A.cand0 + id;
+            B.cand_flags[c] = 0;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = 0.0;
+        }
+        return;
+    }
+    const bool low = flags & FRENET_ROW_LOWSPEED;
+    const double dt = P.sample_period;
+    const double s0 = B.state[(int64_t)A.b * 6 + 3];
+    Poly pl;
+    pl.load(B.coef_lon + br * 6);
+
+    // Phase A: longitudinal samples, once per row (the reference recomputes nothing either, but
+    // deep-copies them into each of the n_d candidates; here the candidates share the row's arrays).
+    double* lon = B.lon + A.lon_off;
+    for (int k = tid; k < A.N; k += blockDim.x) {
+        const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
+        const double s = pl.val(t);
+        lon[k] = s;
+        lon[A.lonF + k] = pl.d1(t);
+        lon[2 * A.lonF + k] = pl.d2(t);
+        lon[3 * A.lonF + k] = pl.d3(t);
+        if (low) sigma[k] = fabs(s - s0);
+    }
+    if (warp == 0) {   // longitudinal cost and limits (trajectory_planner.py:143-144, 153-154)
+        double acc = 0.0, vmax = 0.0, amax = 0.0;
+        for (int k = lane; k < A.N; k += kWarp) {
+            const double t = (double)k * dt;
+            const double j = pl.d3(t);
+            acc = fma(j, j, acc);
+            vmax = fmax(vmax, fabs(pl.d1(t)));
+            amax = fmax(amax, fabs(pl.d2(t)));
+        }
+        acc = warp_sum(acc);
+        vmax = warp_max(vmax);
+        amax = warp_max(amax);
+        if (lane == 0) {
+            const double T = L.axis_t[A.iT];
+            const double t_last = (double)(A.N - 1) * dt;
+            double term;
+            if (P.follow) {
+                const double e = pl.val(t_last) - B.target[((int64_t)A.b * L.n_t + A.iT) * 3];
+                term = __dmul_rn(P.ks, __dmul_rn(e, e));
+            } else {
+                const double e = pl.d1(t_last) - B.scal[(int64_t)A.b * 3 + 1];
+                term = __dmul_rn(P.kdots, __dmul_rn(e, e));
+            }
+            sh_clong = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, T)), term);
+            sh_rowfeas = (vmax <= P.v_max) && (amax <= P.a_max);
+        }
+    }
+    __syncthreads();
+    const double clong = sh_clong;
+    const bool rowfeas = sh_rowfeas;
+    const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
+    const double dd = B.scal[(int64_t)A.b * 3];
+
+    // Phase B: a warp per candidate, lanes over time steps.
+    for (int id = warp; id < L.n_d; id += nwarps) {
+        const int64_t c = A.cand0 + id;
+        Poly pq;
+        pq.load(B.coef_lat + c * 6);
+        double* lat = B.lat + A.lat_off + (int64_t)id * A.npad;
+        double acc = 0.0, amax = 0.0;
+        for (int k = lane; k < A.N; k += kWarp) {
+            const double u = low ? sigma[k] : (double)k * dt;
+            const double j = pq.d3(u);
+            const double acc2 = pq.d2(u);
+            lat[k] = pq.val(u);
+            lat[A.latF + k] = pq.d1(u);
+            lat[2 * A.latF + k] = acc2;
+            lat[3 * A.latF + k] = j;
+            acc = fma(j, j, acc);
+            amax = fmax(amax, fabs(acc2));
+        }
+        acc = warp_sum(acc);
+        amax = warp_max(amax);
+        if (lane == 0) {   // :165-167 / :174-176
+            const double e = L.axis_d[id] - dd;
+            const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
+            B.cost[c] = clat;
+            B.cost[A.candF + c] = P.follow ? 0.0 : clong;
+            B.cost[2 * A.candF + c] = P.follow ? clong : 0.0;
+            B.cost[3 * A.candF + c] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
+            B.cand_flags[c] = FRENET_CAND_VALID | ((rowfeas && amax <= P.a_max) ? FRENET_CAND_KINEMATIC_OK : 0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference paths (K3)
+// ------------------------------------------------------------------------------------------------
+// Rounded rectangle, lib/trajectory/circle_trajectory.py:31-64.  c = descriptor block:
+// l, h, r, dt, period, b[0..6] (branch boundaries evaluated on the host in the reference's order).
+__device__ __forceinline__ void circle_pt(const double* __restrict__ c, double t, double& x, double& y) {
+    const double l = c[0], h = c[1], r = c[2], period = c[4];
+    const double* b = c + 5;
+    if (t >= period) t = fmod(t, period);
+    if (t >= 0.0 && t < b[0]) {
+        x = t; y = 0.0;
+    } else if (t >= b[0] && t < b[1]) {
+        double sn, cs; sincos((t - l) / r, &sn, &cs);
+        x = l + r * sn; y = r - r * cs;
+    } else if (t >= b[1] && t < b[2]) {
+        x = l + r; y = t - l - 2.0 * r * CUDART_PI / 4.0 + r;
+    } else if (t >= b[2] && t < b[3]) {
+        double sn, cs; sincos((t - b[2]) / r, &sn, &cs);
+        x = l + cs * r; y = r + h + sn * r;
+    } else if (t >= b[3] && t < b[4]) {
+        x = l - (t - l - r * CUDART_PI - h); y = 2.0 * r + h;
+    } else if (t >= b[4] && t < b[5]) {
+        double sn, cs; sincos((t - b[4]) / r, &sn, &cs);
+        x = -sn * r; y = r + h + r * cs;
+    } else if (t >= b[5] && t < b[6]) {
+        x = -r; y = r + h - (t - b[5]);
+    } else {   // last arc; negative arc lengths land here too (:62-64)
+        double sn, cs; sincos((t - b[6]) / r, &sn, &cs);
+        x = -r * cs; y = r - r * sn;
+    }
+}
+
+// Natural cubic spline over chord length, lib/trajectory/spline_trajectory.py:42-73, 146-158.
+// tab rows: knot, ax, bx, cx, dx, ay, by, cy, dy.  Outside the knot range the reference returns the
+// first / last knot ABSCISSA for value and derivative alike; kept.
+__device__ __forceinline__ void spline_eval(const double* __restrict__ tab, int n, double t, double& x, double& y, double& gx,
+                                            double& gy) {
+    const double first = tab[0], last = tab[(n - 1) * 9];
+    if (t < first) { x = y = gx = gy = first; return; }
+    if (t >= last) { x = y = gx = gy = last; return; }
+    int lo = 0, hi = n - 1;   // bisect_right(knots, t) - 1
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid * 9] <= t) lo = mid; else hi = mid;
+    }
+    const double* q = tab + lo * 9;
+    const double dx = t - q[0];
+    const double dx2 = dx * dx, dx3 = dx2 * dx;
+    x = q[1] + q[2] * dx + q[3] * dx2 + q[4] * dx3;
+    y = q[5] + q[6] * dx + q[7] * dx2 + q[8] * dx3;
+    gx = q[2] + 2.0 * q[3] * dx + 3.0 * q[4] * dx2;
+    gy = q[6] + 2.0 * q[7] * dx + 3.0 * q[8] * dx2;
+}
+
+// Path point and unit normal at arc length s: n = (-sin th, cos th), th = arctan2 of the path's
+// first derivative (compute_ortogonal_vect, lib/tests/test_obstacle_planner.py:53-56).  The circle's
+// derivative is the reference's forward chord over dt (circle_trajectory.py:66-72).
+__device__ __forceinline__ void path_frame(int kind, const double* __restrict__ circle, const double* __restrict__ tab, int n_knots,
+                                           double s, double& px, double& py, double& nx, double& ny) {
+    double gx, gy;
+    if (kind == FRENET_PATH_CIRCLE) {
+        circle_pt(circle, s, px, py);
+        double qx, qy;
+        const double h = circle[3];
+        circle_pt(circle, s + h, qx, qy);
+        gx = (qx - px) / h;
+        gy = (qy - py) / h;
+    } else {
+        spline_eval(tab, n_knots, s, px, py, gx, gy);
+    }
+    const double th = atan2(gy, gx);
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    nx = -sn;
+    ny = cs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: Frenet -> Cartesian, one CTA per row; the path frame is computed once per (row, step)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, FrenetPath path, FrenetBuffers B) {
+    extern __shared__ double sm[];
+    double* fpx = sm;
+    double* fpy = fpx + L.n_pad_max;
+    double* fnx = fpy + L.n_pad_max;
+    double* fny = fnx + L.n_pad_max;
+    double* tab = fny + L.n_pad_max;   // [n_knots][9] spline table staged in shared memory
+
+    const int64_t br = blockIdx.x;
+    const int flags = B.row_flags[br];
+    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) return;
+    const RowAddr A = row_addr(L, br);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+    if (path.kind == FRENET_PATH_SPLINE) {
+        for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+        __syncthreads();
+    }
+    const double* s_row = B.lon + A.lon_off;
+    for (int k = tid; k < A.N; k += blockDim.x) {
+        double px, py, nx, ny;
+        path_frame(path.kind, path.circle, tab, path.n_knots, s_row[k], px, py, nx, ny);
+        fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
+    }
+    __syncthreads();
+    for (int id = warp; id < L.n_d; id += nwarps) {
+        const int64_t off = A.lat_off + (int64_t)id * A.npad;
+        const double* d = B.lat + off;
+        double* x = B.xy + off;
+        double* y = x + A.latF;
+        for (int k = lane; k < A.N; k += kWarp) {
+            const double dk = d[k];
+            x[k] = __dadd_rn(fpx[k], __dmul_rn(fnx[k], dk));   // pt + n * d, unfused like the reference
+            y[k] = __dadd_rn(fpy[k], __dmul_rn(fny[k], dk));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) points_to_cartesian(FrenetPath path, const double* __restrict__ s, const double* __restrict__ d,
+                                                           int64_t n, double* __restrict__ x, double* __restrict__ y) {
+    extern __shared__ double tab[];
+    if (path.kind == FRENET_PATH_SPLINE) {
+        for (int i = threadIdx.x; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+        __syncthreads();
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double px, py, nx, ny;
+        path_frame(path.kind, path.circle, tab, path.n_knots, s[i], px, py, nx, ny);
+        const double di = d[i];
+        x[i] = __dadd_rn(px, __dmul_rn(nx, di));
+        y[i] = __dadd_rn(py, __dmul_rn(ny, di));
+    }
+}
+
+// EXTENSION (no reference code): discrete curvature of the Cartesian polyline at interior samples,
+// kappa = 2 |a x b| / (|a| |b| |a + b|), compared squared and division-free (oracle: curvature_feasible).
+__global__ void __launch_bounds__(kRowThreads) k3_curvature(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+    const int64_t br = blockIdx.x;
+    const RowAddr A = row_addr(L, br);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int flags = B.row_flags[br];
+    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
+        for (int id = tid; id < L.n_d; id += blockDim.x) B.curv_ok[A.cand0 + id] = 0;
+        return;
+    }
+    const double k2max = P.kappa_max * P.kappa_max;
+    for (int id = warp; id < L.n_d; id += nwarps) {
+        const int64_t off = A.lat_off + (int64_t)id * A.npad;
+        const double* x = B.xy + off;
+        const double* y = x + A.latF;
+        bool bad = false;
+        for (int k = 1 + lane; k + 1 < A.N; k += kWarp) {
+            const double ax = x[k] - x[k - 1], ay = y[k] - y[k - 1];
+            const double bx = x[k + 1] - x[k], by = y[k + 1] - y[k];
+            const double cx = x[k + 1] - x[k - 1], cy = y[k + 1] - y[k - 1];
+            const double cr = __dadd_rn(__dmul_rn(ax, by), -__dmul_rn(ay, bx));
+            const double lhs = __dmul_rn(4.0, __dmul_rn(cr, cr));
+            const double la = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+            const double lb = __dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by));
+            const double lc = __dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy));
+            const double rhs = __dmul_rn(k2max, __dmul_rn(__dmul_rn(la, lb), lc));
+            bad |= lhs > rhs;
+        }
+        bad = __any_sync(kFull, bad);
+        if (lane == 0) B.curv_ok[A.cand0 + id] = bad ? 0 : 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: collision, one CTA per row; obstacles staged in shared memory
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+    extern __shared__ double sm[];
+    const int O = B.n_obs;
+    double* ox = sm;
+    double* oy = sm + O;
+
+    const int64_t br = blockIdx.x;
+    const RowAddr A = row_addr(L, br);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int flags = B.row_flags[br];
+    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
+        for (int id = tid; id < L.n_d; id += blockDim.x) {
+            B.coll_free[A.cand0 + id] = 0;
+            B.first_blocker[A.cand0 + id] = -1;
+        }
+        return;
+    }
+    // Stage this scenario's obstacle snapshot; obstacles the sensor did not report are parked at
+    // infinity so the cull below never selects them (check_paths tests sensed obstacles only).
+    for (int o = tid; o < O; o += blockDim.x) {
+        const bool on = B.obs_active == nullptr || B.obs_active[(int64_t)A.b * O + o] != 0;
+        ox[o] = on ? B.obs_xy[((int64_t)A.b * O + o) * 2] : CUDART_INF;
+        oy[o] = on ? B.obs_xy[((int64_t)A.b * O + o) * 2 + 1] : CUDART_INF;
+    }
+    __syncthreads();
+    const double R = sqrt(P.radius_sq);
+    const int kNone = 0x7fffffff;
+
+    for (int id = warp; id < L.n_d; id += nwarps) {
+        const int64_t off = A.lat_off + (int64_t)id * A.npad;
+        const double* xs = B.xy + off;
+        const double* ys = xs + A.latF;
+        int best = kNone;   // lowest blocking obstacle index found so far (warp-uniform)
+        for (int kb = 0; kb < A.N; kb += kWarp) {
+            const int k = kb + lane;
+            const bool valid = k < A.N;
+            const int nvalid = min(kWarp, A.N - kb);
+            const double x = xs[valid ? k : kb], y = ys[valid ? k : kb];
+            // Bounding circle of this chunk's points: centre = middle point, radius rounded up.
+            const int mid = (nvalid - 1) >> 1;
+            const double cx = __shfl_sync(kFull, x, mid), cy = __shfl_sync(kFull, y, mid);
+            const double ex = x - cx, ey = y - cy;
+            const float r2 = __double2float_ru(fma(ex, ex, ey * ey));
+            const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));   // r2 >= 0: uint order == float order
+            const double reach = R + (double)__fsqrt_ru(r2max);
+            const double thr = reach * reach * (1.0 + 1e-9);
+            for (int ob = 0; ob < O && ob < best; ob += kWarp) {
+                const int o = ob + lane;
+                bool near = false;
+                if (o < O && o < best) {
+                    const double ux = ox[o] - cx, uy = oy[o] - cy;
+                    near = fma(ux, ux, uy * uy) <= thr;
+                }
+                unsigned m = __ballot_sync(kFull, near);
+                while (m) {   // ascending obstacle index: the first hit is this chunk's lowest blocker
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int oj = ob + j;
+                    const double dx = x - ox[oj], dy = y - oy[oj];
+                    const bool hit = valid && (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= P.radius_sq);   // :48
+                    if (__any_sync(kFull, hit)) {
+                        best = oj;
+                        m = 0;
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            B.coll_free[A.cand0 + id] = best == kNone ? 1 : 0;
+            B.first_blocker[A.cand0 + id] = best == kNone ? -1 : best;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: first-wins argmin, one CTA per scenario
+// ------------------------------------------------------------------------------------------------
+struct Best {
+    double v;
+    int i;
+    __device__ __forceinline__ void init() { v = CUDART_INF; i = 0x7fffffff; }
+    __device__ __forceinline__ void take(double nv, int ni) {   // lexicographic (cost, index); NaN never wins
+        if (nv < v || (nv == v && ni < i)) { v = nv; i = ni; }
+    }
+};
+
+constexpr int kKeys = 5;   // ctot, cd, cv, ct, masked ctot
+constexpr int kArgminThreads = 512;
+
+__global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, FrenetBuffers B, int use_mask) {
+    __shared__ double sv[kKeys][kArgminThreads / 32];
+    __shared__ int si[kKeys][kArgminThreads / 32];
+    __shared__ int scount[2][kArgminThreads / 32];
+    const int b = blockIdx.x;
+    const int C = L.n_v_cap * L.n_t * L.n_d;
+    const int64_t base = (int64_t)b * C;
+    const int64_t candF = (int64_t)L.n_scen * C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    Best best[kKeys];
+#pragma unroll
+    for (int q = 0; q < kKeys; ++q) best[q].init();
+    int nvalid = 0, nsurv = 0;
+    for (int c = tid; c < C; c += blockDim.x) {
+        const int fl = B.cand_flags[base + c];
+        if (!(fl & FRENET_CAND_VALID)) continue;
+        ++nvalid;
+        const double ctot = B.cost[3 * candF + base + c];
+        best[0].take(ctot, c);
+        best[1].take(B.cost[base + c], c);
+        best[2].take(B.cost[candF + base + c], c);
+        best[3].take(B.cost[2 * candF + base + c], c);
+        bool pass = true;
+        if (use_mask & 1) pass = pass && (fl & FRENET_CAND_KINEMATIC_OK);
+        if (use_mask & 2) pass = pass && B.curv_ok[base + c];
+        if (use_mask & 4) pass = pass && B.coll_free[base + c];
+        if (pass) {
+            ++nsurv;
+            best[4].take(ctot, c);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kKeys; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(kFull, best[q].v, o);
+            const int oi = __shfl_xor_sync(kFull, best[q].i, o);
+            best[q].take(ov, oi);
+        }
+        if (lane == 0) { sv[q][warp] = best[q].v; si[q][warp] = best[q].i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nvalid += __shfl_xor_sync(kFull, nvalid, o);
+        nsurv += __shfl_xor_sync(kFull, nsurv, o);
+    }
+    if (lane == 0) { scount[0][warp] = nvalid; scount[1][warp] = nsurv; }
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = blockDim.x >> 5;
+        Best out[kKeys];
+        int tv = 0, ts = 0;
+        for (int q = 0; q < kKeys; ++q) {
+            out[q].init();
+            for (int w = 0; w < nw; ++w) out[q].take(sv[q][w], si[q][w]);
+        }
+        for (int w = 0; w < nw; ++w) { tv += scount[0][w]; ts += scount[1][w]; }
+        FrenetResult res;
+        auto idx = [](const Best& x) { return x.i == 0x7fffffff ? -1 : x.i; };
+        res.argmin_ctot = idx(out[0]);
+        res.argmin_cd = idx(out[1]);
+        res.argmin_cv = idx(out[2]);
+        res.argmin_ct = idx(out[3]);
+        res.argmin_masked = idx(out[4]);
+        res.n_valid = tv;
+        res.n_survivors = ts;
+        res.status = tv == 0 ? FRENET_STATUS_EMPTY : (res.argmin_masked < 0 ? FRENET_STATUS_NO_FEASIBLE : FRENET_STATUS_OK);
+        res.min_ctot = out[0].v;
+        res.min_masked_ctot = out[4].v;
+        res.reserved[0] = res.reserved[1] = 0.0;
+        B.result[b] = res;
+    }
+}
+
+// Winner gather: the sampled state optimal_at_time indexes (trajectory_planner.py:183-195), 11 rows.
+__global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetParams P, FrenetBuffers B, int sel, int has_xy) {
+    const int b = blockIdx.x;
+    const FrenetResult& res = B.result[b];
+    const int c = sel == FRENET_SEL_CTOT ? res.argmin_ctot
+                : sel == FRENET_SEL_CD   ? res.argmin_cd
+                : sel == FRENET_SEL_CV   ? res.argmin_cv
+                : sel == FRENET_SEL_CT   ? res.argmin_ct
+                                         : res.argmin_masked;
+    if (c < 0) {
+        if (threadIdx.x == 0) B.winner_steps[b] = 0;
+        return;
+    }
+    const int r = c / L.n_d, id = c % L.n_d;
+    const RowAddr A = row_addr(L, (int64_t)b * L.n_v_cap * L.n_t + r);
+    double* w = B.winner + (int64_t)b * 11 * L.n_pad_max;
+    const double t0 = B.scal[(int64_t)b * 3 + 2];
+    const int64_t loff = A.lat_off + (int64_t)id * A.npad;
+    for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
+        w[k] = (double)k * P.sample_period + t0;   // f.t[i] += t_initial (:178-179)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            w[(1 + f) * L.n_pad_max + k] = B.lat[f * A.latF + loff + k];
+            w[(5 + f) * L.n_pad_max + k] = B.lon[f * A.lonF + A.lon_off + k];
+        }
+        if (has_xy) {
+            w[9 * L.n_pad_max + k] = B.xy[loff + k];
+            w[10 * L.n_pad_max + k] = B.xy[A.latF + loff + k];
+        }
+    }
+    if (threadIdx.x == 0) B.winner_steps[b] = A.N;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+int check_lattice(const FrenetLattice* L) {
+    if (!L) return fail(FRENET_ERR_BAD_ARG, "lattice is NULL");
+    if (L->n_scen <= 0 || L->n_v_cap <= 0 || L->n_t <= 0 || L->n_d <= 0 || L->n_pad_max <= 0)
+        return fail(FRENET_ERR_BAD_ARG, "lattice sizes must be positive");
+    if (!L->axis_d || !L->axis_t || !L->n_steps || !L->t_offset || !L->axis_v || !L->n_v)
+        return fail(FRENET_ERR_BAD_ARG, "lattice axis pointer is NULL");
+    if (L->row_elems <= 0 || L->cand_elems != L->row_elems * L->n_d || (L->row_elems & 3))
+        return fail(FRENET_ERR_BAD_ARG, "inconsistent lattice strides");
+    if ((int64_t)L->n_scen * L->n_v_cap * L->n_t > 0x7fffffffLL)
+        return fail(FRENET_ERR_BAD_ARG, "too many rows for one launch");
+    return FRENET_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* name) {
+    if (bytes > (size_t)kMaxSmem) return fail(FRENET_ERR_CAPACITY, name);
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fail(FRENET_ERR_CUDA, name, e);
+    }
+    return FRENET_OK;
+}
+
+inline unsigned n_rows(const FrenetLattice* L) { return (unsigned)((int64_t)L->n_scen * L->n_v_cap * L->n_t); }
+
+}  // namespace
+
+extern "C" {
+
+int frenet_abi_version(void) { return FRENET_B200_ABI_VERSION; }
+const char* frenet_last_error(void) { return g_err; }
+
+int frenet_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int frenet_k1_coefficients(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!P || !B || !B->state || !B->coef_lon || !B->coef_lat || !B->row_S || !B->row_flags)
+        return fail(FRENET_ERR_BAD_ARG, "k1: NULL buffer");
+    if (P->follow && !B->target) return fail(FRENET_ERR_BAD_ARG, "k1: follow mode needs target triples");
+    const int64_t total = (int64_t)L->n_scen * L->n_v_cap * L->n_t * L->n_d;
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return fail(FRENET_ERR_BAD_ARG, "k1: too many candidates for one launch");
+    k1_coefficients<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*L, *P, *B);
+    FRENET_CHECK_LAUNCH("k1_coefficients");
+    return FRENET_OK;
+}
+
+int frenet_k2_evaluate(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!P || !B || !B->state || !B->scal || !B->coef_lon || !B->coef_lat || !B->row_S || !B->row_flags || !B->lon || !B->lat ||
+        !B->cost || !B->cand_flags)
+        return fail(FRENET_ERR_BAD_ARG, "k2: NULL buffer");
+    if (P->follow && !B->target) return fail(FRENET_ERR_BAD_ARG, "k2: follow mode needs target triples");
+    const size_t smem = (size_t)L->n_pad_max * sizeof(double);
+    if (int rc = set_smem(k2_evaluate, smem, "k2: horizon too long for shared memory")) return rc;
+    k2_evaluate<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
+    FRENET_CHECK_LAUNCH("k2_evaluate");
+    return FRENET_OK;
+}
+
+static int check_path(const FrenetPath* path) {
+    if (!path) return fail(FRENET_ERR_BAD_ARG, "path is NULL");
+    if (path->kind == FRENET_PATH_SPLINE) {
+        if (path->n_knots < 2 || !path->spline_table) return fail(FRENET_ERR_BAD_ARG, "spline path needs >= 2 knots and a table");
+    } else if (path->kind != FRENET_PATH_CIRCLE) {
+        return fail(FRENET_ERR_BAD_ARG, "unknown path kind");
+    }
+    return FRENET_OK;
+}
+
+int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B,
+                        frenet_stream_t stream) {
+    (void)P;
+    if (int rc = check_lattice(L)) return rc;
+    if (int rc = check_path(path)) return rc;
+    if (!B || !B->row_flags || !B->lon || !B->lat || !B->xy) return fail(FRENET_ERR_BAD_ARG, "k3: NULL buffer");
+    const size_t smem = ((size_t)4 * L->n_pad_max + (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0)) * sizeof(double);
+    if (int rc = set_smem(k3_cartesian, smem, "k3: horizon / spline table too large for shared memory")) return rc;
+    k3_cartesian<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *path, *B);
+    FRENET_CHECK_LAUNCH("k3_cartesian");
+    return FRENET_OK;
+}
+
+int frenet_k3_curvature(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!P || !B || !B->row_flags || !B->xy || !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "curvature: NULL buffer");
+    k3_curvature<<<n_rows(L), kRowThreads, 0, (cudaStream_t)stream>>>(*L, *P, *B);
+    FRENET_CHECK_LAUNCH("k3_curvature");
+    return FRENET_OK;
+}
+
+int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!P || !B || !B->row_flags || !B->xy || !B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "k4: NULL buffer");
+    if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "k4: obstacle table missing");
+    const size_t smem = (size_t)2 * B->n_obs * sizeof(double);
+    if (int rc = set_smem(k4_collision, smem, "k4: too many obstacles for shared memory")) return rc;
+    k4_collision<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
+    FRENET_CHECK_LAUNCH("k4_collision");
+    return FRENET_OK;
+}
+
+int frenet_k5_argmin(const FrenetLattice* L, const FrenetBuffers* B, int32_t use_mask, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!B || !B->cost || !B->cand_flags || !B->result) return fail(FRENET_ERR_BAD_ARG, "k5: NULL buffer");
+    if ((use_mask & 2) && !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "k5: curvature mask requested but curv_ok is NULL");
+    if ((use_mask & 4) && !B->coll_free) return fail(FRENET_ERR_BAD_ARG, "k5: collision mask requested but coll_free is NULL");
+    k5_argmin<<<L->n_scen, kArgminThreads, 0, (cudaStream_t)stream>>>(*L, *B, use_mask);
+    FRENET_CHECK_LAUNCH("k5_argmin");
+    return FRENET_OK;
+}
+
+int frenet_gather_winner(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, int32_t sel, int32_t has_xy,
+                         frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!P || !B || !B->result || !B->winner || !B->winner_steps || !B->lon || !B->lat || !B->scal)
+        return fail(FRENET_ERR_BAD_ARG, "gather: NULL buffer");
+    if (has_xy && !B->xy) return fail(FRENET_ERR_BAD_ARG, "gather: xy requested but NULL");
+    if (sel < FRENET_SEL_CTOT || sel > FRENET_SEL_MASKED) return fail(FRENET_ERR_BAD_ARG, "gather: bad selector");
+    gather_winner<<<L->n_scen, 128, 0, (cudaStream_t)stream>>>(*L, *P, *B, sel, has_xy);
+    FRENET_CHECK_LAUNCH("gather_winner");
+    return FRENET_OK;
+}
+
+int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int32_t stages,
+                int32_t use_mask, int32_t gather_sel, frenet_stream_t stream) {
+    int rc = FRENET_OK;
+    if ((stages & FRENET_STAGE_K1) && (rc = frenet_k1_coefficients(L, P, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_K2) && (rc = frenet_k2_evaluate(L, P, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_K3) && (rc = frenet_k3_cartesian(L, P, path, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_CURVATURE) && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_K4) && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
+    if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, (stages & FRENET_STAGE_K3) ? 1 : 0, stream)))
+        return rc;
+    return rc;
+}
+
+int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
+                               frenet_stream_t stream) {
+    if (int rc = check_path(path)) return rc;
+    if (n < 0 || (n > 0 && (!s || !d || !x || !y))) return fail(FRENET_ERR_BAD_ARG, "points: NULL buffer");
+    if (n == 0) return FRENET_OK;
+    const size_t smem = (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0) * sizeof(double);
+    if (int rc = set_smem(points_to_cartesian, smem, "points: spline table too large for shared memory")) return rc;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;   // grid-stride beyond one full wave of 8 CTAs per SM
+    points_to_cartesian<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*path, s, d, n, x, y);
+    FRENET_CHECK_LAUNCH("points_to_cartesian");
+    return FRENET_OK;
+}
+
+}  // extern "C"

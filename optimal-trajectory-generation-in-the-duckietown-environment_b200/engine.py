@@ -1,0 +1,347 @@
+"""Device-side engine: owns the HBM buffers of a batch of planner instances and drives the C ABI.
+
+Everything numeric happens in `libfrenet_b200.so` (csrc/frenet_kernels.cu).  This module only
+  * turns lattice intervals into axes and step counts with the same NumPy calls the reference uses
+    (`np.arange`, SURVEY.md section 7.3 "bit-faithful lattice"),
+  * lays the buffers out in HBM (include/frenet_b200.h documents the layout),
+  * stages the small per-call inputs in ONE pinned host block and the small per-call outputs
+    (result records + winner trajectories) in another, so a replan costs one H2D copy, one
+    `frenet_plan` call and one D2H copy,
+  * hands NumPy views of device data back on request.
+
+PyTorch is used for device memory, pinned memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .trajectory.paths import path_descriptor_of, PATH_KIND_SPLINE
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("the Frenet planner hot path runs on a CUDA device only (sm_100a); "
+                           "no CUDA device is visible and there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class LatticeGeometry:
+    """Axes shared by every scenario of a batch: lateral offsets D, horizons T, step counts.
+
+    `np.arange(0, T + period, period)` defines the samples of a horizon
+    (lib/planner/trajectory_planner.py:139,148); only its length is needed on the device because
+    sample k of that array is exactly `k * period`.
+    """
+
+    def __init__(self, D, T, period: float):
+        self.D = np.ascontiguousarray(D, dtype=np.float64)
+        self.T = np.ascontiguousarray(T, dtype=np.float64)
+        self.period = float(period)
+        self.n_steps = np.array([len(np.arange(0, Tj + period, period)) for Tj in self.T], dtype=np.int32)
+        npad = (self.n_steps + 3) // 4 * 4
+        self.n_pad = npad.astype(np.int32)
+        self.t_offset = np.concatenate([[0], np.cumsum(npad)]).astype(np.int32)
+        self.n_t, self.n_d = len(self.T), len(self.D)
+        self.n_pad_max = int(npad.max()) if self.n_t else 0
+        self.sum_pad = int(self.t_offset[-1])
+        self.key = (self.D.tobytes(), self.T.tobytes(), self.period)
+
+    @staticmethod
+    def from_intervals(di_interval, t_interval, period):
+        return LatticeGeometry(np.arange(*di_interval), np.arange(*t_interval), period)
+
+    def steps_of_candidates(self, n_v: int) -> np.ndarray:
+        """Step count of every candidate in list order for an axis of n_v longitudinal targets."""
+        return np.tile(np.repeat(self.n_steps, self.n_d), n_v)
+
+    def cand_timesteps(self, n_v) -> int:
+        return int(np.sum(self.n_steps.astype(np.int64)) * self.n_d * np.sum(n_v))
+
+
+@dataclass
+class PathHandle:
+    desc: nat.FrenetPath
+    table: torch.Tensor | None    # keeps the device spline table alive
+    kind: int
+
+
+def make_path_handle(trajectory, device) -> PathHandle:
+    kind, n_knots, block, table = path_descriptor_of(trajectory)
+    desc = nat.FrenetPath()
+    desc.kind = kind
+    desc.n_knots = n_knots
+    for i in range(16):
+        desc.circle[i] = float(block[i])
+    tab = None
+    if kind == PATH_KIND_SPLINE:
+        tab = torch.from_numpy(np.ascontiguousarray(table, dtype=np.float64)).to(device)
+        desc.spline_table = tab.data_ptr()
+    return PathHandle(desc, tab, kind)
+
+
+def make_params(p, variant_rule: int, sample_period: float, follow: bool, radius_sq: float = 0.7 ** 2) -> nat.FrenetParams:
+    """FrenetParams from any object carrying the reference's planner attributes."""
+    P = nat.FrenetParams()
+    for k in ("kj", "kt", "kd", "ks", "kdots", "klat", "klong", "low_speed_threshold"):
+        setattr(P, k, float(getattr(p, k)))
+    P.sample_period = float(sample_period)
+    P.s_thresh = float(getattr(p, "S_thresh", 0.0))
+    P.v_max = float(getattr(p, "v_max", math.inf))
+    P.a_max = float(getattr(p, "a_max", math.inf))
+    P.kappa_max = float(getattr(p, "kappa_max", math.inf))
+    P.radius_sq = float(radius_sq)
+    P.lowspeed_rule = int(variant_rule)
+    P.follow = 1 if follow else 0
+    return P
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class FrenetEngine:
+    """HBM buffers + launch logic for `n_scen` independent planner instances sharing one lattice geometry."""
+
+    def __init__(self, n_scen: int = 1, device=None):
+        self.device = require_cuda() if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FrenetEngine needs a CUDA device")
+        self.n_scen = int(n_scen)
+        self.geom: LatticeGeometry | None = None
+        self.n_v_cap = 0
+        self.n_obs = 0
+        self.L = nat.FrenetLattice()
+        self.B = nat.FrenetBuffers()
+        self._cap_key = None
+        self._paths = {}
+        self.generation = 0
+        self.has_xy = False
+        self.has_collision = False
+
+    # -- allocation ---------------------------------------------------------------------------
+    def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0):
+        """(Re)allocate for a geometry / capacities; cheap when nothing changed."""
+        n_obs = int(n_obs)
+        key = (geom.key, int(n_v_cap), n_obs)
+        if key == self._cap_key:
+            return
+        dev, Bn = self.device, self.n_scen
+        self.geom, self.n_v_cap, self.n_obs = geom, int(n_v_cap), n_obs
+        nT, nD = geom.n_t, geom.n_d
+        R = self.n_v_cap * nT
+        Cc = R * nD
+        self.R, self.C = R, Cc
+        row_elems = self.n_v_cap * geom.sum_pad
+        cand_elems = row_elems * nD
+        self.row_elems, self.cand_elems = row_elems, cand_elems
+
+        # geometry arrays (one small upload per geometry change)
+        g = np.zeros(_align(nD * 8) + _align(nT * 8) + _align(nT * 4) + _align((nT + 1) * 4), dtype=np.uint8)
+        o_d, o_t = 0, _align(nD * 8)
+        o_n = o_t + _align(nT * 8)
+        o_o = o_n + _align(nT * 4)
+        g[o_d:o_d + nD * 8] = geom.D.view(np.uint8)
+        g[o_t:o_t + nT * 8] = geom.T.view(np.uint8)
+        g[o_n:o_n + nT * 4] = geom.n_steps.view(np.uint8)
+        g[o_o:o_o + (nT + 1) * 4] = geom.t_offset.view(np.uint8)
+        self._geom_dev = torch.from_numpy(g).to(dev)
+        gp = self._geom_dev.data_ptr()
+
+        # packed small inputs: one pinned host block, one device block
+        sizes = [("state", Bn * 6 * 8), ("scal", Bn * 3 * 8), ("axis_v", Bn * self.n_v_cap * 8), ("target", Bn * nT * 3 * 8),
+                 ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("n_v", Bn * 4), ("obs_active", Bn * max(n_obs, 1))]
+        offs, tot = {}, 0
+        for name, sz in sizes:
+            offs[name] = tot
+            tot += _align(sz)
+        self._in_host = torch.empty(tot, dtype=torch.uint8, pin_memory=True)
+        self._in_dev = torch.empty(tot, dtype=torch.uint8, device=dev)
+        hv = self._in_host.numpy()
+        self.state = hv[offs["state"]:offs["state"] + Bn * 48].view(np.float64).reshape(Bn, 6)
+        self.scal = hv[offs["scal"]:offs["scal"] + Bn * 24].view(np.float64).reshape(Bn, 3)
+        self.axis_v = hv[offs["axis_v"]:offs["axis_v"] + Bn * self.n_v_cap * 8].view(np.float64).reshape(Bn, self.n_v_cap)
+        self.target = hv[offs["target"]:offs["target"] + Bn * nT * 24].view(np.float64).reshape(Bn, nT, 3)
+        no = max(n_obs, 1)
+        self.obs_xy = hv[offs["obs_xy"]:offs["obs_xy"] + Bn * no * 16].view(np.float64).reshape(Bn, no, 2)
+        self.n_v = hv[offs["n_v"]:offs["n_v"] + Bn * 4].view(np.int32)
+        self.obs_active = hv[offs["obs_active"]:offs["obs_active"] + Bn * no].reshape(Bn, no)
+        hv[:] = 0
+        self.obs_active[:] = 1
+        ip = self._in_dev.data_ptr()
+        self._in_offs = offs
+
+        # packed small outputs
+        osz = [("winner", Bn * 11 * geom.n_pad_max * 8), ("result", Bn * nat.RESULT_BYTES), ("winner_steps", Bn * 4)]
+        ooffs, otot = {}, 0
+        for name, sz in osz:
+            ooffs[name] = otot
+            otot += _align(sz)
+        self._out_host = torch.empty(otot, dtype=torch.uint8, pin_memory=True)
+        self._out_dev = torch.zeros(otot, dtype=torch.uint8, device=dev)
+        ov = self._out_host.numpy()
+        ov[:] = 0
+        self.winner = ov[:Bn * 11 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 11, geom.n_pad_max)
+        self.result = ov[ooffs["result"]:ooffs["result"] + Bn * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE))
+        self.winner_steps = ov[ooffs["winner_steps"]:ooffs["winner_steps"] + Bn * 4].view(np.int32)
+        op = self._out_dev.data_ptr()
+
+        # large state
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.coef_lon = torch.empty((Bn, R, 6), **f64)
+        self.coef_lat = torch.empty((Bn, Cc, 6), **f64)
+        self.row_S = torch.empty((Bn, R), **f64)
+        self.row_flags = torch.empty((Bn, R), dtype=torch.int32, device=dev)
+        self.lon = torch.empty((4, Bn, row_elems), **f64)
+        self.lat = torch.empty((4, Bn, cand_elems), **f64)
+        self.xy = torch.empty((2, Bn, cand_elems), **f64)
+        self.cost = torch.empty((4, Bn, Cc), **f64)
+        self.cand_flags = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
+        self.curv_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
+        self.coll_free = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
+        self.first_blocker = torch.empty((Bn, Cc), dtype=torch.int32, device=dev)
+
+        L = self.L
+        L.n_scen, L.n_v_cap, L.n_t, L.n_d, L.n_pad_max = Bn, self.n_v_cap, nT, nD, geom.n_pad_max
+        L.row_elems, L.cand_elems = row_elems, cand_elems
+        L.axis_d, L.axis_t, L.n_steps, L.t_offset = gp + o_d, gp + o_t, gp + o_n, gp + o_o
+        L.axis_v, L.n_v = ip + offs["axis_v"], ip + offs["n_v"]
+        Bf = self.B
+        Bf.state, Bf.scal, Bf.target = ip + offs["state"], ip + offs["scal"], ip + offs["target"]
+        Bf.obs_xy, Bf.obs_active, Bf.n_obs = ip + offs["obs_xy"], ip + offs["obs_active"], n_obs
+        Bf.coef_lon, Bf.coef_lat = self.coef_lon.data_ptr(), self.coef_lat.data_ptr()
+        Bf.row_S, Bf.row_flags = self.row_S.data_ptr(), self.row_flags.data_ptr()
+        Bf.lon, Bf.lat, Bf.cost, Bf.cand_flags = self.lon.data_ptr(), self.lat.data_ptr(), self.cost.data_ptr(), self.cand_flags.data_ptr()
+        Bf.xy, Bf.curv_ok = self.xy.data_ptr(), self.curv_ok.data_ptr()
+        Bf.coll_free, Bf.first_blocker = self.coll_free.data_ptr(), self.first_blocker.data_ptr()
+        Bf.result = op + ooffs["result"]
+        Bf.winner, Bf.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
+        self._cap_key = key
+
+    def hbm_bytes(self) -> int:
+        ts = [self.coef_lon, self.coef_lat, self.row_S, self.row_flags, self.lon, self.lat, self.xy, self.cost, self.cand_flags,
+              self.curv_ok, self.coll_free, self.first_blocker, self._in_dev, self._out_dev, self._geom_dev]
+        return sum(t.numel() * t.element_size() for t in ts)
+
+    @staticmethod
+    def bytes_per_scenario(geom: LatticeGeometry, n_v_cap: int) -> int:
+        row = n_v_cap * geom.sum_pad
+        cand = row * geom.n_d
+        C_ = n_v_cap * geom.n_t * geom.n_d
+        return 8 * (4 * row + 6 * cand) + C_ * (6 * 8 + 4 * 8 + 3 + 4) + n_v_cap * geom.n_t * (6 * 8 + 8 + 4)
+
+    # -- path handles --------------------------------------------------------------------------
+    def path_handle(self, trajectory) -> PathHandle:
+        key = id(trajectory)
+        h = self._paths.get(key)
+        if h is None or h[0] is not trajectory:
+            h = (trajectory, make_path_handle(trajectory, self.device))
+            self._paths[key] = h
+        return h[1]
+
+    # -- launches ------------------------------------------------------------------------------
+    def upload(self, stream=None):
+        """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles)."""
+        self._in_dev.copy_(self._in_host, non_blocking=True)
+
+    def launch(self, params: nat.FrenetParams, path: PathHandle | None, stages: int, use_mask: int = 0,
+               gather_sel: int = nat.SEL_CTOT, n_obs: int | None = None):
+        """Enqueue the selected pipeline stages on torch's current stream (asynchronous)."""
+        if n_obs is not None:
+            if n_obs > self.n_obs:
+                raise ValueError(f"{n_obs} obstacles exceed the configured capacity {self.n_obs}")
+            self.B.n_obs = int(n_obs)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        pp = C.byref(path.desc) if path is not None else None
+        nat.check(nat.lib.frenet_plan(C.byref(self.L), C.byref(params), pp, C.byref(self.B), int(stages), int(use_mask),
+                                      int(gather_sel), C.c_void_p(stream)))
+        if stages & nat.STAGE_K2:
+            self.generation += 1
+            self.has_xy = False
+            self.has_collision = False
+        if stages & nat.STAGE_K3:
+            self.has_xy = True
+        if stages & nat.STAGE_K4:
+            self.has_collision = True
+
+    def download(self, sync: bool = True):
+        """One D2H copy of the packed per-call outputs (result records, winner trajectories)."""
+        self._out_host.copy_(self._out_dev, non_blocking=True)
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def run(self, params, path, stages, use_mask=0, gather_sel=nat.SEL_CTOT, n_obs=None):
+        """upload -> pipeline -> download, synchronous."""
+        self.upload()
+        self.launch(params, path, stages, use_mask, gather_sel, n_obs)
+        self.download(sync=True)
+
+    # -- views of device data ------------------------------------------------------------------
+    def cand_offsets(self, n_v: int):
+        """(offset into a lateral field, row offset into a longitudinal field, steps) per candidate in list order."""
+        g = self.geom
+        iv = np.repeat(np.arange(n_v), g.n_t * g.n_d)
+        iT = np.tile(np.repeat(np.arange(g.n_t), g.n_d), n_v)
+        idd = np.tile(np.arange(g.n_d), n_v * g.n_t)
+        within = iv.astype(np.int64) * g.sum_pad + g.t_offset[iT]
+        return within * g.n_d + idd * g.n_pad[iT], within, g.n_steps[iT]
+
+    def fetch_scenario(self, b: int = 0, with_xy: bool | None = None, with_collision: bool | None = None) -> dict:
+        """D2H of one scenario's full lattice state as NumPy arrays (raw padded layout + offsets)."""
+        with_xy = self.has_xy if with_xy is None else with_xy
+        with_collision = self.has_collision if with_collision is None else with_collision
+        nv = int(self.n_v[b])
+        out = dict(n_v=nv, lon=self.lon[:, b].cpu().numpy(), lat=self.lat[:, b].cpu().numpy(),
+                   cost=self.cost[:, b].cpu().numpy(), cand_flags=self.cand_flags[b].cpu().numpy(),
+                   coef_lon=self.coef_lon[b].cpu().numpy(), coef_lat=self.coef_lat[b].cpu().numpy(),
+                   row_S=self.row_S[b].cpu().numpy(), row_flags=self.row_flags[b].cpu().numpy())
+        if with_xy:
+            out["xy"] = self.xy[:, b].cpu().numpy()
+        if with_collision:
+            out["coll_free"] = self.coll_free[b].cpu().numpy()
+            out["first_blocker"] = self.first_blocker[b].cpu().numpy()
+        out["lat_off"], out["lon_off"], out["nsteps"] = self.cand_offsets(nv)
+        return out
+
+    def padded_fields(self, sc: dict) -> dict:
+        """Scenario dict -> [C][Nmax] NaN-padded arrays in the golden-fixture layout (tests, lazy views)."""
+        g = self.geom
+        C_ = sc["n_v"] * g.n_t * g.n_d
+        nmax = int(g.n_steps.max())
+        k = np.arange(nmax)
+        n = sc["nsteps"]
+        valid = k[None, :] < n[:, None]
+        il = np.where(valid, sc["lat_off"][:, None] + k[None, :], 0)
+        io = np.where(valid, sc["lon_off"][:, None] + k[None, :], 0)
+        res = {"nsteps": n.astype(np.int32)}
+        for j, name in enumerate(("d", "dot_d", "ddot_d", "dddot_d")):
+            res[name] = np.where(valid, sc["lat"][j][il], np.nan)
+        for j, name in enumerate(("s", "dot_s", "ddot_s", "dddot_s")):
+            res[name] = np.where(valid, sc["lon"][j][io], np.nan)
+        if "xy" in sc:
+            res["x"] = np.where(valid, sc["xy"][0][il], np.nan)
+            res["y"] = np.where(valid, sc["xy"][1][il], np.nan)
+        for j, name in enumerate(("cd", "cv", "ct", "ctot")):
+            res[name] = sc["cost"][j][:C_]
+        res["valid"] = (sc["cand_flags"][:C_] & nat.CAND_VALID) != 0
+        res["kinematic_ok"] = (sc["cand_flags"][:C_] & nat.CAND_KINEMATIC_OK) != 0
+        if "coll_free" in sc:
+            res["coll_free"] = sc["coll_free"][:C_] != 0
+            res["first_blocker"] = sc["first_blocker"][:C_]
+        return res
+
+    def points_to_cartesian(self, path: PathHandle, s, d):
+        """Point-wise Frenet -> Cartesian on the device; s, d array-likes of equal length; returns (x, y) NumPy."""
+        s = torch.as_tensor(np.ascontiguousarray(s, dtype=np.float64)).to(self.device)
+        d = torch.as_tensor(np.ascontiguousarray(d, dtype=np.float64)).to(self.device)
+        x = torch.empty_like(s)
+        y = torch.empty_like(s)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_points_to_cartesian(C.byref(path.desc), s.data_ptr(), d.data_ptr(), s.numel(), x.data_ptr(),
+                                                     y.data_ptr(), C.c_void_p(stream)))
+        return x.cpu().numpy(), y.cpu().numpy()

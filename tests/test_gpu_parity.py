@@ -1,0 +1,408 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference goldens and the oracle.
+
+Tolerances (BASELINE.json north star): candidate feasibility / collision masks and argmin indices
+are exact, except where a cost or limit lies within 1e-6 relative of a threshold or tie; polynomial
+coefficients, costs and Cartesian poses agree within 1e-5 relative in fp64.  The CUDA path is in
+fact held to GPU_RTOL below, far tighter than the contract.
+"""
+import numpy as np
+import pytest
+
+from _golden import golden, prefixed, compare_packed, assert_close, near_tie, pack_lattice, RTOL
+from oracle import frenet_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+GPU_RTOL = 1e-9
+R2 = fo.ROBOT_RADIUS ** 2
+
+
+def _imports():
+    import _gpu
+    from otg_b200 import _native as nat
+    from otg_b200.trajectory import CircleTrajectory2D, SplineTrajectory2D
+    return _gpu, nat, CircleTrajectory2D, SplineTrajectory2D
+
+
+def _check_argmin(got_idx, ref_idx, costs, what):
+    """Exact, except for ties within 1e-6 relative (north star)."""
+    if got_idx == ref_idx:
+        return
+    assert got_idx >= 0 and ref_idx >= 0 and near_tie(costs, got_idx, ref_idx), f"{what}: argmin {got_idx} vs {ref_idx}"
+
+
+def _margin_ok(x, y, nsteps, obs, got, ref):
+    """Collision masks may differ only for candidates whose closest approach is within 1e-6 of the radius."""
+    bad = np.nonzero(got != ref)[0]
+    for c in bad:
+        n = nsteps[c]
+        d2 = ((x[c, :n, None] - obs[None, :, 0]) ** 2 + (y[c, :n, None] - obs[None, :, 1]) ** 2)
+        if not (np.abs(d2 - R2) <= 1e-6 * R2).any():
+            return False
+    return True
+
+
+# ------------------------------------------------------------------------------------------------
+def test_kat_variants_match_reference():
+    _gpu, nat, *_ = _imports()
+    z = golden("kat_variants")
+    for i in range(int(z["n_cases"])):
+        c = prefixed(z, f"c{i}_")
+        prm = fo.OracleParams.defaults(str(c["variant"]))
+        eng = _gpu.run_batch(prm, c["p0"], c["s0"], float(c["t0"]), dd=float(c["dd"]))
+        sc = eng.fetch_scenario(0)
+        f = eng.padded_fields(sc)
+        got = _gpu.compact(f)
+        compare_packed(got, c, GPU_RTOL, f"kat{i}")
+        # coefficients against the oracle (np.linalg.solve like the reference)
+        L = fo.generate(prm, c["p0"], c["s0"], float(c["t0"]), dd=float(c["dd"]))
+        C_, R_ = L.n_candidates, L.clon.shape[0]
+        assert_close(sc["coef_lon"][:R_], L.clon, GPU_RTOL, f"kat{i}.coef_lon", atol_scale=max(1.0, np.abs(L.clon).max()))
+        keep = L.keep
+        assert_close(sc["coef_lat"][:C_][keep], L.clat[keep], GPU_RTOL, f"kat{i}.coef_lat", atol_scale=max(1.0, np.abs(L.clat).max()))
+        assert np.array_equal(f["valid"], keep)
+        assert f["kinematic_ok"][keep].all()           # infinite limits == reference (no limits)
+        res = eng.result[0]
+        valid_idx = np.nonzero(f["valid"])[0]
+        for key, field in (("ctot", "argmin_ctot"), ("cd", "argmin_cd"), ("cv", "argmin_cv")):
+            got_c = int(np.searchsorted(valid_idx, res[field]))
+            _check_argmin(got_c, int(c[f"argmin_{key}"]), c[key], f"kat{i}.{key}")
+        assert res["n_valid"] == len(valid_idx) and res["status"] == nat.STATUS_OK
+        # winner gather == the golden winner's arrays
+        w = int(c["argmin_ctot"])
+        n = int(c["nsteps"][w])
+        assert eng.winner_steps[0] == n
+        for row, name in enumerate(("t", "d", "dot_d", "ddot_d", "dddot_d", "s", "dot_s", "ddot_s", "dddot_s")):
+            assert_close(eng.winner[0, row, :n], c[name][w, :n], GPU_RTOL, f"kat{i}.winner.{name}")
+
+
+def test_mirror_ties_first_wins():
+    """p0 = (0,0,0), dd = 0: +d / -d candidates have bit-identical ctot; the lower index wins."""
+    _gpu, *_ = _imports()
+    prm = fo.OracleParams.defaults("v1")
+    eng = _gpu.run_batch(prm, (0, 0, 0), (0, 3.0, 0), 0.1)
+    f = eng.padded_fields(eng.fetch_scenario(0))
+    nD = eng.geom.n_d
+    ctot = f["ctot"].reshape(-1, nD)
+    # D = -4 .. 3.5: index j and nD - j mirror each other (j = 1 .. nD/2 - 1)
+    for j in range(1, nD // 2):
+        assert np.array_equal(ctot[:, j], ctot[:, nD - j])
+    L = fo.generate(prm, (0, 0, 0), (0, 3.0, 0), 0.1)
+    assert eng.result[0]["argmin_ctot"] == fo.first_argmin(L.ctot)
+
+
+def test_paths_pointwise():
+    _gpu, nat, Circle, Spline = _imports()
+    from otg_b200.engine import FrenetEngine
+    z = golden("paths")
+    eng = FrenetEngine(1)
+    for name, tr in (("circle", Circle(8, 5, 2)), ("spline", Spline(list(z["spline_wx"]), list(z["spline_wy"])))):
+        x, y = eng.points_to_cartesian(eng.path_handle(tr), z[f"{name}_s"], z[f"{name}_d"])
+        assert_close(np.stack([x, y], 1), z[f"{name}_xy"], GPU_RTOL, f"{name}.xy", atol_scale=60.0)
+
+
+def _sim_batch(kind):
+    _gpu, nat, Circle, _ = _imports()
+    z = golden(f"sim_planner_{kind}")
+    prm = fo.OracleParams.defaults("v1")
+    kw = {}
+    if kind != "full":
+        active = np.zeros((499, 10), dtype=np.uint8)
+        for i in range(499):
+            active[i, z["obs_idx"][i, :z["n_sensed"][i]]] = 1
+        kw = dict(trajectory=Circle(8, 5, 2), obstacles=z["obs_all_xy"], active=active)
+    eng = _gpu.run_batch(prm, z["p0"], z["s0"], z["time"], **kw)
+    return z, eng, nat
+
+
+@pytest.mark.parametrize("kind", ["full", "static", "moving"])
+def test_sim_replans_match_reference(kind):
+    """All 499 recorded replans of the closed-loop reference run, as one batch of 499 scenarios."""
+    z, eng, nat = _sim_batch(kind)
+    res = eng.result
+    cost_steps = {int(s): j for j, s in enumerate(z["cost_steps"])}
+    n_tie = 0
+    for i in range(499):
+        C_ = int(z["ncand"][i])
+        assert res["n_valid"][i] == C_
+        if res["argmin_ctot"][i] != z["argmin"][i]:
+            n_tie += 1
+            ct = eng.cost[3, i].cpu().numpy()
+            _check_argmin(int(res["argmin_ctot"][i]), int(z["argmin"][i]), ct, f"{kind}/step{i}")
+        assert res["min_ctot"][i] == pytest.approx(z["ctot_min"][i], rel=GPU_RTOL)
+    assert n_tie == 0
+    cost = eng.cost.cpu().numpy()
+    for i, j in cost_steps.items():
+        C_ = int(z["ncand"][i])
+        for q, k in enumerate(("cd", "cv", "ct", "ctot")):
+            if k in z:
+                assert_close(cost[q, i, :C_], z[k][j, :C_], GPU_RTOL, f"{kind}/step{i}.{k}")
+    for i in z["full_steps"]:
+        f = eng.padded_fields(eng.fetch_scenario(int(i)))
+        compare_packed(f, prefixed(z, f"s{i}_"), GPU_RTOL, f"{kind}/step{i}")
+        if kind != "full":
+            g = prefixed(z, f"s{i}_")
+            assert_close(f["x"], g["x"], GPU_RTOL, f"{kind}/step{i}.x", atol_scale=20.0)
+            assert_close(f["y"], g["y"], GPU_RTOL, f"{kind}/step{i}.y", atol_scale=20.0)
+    if kind == "full":
+        return
+    keep = eng.coll_free.cpu().numpy()
+    first = eng.first_blocker.cpu().numpy()
+    n_diff = 0
+    for i in range(499):
+        C_ = int(z["ncand"][i])
+        assert np.array_equal(keep[i, :C_], z["keep"][i, :C_]), f"{kind}/step{i}: collision mask"
+        if kind == "moving":   # golden blocker = position in the sensed list; ours = index in the full list
+            ns = int(z["n_sensed"][i])
+            pos = {int(o): j for j, o in enumerate(z["obs_idx"][i, :ns])}
+            ours = np.array([pos.get(int(o), -1) for o in first[i, :C_]], dtype=np.int8)
+            assert np.array_equal(ours, z["first_blocker"][i, :C_]), f"{kind}/step{i}: first blocker"
+        assert res["argmin_masked"][i] == z["argmin_masked"][i], f"{kind}/step{i}: masked argmin"
+        assert res["n_survivors"][i] == int(z["keep"][i, :C_].sum())
+        n_diff += int(res["argmin_masked"][i] != res["argmin_ctot"][i])
+    assert n_diff == (86 if kind == "static" else 97)
+
+
+def test_follow_mode_v1():
+    _gpu, nat, *_ = _imports()
+    z = golden("follow_mode")
+    prm = fo.OracleParams.defaults("v1")
+    for j in range(3):
+        g = prefixed(z, f"r{j}_")
+        eng = _gpu.run_batch(prm, g["p0"], g["s0"], float(g["time"]), targets=g["triples"][None])
+        f = eng.padded_fields(eng.fetch_scenario(0))
+        compare_packed(f, g, GPU_RTOL, f"follow{j}")
+        assert eng.result[0]["argmin_ctot"] == int(g["argmin"])
+
+
+def test_optimal_variant_targets_and_mutation():
+    _gpu, nat, *_ = _imports()
+    z = golden("optimal_targets")
+    prm = fo.OracleParams.defaults("optimal")
+    T = np.arange(*prm.t_interval())
+    for name in ("stop", "merge", "follow"):
+        tgt = {k: z[f"{name}_target_{k}"] for k in ("t", "s", "dot_s", "ddot_s", "dddot_s")}
+        trip = fo.optimal_target_triples(tgt, T, 0, prm.delta_t)
+        eng = _gpu.run_batch(prm, (3, 0.3, 0), (0, 2, -0.5), 0.0, targets=trip[None], gather_sel=nat.SEL_CT)
+        f = eng.padded_fields(eng.fetch_scenario(0))
+        g = prefixed(z, f"{name}_init_")
+        got = _gpu.compact(f)
+        compare_packed(got, g, GPU_RTOL, f"optimal/{name}")
+        vi = np.nonzero(f["valid"])[0]
+        assert int(np.searchsorted(vi, eng.result[0]["argmin_ct"])) == int(g["argmin_ct"])
+        assert int(np.searchsorted(vi, eng.result[0]["argmin_ctot"])) == int(g["argmin_ctot"])
+        for j, tn in enumerate((0, 2.5, 5)):
+            g = prefixed(z, f"{name}_ct{j}_")
+            trip = fo.optimal_target_triples(tgt, T, tn, prm.delta_t)
+            eng = _gpu.run_batch(prm, g["p0"], g["s0"], tn, targets=trip[None], engine=eng)
+            f = eng.padded_fields(eng.fetch_scenario(0))
+            compare_packed(_gpu.compact(f), g, GPU_RTOL, f"optimal/{name}/ct{j}", fields=("s", "d"))
+            vi = np.nonzero(f["valid"])[0]
+            assert int(np.searchsorted(vi, eng.result[0]["argmin_ct"])) == int(g["argmin_ct"])
+    g = prefixed(z, "mutated_")
+    eng = _gpu.run_batch(prm.with_(klat=0.3), g["p0"], g["s0"], 0.0, t_interval=(prm.min_t, prm.max_t, prm.dt / 2),
+                         di_interval=(-1, 2.45, 0.2))
+    f = eng.padded_fields(eng.fetch_scenario(0))
+    compare_packed(_gpu.compact(f), g, GPU_RTOL, "optimal/mutated")
+    vi = np.nonzero(f["valid"])[0]
+    assert int(np.searchsorted(vi, eng.result[0]["argmin_ctot"])) == int(g["argmin"])
+
+
+# ------------------------------------------------------------------------------------------------
+def _dense_prm():
+    from otg_b200 import workloads
+    return fo.OracleParams.defaults("v1").with_(**workloads.DENSE_PARAMS)
+
+
+def test_dense_config4_matches_reference():
+    _gpu, nat, _, Spline = _imports()
+    from otg_b200 import workloads
+    z = golden("dense_config4")
+    sc = workloads.config4_scenario()
+    tr = Spline(workloads.SPLINE_WX, workloads.SPLINE_WY)
+    from otg_b200.engine import FrenetEngine
+    e0 = FrenetEngine(1)
+    ox, oy = e0.points_to_cartesian(e0.path_handle(tr), sc["obs_s"], sc["obs_d"])
+    assert_close(np.stack([ox, oy], 1), z["obs_xy"], GPU_RTOL, "config4 obstacles", atol_scale=60.0)
+    eng = _gpu.run_batch(_dense_prm(), sc["p0"], sc["s0"], sc["t0"], dd=sc["dd"], trajectory=tr,
+                         obstacles=np.stack([ox, oy], 1)[None], gather_sel=nat.SEL_MASKED)
+    res = eng.result[0]
+    assert res["n_valid"] == 9600 and res["argmin_ctot"] == int(z["argmin"]) == 6361
+    assert res["min_ctot"] == pytest.approx(0.33889646121037686, rel=GPU_RTOL)
+    s = eng.fetch_scenario(0)
+    f = eng.padded_fields(s)
+    assert np.array_equal(f["nsteps"], z["nsteps"]) and int(f["nsteps"].sum()) == 954720
+    for k in ("cd", "cv", "ctot"):
+        assert_close(f[k], z[k], GPU_RTOL, f"config4.{k}")
+    assert np.array_equal(f["coll_free"].astype(np.uint8), z["keep"])
+    assert np.array_equal(f["first_blocker"].astype(np.int16), z["first_blocker"])
+    assert res["argmin_masked"] == int(z["argmin_masked"]) and res["n_survivors"] == int(z["keep"].sum())
+    names = ("d", "dot_d", "ddot_d", "dddot_d", "s", "dot_s", "ddot_s", "dddot_s", "x", "y")
+    chk = np.stack([np.nansum(f[n], axis=1) for n in names], 1)
+    assert_close(chk, z["checksum"][:, 1:], GPU_RTOL, "config4 checksums", atol_scale=float(np.abs(z["checksum"]).max()))
+    idx = z["sample_idx"]
+    for n in names:
+        assert_close(f[n][idx], z[f"sample_{n}"], GPU_RTOL, f"config4 sample {n}", atol_scale=60.0)
+    # masked winner gather carries x, y
+    w = int(z["argmin_masked"])
+    n = int(z["nsteps"][w])
+    assert eng.winner_steps[0] == n
+    assert_close(eng.winner[0, 9, :n], f["x"][w, :n], 0.0, "winner x", atol_scale=1.0)
+    assert_close(eng.winner[0, 10, :n], f["y"][w, :n], 0.0, "winner y", atol_scale=1.0)
+
+
+def test_config5_sample_matches_reference():
+    _gpu, nat, _, Spline = _imports()
+    from otg_b200 import workloads
+    z = golden("config5_sample")
+    sc = workloads.config5_scenarios()
+    idx = z["scenario_idx"]
+    tr = Spline(workloads.SPLINE_WX, workloads.SPLINE_WY)
+    eng = _gpu.run_batch(_dense_prm(), sc["p0"][idx], sc["s0"][idx], sc["t0"][idx], dd=sc["dd"][idx], trajectory=tr,
+                         obstacles=z["obs_xy"])
+    res = eng.result
+    keep = eng.coll_free.cpu().numpy()
+    first = eng.first_blocker.cpu().numpy()
+    cost = eng.cost.cpu().numpy()
+    for i in range(len(idx)):
+        C_ = int(z["ncand"][i])
+        assert res["n_valid"][i] == C_
+        assert_close(cost[0, i, :C_], z["cd"][i, :C_], GPU_RTOL, f"config5[{i}].cd")
+        assert_close(cost[3, i, :C_], z["ctot"][i, :C_], GPU_RTOL, f"config5[{i}].ctot")
+        assert res["argmin_ctot"][i] == z["argmin"][i]
+        assert np.array_equal(keep[i, :C_], z["keep"][i, :C_])
+        assert np.array_equal(first[i, :C_].astype(np.int16), z["first_blocker"][i, :C_])
+        assert res["argmin_masked"][i] == z["argmin_masked"][i]
+        assert res["status"][i] == (nat.STATUS_OK if z["argmin_masked"][i] >= 0 else nat.STATUS_NO_FEASIBLE)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_batch_against_oracle_with_limits_and_curvature():
+    """Random batch on both paths vs the oracle, with FINITE kinematic / curvature limits (extension: the oracle
+    is the definition) and a partially active obstacle table."""
+    _gpu, nat, Circle, Spline = _imports()
+    from otg_b200 import workloads
+    rng = np.random.default_rng(123)
+    B = 24
+    p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.5, .5, B), rng.uniform(-.5, .5, B)], 1)
+    s0 = np.stack([rng.uniform(0, 25, B), rng.uniform(0, 4, B), rng.uniform(-.5, .5, B)], 1)
+    dd = rng.uniform(-1, 1, B)
+    t0 = rng.uniform(0, 5, B)
+    prm = fo.OracleParams.defaults("v1").with_(v_max=5.3, a_max=3.1, kappa_max=1.5)   # off the integer target speeds: no exact ties at the limit
+    for tr, op in ((Circle(8, 5, 2), fo.CirclePath(8, 5, 2)),
+                   (Spline(workloads.SPLINE_WX, workloads.SPLINE_WY), fo.SplinePath(workloads.SPLINE_WX, workloads.SPLINE_WY))):
+        so = s0[:, 0:1] + rng.uniform(1, 12, (B, 12))
+        do = rng.uniform(-5, 5, (B, 12))
+        ox, oy = fo.frenet_to_cartesian(op, so, do)
+        obs = np.stack([ox, oy], 2)
+        active = (rng.uniform(size=(B, 12)) < 0.7).astype(np.uint8)
+        eng = _gpu.run_batch(prm, p0, s0, t0, dd=dd, trajectory=tr, obstacles=obs, active=active,
+                             use_mask=nat.MASK_KINEMATIC, curvature=True)
+        curv = eng.curv_ok.cpu().numpy()
+        n_infeasible = 0
+        for b in range(B):
+            L = fo.generate(prm, p0[b], s0[b], t0[b], dd=dd[b])
+            f = eng.padded_fields(eng.fetch_scenario(b))
+            compare_packed(f, pack_lattice(L, t_field=False), GPU_RTOL, f"batch[{b}]")
+            x, y = fo.lattice_to_cartesian(op, L)
+            nmax = f["x"].shape[1]
+            valid = np.arange(nmax)[None, :] < L.nsteps[:, None]
+            assert_close(f["x"], np.where(valid, x[:, :nmax], np.nan), GPU_RTOL, f"batch[{b}].x", per_row=True)
+            assert_close(f["y"], np.where(valid, y[:, :nmax], np.nan), GPU_RTOL, f"batch[{b}].y", per_row=True)
+            C_ = L.n_candidates
+            assert np.array_equal(f["kinematic_ok"], L.feasible), f"batch[{b}] kinematic mask"
+            ok, first = fo.check_collisions(x, y, L.nsteps, obs[b][active[b] != 0])
+            got_ok = f["coll_free"]
+            assert np.array_equal(got_ok, ok) or _margin_ok(x, y, L.nsteps, obs[b][active[b] != 0], got_ok, ok)
+            act_idx = np.nonzero(active[b])[0]
+            ours = f["first_blocker"]
+            assert np.array_equal(np.where(ours >= 0, ours, -1), np.where(first >= 0, act_idx[np.maximum(first, 0)], -1))
+            cok = fo.curvature_feasible(x, y, L.nsteps, prm.kappa_max)
+            assert np.array_equal(curv[b, :C_] != 0, cok), f"batch[{b}] curvature mask"
+            mask = L.feasible & ok & cok
+            n_infeasible += int((~mask).sum())
+            _check_argmin(int(eng.result[b]["argmin_masked"]), fo.first_argmin(L.ctot, mask), L.ctot, f"batch[{b}] masked")
+            assert eng.result[b]["n_survivors"] == int(mask.sum())
+        assert n_infeasible > 0
+
+
+def test_full_size_properties():
+    """Config-5-sized scenarios (dense lattice, 128 obstacles): size-independent properties."""
+    _gpu, nat, _, Spline = _imports()
+    from otg_b200 import workloads
+    sc = workloads.config5_scenarios()
+    B = 32
+    sl = slice(100, 100 + B)
+    tr = Spline(workloads.SPLINE_WX, workloads.SPLINE_WY)
+    op = fo.SplinePath(workloads.SPLINE_WX, workloads.SPLINE_WY)
+    fs, fd = workloads.moving_obstacle_frenet(sc["obs_s"][sl], sc["obs_d"][sl], sc["obs_speed"][sl], sc["obs_offset"][sl],
+                                              sc["t0"][sl, None])
+    ox, oy = fo.frenet_to_cartesian(op, fs, fd)
+    obs = np.stack([ox, oy], 2)
+    eng = _gpu.run_batch(_dense_prm(), sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], trajectory=tr, obstacles=obs)
+    res1 = eng.result.copy()
+    keep1 = eng.coll_free.cpu().numpy().copy()
+    cost1 = eng.cost.cpu().numpy().copy()
+    flags = eng.cand_flags.cpu().numpy()
+    # (1) masked winner is a valid, collision-free candidate and no survivor is cheaper
+    for b in range(B):
+        v = (flags[b] & nat.CAND_VALID) != 0
+        m = v & (keep1[b] != 0)
+        assert res1["n_valid"][b] == v.sum() and res1["n_survivors"][b] == m.sum()
+        if m.any():
+            w = res1["argmin_masked"][b]
+            assert m[w] and cost1[3, b, w] == cost1[3, b][m].min() and w == np.nonzero(m)[0][np.argmin(cost1[3, b][m])]
+        else:
+            assert res1["argmin_masked"][b] == -1 and res1["status"][b] == nat.STATUS_NO_FEASIBLE
+        assert res1["argmin_ctot"][b] == np.nonzero(v)[0][np.argmin(cost1[3, b][v])]
+    # (2) bit-identical on a second run (deterministic reductions)
+    eng2 = _gpu.run_batch(_dense_prm(), sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], trajectory=tr, obstacles=obs,
+                          engine=eng)
+    assert np.array_equal(eng2.result, res1) and np.array_equal(eng2.cost.cpu().numpy(), cost1)
+    # (3) no active obstacle -> every valid candidate survives and masked == unmasked argmin
+    eng3 = _gpu.run_batch(_dense_prm(), sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], trajectory=tr, obstacles=obs,
+                          active=np.zeros((B, 128), dtype=np.uint8), engine=eng)
+    assert np.array_equal(eng3.result["argmin_masked"], eng3.result["argmin_ctot"])
+    assert np.array_equal(eng3.result["n_survivors"], eng3.result["n_valid"])
+    # (4) a subset of scenarios against the oracle (masks exact up to the radius margin)
+    eng4 = _gpu.run_batch(_dense_prm(), sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], trajectory=tr, obstacles=obs,
+                          engine=eng)
+    for b in (0, 13, 31):
+        L = fo.generate(_dense_prm(), sc["p0"][sl][b], sc["s0"][sl][b], 0.1, dd=sc["dd"][sl][b])
+        x, y = fo.lattice_to_cartesian(op, L)
+        ok, first = fo.check_collisions(x, y, L.nsteps, obs[b])
+        C_ = L.n_candidates
+        got = eng4.coll_free[b, :C_].cpu().numpy() != 0
+        assert np.array_equal(got, ok) or _margin_ok(x, y, L.nsteps, obs[b], got, ok)
+        assert_close(eng4.cost[3, b, :C_].cpu().numpy(), L.ctot, GPU_RTOL, f"full[{b}].ctot")
+        _check_argmin(int(eng4.result[b]["argmin_masked"]), fo.first_argmin(L.ctot, ok), L.ctot, f"full[{b}]")
+
+
+def test_error_codes_and_edge_cases():
+    _gpu, nat, Circle, _ = _imports()
+    import ctypes as C
+    from otg_b200.engine import FrenetEngine
+    eng = _gpu.run_batch(fo.OracleParams.defaults("v1"), (0, 0, 0), (0, 0, 0), 0.1)
+    # a NULL buffer is a bad-argument error, not a crash
+    saved = eng.B.cost
+    eng.B.cost = None
+    rc = nat.lib.frenet_k2_evaluate(C.byref(eng.L), C.byref(nat.FrenetParams()), C.byref(eng.B), None)
+    assert rc == nat.ERR_BAD_ARG and b"NULL" in nat.lib.frenet_last_error()
+    eng.B.cost = saved
+    # empty point set
+    x, y = eng.points_to_cartesian(eng.path_handle(Circle(8, 5, 2)), np.zeros(0), np.zeros(0))
+    assert x.shape == (0,)
+    # every candidate blocked: obstacle on the shared start point -> NO_FEASIBLE, masked argmin -1 (reference: min([]) raises)
+    tr = Circle(8, 5, 2)
+    eng = _gpu.run_batch(fo.OracleParams.defaults("v1"), (0, 0, 0), (1.0, 1.0, 0), 0.1, trajectory=tr,
+                         obstacles=np.array([[[1.0, 0.0]]]))
+    assert eng.result[0]["status"] == nat.STATUS_NO_FEASIBLE and eng.result[0]["argmin_masked"] == -1
+    assert eng.result[0]["n_survivors"] == 0 and eng.result[0]["argmin_ctot"] >= 0
+    assert (eng.first_blocker[0, :eng.result[0]["n_valid"]].cpu().numpy() == 0).all()
+    # Optimal variant with every row dropped (ds0 < threshold and S <= S_thresh everywhere) -> EMPTY
+    prm = fo.OracleParams.defaults("optimal")
+    eng = _gpu.run_batch(prm, (0, 0, 0), (0, -3.0, 0), 0.0)
+    L = fo.generate(prm, (0, 0, 0), (0, -3.0, 0), 0.0)
+    assert eng.result[0]["n_valid"] == int(L.keep.sum())
+    if not L.keep.any():
+        assert eng.result[0]["status"] == nat.STATUS_EMPTY and eng.result[0]["argmin_ctot"] == -1
