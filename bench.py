@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the Frenet lattice planner hot path (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: BASELINE.json config 5, the batched moving-obstacle sweep - dense lattice (~1.1e4 candidates x
+51..147 steps), spline reference path, 128 moving obstacles per scenario.  A STEP is one pass of the whole
+pipeline (obstacle placement, K1..K5, winner gather) over this rank's shard of 512 scenarios; at 8 GPUs one
+step is the full 4096-scenario sweep ("weak" scaling: 512 scenarios per GPU).  Metric: candidate-timesteps/s,
+every one of them sampled, costed, feasibility-checked, transformed to Cartesian and collision-checked.
+
+  value : device-timed (CUDA events), inputs resident in HBM.
+  e2e   : the same through the public API (`BatchPlanner.stage_inputs/launch/result`) with HOST buffers: H2D of
+          states + obstacle parameters from pinned memory and D2H of result records + winner trajectories
+          inside the timed region.
+  roofline / kernels : each kernel timed alone with CUDA events over the same buffers.
+  cpu_baseline : the NumPy oracle (oracle/frenet_oracle.py - a vectorised port of the reference; the reference
+          itself is pure Python and cannot travel to the GPU box) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCEN_PER_GPU = 512
+N_OBS = 128
+METRIC = "candidate-timesteps/sec (feasibility+collision-checked)"
+
+
+def workload(lo, hi):
+    import otg_b200  # noqa: F401
+    from otg_b200 import workloads as w
+    sc = w.config5_scenarios()
+    t0 = sc["t0"][lo:hi]
+    fs, fd = w.moving_obstacle_frenet(sc["obs_s"][lo:hi], sc["obs_d"][lo:hi], sc["obs_speed"][lo:hi], sc["obs_offset"][lo:hi], t0[:, None])
+    return dict(p0=sc["p0"][lo:hi], s0=sc["s0"][lo:hi], dd=sc["dd"][lo:hi], t0=t0, obs_s=fs, obs_d=fd)
+
+
+def dense_params():
+    import otg_b200  # noqa: F401
+    from otg_b200 import workloads as w
+    from otg_b200.planner import TrajectoryPlannerParams
+    return TrajectoryPlannerParams(**w.DENSE_PARAMS)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_one(args):
+    p0, s0, t0, dd, fs, fd = args
+    from otg_b200 import workloads as w
+    from oracle import frenet_oracle as fo
+    prm = fo.OracleParams.defaults("v1").with_(**w.DENSE_PARAMS)
+    sp = fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY)
+    ox, oy = fo.frenet_to_cartesian(sp, fs, fd)
+    L = fo.generate(prm, p0, s0, t0, dd=dd)
+    x, y = fo.lattice_to_cartesian(sp, L)
+    ok, _ = fo.check_collisions(x, y, L.nsteps, np.stack([ox, oy], 1))
+    fo.first_argmin(L.ctot, ok)
+    return int(L.nsteps.sum())
+
+
+def cpu_pass(pool, wl, n):
+    jobs = [(wl["p0"][i], wl["s0"][i], float(wl["t0"][i]), float(wl["dd"][i]), wl["obs_s"][i], wl["obs_d"][i]) for i in range(n)]
+    t = time.perf_counter()
+    cts = sum(pool.map(_cpu_one, jobs, chunksize=1))
+    return cts, time.perf_counter() - t
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU implementation of the path (oracle port) with all host cores, same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = 2 * cores   # scenarios per step: a bounded sample of the 512-scenario shard (about 1.5 s of work per core)
+    wl = workload(0, n)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_pass(pool, wl, min(n, cores))
+        tot_c, tot_t = 0, 0.0
+        for _ in range(args.steps):
+            c, t = cpu_pass(pool, wl, n)
+            tot_c += c
+            tot_t += t
+    v = tot_c / tot_t
+    sample = f"{n} of the {SCEN_PER_GPU} scenarios of one GPU shard per step, {cores} worker processes"
+    line = {"metric": METRIC, "value": v, "unit": "candidate-timesteps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "candidate-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "candidate-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(n_gpus):
+    return {"workload": "BASELINE config 5: batched moving-obstacle sweep, dense V1 lattice (d_road_width=0.1, dt=0.1, "
+                        "num_sample=3, delta_t=0.02; 9600-11200 candidates x 51..147 steps), spline path, 128 moving "
+                        "obstacles per scenario, R=0.7",
+            "scenarios_per_gpu": SCEN_PER_GPU, "scenarios_per_step": SCEN_PER_GPU * n_gpus, "n_obstacles": N_OBS,
+            "parallelism": f"scenario-sharded x{n_gpus}, one gather of result records",
+            "l2": "each step writes ~28 GB of lattice state per GPU (>> 126 MB L2): no L2 flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_kernels(bp, reps):
+    """Each kernel alone, CUDA events on the launching stream, over the buffers of the last step."""
+    import ctypes as C
+    import torch
+    from otg_b200 import _native as nat
+    e = bp.engine
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L, P, Bf, path = C.byref(e.L), C.byref(bp.params), C.byref(e.B), C.byref(bp.path.desc)
+    calls = {
+        "k1_coefficients": lambda: nat.lib.frenet_k1_coefficients(L, P, Bf, stream),
+        "k2_evaluate": lambda: nat.lib.frenet_k2_evaluate(L, P, Bf, stream),
+        "k3_cartesian": lambda: nat.lib.frenet_k3_cartesian(L, P, path, Bf, stream),
+        "k4_collision": lambda: nat.lib.frenet_k4_collision(L, P, Bf, stream),
+        "k5_argmin": lambda: nat.lib.frenet_k5_argmin(L, Bf, bp.use_mask, stream),
+        "gather_winner": lambda: nat.lib.frenet_gather_winner(L, P, Bf, nat.SEL_MASKED, 1, stream),
+    }
+    out = {}
+    for name, fn in calls.items():
+        nat.check(fn())
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
+            a.record()
+            nat.check(fn())
+            b.record()
+        torch.cuda.synchronize()
+        out[name] = float(np.mean([a.elapsed_time(b) for a, b in evs]))   # ms
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import otg_b200  # noqa: F401
+    from otg_b200.batch import BatchPlanner, gather_results, shard_range
+    from otg_b200.trajectory import SplineTrajectory2D
+    from otg_b200 import workloads as w
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_total = SCEN_PER_GPU * world
+    lo, hi = shard_range(n_total, rank, world)
+    wl = workload(lo, hi)
+    bp = BatchPlanner(dense_params(), SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY), hi - lo, N_OBS, "v1", dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(records):
+        return gather_results(records, n_total, None, dev) if world > 1 else records
+
+    # ---- resident arm: `value` ----
+    bp.stage_inputs(**wl)
+    bp.engine.upload()
+    for _ in range(args.warmup):
+        bp.launch_resident()
+        bp.engine.download(sync=True)
+        gather(bp.engine.result)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        bp.launch_resident()
+        bp.engine.download(sync=True)     # records + winners leave the device every step
+        gather(bp.engine.result)           # the one collective of the path
+    ev1.record()
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if clocks else None
+    cts_step_local = bp.cand_timesteps()
+
+    # ---- end-to-end arm: host buffers through the public API ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bp.stage_inputs(**wl)
+        bp.launch()
+        res = bp.result()
+        allrec = gather(res.records)
+    barrier()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+
+    t = torch.tensor([ms_dev, ms_e2e, float(cts_step_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_dev, ms_e2e, cts_step = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        cts_step = float(cts_step_local)
+
+    if rank == 0:
+        kern = time_kernels(bp, max(3, args.steps))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        g = bp.geom
+        cts, nrow_ts = cts_step_local, int(g.n_steps.astype(np.int64).sum()) * bp._n_v_sum
+        ncand = g.n_t * g.n_d * bp._n_v_sum
+        # algorithmic bytes per launch: what the kernel must read + write once
+        algo = {
+            "k2_evaluate": 32 * cts + 32 * nrow_ts + ncand * (48 + 33),
+            "k3_cartesian": 24 * cts + 8 * nrow_ts,
+            "k4_collision": 16 * cts + ncand * 5,
+        }
+        kernels = {}
+        for name, ms in kern.items():
+            kernels[name] = {"ms": ms}
+            if name in algo:
+                kernels[name].update(algorithmic_gb=algo[name] / 1e9, gbs=algo[name] / (ms * 1e-3) / 1e9,
+                                     frac_of_hbm_peak=algo[name] / (ms * 1e-3) / 1e9 / peak)
+        dom = max(algo, key=lambda k: kern[k])
+        pipeline_ms = sum(kern.values())
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                    "share_of_step": kern[dom] / pipeline_ms}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+        if os.path.exists(tr):
+            roofline["traffic"] = json.load(open(tr)).get(dom)
+
+        # CPU baseline on rank 0, N = 1 only: bounded sample of the same workload
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n = min(2 * cores, SCEN_PER_GPU)
+            with mp.get_context("spawn").Pool(cores) as pool:
+                cpu_pass(pool, wl, min(cores, n))   # warm the workers
+                c, tcpu = cpu_pass(pool, wl, n)
+            cpu = {"value": c / tcpu, "unit": "candidate-timesteps/s", "cores": cores, "kind": "port",
+                   "sample": f"first {n} of the {SCEN_PER_GPU} scenarios of the step, oracle (NumPy port) in {cores} processes, {tcpu:.1f} s"}
+
+        line = {"metric": METRIC, "value": cts_step * args.steps / (ms_dev * 1e-3), "unit": "candidate-timesteps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(world),
+                "e2e": {"value": cts_step * args.steps / (ms_e2e * 1e-3), "unit": "candidate-timesteps/s",
+                        "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": bp.h2d_bytes * world,
+                        "d2h_bytes_per_step": bp.d2h_bytes * world},
+                "gpu_launches": bp.launches_per_plan * args.steps,
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
+                "candidate_timesteps_per_step": cts_step,
+                "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scenarios", type=int, default=SCEN_PER_GPU, help="scenarios per GPU and step (512 = the benchmark; "
+                    "smaller only for profiler captures)")
+    args = ap.parse_args()
+    global SCEN_PER_GPU
+    SCEN_PER_GPU = args.scenarios
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

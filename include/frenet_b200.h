@@ -73,6 +73,7 @@ enum { FRENET_CAND_VALID = 1, FRENET_CAND_KINEMATIC_OK = 2 };
 enum { FRENET_PATH_CIRCLE = 0, FRENET_PATH_SPLINE = 1 };
 
 /* selector for frenet_gather_winner */
+#define FRENET_WINNER_ROWS 12
 enum { FRENET_SEL_CTOT = 0, FRENET_SEL_CD = 1, FRENET_SEL_CV = 2, FRENET_SEL_CT = 3, FRENET_SEL_MASKED = 4 };
 
 /* Weights and thresholds: the attributes of TrajectoryPlannerParams (lib/planner/trajectory_planner.py:38-67)
@@ -160,7 +161,8 @@ typedef struct FrenetBuffers {
     /* K5 outputs */
     FrenetResult* result;      /* [n_scen] */
     /* winner gather */
-    double* winner;            /* [n_scen][11][n_pad_max]: t, d, dd, ddd, dddd, s, ds, dds, ddds, x, y */
+    double* winner;            /* [n_scen][12][n_pad_max]: t, d, dd, ddd, dddd, s, ds, dds, ddds, x, y, then a row holding
+                                  the winner's (cd, cv, ct, ctot) in its first four entries */
     int32_t* winner_steps;     /* [n_scen] number of valid samples, 0 if no winner */
 } FrenetBuffers;
 
@@ -213,9 +215,10 @@ int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetP
 
 /* Point-wise Frenet -> Cartesian (obstacle placement, target point): (x, y) = pt(s) + n(s) * d.
  * Replaces `trajectory.compute_pt(s) + compute_ortogonal_vect(trajectory, s) * d`
- * (lib/tests/test_obstacle_planner.py:21; lib/sensor/dynamic_obstacle.py:46-56). */
+ * (lib/tests/test_obstacle_planner.py:21; lib/sensor/dynamic_obstacle.py:46-56).
+ * Point i is written to x[i * out_stride], y[i * out_stride] (out_stride 2 with y = x + 1 fills an [n][2] table). */
 int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
-                               frenet_stream_t stream);
+                               int64_t out_stride, frenet_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -98,7 +98,7 @@ def _load():
         "frenet_plan": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
         "frenet_points_to_cartesian": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                                 C.c_void_p]),
+                                                 C.c_int64, C.c_void_p]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)    # AttributeError here = header and library out of sync

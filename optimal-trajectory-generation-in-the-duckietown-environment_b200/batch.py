@@ -1,0 +1,206 @@
+"""Batched planning: many independent planner instances ("scenarios") per GPU, scenario-sharded across GPUs.
+
+This is the public API of the batched moving-obstacle workload (BASELINE.json config 5).  One
+`BatchPlanner.plan(...)` call is, for every scenario, exactly what one iteration of the reference's
+moving-obstacle driver does (lib/tests/test_moving_obstacle_planner.py:86-98):
+
+    planner.replanner(t)            -> K1 + K2 (+ unmasked K5)
+    frenet_to_glob(...)             -> K3
+    sensor.step_obstacle(t)         -> host time law + device Frenet->Cartesian of the obstacle table
+    check_paths(...)                -> K4
+    min(paths, key=ctot)            -> K5 masked
+
+Scenarios are independent, so multi-GPU execution is plain scenario-index sharding with a single
+gather of the fixed-size result records at the end (`gather_results`); there is no other exchange.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import lattice as lat
+from .engine import FrenetEngine, LatticeGeometry, make_params
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block of scenario indices owned by `rank` (blocks differ by at most one scenario)."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(local: np.ndarray, n_total: int, group=None, device=None) -> np.ndarray:
+    """All-gather the per-scenario FrenetResult records of every rank (one collective, NCCL on GPUs, gloo on CPU).
+
+    `local` is this rank's structured record array for its `shard_range`; returns all `n_total` records in
+    scenario order on every rank.  Without an initialised process group this is the identity."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cap = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    buf = np.zeros(cap * nat.RESULT_BYTES, dtype=np.uint8)
+    buf[:local.size * nat.RESULT_BYTES] = local.view(np.uint8).reshape(-1)
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world * cap * nat.RESULT_BYTES, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    flat = out.cpu().numpy().reshape(world, cap * nat.RESULT_BYTES)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(flat[r, :(hi - lo) * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE)))
+    return np.concatenate(parts)
+
+
+@dataclass
+class BatchResult:
+    records: np.ndarray        # FrenetResult per scenario (structured array)
+    winner: np.ndarray         # [B][12][n_pad_max] masked winner: t, d, dd, ddd, dddd, s, ds, dds, ddds, x, y, (cd, cv, ct, ctot)
+    winner_steps: np.ndarray   # [B]
+    cand_timesteps: int        # candidate-timesteps evaluated (sum over valid candidates of their step counts)
+
+    def next_state(self, b: int, time: float, period: float):
+        """(s, ds, dds), (d, dd, ddd) of the winner at `time` - optimal_at_time, trajectory_planner.py:183-195."""
+        n = int(self.winner_steps[b])
+        if n == 0:
+            raise ValueError(f"scenario {b}: no feasible candidate")
+        w = self.winner[b]
+        t = w[0, :n]
+        k = 0 if time <= t[0] else (n - 1 if time >= t[-1] else round((time - t[0]) / period))
+        return (w[5, k], w[6, k], w[7, k]), (w[1, k], w[2, k], w[3, k])
+
+
+class BatchPlanner:
+    """`n_scen` planner instances with common parameters and lattice geometry on one GPU.
+
+    params:     any object with the reference's planner attributes (e.g. `TrajectoryPlannerParams(...)`).
+    variant:    "v1" | "dt" | "dt_obstacles" | "optimal" (which reference class's rules apply).
+    trajectory: reference path (CircleTrajectory2D / SplineTrajectory2D), shared by all scenarios.
+    """
+
+    def __init__(self, params, trajectory, n_scen: int, n_obs: int = 0, variant: str = "v1", device=None,
+                 robot_radius: float = 0.7):
+        self.p = params
+        self.variant = variant
+        self.n_scen = int(n_scen)
+        self.n_obs = int(n_obs)
+        self.engine = FrenetEngine(self.n_scen, device)
+        self.period = lat.sample_period(params, variant)
+        self.geom = LatticeGeometry.from_intervals(lat.di_interval(params, variant), lat.t_interval(params, variant), self.period)
+        self.engine.configure(self.geom, lat.max_long_axis_len(params), self.n_obs)
+        self.path = self.engine.path_handle(trajectory)
+        self.radius_sq = robot_radius ** 2
+        self.params = make_params(params, lat.VARIANTS[variant]["rule"], self.period, False, self.radius_sq)
+        self.stages = nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K3 | nat.STAGE_K5 | nat.STAGE_GATHER
+        self.use_mask = 0
+        if self.n_obs > 0:
+            self.stages |= nat.STAGE_K4
+            self.use_mask |= nat.MASK_COLLISION
+        if np.isfinite(self.params.v_max) or np.isfinite(self.params.a_max):
+            self.use_mask |= nat.MASK_KINEMATIC
+        if np.isfinite(self.params.kappa_max):
+            self.stages |= nat.STAGE_CURVATURE
+            self.use_mask |= nat.MASK_CURVATURE
+        self._n_v_sum = 0
+
+    # -- host -> pinned staging ----------------------------------------------------------------
+    def stage_inputs(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None):
+        """Write one batch of host inputs into the pinned staging block (no device work yet)."""
+        e, B = self.engine, self.n_scen
+        p0 = np.asarray(p0, dtype=np.float64).reshape(B, 3)
+        s0 = np.asarray(s0, dtype=np.float64).reshape(B, 3)
+        e.state[:, :3], e.state[:, 3:] = p0, s0
+        e.scal[:, 0] = 0.0 if dd is None else dd
+        e.scal[:, 1] = self.p.desired_speed if desired_speed is None else desired_speed
+        e.scal[:, 2] = t0
+        # per-scenario target-speed axis: the reference's rounding rule (trajectory_planner.py:120), vectorised.
+        # np.round is round-half-to-even like Python's round() on floats.
+        q, n = self.p.d_d_s, self.p.num_sample
+        lo = np.round(s0[:, 1] - q * n)
+        hi = np.round(s0[:, 1] + q * n + q)
+        nv = np.ceil((hi - lo) / q).astype(np.int32)
+        if int(nv.max()) > e.n_v_cap:
+            raise ValueError("longitudinal axis longer than the configured capacity")
+        e.axis_v[:] = lo[:, None] + np.arange(e.n_v_cap)[None, :] * q     # == np.arange(lo, hi, q) (start + i * step)
+        e.n_v[:] = nv
+        self._n_v_sum = int(nv.sum())
+        self._obs_frenet = obs_s is not None
+        if self.n_obs:
+            if obs_s is not None:
+                e.obs_sd[0], e.obs_sd[1] = obs_s, obs_d
+            elif obs_xy is not None:
+                e.obs_xy[:] = obs_xy
+            e.obs_active[:] = 1 if obs_active is None else obs_active
+
+    def launch(self):
+        """H2D of the staged inputs, the pipeline, D2H of records + winners; asynchronous on the current stream."""
+        e = self.engine
+        e.upload()
+        if self.n_obs and self._obs_frenet:
+            e.place_obstacles(self.path)
+        e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
+        e.download(sync=False)
+
+    def launch_resident(self):
+        """The pipeline alone on inputs already in HBM (no host traffic)."""
+        e = self.engine
+        if self.n_obs and self._obs_frenet:
+            e.place_obstacles(self.path)
+        e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
+
+    @property
+    def launches_per_plan(self) -> int:
+        return bin(self.stages).count("1") + (1 if (self.n_obs and getattr(self, "_obs_frenet", False)) else 0)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.engine._in_host.numel()
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.engine._out_host.numel()
+
+    def cand_timesteps(self) -> int:
+        return int(self.geom.n_steps.astype(np.int64).sum()) * self.geom.n_d * self._n_v_sum
+
+    def result(self) -> BatchResult:
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        e = self.engine
+        return BatchResult(e.result.copy(), e.winner.copy(), e.winner_steps.copy(), self.cand_timesteps())
+
+    def plan(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None) -> BatchResult:
+        """Host arrays in, per-scenario results out (synchronous)."""
+        self.stage_inputs(p0, s0, t0, dd, desired_speed, obs_s, obs_d, obs_xy, obs_active)
+        self.launch()
+        return self.result()
+
+
+def plan_sharded(params, trajectory, scenarios: dict, variant: str = "v1", tile: int = 512, group=None):
+    """Plan all scenarios of `scenarios` (dict of arrays with a leading scenario axis: p0, s0, t0, dd and
+    obs_s/obs_d or obs_xy) on this process's GPU shard and gather every rank's records.
+
+    Returns (records for ALL scenarios in index order, BatchResult list of this rank's tiles)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    n_total = len(scenarios["t0"])
+    lo, hi = shard_range(n_total, rank, world)
+    n_obs = scenarios["obs_s"].shape[1] if "obs_s" in scenarios else (scenarios["obs_xy"].shape[1] if "obs_xy" in scenarios else 0)
+    planner = None
+    tiles, recs = [], []
+    for a in range(lo, hi, tile):
+        b = min(a + tile, hi)
+        if planner is None or planner.n_scen != b - a:
+            planner = BatchPlanner(params, trajectory, b - a, n_obs, variant)
+        kw = {k: scenarios[k][a:b] for k in ("dd", "obs_s", "obs_d", "obs_xy", "obs_active") if k in scenarios}
+        res = planner.plan(scenarios["p0"][a:b], scenarios["s0"][a:b], scenarios["t0"][a:b], **kw)
+        tiles.append(res)
+        recs.append(res.records)
+    local = np.concatenate(recs) if recs else np.zeros(0, dtype=np.dtype(nat.RESULT_DTYPE))
+    dev = torch.device("cuda", torch.cuda.current_device()) if world > 1 and dist.get_backend(group) == "nccl" else None
+    return gather_results(local, n_total, group, dev), tiles

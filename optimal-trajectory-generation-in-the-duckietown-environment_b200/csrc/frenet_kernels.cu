@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
 }
 
 __global__ void __launch_bounds__(256) points_to_cartesian(FrenetPath path, const double* __restrict__ s, const double* __restrict__ d,
-                                                           int64_t n, double* __restrict__ x, double* __restrict__ y) {
+                                                           int64_t n, double* x, double* y, int64_t out_stride) {
     extern __shared__ double tab[];
     if (path.kind == FRENET_PATH_SPLINE) {
         for (int i = threadIdx.x; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(256) points_to_cartesian(FrenetPath path, cons
         double px, py, nx, ny;
         path_frame(path.kind, path.circle, tab, path.n_knots, s[i], px, py, nx, ny);
         const double di = d[i];
-        x[i] = __dadd_rn(px, __dmul_rn(nx, di));
-        y[i] = __dadd_rn(py, __dmul_rn(ny, di));
+        x[i * out_stride] = __dadd_rn(px, __dmul_rn(nx, di));
+        y[i * out_stride] = __dadd_rn(py, __dmul_rn(ny, di));
     }
 }
 
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
     }
 }
 
-// Winner gather: the sampled state optimal_at_time indexes (trajectory_planner.py:183-195), 11 rows.
+// Winner gather: the sampled state optimal_at_time indexes (trajectory_planner.py:183-195), 11 rows + a cost row.
 __global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetParams P, FrenetBuffers B, int sel, int has_xy) {
     const int b = blockIdx.x;
     const FrenetResult& res = B.result[b];
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetPara
     }
     const int r = c / L.n_d, id = c % L.n_d;
     const RowAddr A = row_addr(L, (int64_t)b * L.n_v_cap * L.n_t + r);
-    double* w = B.winner + (int64_t)b * 11 * L.n_pad_max;
+    double* w = B.winner + (int64_t)b * FRENET_WINNER_ROWS * L.n_pad_max;
     const double t0 = B.scal[(int64_t)b * 3 + 2];
     const int64_t loff = A.lat_off + (int64_t)id * A.npad;
     for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
@@ -674,6 +674,7 @@ __global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetPara
             w[10 * L.n_pad_max + k] = B.xy[A.latF + loff + k];
         }
     }
+    if (threadIdx.x < 4) w[11 * L.n_pad_max + threadIdx.x] = B.cost[threadIdx.x * A.candF + A.cand0 + id];
     if (threadIdx.x == 0) B.winner_steps[b] = A.N;
 }
 
@@ -826,15 +827,16 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
 }
 
 int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
-                               frenet_stream_t stream) {
+                               int64_t out_stride, frenet_stream_t stream) {
     if (int rc = check_path(path)) return rc;
     if (n < 0 || (n > 0 && (!s || !d || !x || !y))) return fail(FRENET_ERR_BAD_ARG, "points: NULL buffer");
+    if (out_stride < 1) return fail(FRENET_ERR_BAD_ARG, "points: out_stride must be >= 1");
     if (n == 0) return FRENET_OK;
     const size_t smem = (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0) * sizeof(double);
     if (int rc = set_smem(points_to_cartesian, smem, "points: spline table too large for shared memory")) return rc;
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;   // grid-stride beyond one full wave of 8 CTAs per SM
-    points_to_cartesian<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*path, s, d, n, x, y);
+    points_to_cartesian<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*path, s, d, n, x, y, out_stride);
     FRENET_CHECK_LAUNCH("points_to_cartesian");
     return FRENET_OK;
 }

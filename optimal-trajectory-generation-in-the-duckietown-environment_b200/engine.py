@@ -155,7 +155,8 @@ class FrenetEngine:
 
         # packed small inputs: one pinned host block, one device block
         sizes = [("state", Bn * 6 * 8), ("scal", Bn * 3 * 8), ("axis_v", Bn * self.n_v_cap * 8), ("target", Bn * nT * 3 * 8),
-                 ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("n_v", Bn * 4), ("obs_active", Bn * max(n_obs, 1))]
+                 ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("obs_sd", Bn * max(n_obs, 1) * 2 * 8), ("n_v", Bn * 4),
+                 ("obs_active", Bn * max(n_obs, 1))]
         offs, tot = {}, 0
         for name, sz in sizes:
             offs[name] = tot
@@ -169,6 +170,7 @@ class FrenetEngine:
         self.target = hv[offs["target"]:offs["target"] + Bn * nT * 24].view(np.float64).reshape(Bn, nT, 3)
         no = max(n_obs, 1)
         self.obs_xy = hv[offs["obs_xy"]:offs["obs_xy"] + Bn * no * 16].view(np.float64).reshape(Bn, no, 2)
+        self.obs_sd = hv[offs["obs_sd"]:offs["obs_sd"] + Bn * no * 16].view(np.float64).reshape(2, Bn, no)   # [s|d][B][O]
         self.n_v = hv[offs["n_v"]:offs["n_v"] + Bn * 4].view(np.int32)
         self.obs_active = hv[offs["obs_active"]:offs["obs_active"] + Bn * no].reshape(Bn, no)
         hv[:] = 0
@@ -177,7 +179,7 @@ class FrenetEngine:
         self._in_offs = offs
 
         # packed small outputs
-        osz = [("winner", Bn * 11 * geom.n_pad_max * 8), ("result", Bn * nat.RESULT_BYTES), ("winner_steps", Bn * 4)]
+        osz = [("winner", Bn * 12 * geom.n_pad_max * 8), ("result", Bn * nat.RESULT_BYTES), ("winner_steps", Bn * 4)]
         ooffs, otot = {}, 0
         for name, sz in osz:
             ooffs[name] = otot
@@ -186,7 +188,7 @@ class FrenetEngine:
         self._out_dev = torch.zeros(otot, dtype=torch.uint8, device=dev)
         ov = self._out_host.numpy()
         ov[:] = 0
-        self.winner = ov[:Bn * 11 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 11, geom.n_pad_max)
+        self.winner = ov[:Bn * 12 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 12, geom.n_pad_max)
         self.result = ov[ooffs["result"]:ooffs["result"] + Bn * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE))
         self.winner_steps = ov[ooffs["winner_steps"]:ooffs["winner_steps"] + Bn * 4].view(np.int32)
         op = self._out_dev.data_ptr()
@@ -269,6 +271,18 @@ class FrenetEngine:
         if stages & nat.STAGE_K4:
             self.has_collision = True
 
+    def place_obstacles(self, path: PathHandle):
+        """Frenet -> Cartesian of the uploaded obstacle table `obs_sd` ([2][B][O]: arc lengths, lateral offsets)
+        straight into the device `obs_xy` table ([B][O][2]) that K4 reads - the device side of
+        `sensor.step_obstacle` + `ObstacleTrajectory.compute_pt` (lib/sensor/proximity_sensor.py:82-89,
+        lib/sensor/dynamic_obstacle.py:46-56)."""
+        ip = self._in_dev.data_ptr()
+        n = self.n_scen * max(self.n_obs, 1)
+        sd = ip + self._in_offs["obs_sd"]
+        xy = ip + self._in_offs["obs_xy"]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_points_to_cartesian(C.byref(path.desc), sd, sd + n * 8, n, xy, xy + 8, 2, C.c_void_p(stream)))
+
     def download(self, sync: bool = True):
         """One D2H copy of the packed per-call outputs (result records, winner trajectories)."""
         self._out_host.copy_(self._out_dev, non_blocking=True)
@@ -343,5 +357,5 @@ class FrenetEngine:
         y = torch.empty_like(s)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(nat.lib.frenet_points_to_cartesian(C.byref(path.desc), s.data_ptr(), d.data_ptr(), s.numel(), x.data_ptr(),
-                                                     y.data_ptr(), C.c_void_p(stream)))
+                                                     y.data_ptr(), 1, C.c_void_p(stream)))
         return x.cpu().numpy(), y.cpu().numpy()

@@ -50,8 +50,8 @@ def long_axis(p, ds0, follow: bool) -> np.ndarray:
 
 def max_long_axis_len(p) -> int:
     """Upper bound of len(long_axis) over all ds0: span (2 n + 1) d_d_s, both ends rounded to integers."""
-    span = 2 * p.d_d_s * p.num_sample + p.d_d_s + 1.0
-    return int(np.ceil(span / p.d_d_s)) + 1
+    span = 2 * p.d_d_s * p.num_sample + p.d_d_s + 1.0     # each end moves by at most 0.5 when rounded
+    return int(np.ceil(span / p.d_d_s))
 
 
 def sample_period(p, variant: str) -> float:
