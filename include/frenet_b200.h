@@ -169,7 +169,8 @@ typedef struct FrenetBuffers {
 /* pipeline stage bits for frenet_plan */
 enum {
     FRENET_STAGE_K1 = 1, FRENET_STAGE_K2 = 2, FRENET_STAGE_K3 = 4, FRENET_STAGE_K4 = 8,
-    FRENET_STAGE_K5 = 16, FRENET_STAGE_GATHER = 32, FRENET_STAGE_CURVATURE = 64
+    FRENET_STAGE_K5 = 16, FRENET_STAGE_GATHER = 32, FRENET_STAGE_CURVATURE = 64,
+    FRENET_STAGE_NO_FUSE = 128 /* launch K2, K3, K4 separately even when frenet_plan could fuse them */
 };
 
 int frenet_abi_version(void);
@@ -186,6 +187,11 @@ int frenet_k1_coefficients(const FrenetLattice* lat, const FrenetParams* prm, co
 /* K2 - evaluate / cost / feasibility: samples every candidate, accumulates jerk sums and cd/cv/ct/ctot.
  * Replaces the sampling and cost lines of generate_range_polynomials (trajectory_planner.py:139-176). */
 int frenet_k2_evaluate(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, frenet_stream_t stream);
+
+/* K2 + K3 (+ K4) as one kernel: every sample is evaluated, transformed (and collision-tested) while it is in
+ * registers and written to HBM once.  Outputs are identical to the separate launches. */
+int frenet_k2_fused(const FrenetLattice* lat, const FrenetParams* prm, const FrenetPath* path, const FrenetBuffers* buf,
+                    int32_t with_collision, frenet_stream_t stream);
 
 /* K3 - Frenet -> Cartesian of every candidate against the circle / spline reference path.
  * Replaces frenet_to_glob + compute_ortogonal_vect (lib/tests/test_obstacle_planner.py:18-25, 53-56). */
@@ -209,7 +215,8 @@ int frenet_k5_argmin(const FrenetLattice* lat, const FrenetBuffers* buf, int32_t
 int frenet_gather_winner(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, int32_t sel, int32_t has_xy,
                          frenet_stream_t stream);
 
-/* The pipeline: launches the stages selected in `stages` in order K1, K2, K3, (curvature), K4, K5, gather. */
+/* The pipeline: launches the stages selected in `stages` in order K1, K2, K3, (curvature), K4, K5, gather;
+ * K2+K3(+K4) are fused into one launch when selected together (FRENET_STAGE_NO_FUSE keeps them apart). */
 int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetPath* path, const FrenetBuffers* buf,
                 int32_t stages, int32_t use_mask, int32_t gather_sel, frenet_stream_t stream);
 

@@ -21,7 +21,7 @@ ROW_EXISTS, ROW_LOWSPEED, ROW_DROPPED = 1, 2, 4
 CAND_VALID, CAND_KINEMATIC_OK = 1, 2
 PATH_CIRCLE, PATH_SPLINE = 0, 1
 SEL_CTOT, SEL_CD, SEL_CV, SEL_CT, SEL_MASKED = 0, 1, 2, 3, 4
-STAGE_K1, STAGE_K2, STAGE_K3, STAGE_K4, STAGE_K5, STAGE_GATHER, STAGE_CURVATURE = 1, 2, 4, 8, 16, 32, 64
+STAGE_K1, STAGE_K2, STAGE_K3, STAGE_K4, STAGE_K5, STAGE_GATHER, STAGE_CURVATURE, STAGE_NO_FUSE = 1, 2, 4, 8, 16, 32, 64, 128
 MASK_KINEMATIC, MASK_CURVATURE, MASK_COLLISION = 1, 2, 4
 
 c_double_p = C.c_void_p   # device pointers are passed as integers (tensor.data_ptr())
@@ -90,6 +90,7 @@ def _load():
         "frenet_device_count": (C.c_int, []),
         "frenet_k1_coefficients": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_void_p]),
         "frenet_k2_evaluate": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_void_p]),
+        "frenet_k2_fused": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_void_p]),
         "frenet_k3_cartesian": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_void_p]),
         "frenet_k3_curvature": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_void_p]),
         "frenet_k4_collision": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_void_p]),

@@ -155,7 +155,12 @@ class BatchPlanner:
 
     @property
     def launches_per_plan(self) -> int:
-        return bin(self.stages).count("1") + (1 if (self.n_obs and getattr(self, "_obs_frenet", False)) else 0)
+        n = bin(self.stages).count("1")
+        if (self.stages & nat.STAGE_K2) and (self.stages & nat.STAGE_K3):     # frenet_plan fuses K2+K3 (+K4)
+            n -= 1
+            if (self.stages & nat.STAGE_K4) and not (self.stages & nat.STAGE_CURVATURE):
+                n -= 1
+        return n + (1 if (self.n_obs and getattr(self, "_obs_frenet", False)) else 0)
 
     @property
     def h2d_bytes(self) -> int:

@@ -205,112 +205,7 @@ __global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: evaluate / cost / feasibility, one CTA per row
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
-    extern __shared__ double sigma[];   // [n_pad_max] |s_k - s0| (low-speed lateral argument)
-    __shared__ double sh_clong;
-    __shared__ int sh_rowfeas;
-
-    const int64_t br = blockIdx.x;
-    const RowAddr A = row_addr(L, br);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int flags = B.row_flags[br];
-
-    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
-        for (int id = tid; id < L.n_d; id += blockDim.x) {
-            const int64_t c = A.cand0 + id;
-            B.cand_flags[c] = 0;
-#pragma unroll
-            for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = 0.0;
-        }
-        return;
-    }
-    const bool low = flags & FRENET_ROW_LOWSPEED;
-    const double dt = P.sample_period;
-    const double s0 = B.state[(int64_t)A.b * 6 + 3];
-    Poly pl;
-    pl.load(B.coef_lon + br * 6);
-
-    // Phase A: longitudinal samples, once per row (the reference recomputes nothing either, but
-    // deep-copies them into each of the n_d candidates; here the candidates share the row's arrays).
-    double* lon = B.lon + A.lon_off;
-    for (int k = tid; k < A.N; k += blockDim.x) {
-        const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
-        const double s = pl.val(t);
-        lon[k] = s;
-        lon[A.lonF + k] = pl.d1(t);
-        lon[2 * A.lonF + k] = pl.d2(t);
-        lon[3 * A.lonF + k] = pl.d3(t);
-        if (low) sigma[k] = fabs(s - s0);
-    }
-    if (warp == 0) {   // longitudinal cost and limits (trajectory_planner.py:143-144, 153-154)
-        double acc = 0.0, vmax = 0.0, amax = 0.0;
-        for (int k = lane; k < A.N; k += kWarp) {
-            const double t = (double)k * dt;
-            const double j = pl.d3(t);
-            acc = fma(j, j, acc);
-            vmax = fmax(vmax, fabs(pl.d1(t)));
-            amax = fmax(amax, fabs(pl.d2(t)));
-        }
-        acc = warp_sum(acc);
-        vmax = warp_max(vmax);
-        amax = warp_max(amax);
-        if (lane == 0) {
-            const double T = L.axis_t[A.iT];
-            const double t_last = (double)(A.N - 1) * dt;
-            double term;
-            if (P.follow) {
-                const double e = pl.val(t_last) - B.target[((int64_t)A.b * L.n_t + A.iT) * 3];
-                term = __dmul_rn(P.ks, __dmul_rn(e, e));
-            } else {
-                const double e = pl.d1(t_last) - B.scal[(int64_t)A.b * 3 + 1];
-                term = __dmul_rn(P.kdots, __dmul_rn(e, e));
-            }
-            sh_clong = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, T)), term);
-            sh_rowfeas = (vmax <= P.v_max) && (amax <= P.a_max);
-        }
-    }
-    __syncthreads();
-    const double clong = sh_clong;
-    const bool rowfeas = sh_rowfeas;
-    const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
-    const double dd = B.scal[(int64_t)A.b * 3];
-
-    // Phase B: a warp per candidate, lanes over time steps.
-    for (int id = warp; id < L.n_d; id += nwarps) {
-        const int64_t c = A.cand0 + id;
-        Poly pq;
-        pq.load(B.coef_lat + c * 6);
-        double* lat = B.lat + A.lat_off + (int64_t)id * A.npad;
-        double acc = 0.0, amax = 0.0;
-        for (int k = lane; k < A.N; k += kWarp) {
-            const double u = low ? sigma[k] : (double)k * dt;
-            const double j = pq.d3(u);
-            const double acc2 = pq.d2(u);
-            lat[k] = pq.val(u);
-            lat[A.latF + k] = pq.d1(u);
-            lat[2 * A.latF + k] = acc2;
-            lat[3 * A.latF + k] = j;
-            acc = fma(j, j, acc);
-            amax = fmax(amax, fabs(acc2));
-        }
-        acc = warp_sum(acc);
-        amax = warp_max(amax);
-        if (lane == 0) {   // :165-167 / :174-176
-            const double e = L.axis_d[id] - dd;
-            const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
-            B.cost[c] = clat;
-            B.cost[A.candF + c] = P.follow ? 0.0 : clong;
-            B.cost[2 * A.candF + c] = P.follow ? clong : 0.0;
-            B.cost[3 * A.candF + c] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
-            B.cand_flags[c] = FRENET_CAND_VALID | ((rowfeas && amax <= P.a_max) ? FRENET_CAND_KINEMATIC_OK : 0);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Reference paths (K3)
+// Reference paths (used by K3 and the fused K2)
 // ------------------------------------------------------------------------------------------------
 // Rounded rectangle, lib/trajectory/circle_trajectory.py:31-64.  c = descriptor block:
 // l, h, r, dt, period, b[0..6] (branch boundaries evaluated on the host in the reference's order).
@@ -387,8 +282,249 @@ __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Collision test of one 32-step chunk of one candidate (shared by K4 and the fused kernel)
+// ------------------------------------------------------------------------------------------------
+constexpr int kNoBlocker = 0x7fffffff;
+
+// x, y: this lane's point (lanes beyond the candidate's last step carry a copy of a valid point and valid = false).
+// ox, oy: obstacle table in shared memory (obstacles the sensor did not report are parked at +inf).
+// best: lowest blocking obstacle index found so far for this candidate (warp-uniform); returns the updated value.
+// Obstacles are culled per chunk with a lane-parallel test against the chunk's bounding circle (conservative:
+// radius rounded up, threshold inflated), then the exact reference test (lib/tests/test_obstacle_planner.py:48)
+// runs on the few survivors in ascending index order, so the first hit is the chunk's lowest blocker.
+__device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int nvalid, const double* __restrict__ ox,
+                                             const double* __restrict__ oy, int O, double R, double radius_sq, int best, int lane) {
+    const int mid = (nvalid - 1) >> 1;
+    const double cx = __shfl_sync(kFull, x, mid), cy = __shfl_sync(kFull, y, mid);
+    const double ex = x - cx, ey = y - cy;
+    const float r2 = __double2float_ru(fma(ex, ex, ey * ey));
+    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));   // r2 >= 0: uint order == float order
+    const double reach = R + (double)__fsqrt_ru(r2max);
+    const double thr = reach * reach * (1.0 + 1e-9);
+    for (int ob = 0; ob < O && ob < best; ob += kWarp) {
+        const int o = ob + lane;
+        bool near = false;
+        if (o < O && o < best) {
+            const double ux = ox[o] - cx, uy = oy[o] - cy;
+            near = fma(ux, ux, uy * uy) <= thr;
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const int oj = ob + j;
+            const double dx = x - ox[oj], dy = y - oy[oj];
+            const bool hit = valid && (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= radius_sq);
+            if (__any_sync(kFull, hit)) {
+                best = oj;
+                m = 0;
+            }
+        }
+    }
+    return best;
+}
+
+// Stage a scenario's obstacle snapshot in shared memory.
+__device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double* ox, double* oy) {
+    const int O = B.n_obs;
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+        const bool on = B.obs_active == nullptr || B.obs_active[(int64_t)b * O + o] != 0;
+        ox[o] = on ? B.obs_xy[((int64_t)b * O + o) * 2] : CUDART_INF;
+        oy[o] = on ? B.obs_xy[((int64_t)b * O + o) * 2 + 1] : CUDART_INF;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (+K3 +K4 fused): evaluate / cost / feasibility, one CTA per row
+// ------------------------------------------------------------------------------------------------
+// kXY:     also transform every sample to Cartesian (K3) while it is in registers and store x, y.
+// kColl:   also run the collision test (K4) on the Cartesian point while it is in registers.
+// kLimits: track max |acceleration| / |speed| for the (extension) kinematic limits; without it the
+//          KINEMATIC_OK flag is set unconditionally, which is the reference's behaviour.
+// The fused variants write each candidate-timestep exactly once (48 B: d, d', d'', d''', x, y) and read
+// nothing back; the unfused sequence K2 -> K3 -> K4 moves 72 B for the same result.
+template <bool kXY, bool kColl, bool kLimits>
+__global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
+    extern __shared__ double sm[];
+    const int npm = L.n_pad_max;
+    double* su = sm;                               // [npm] lateral argument: t_k, or |s_k - s0| in low-speed mode
+    double* coef = su + npm;                       // [n_d][6] lateral coefficients of this row (from K1)
+    double* fpx = coef + L.n_d * 6;                // [npm] x 4: path frame (kXY)
+    double* fpy = fpx + (kXY ? npm : 0);
+    double* fnx = fpy + (kXY ? npm : 0);
+    double* fny = fnx + (kXY ? npm : 0);
+    double* tab = fny + (kXY ? npm : 0);           // [n_knots][9] spline table (kXY, spline path)
+    double* ox = tab + ((kXY && path.kind == FRENET_PATH_SPLINE) ? path.n_knots * 9 : 0);   // [n_obs] x 2 (kColl)
+    double* oy = ox + (kColl ? B.n_obs : 0);
+    __shared__ double red[3][kRowThreads / 32];
+    __shared__ double sh_clong;
+    __shared__ int sh_rowfeas;
+
+    const int64_t br = blockIdx.x;
+    const RowAddr A = row_addr(L, br);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int flags = B.row_flags[br];
+
+    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
+        for (int id = tid; id < L.n_d; id += blockDim.x) {
+            const int64_t c = A.cand0 + id;
+            B.cand_flags[c] = 0;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = 0.0;
+            if (kColl) {
+                B.coll_free[c] = 0;
+                B.first_blocker[c] = -1;
+            }
+        }
+        return;
+    }
+    const bool low = flags & FRENET_ROW_LOWSPEED;
+    const double dt = P.sample_period;
+    const double s0 = B.state[(int64_t)A.b * 6 + 3];
+
+    // Phase 0: stage the row's lateral coefficients, the spline table and the obstacle snapshot.
+    {
+        const double* cq = B.coef_lat + A.cand0 * 6;
+        for (int i = tid; i < L.n_d * 6; i += blockDim.x) coef[i] = cq[i];
+        if (kXY && path.kind == FRENET_PATH_SPLINE) {
+            for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+        }
+        if (kColl) stage_obstacles(B, A.b, ox, oy);
+        if (kXY && path.kind == FRENET_PATH_SPLINE) __syncthreads();   // phase A reads the table
+    }
+
+    // Phase A: longitudinal samples, once per row (the reference deep-copies them into each of the n_d
+    // candidates; here the candidates share the row's arrays), the lateral argument and the path frame.
+    {
+        Poly pl;
+        pl.load(B.coef_lon + br * 6);
+        double* lon = B.lon + A.lon_off;
+        double acc = 0.0, vmax = 0.0, amax = 0.0;
+        for (int k = tid; k < A.N; k += blockDim.x) {
+            const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
+            const double s = pl.val(t), v = pl.d1(t), a = pl.d2(t), j = pl.d3(t);
+            lon[k] = s;
+            lon[A.lonF + k] = v;
+            lon[2 * A.lonF + k] = a;
+            lon[3 * A.lonF + k] = j;
+            su[k] = low ? fabs(s - s0) : t;
+            acc = fma(j, j, acc);
+            if (kLimits) {
+                vmax = fmax(vmax, fabs(v));
+                amax = fmax(amax, fabs(a));
+            }
+            if (kXY) {
+                double px, py, nx, ny;
+                path_frame(path.kind, path.circle, tab, path.n_knots, s, px, py, nx, ny);
+                fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
+            }
+        }
+        // longitudinal jerk sum and limits: per-warp partials combined in a fixed order (deterministic)
+        acc = warp_sum(acc);
+        if (kLimits) {
+            vmax = warp_max(vmax);
+            amax = warp_max(amax);
+        }
+        if (lane == 0) {
+            red[0][warp] = acc;
+            red[1][warp] = vmax;
+            red[2][warp] = amax;
+        }
+        __syncthreads();
+        if (tid == 0) {   // trajectory_planner.py:143-144, 153-154
+            double jsum = 0.0, vm = 0.0, am = 0.0;
+            for (int w = 0; w < nwarps; ++w) {
+                jsum += red[0][w];
+                vm = fmax(vm, red[1][w]);
+                am = fmax(am, red[2][w]);
+            }
+            const double T = L.axis_t[A.iT];
+            const double t_last = (double)(A.N - 1) * dt;
+            double term;
+            if (P.follow) {
+                const double e = pl.val(t_last) - B.target[((int64_t)A.b * L.n_t + A.iT) * 3];
+                term = __dmul_rn(P.ks, __dmul_rn(e, e));
+            } else {
+                const double e = pl.d1(t_last) - B.scal[(int64_t)A.b * 3 + 1];
+                term = __dmul_rn(P.kdots, __dmul_rn(e, e));
+            }
+            sh_clong = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, jsum), __dmul_rn(P.kt, T)), term);
+            sh_rowfeas = kLimits ? ((vm <= P.v_max) && (am <= P.a_max)) : 1;
+        }
+        __syncthreads();
+    }
+    const double clong = sh_clong;
+    const bool rowfeas = sh_rowfeas;
+    const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
+    const double dd = B.scal[(int64_t)A.b * 3];
+    const double R = kColl ? sqrt(P.radius_sq) : 0.0;
+
+    // Phase B: a warp per candidate, lanes over time steps; no global loads in this loop.
+    for (int id = warp; id < L.n_d; id += nwarps) {
+        const int64_t c = A.cand0 + id;
+        Poly pq;
+        pq.load(coef + id * 6);
+        const int64_t off = A.lat_off + (int64_t)id * A.npad;
+        double* o0 = B.lat + off + lane;
+        double* o1 = o0 + A.latF;
+        double* o2 = o1 + A.latF;
+        double* o3 = o2 + A.latF;
+        double* oxp = kXY ? B.xy + off + lane : nullptr;
+        double* oyp = kXY ? oxp + A.latF : nullptr;
+        double acc = 0.0, amax = 0.0;
+        int best = kNoBlocker;
+#pragma unroll 1
+        for (int kb = 0; kb < A.N; kb += kWarp) {
+            const int k = kb + lane;
+            const bool valid = k < A.N;
+            const int kk = valid ? k : kb;   // out-of-range lanes shadow the chunk's first step (never stored)
+            const double u = su[kk];
+            const double j = pq.d3(u);
+            const double a2 = pq.d2(u);
+            const double v1 = pq.d1(u);
+            const double d0 = pq.val(u);
+            if (valid) {
+                o0[kb] = d0;
+                o1[kb] = v1;
+                o2[kb] = a2;
+                o3[kb] = j;
+                acc = fma(j, j, acc);
+                if (kLimits) amax = fmax(amax, fabs(a2));
+            }
+            if (kXY) {
+                const double x = __dadd_rn(fpx[kk], __dmul_rn(fnx[kk], d0));   // pt + n * d, unfused like the reference
+                const double y = __dadd_rn(fpy[kk], __dmul_rn(fny[kk], d0));
+                if (valid) {
+                    oxp[kb] = x;
+                    oyp[kb] = y;
+                }
+                if (kColl) best = collide_chunk(x, y, valid, min(kWarp, A.N - kb), ox, oy, B.n_obs, R, P.radius_sq, best, lane);
+            }
+        }
+        acc = warp_sum(acc);
+        if (kLimits) amax = warp_max(amax);
+        if (lane == 0) {   // :165-167 / :174-176
+            const double e = L.axis_d[id] - dd;
+            const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
+            B.cost[c] = clat;
+            B.cost[A.candF + c] = P.follow ? 0.0 : clong;
+            B.cost[2 * A.candF + c] = P.follow ? clong : 0.0;
+            B.cost[3 * A.candF + c] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
+            const bool kin = kLimits ? (rowfeas && amax <= P.a_max) : true;
+            B.cand_flags[c] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0);
+            if (kColl) {
+                B.coll_free[c] = best == kNoBlocker ? 1 : 0;
+                B.first_blocker[c] = best == kNoBlocker ? -1 : best;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: Frenet -> Cartesian, one CTA per row; the path frame is computed once per (row, step)
 // ------------------------------------------------------------------------------------------------
+constexpr int kChunksInFlight = 4;   // chunks whose loads are issued before the first use (latency hiding)
+
 __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, FrenetPath path, FrenetBuffers B) {
     extern __shared__ double sm[];
     double* fpx = sm;
@@ -419,10 +555,21 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
         const double* d = B.lat + off;
         double* x = B.xy + off;
         double* y = x + A.latF;
-        for (int k = lane; k < A.N; k += kWarp) {
-            const double dk = d[k];
-            x[k] = __dadd_rn(fpx[k], __dmul_rn(fnx[k], dk));   // pt + n * d, unfused like the reference
-            y[k] = __dadd_rn(fpy[k], __dmul_rn(fny[k], dk));
+        for (int kb = 0; kb < A.N; kb += kWarp * kChunksInFlight) {
+            double dv[kChunksInFlight];
+#pragma unroll
+            for (int q = 0; q < kChunksInFlight; ++q) {
+                const int k = kb + q * kWarp + lane;
+                dv[q] = k < A.N ? d[k] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < kChunksInFlight; ++q) {
+                const int k = kb + q * kWarp + lane;
+                if (k < A.N) {
+                    x[k] = __dadd_rn(fpx[k], __dmul_rn(fnx[k], dv[q]));   // pt + n * d, unfused like the reference
+                    y[k] = __dadd_rn(fpy[k], __dmul_rn(fny[k], dv[q]));
+                }
+            }
         }
     }
 }
@@ -497,59 +644,37 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
         }
         return;
     }
-    // Stage this scenario's obstacle snapshot; obstacles the sensor did not report are parked at
-    // infinity so the cull below never selects them (check_paths tests sensed obstacles only).
-    for (int o = tid; o < O; o += blockDim.x) {
-        const bool on = B.obs_active == nullptr || B.obs_active[(int64_t)A.b * O + o] != 0;
-        ox[o] = on ? B.obs_xy[((int64_t)A.b * O + o) * 2] : CUDART_INF;
-        oy[o] = on ? B.obs_xy[((int64_t)A.b * O + o) * 2 + 1] : CUDART_INF;
-    }
+    // Obstacles the sensor did not report are parked at infinity so the cull never selects them
+    // (check_paths tests sensed obstacles only).
+    stage_obstacles(B, A.b, ox, oy);
     __syncthreads();
     const double R = sqrt(P.radius_sq);
-    const int kNone = 0x7fffffff;
 
     for (int id = warp; id < L.n_d; id += nwarps) {
         const int64_t off = A.lat_off + (int64_t)id * A.npad;
         const double* xs = B.xy + off;
         const double* ys = xs + A.latF;
-        int best = kNone;   // lowest blocking obstacle index found so far (warp-uniform)
-        for (int kb = 0; kb < A.N; kb += kWarp) {
-            const int k = kb + lane;
-            const bool valid = k < A.N;
-            const int nvalid = min(kWarp, A.N - kb);
-            const double x = xs[valid ? k : kb], y = ys[valid ? k : kb];
-            // Bounding circle of this chunk's points: centre = middle point, radius rounded up.
-            const int mid = (nvalid - 1) >> 1;
-            const double cx = __shfl_sync(kFull, x, mid), cy = __shfl_sync(kFull, y, mid);
-            const double ex = x - cx, ey = y - cy;
-            const float r2 = __double2float_ru(fma(ex, ex, ey * ey));
-            const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));   // r2 >= 0: uint order == float order
-            const double reach = R + (double)__fsqrt_ru(r2max);
-            const double thr = reach * reach * (1.0 + 1e-9);
-            for (int ob = 0; ob < O && ob < best; ob += kWarp) {
-                const int o = ob + lane;
-                bool near = false;
-                if (o < O && o < best) {
-                    const double ux = ox[o] - cx, uy = oy[o] - cy;
-                    near = fma(ux, ux, uy * uy) <= thr;
-                }
-                unsigned m = __ballot_sync(kFull, near);
-                while (m) {   // ascending obstacle index: the first hit is this chunk's lowest blocker
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int oj = ob + j;
-                    const double dx = x - ox[oj], dy = y - oy[oj];
-                    const bool hit = valid && (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= P.radius_sq);   // :48
-                    if (__any_sync(kFull, hit)) {
-                        best = oj;
-                        m = 0;
-                    }
-                }
+        int best = kNoBlocker;   // lowest blocking obstacle index found so far (warp-uniform)
+        for (int kb = 0; kb < A.N; kb += kWarp * kChunksInFlight) {
+            double xv[kChunksInFlight], yv[kChunksInFlight];
+#pragma unroll
+            for (int q = 0; q < kChunksInFlight; ++q) {
+                const int k0 = kb + q * kWarp;
+                const int k = k0 + lane;
+                const int kk = k < A.N ? k : (k0 < A.N ? k0 : kb);
+                xv[q] = xs[kk];
+                yv[q] = ys[kk];
+            }
+#pragma unroll
+            for (int q = 0; q < kChunksInFlight; ++q) {
+                const int k0 = kb + q * kWarp;
+                if (k0 < A.N)
+                    best = collide_chunk(xv[q], yv[q], k0 + lane < A.N, min(kWarp, A.N - k0), ox, oy, O, R, P.radius_sq, best, lane);
             }
         }
         if (lane == 0) {
-            B.coll_free[A.cand0 + id] = best == kNone ? 1 : 0;
-            B.first_blocker[A.cand0 + id] = best == kNone ? -1 : best;
+            B.coll_free[A.cand0 + id] = best == kNoBlocker ? 1 : 0;
+            B.first_blocker[A.cand0 + id] = best == kNoBlocker ? -1 : best;
         }
     }
 }
@@ -706,6 +831,44 @@ int set_smem(K kernel, size_t bytes, const char* name) {
 
 inline unsigned n_rows(const FrenetLattice* L) { return (unsigned)((int64_t)L->n_scen * L->n_v_cap * L->n_t); }
 
+int check_path(const FrenetPath* path) {
+    if (!path) return fail(FRENET_ERR_BAD_ARG, "path is NULL");
+    if (path->kind == FRENET_PATH_SPLINE) {
+        if (path->n_knots < 2 || !path->spline_table) return fail(FRENET_ERR_BAD_ARG, "spline path needs >= 2 knots and a table");
+    } else if (path->kind != FRENET_PATH_CIRCLE) {
+        return fail(FRENET_ERR_BAD_ARG, "unknown path kind");
+    }
+    return FRENET_OK;
+}
+
+template <bool kXY, bool kColl>
+int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, cudaStream_t stream) {
+    const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
+    const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
+    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 6 + (spline ? (size_t)9 * path->n_knots : 0) +
+                         (kColl ? (size_t)2 * B->n_obs : 0)) * sizeof(double);
+    static const FrenetPath no_path = {};
+    const FrenetPath& pd = kXY ? *path : no_path;
+    if (limits) {
+        if (int rc = set_smem(k2_evaluate<kXY, kColl, true>, smem, "k2: row does not fit shared memory")) return rc;
+        k2_evaluate<kXY, kColl, true><<<n_rows(L), kRowThreads, smem, stream>>>(*L, *P, pd, *B);
+    } else {
+        if (int rc = set_smem(k2_evaluate<kXY, kColl, false>, smem, "k2: row does not fit shared memory")) return rc;
+        k2_evaluate<kXY, kColl, false><<<n_rows(L), kRowThreads, smem, stream>>>(*L, *P, pd, *B);
+    }
+    FRENET_CHECK_LAUNCH("k2_evaluate");
+    return FRENET_OK;
+}
+
+int check_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!P || !B || !B->state || !B->scal || !B->coef_lon || !B->coef_lat || !B->row_S || !B->row_flags || !B->lon || !B->lat ||
+        !B->cost || !B->cand_flags)
+        return fail(FRENET_ERR_BAD_ARG, "k2: NULL buffer");
+    if (P->follow && !B->target) return fail(FRENET_ERR_BAD_ARG, "k2: follow mode needs target triples");
+    return FRENET_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -736,26 +899,19 @@ int frenet_k1_coefficients(const FrenetLattice* L, const FrenetParams* P, const 
 }
 
 int frenet_k2_evaluate(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
-    if (int rc = check_lattice(L)) return rc;
-    if (!P || !B || !B->state || !B->scal || !B->coef_lon || !B->coef_lat || !B->row_S || !B->row_flags || !B->lon || !B->lat ||
-        !B->cost || !B->cand_flags)
-        return fail(FRENET_ERR_BAD_ARG, "k2: NULL buffer");
-    if (P->follow && !B->target) return fail(FRENET_ERR_BAD_ARG, "k2: follow mode needs target triples");
-    const size_t smem = (size_t)L->n_pad_max * sizeof(double);
-    if (int rc = set_smem(k2_evaluate, smem, "k2: horizon too long for shared memory")) return rc;
-    k2_evaluate<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
-    FRENET_CHECK_LAUNCH("k2_evaluate");
-    return FRENET_OK;
+    if (int rc = check_k2(L, P, B)) return rc;
+    return launch_k2<false, false>(L, P, nullptr, B, (cudaStream_t)stream);
 }
 
-static int check_path(const FrenetPath* path) {
-    if (!path) return fail(FRENET_ERR_BAD_ARG, "path is NULL");
-    if (path->kind == FRENET_PATH_SPLINE) {
-        if (path->n_knots < 2 || !path->spline_table) return fail(FRENET_ERR_BAD_ARG, "spline path needs >= 2 knots and a table");
-    } else if (path->kind != FRENET_PATH_CIRCLE) {
-        return fail(FRENET_ERR_BAD_ARG, "unknown path kind");
-    }
-    return FRENET_OK;
+int frenet_k2_fused(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B,
+                    int32_t with_collision, frenet_stream_t stream) {
+    if (int rc = check_k2(L, P, B)) return rc;
+    if (int rc = check_path(path)) return rc;
+    if (!B->xy) return fail(FRENET_ERR_BAD_ARG, "fused: xy buffer is NULL");
+    if (!with_collision) return launch_k2<true, false>(L, P, path, B, (cudaStream_t)stream);
+    if (!B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "fused: collision output is NULL");
+    if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "fused: obstacle table missing");
+    return launch_k2<true, true>(L, P, path, B, (cudaStream_t)stream);
 }
 
 int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B,
@@ -816,10 +972,18 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
                 int32_t use_mask, int32_t gather_sel, frenet_stream_t stream) {
     int rc = FRENET_OK;
     if ((stages & FRENET_STAGE_K1) && (rc = frenet_k1_coefficients(L, P, B, stream))) return rc;
-    if ((stages & FRENET_STAGE_K2) && (rc = frenet_k2_evaluate(L, P, B, stream))) return rc;
-    if ((stages & FRENET_STAGE_K3) && (rc = frenet_k3_cartesian(L, P, path, B, stream))) return rc;
+    // K2 and K3 (and K4 when nothing sits between them) run as ONE kernel unless the caller asks for separate launches:
+    // same arithmetic, same outputs, but every sample is written once instead of being re-read by K3 and K4.
+    const bool fuse = (stages & FRENET_STAGE_K2) && (stages & FRENET_STAGE_K3) && !(stages & FRENET_STAGE_NO_FUSE);
+    const bool fuse_k4 = fuse && (stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_CURVATURE);
+    if (fuse) {
+        if ((rc = frenet_k2_fused(L, P, path, B, fuse_k4 ? 1 : 0, stream))) return rc;
+    } else {
+        if ((stages & FRENET_STAGE_K2) && (rc = frenet_k2_evaluate(L, P, B, stream))) return rc;
+        if ((stages & FRENET_STAGE_K3) && (rc = frenet_k3_cartesian(L, P, path, B, stream))) return rc;
+    }
     if ((stages & FRENET_STAGE_CURVATURE) && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
-    if ((stages & FRENET_STAGE_K4) && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_K4) && !fuse_k4 && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
     if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, (stages & FRENET_STAGE_K3) ? 1 : 0, stream)))
         return rc;

@@ -26,7 +26,7 @@ def planner_attrs(prm: fo.OracleParams) -> Attr:
 
 def run_batch(prm: fo.OracleParams, p0, s0, t0, dd=None, desired=None, targets=None, trajectory=None, obstacles=None,
               active=None, use_mask=0, di_interval=None, t_interval=None, gather_sel=nat.SEL_CTOT, curvature=False,
-              engine=None):
+              engine=None, no_fuse=False):
     """Runs B scenarios through K1..K5 (+K3/K4 when a path / obstacles are given).  Returns the engine."""
     a = planner_attrs(prm)
     p0 = np.atleast_2d(np.asarray(p0, dtype=np.float64))
@@ -65,6 +65,8 @@ def run_batch(prm: fo.OracleParams, p0, s0, t0, dd=None, desired=None, targets=N
         eng.obs_active[:] = 1 if active is None else np.asarray(active, dtype=np.uint8)
         stages |= nat.STAGE_K4
         use_mask |= nat.MASK_COLLISION
+    if no_fuse:
+        stages |= nat.STAGE_NO_FUSE
     P = make_params(a, lat.VARIANTS[prm.variant]["rule"], lat.sample_period(a, prm.variant), follow)
     eng.run(P, path, stages, use_mask, gather_sel)
     return eng

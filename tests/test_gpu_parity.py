@@ -406,3 +406,53 @@ def test_error_codes_and_edge_cases():
     assert eng.result[0]["n_valid"] == int(L.keep.sum())
     if not L.keep.any():
         assert eng.result[0]["status"] == nat.STATUS_EMPTY and eng.result[0]["argmin_ctot"] == -1
+
+
+def test_fused_kernel_equals_separate_launches():
+    """frenet_plan fuses K2+K3+K4 into one kernel; the separate launches (FRENET_STAGE_NO_FUSE, what the driver
+    functions use one by one) must give bit-identical buffers."""
+    _gpu, nat, Circle, Spline = _imports()
+    from otg_b200 import workloads
+    z = golden("sim_planner_moving")
+    active = np.zeros((499, 10), dtype=np.uint8)
+    for i in range(499):
+        active[i, z["obs_idx"][i, :z["n_sensed"][i]]] = 1
+    sc = workloads.config5_scenarios()
+    idx = golden("config5_sample")["scenario_idx"]
+    cases = [
+        (fo.OracleParams.defaults("v1"), dict(p0=z["p0"], s0=z["s0"], t0=z["time"], trajectory=Circle(8, 5, 2),
+                                              obstacles=z["obs_all_xy"], active=active)),
+        (_dense_prm(), dict(p0=sc["p0"][idx], s0=sc["s0"][idx], t0=sc["t0"][idx], dd=sc["dd"][idx],
+                            trajectory=Spline(workloads.SPLINE_WX, workloads.SPLINE_WY), obstacles=golden("config5_sample")["obs_xy"])),
+        (fo.OracleParams.defaults("v1").with_(v_max=5.3, a_max=3.1), dict(p0=z["p0"][:64], s0=z["s0"][:64], t0=z["time"][:64],
+                                                                         trajectory=Circle(8, 5, 2), use_mask=1)),
+    ]
+    names = ("lon", "lat", "xy", "cost", "cand_flags", "coll_free", "first_blocker", "coef_lon", "coef_lat")
+    for prm, kw in cases:
+        kw = dict(kw)
+        p0, s0, t0 = kw.pop("p0"), kw.pop("s0"), kw.pop("t0")
+        a = _gpu.run_batch(prm, p0, s0, t0, **kw)
+        res_a = a.result.copy()
+        win_a = a.winner.copy()
+        bufs = {n: getattr(a, n).cpu().numpy().copy() for n in names}
+        valid = (bufs["cand_flags"] & nat.CAND_VALID) != 0
+        b = _gpu.run_batch(prm, p0, s0, t0, no_fuse=True, **kw)
+        assert np.array_equal(b.result, res_a)
+        assert np.array_equal(b.winner_steps, a.winner_steps)
+        for i in range(len(res_a)):
+            n = int(a.winner_steps[i])
+            assert np.array_equal(b.winner[i, :11, :n], win_a[i, :11, :n], equal_nan=True)
+        for n in ("cost", "cand_flags", "coef_lon", "coef_lat"):
+            assert np.array_equal(getattr(b, n).cpu().numpy(), bufs[n], equal_nan=True), n
+        if "obstacles" in kw:
+            for n in ("coll_free", "first_blocker"):
+                assert np.array_equal(getattr(b, n).cpu().numpy()[valid], bufs[n][valid]), n
+        for sidx in (0, len(res_a) - 1):
+            fa = a.padded_fields(a.fetch_scenario(sidx))
+        # the sampled state: compare every valid candidate's unpadded samples of three scenarios
+        for sidx in (0, len(res_a) // 2, len(res_a) - 1):
+            fb = b.padded_fields(b.fetch_scenario(sidx))
+            a2 = _gpu.run_batch(prm, p0, s0, t0, engine=a, **kw)
+            fa = a2.padded_fields(a2.fetch_scenario(sidx))
+            for n in ("d", "dot_d", "ddot_d", "dddot_d", "s", "dot_s", "ddot_s", "dddot_s", "x", "y"):
+                assert np.array_equal(fa[n], fb[n], equal_nan=True), (sidx, n)
