@@ -24,15 +24,19 @@
  * owns one longitudinal polynomial, candidate c = r * n_d + i_d one lateral polynomial - the
  * order in which `generate_range_polynomials` appends (lib/planner/trajectory_planner.py:128-180).
  * Horizon i_T has n_steps[i_T] samples t_k = k * sample_period (np.arange(0, T + dt, dt)), stored
- * padded to a multiple of 4 doubles: t_offset[i_T] is the prefix sum of the padded counts.
+ * padded to npad(i_T) = n_steps rounded up to a multiple of 4 doubles; t_offset[i_T] is the prefix sum
+ * of the padded counts.  With  within(r) = i_v * t_offset[n_t] + t_offset[i_T] :
  *
- *   longitudinal field (s, ds, dds, ddds): element (b, r, k)  at  b * row_elems  + i_v * t_offset[n_t] + t_offset[i_T] + k
- *   lateral field / x / y:                 element (b, c, k)  at  b * cand_elems + (i_v * t_offset[n_t] + t_offset[i_T]) * n_d
- *                                                                 + i_d * (t_offset[i_T + 1] - t_offset[i_T]) + k
- *   per-candidate arrays:                  element (b, c)     at  b * n_v_cap * n_t * n_d + c
- *   per-row arrays:                        element (b, r)     at  b * n_v_cap * n_t + r
+ *   longitudinal block of row r   (4 fields s, ds, dds, ddds, each npad long, back to back):
+ *        lon[ (b * row_elems  + within(r)) * 4              + f * npad + k ]
+ *   candidate block of c = (r, i_d)  (6 fields d, dd, ddd, dddd, x, y, each npad long, back to back):
+ *        lat[ (b * cand_elems + within(r) * n_d) * 6 + i_d * 6 * npad + f * npad + k ]
+ *   per-candidate arrays:  element (b, c) at  b * n_v_cap * n_t * n_d + c
+ *   per-row arrays:        element (b, r) at  b * n_v_cap * n_t + r
  *
- * The longitudinal samples are stored once per row: the n_d candidates of a row share them (the
+ * Every field of a candidate is a contiguous, 32-byte aligned run of doubles (k fastest), and the six
+ * fields of one candidate sit next to each other, so a warp that owns a candidate writes one compact
+ * region.  The longitudinal samples are stored once per row: the n_d candidates of a row share them (the
  * reference deep-copies them into every candidate, lib/planner/trajectory_planner.py:157).
  */
 #ifndef FRENET_B200_H
@@ -148,12 +152,11 @@ typedef struct FrenetBuffers {
     double* row_S;             /* [n_scen][R] arc length travelled (low-speed horizon) */
     int32_t* row_flags;        /* [n_scen][R] FRENET_ROW_* */
     /* K2 outputs */
-    double* lon;               /* 4 fields [4][n_scen][row_elems]:  s, ds, dds, ddds */
-    double* lat;               /* 4 fields [4][n_scen][cand_elems]: d, dd, ddd, dddd */
+    double* lon;               /* [n_scen][row_elems * 4]:  per row  s, ds, dds, ddds (layout above) */
+    double* lat;               /* [n_scen][cand_elems * 6]: per candidate d, dd, ddd, dddd (K2) and x, y (K3) */
     double* cost;              /* 4 arrays [4][n_scen][C]: cd, cv, ct, ctot (unset keys are 0.0 like Frenet()) */
     uint8_t* cand_flags;       /* [n_scen][C] FRENET_CAND_* */
     /* K3 outputs */
-    double* xy;                /* 2 fields [2][n_scen][cand_elems]: x, y */
     uint8_t* curv_ok;          /* [n_scen][C] EXTENSION curvature limit, or NULL (kappa_max = +inf) */
     /* K4 outputs */
     uint8_t* coll_free;        /* [n_scen][C] 1 = no collision (check_collisions -> True) */

@@ -62,7 +62,7 @@ class FrenetBuffers(C.Structure):
                 ("obs_active", C.c_void_p), ("n_obs", C.c_int32), ("reserved", C.c_int32),
                 ("coef_lon", C.c_void_p), ("coef_lat", C.c_void_p), ("row_S", C.c_void_p), ("row_flags", C.c_void_p),
                 ("lon", C.c_void_p), ("lat", C.c_void_p), ("cost", C.c_void_p), ("cand_flags", C.c_void_p),
-                ("xy", C.c_void_p), ("curv_ok", C.c_void_p),
+                ("curv_ok", C.c_void_p),
                 ("coll_free", C.c_void_p), ("first_blocker", C.c_void_p),
                 ("result", C.c_void_p),
                 ("winner", C.c_void_p), ("winner_steps", C.c_void_p)]

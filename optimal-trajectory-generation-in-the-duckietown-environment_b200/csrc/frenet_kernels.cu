@@ -78,26 +78,41 @@ __device__ __forceinline__ void quartic_bvp(double s0, double ds0, double dds0, 
     a[5] = 0.0;
 }
 
-// Value and three derivatives (trajectory_1d.py:42-71, 99-130), Horner form with the integer
-// multiples of the coefficients folded in once per polynomial.
+// Value and three derivatives (trajectory_1d.py:42-71, 99-130) by repeated synthetic division
+// (Horner applied to its own intermediate sums): 14 FMAs + 2 scalings from the six coefficients
+// alone, so a polynomial occupies 12 registers instead of the 30 that pre-multiplied derivative
+// coefficients would need.
 struct Poly {
-    double a0, a1, a2, a3, a4, a5;  // value
-    double b2, b3, b4, b5;          // 2a2, 3a3, 4a4, 5a5
-    double c3, c4, c5;              // 6a3, 12a4, 20a5
-    double e4, e5;                  // 24a4, 60a5
+    double a0, a1, a2, a3, a4, a5;
 
     __device__ __forceinline__ void load(const double* __restrict__ a) {
         a0 = a[0]; a1 = a[1]; a2 = a[2]; a3 = a[3]; a4 = a[4]; a5 = a[5];
-        b2 = 2.0 * a2; b3 = 3.0 * a3; b4 = 4.0 * a4; b5 = 5.0 * a5;
-        c3 = 6.0 * a3; c4 = 12.0 * a4; c5 = 20.0 * a5;
-        e4 = 24.0 * a4; e5 = 60.0 * a5;
+    }
+    // v0 = p(t), v1 = p'(t), v2 = p''(t), v3 = p'''(t)
+    __device__ __forceinline__ void eval(double t, double& v0, double& v1, double& v2, double& v3) const {
+        const double b4 = fma(a5, t, a4);
+        const double b3 = fma(b4, t, a3);
+        const double b2 = fma(b3, t, a2);
+        const double b1 = fma(b2, t, a1);
+        v0 = fma(b1, t, a0);
+        const double c4 = fma(a5, t, b4);
+        const double c3 = fma(c4, t, b3);
+        const double c2 = fma(c3, t, b2);
+        v1 = fma(c2, t, b1);
+        const double d4 = fma(a5, t, c4);
+        const double d3 = fma(d4, t, c3);
+        v2 = 2.0 * fma(d3, t, c2);
+        const double e4 = fma(a5, t, d4);
+        v3 = 6.0 * fma(e4, t, d3);
     }
     __device__ __forceinline__ double val(double t) const {
         return fma(fma(fma(fma(fma(a5, t, a4), t, a3), t, a2), t, a1), t, a0);
     }
-    __device__ __forceinline__ double d1(double t) const { return fma(fma(fma(fma(b5, t, b4), t, b3), t, b2), t, a1); }
-    __device__ __forceinline__ double d2(double t) const { return fma(fma(fma(c5, t, c4), t, c3), t, b2); }
-    __device__ __forceinline__ double d3(double t) const { return fma(fma(e5, t, e4), t, c3); }
+    __device__ __forceinline__ double d1(double t) const {
+        double v0, v1, v2, v3;
+        eval(t, v0, v1, v2, v3);
+        return v1;
+    }
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -111,13 +126,17 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// Row addressing shared by the per-row kernels.
+// Row addressing shared by the per-row kernels (layout: include/frenet_b200.h).
+constexpr int kLonFields = 4;    // s, ds, dds, ddds
+constexpr int kCandFields = 6;   // d, dd, ddd, dddd, x, y
+constexpr int kFrame = 6;        // doubles per step of the shared-memory path frame: px, py, nx, ny, u, (pad)
+
 struct RowAddr {
     int b, r, iv, iT, N, npad;
-    int64_t lon_off;   // into one longitudinal field
-    int64_t lat_off;   // into one lateral field: first candidate of the row
-    int64_t cand0;     // into per-candidate arrays
-    int64_t lonF, latF, candF;   // field strides
+    int64_t lon_off;    // first element of the row's longitudinal block [4][npad]
+    int64_t cand_off;   // first element of the row's first candidate block [6][npad]; candidate id at + id * 6 * npad
+    int64_t cand0;      // into per-candidate arrays
+    int64_t candF;      // stride between the four cost arrays
 };
 
 __device__ __forceinline__ RowAddr row_addr(const FrenetLattice& L, int64_t br) {
@@ -132,11 +151,9 @@ __device__ __forceinline__ RowAddr row_addr(const FrenetLattice& L, int64_t br) 
     A.npad = L.t_offset[A.iT + 1] - off;
     const int64_t sumpad = L.t_offset[L.n_t];
     const int64_t within = (int64_t)A.iv * sumpad + off;
-    A.lon_off = (int64_t)A.b * L.row_elems + within;
-    A.lat_off = (int64_t)A.b * L.cand_elems + within * L.n_d;
+    A.lon_off = ((int64_t)A.b * L.row_elems + within) * kLonFields;
+    A.cand_off = ((int64_t)A.b * L.cand_elems + within * L.n_d) * kCandFields;
     A.cand0 = br * L.n_d;
-    A.lonF = (int64_t)L.n_scen * L.row_elems;
-    A.latF = (int64_t)L.n_scen * L.cand_elems;
     A.candF = (int64_t)L.n_scen * R * L.n_d;
     return A;
 }
@@ -287,13 +304,13 @@ __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ 
 constexpr int kNoBlocker = 0x7fffffff;
 
 // x, y: this lane's point (lanes beyond the candidate's last step carry a copy of a valid point and valid = false).
-// ox, oy: obstacle table in shared memory (obstacles the sensor did not report are parked at +inf).
+// obs: obstacle table in shared memory as (x, y) pairs; obstacles the sensor did not report are parked at +inf.
 // best: lowest blocking obstacle index found so far for this candidate (warp-uniform); returns the updated value.
 // Obstacles are culled per chunk with a lane-parallel test against the chunk's bounding circle (conservative:
 // radius rounded up, threshold inflated), then the exact reference test (lib/tests/test_obstacle_planner.py:48)
 // runs on the few survivors in ascending index order, so the first hit is the chunk's lowest blocker.
-__device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int nvalid, const double* __restrict__ ox,
-                                             const double* __restrict__ oy, int O, double R, double radius_sq, int best, int lane) {
+__device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int nvalid, const double2* __restrict__ obs, int O,
+                                             double R, double radius_sq, int best, int lane) {
     const int mid = (nvalid - 1) >> 1;
     const double cx = __shfl_sync(kFull, x, mid), cy = __shfl_sync(kFull, y, mid);
     const double ex = x - cx, ey = y - cy;
@@ -301,36 +318,35 @@ __device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int
     const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));   // r2 >= 0: uint order == float order
     const double reach = R + (double)__fsqrt_ru(r2max);
     const double thr = reach * reach * (1.0 + 1e-9);
-    for (int ob = 0; ob < O && ob < best; ob += kWarp) {
+    const int lim = min(O, best);   // only lower indices can still improve `best`
+    for (int ob = 0; ob < lim; ob += kWarp) {
         const int o = ob + lane;
         bool near = false;
-        if (o < O && o < best) {
-            const double ux = ox[o] - cx, uy = oy[o] - cy;
+        if (o < lim) {
+            const double2 q = obs[o];
+            const double ux = q.x - cx, uy = q.y - cy;
             near = fma(ux, ux, uy * uy) <= thr;
         }
         unsigned m = __ballot_sync(kFull, near);
         while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
-            const int oj = ob + j;
-            const double dx = x - ox[oj], dy = y - oy[oj];
+            const double2 q = obs[ob + j];
+            const double dx = x - q.x, dy = y - q.y;
             const bool hit = valid && (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= radius_sq);
-            if (__any_sync(kFull, hit)) {
-                best = oj;
-                m = 0;
-            }
+            if (__any_sync(kFull, hit)) return ob + j;   // ascending order: nothing after it can be lower
         }
     }
     return best;
 }
 
 // Stage a scenario's obstacle snapshot in shared memory.
-__device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double* ox, double* oy) {
+__device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double2* obs) {
     const int O = B.n_obs;
+    const double2* src = reinterpret_cast<const double2*>(B.obs_xy) + (int64_t)b * O;
     for (int o = threadIdx.x; o < O; o += blockDim.x) {
         const bool on = B.obs_active == nullptr || B.obs_active[(int64_t)b * O + o] != 0;
-        ox[o] = on ? B.obs_xy[((int64_t)b * O + o) * 2] : CUDART_INF;
-        oy[o] = on ? B.obs_xy[((int64_t)b * O + o) * 2 + 1] : CUDART_INF;
+        obs[o] = on ? src[o] : make_double2(CUDART_INF, CUDART_INF);
     }
 }
 
@@ -343,19 +359,17 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 //          KINEMATIC_OK flag is set unconditionally, which is the reference's behaviour.
 // The fused variants write each candidate-timestep exactly once (48 B: d, d', d'', d''', x, y) and read
 // nothing back; the unfused sequence K2 -> K3 -> K4 moves 72 B for the same result.
+// Shared memory (doubles): [2 * n_obs] obstacles (kColl) | [n_pad_max][kFrame or 1] frame | [n_d][6] lateral
+// coefficients | [n_knots][9] spline table (kXY).
 template <bool kXY, bool kColl, bool kLimits>
 __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
-    extern __shared__ double sm[];
-    const int npm = L.n_pad_max;
-    double* su = sm;                               // [npm] lateral argument: t_k, or |s_k - s0| in low-speed mode
-    double* coef = su + npm;                       // [n_d][6] lateral coefficients of this row (from K1)
-    double* fpx = coef + L.n_d * 6;                // [npm] x 4: path frame (kXY)
-    double* fpy = fpx + (kXY ? npm : 0);
-    double* fnx = fpy + (kXY ? npm : 0);
-    double* fny = fnx + (kXY ? npm : 0);
-    double* tab = fny + (kXY ? npm : 0);           // [n_knots][9] spline table (kXY, spline path)
-    double* ox = tab + ((kXY && path.kind == FRENET_PATH_SPLINE) ? path.n_knots * 9 : 0);   // [n_obs] x 2 (kColl)
-    double* oy = ox + (kColl ? B.n_obs : 0);
+    extern __shared__ __align__(16) double sm[];
+    constexpr int FS = kXY ? kFrame : 1;   // frame stride: (px, py, nx, ny, u, pad) or just u
+    constexpr int FU = kXY ? 4 : 0;        // position of u inside a frame entry
+    double2* obs = reinterpret_cast<double2*>(sm);
+    double* frame = sm + (kColl ? 2 * B.n_obs : 0);
+    double* coef = frame + L.n_pad_max * FS;
+    double* tab = coef + L.n_d * 6;
     __shared__ double red[3][kRowThreads / 32];
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
@@ -386,11 +400,11 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
     {
         const double* cq = B.coef_lat + A.cand0 * 6;
         for (int i = tid; i < L.n_d * 6; i += blockDim.x) coef[i] = cq[i];
+        if (kColl) stage_obstacles(B, A.b, obs);
         if (kXY && path.kind == FRENET_PATH_SPLINE) {
             for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+            __syncthreads();   // phase A reads the table
         }
-        if (kColl) stage_obstacles(B, A.b, ox, oy);
-        if (kXY && path.kind == FRENET_PATH_SPLINE) __syncthreads();   // phase A reads the table
     }
 
     // Phase A: longitudinal samples, once per row (the reference deep-copies them into each of the n_d
@@ -402,12 +416,13 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
         double acc = 0.0, vmax = 0.0, amax = 0.0;
         for (int k = tid; k < A.N; k += blockDim.x) {
             const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
-            const double s = pl.val(t), v = pl.d1(t), a = pl.d2(t), j = pl.d3(t);
+            double s, v, a, j;
+            pl.eval(t, s, v, a, j);
             lon[k] = s;
-            lon[A.lonF + k] = v;
-            lon[2 * A.lonF + k] = a;
-            lon[3 * A.lonF + k] = j;
-            su[k] = low ? fabs(s - s0) : t;
+            lon[A.npad + k] = v;
+            lon[2 * A.npad + k] = a;
+            lon[3 * A.npad + k] = j;
+            frame[k * FS + FU] = low ? fabs(s - s0) : t;
             acc = fma(j, j, acc);
             if (kLimits) {
                 vmax = fmax(vmax, fabs(v));
@@ -416,7 +431,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
             if (kXY) {
                 double px, py, nx, ny;
                 path_frame(path.kind, path.circle, tab, path.n_knots, s, px, py, nx, ny);
-                fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
+                frame[k * FS] = px; frame[k * FS + 1] = py; frame[k * FS + 2] = nx; frame[k * FS + 3] = ny;
             }
         }
         // longitudinal jerk sum and limits: per-warp partials combined in a fixed order (deterministic)
@@ -455,56 +470,48 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
     }
     const double clong = sh_clong;
     const bool rowfeas = sh_rowfeas;
-    const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
-    const double dd = B.scal[(int64_t)A.b * 3];
     const double R = kColl ? sqrt(P.radius_sq) : 0.0;
+    const int npad = A.npad, N = A.N;
 
     // Phase B: a warp per candidate, lanes over time steps; no global loads in this loop.
     for (int id = warp; id < L.n_d; id += nwarps) {
-        const int64_t c = A.cand0 + id;
         Poly pq;
         pq.load(coef + id * 6);
-        const int64_t off = A.lat_off + (int64_t)id * A.npad;
-        double* o0 = B.lat + off + lane;
-        double* o1 = o0 + A.latF;
-        double* o2 = o1 + A.latF;
-        double* o3 = o2 + A.latF;
-        double* oxp = kXY ? B.xy + off + lane : nullptr;
-        double* oyp = kXY ? oxp + A.latF : nullptr;
+        double* out = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + lane;   // [6][npad] block of this candidate
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
 #pragma unroll 1
-        for (int kb = 0; kb < A.N; kb += kWarp) {
-            const int k = kb + lane;
-            const bool valid = k < A.N;
-            const int kk = valid ? k : kb;   // out-of-range lanes shadow the chunk's first step (never stored)
-            const double u = su[kk];
-            const double j = pq.d3(u);
-            const double a2 = pq.d2(u);
-            const double v1 = pq.d1(u);
-            const double d0 = pq.val(u);
+        for (int kb = 0; kb < N; kb += kWarp) {
+            const bool valid = kb + lane < N;
+            const double* fr = frame + (valid ? kb + lane : kb) * FS;   // out-of-range lanes shadow the chunk's first step
+            double d0, v1, a2, j;
+            pq.eval(fr[FU], d0, v1, a2, j);
             if (valid) {
-                o0[kb] = d0;
-                o1[kb] = v1;
-                o2[kb] = a2;
-                o3[kb] = j;
+                out[kb] = d0;
+                out[npad + kb] = v1;
+                out[2 * npad + kb] = a2;
+                out[3 * npad + kb] = j;
                 acc = fma(j, j, acc);
                 if (kLimits) amax = fmax(amax, fabs(a2));
             }
             if (kXY) {
-                const double x = __dadd_rn(fpx[kk], __dmul_rn(fnx[kk], d0));   // pt + n * d, unfused like the reference
-                const double y = __dadd_rn(fpy[kk], __dmul_rn(fny[kk], d0));
+                const double2 pp = *reinterpret_cast<const double2*>(fr);
+                const double2 nn = *reinterpret_cast<const double2*>(fr + 2);
+                const double x = __dadd_rn(pp.x, __dmul_rn(nn.x, d0));   // pt + n * d, unfused like the reference
+                const double y = __dadd_rn(pp.y, __dmul_rn(nn.y, d0));
                 if (valid) {
-                    oxp[kb] = x;
-                    oyp[kb] = y;
+                    out[4 * npad + kb] = x;
+                    out[5 * npad + kb] = y;
                 }
-                if (kColl) best = collide_chunk(x, y, valid, min(kWarp, A.N - kb), ox, oy, B.n_obs, R, P.radius_sq, best, lane);
+                if (kColl) best = collide_chunk(x, y, valid, min(kWarp, N - kb), obs, B.n_obs, R, P.radius_sq, best, lane);
             }
         }
         acc = warp_sum(acc);
         if (kLimits) amax = warp_max(amax);
         if (lane == 0) {   // :165-167 / :174-176
-            const double e = L.axis_d[id] - dd;
+            const int64_t c = A.cand0 + id;
+            const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
+            const double e = L.axis_d[id] - B.scal[(int64_t)A.b * 3];
             const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
             B.cost[c] = clat;
             B.cost[A.candF + c] = P.follow ? 0.0 : clong;
@@ -526,12 +533,9 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
 constexpr int kChunksInFlight = 4;   // chunks whose loads are issued before the first use (latency hiding)
 
 __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, FrenetPath path, FrenetBuffers B) {
-    extern __shared__ double sm[];
-    double* fpx = sm;
-    double* fpy = fpx + L.n_pad_max;
-    double* fnx = fpy + L.n_pad_max;
-    double* fny = fnx + L.n_pad_max;
-    double* tab = fny + L.n_pad_max;   // [n_knots][9] spline table staged in shared memory
+    extern __shared__ __align__(16) double sm[];
+    double* frame = sm;                        // [n_pad_max][4]: px, py, nx, ny
+    double* tab = sm + L.n_pad_max * 4;        // [n_knots][9] spline table staged in shared memory
 
     const int64_t br = blockIdx.x;
     const int flags = B.row_flags[br];
@@ -547,14 +551,15 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
     for (int k = tid; k < A.N; k += blockDim.x) {
         double px, py, nx, ny;
         path_frame(path.kind, path.circle, tab, path.n_knots, s_row[k], px, py, nx, ny);
-        fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
+        frame[k * 4] = px; frame[k * 4 + 1] = py; frame[k * 4 + 2] = nx; frame[k * 4 + 3] = ny;
     }
     __syncthreads();
+    const int npad = A.npad;
     for (int id = warp; id < L.n_d; id += nwarps) {
-        const int64_t off = A.lat_off + (int64_t)id * A.npad;
-        const double* d = B.lat + off;
-        double* x = B.xy + off;
-        double* y = x + A.latF;
+        double* blk = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad);
+        const double* d = blk;
+        double* x = blk + 4 * npad;
+        double* y = blk + 5 * npad;
         for (int kb = 0; kb < A.N; kb += kWarp * kChunksInFlight) {
             double dv[kChunksInFlight];
 #pragma unroll
@@ -566,8 +571,10 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
             for (int q = 0; q < kChunksInFlight; ++q) {
                 const int k = kb + q * kWarp + lane;
                 if (k < A.N) {
-                    x[k] = __dadd_rn(fpx[k], __dmul_rn(fnx[k], dv[q]));   // pt + n * d, unfused like the reference
-                    y[k] = __dadd_rn(fpy[k], __dmul_rn(fny[k], dv[q]));
+                    const double2 pp = *reinterpret_cast<const double2*>(frame + k * 4);
+                    const double2 nn = *reinterpret_cast<const double2*>(frame + k * 4 + 2);
+                    x[k] = __dadd_rn(pp.x, __dmul_rn(nn.x, dv[q]));   // pt + n * d, unfused like the reference
+                    y[k] = __dadd_rn(pp.y, __dmul_rn(nn.y, dv[q]));
                 }
             }
         }
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
 
 __global__ void __launch_bounds__(256) points_to_cartesian(FrenetPath path, const double* __restrict__ s, const double* __restrict__ d,
                                                            int64_t n, double* x, double* y, int64_t out_stride) {
-    extern __shared__ double tab[];
+    extern __shared__ __align__(16) double tab[];
     if (path.kind == FRENET_PATH_SPLINE) {
         for (int i = threadIdx.x; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
         __syncthreads();
@@ -603,9 +610,8 @@ __global__ void __launch_bounds__(kRowThreads) k3_curvature(FrenetLattice L, Fre
     }
     const double k2max = P.kappa_max * P.kappa_max;
     for (int id = warp; id < L.n_d; id += nwarps) {
-        const int64_t off = A.lat_off + (int64_t)id * A.npad;
-        const double* x = B.xy + off;
-        const double* y = x + A.latF;
+        const double* x = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
+        const double* y = x + A.npad;
         bool bad = false;
         for (int k = 1 + lane; k + 1 < A.N; k += kWarp) {
             const double ax = x[k] - x[k - 1], ay = y[k] - y[k - 1];
@@ -628,10 +634,9 @@ __global__ void __launch_bounds__(kRowThreads) k3_curvature(FrenetLattice L, Fre
 // K4: collision, one CTA per row; obstacles staged in shared memory
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int O = B.n_obs;
-    double* ox = sm;
-    double* oy = sm + O;
+    double2* obs = reinterpret_cast<double2*>(sm);
 
     const int64_t br = blockIdx.x;
     const RowAddr A = row_addr(L, br);
@@ -646,14 +651,13 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
     }
     // Obstacles the sensor did not report are parked at infinity so the cull never selects them
     // (check_paths tests sensed obstacles only).
-    stage_obstacles(B, A.b, ox, oy);
+    stage_obstacles(B, A.b, obs);
     __syncthreads();
     const double R = sqrt(P.radius_sq);
 
     for (int id = warp; id < L.n_d; id += nwarps) {
-        const int64_t off = A.lat_off + (int64_t)id * A.npad;
-        const double* xs = B.xy + off;
-        const double* ys = xs + A.latF;
+        const double* xs = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
+        const double* ys = xs + A.npad;
         int best = kNoBlocker;   // lowest blocking obstacle index found so far (warp-uniform)
         for (int kb = 0; kb < A.N; kb += kWarp * kChunksInFlight) {
             double xv[kChunksInFlight], yv[kChunksInFlight];
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
             for (int q = 0; q < kChunksInFlight; ++q) {
                 const int k0 = kb + q * kWarp;
                 if (k0 < A.N)
-                    best = collide_chunk(xv[q], yv[q], k0 + lane < A.N, min(kWarp, A.N - k0), ox, oy, O, R, P.radius_sq, best, lane);
+                    best = collide_chunk(xv[q], yv[q], k0 + lane < A.N, min(kWarp, A.N - k0), obs, O, R, P.radius_sq, best, lane);
             }
         }
         if (lane == 0) {
@@ -786,17 +790,18 @@ __global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetPara
     const RowAddr A = row_addr(L, (int64_t)b * L.n_v_cap * L.n_t + r);
     double* w = B.winner + (int64_t)b * FRENET_WINNER_ROWS * L.n_pad_max;
     const double t0 = B.scal[(int64_t)b * 3 + 2];
-    const int64_t loff = A.lat_off + (int64_t)id * A.npad;
+    const double* cand = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad);
+    const double* lon = B.lon + A.lon_off;
     for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
         w[k] = (double)k * P.sample_period + t0;   // f.t[i] += t_initial (:178-179)
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-            w[(1 + f) * L.n_pad_max + k] = B.lat[f * A.latF + loff + k];
-            w[(5 + f) * L.n_pad_max + k] = B.lon[f * A.lonF + A.lon_off + k];
+            w[(1 + f) * L.n_pad_max + k] = cand[f * A.npad + k];
+            w[(5 + f) * L.n_pad_max + k] = lon[f * A.npad + k];
         }
         if (has_xy) {
-            w[9 * L.n_pad_max + k] = B.xy[loff + k];
-            w[10 * L.n_pad_max + k] = B.xy[A.latF + loff + k];
+            w[9 * L.n_pad_max + k] = cand[4 * A.npad + k];
+            w[10 * L.n_pad_max + k] = cand[5 * A.npad + k];
         }
     }
     if (threadIdx.x < 4) w[11 * L.n_pad_max + threadIdx.x] = B.cost[threadIdx.x * A.candF + A.cand0 + id];
@@ -845,7 +850,7 @@ template <bool kXY, bool kColl>
 int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, cudaStream_t stream) {
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
-    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 6 + (spline ? (size_t)9 * path->n_knots : 0) +
+    const size_t smem = ((size_t)L->n_pad_max * (kXY ? kFrame : 1) + (size_t)L->n_d * 6 + (spline ? (size_t)9 * path->n_knots : 0) +
                          (kColl ? (size_t)2 * B->n_obs : 0)) * sizeof(double);
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
@@ -907,7 +912,6 @@ int frenet_k2_fused(const FrenetLattice* L, const FrenetParams* P, const FrenetP
                     int32_t with_collision, frenet_stream_t stream) {
     if (int rc = check_k2(L, P, B)) return rc;
     if (int rc = check_path(path)) return rc;
-    if (!B->xy) return fail(FRENET_ERR_BAD_ARG, "fused: xy buffer is NULL");
     if (!with_collision) return launch_k2<true, false>(L, P, path, B, (cudaStream_t)stream);
     if (!B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "fused: collision output is NULL");
     if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "fused: obstacle table missing");
@@ -919,7 +923,7 @@ int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const Fre
     (void)P;
     if (int rc = check_lattice(L)) return rc;
     if (int rc = check_path(path)) return rc;
-    if (!B || !B->row_flags || !B->lon || !B->lat || !B->xy) return fail(FRENET_ERR_BAD_ARG, "k3: NULL buffer");
+    if (!B || !B->row_flags || !B->lon || !B->lat) return fail(FRENET_ERR_BAD_ARG, "k3: NULL buffer");
     const size_t smem = ((size_t)4 * L->n_pad_max + (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0)) * sizeof(double);
     if (int rc = set_smem(k3_cartesian, smem, "k3: horizon / spline table too large for shared memory")) return rc;
     k3_cartesian<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *path, *B);
@@ -929,7 +933,7 @@ int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const Fre
 
 int frenet_k3_curvature(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
-    if (!P || !B || !B->row_flags || !B->xy || !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "curvature: NULL buffer");
+    if (!P || !B || !B->row_flags || !B->lat || !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "curvature: NULL buffer");
     k3_curvature<<<n_rows(L), kRowThreads, 0, (cudaStream_t)stream>>>(*L, *P, *B);
     FRENET_CHECK_LAUNCH("k3_curvature");
     return FRENET_OK;
@@ -937,7 +941,7 @@ int frenet_k3_curvature(const FrenetLattice* L, const FrenetParams* P, const Fre
 
 int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
-    if (!P || !B || !B->row_flags || !B->xy || !B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "k4: NULL buffer");
+    if (!P || !B || !B->row_flags || !B->lat || !B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "k4: NULL buffer");
     if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "k4: obstacle table missing");
     const size_t smem = (size_t)2 * B->n_obs * sizeof(double);
     if (int rc = set_smem(k4_collision, smem, "k4: too many obstacles for shared memory")) return rc;
@@ -961,7 +965,6 @@ int frenet_gather_winner(const FrenetLattice* L, const FrenetParams* P, const Fr
     if (int rc = check_lattice(L)) return rc;
     if (!P || !B || !B->result || !B->winner || !B->winner_steps || !B->lon || !B->lat || !B->scal)
         return fail(FRENET_ERR_BAD_ARG, "gather: NULL buffer");
-    if (has_xy && !B->xy) return fail(FRENET_ERR_BAD_ARG, "gather: xy requested but NULL");
     if (sel < FRENET_SEL_CTOT || sel > FRENET_SEL_MASKED) return fail(FRENET_ERR_BAD_ARG, "gather: bad selector");
     gather_winner<<<L->n_scen, 128, 0, (cudaStream_t)stream>>>(*L, *P, *B, sel, has_xy);
     FRENET_CHECK_LAUNCH("gather_winner");

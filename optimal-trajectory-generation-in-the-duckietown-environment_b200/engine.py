@@ -199,9 +199,8 @@ class FrenetEngine:
         self.coef_lat = torch.empty((Bn, Cc, 6), **f64)
         self.row_S = torch.empty((Bn, R), **f64)
         self.row_flags = torch.empty((Bn, R), dtype=torch.int32, device=dev)
-        self.lon = torch.empty((4, Bn, row_elems), **f64)
-        self.lat = torch.empty((4, Bn, cand_elems), **f64)
-        self.xy = torch.empty((2, Bn, cand_elems), **f64)
+        self.lon = torch.empty((Bn, row_elems * 4), **f64)     # per row:       [4][npad]  s, ds, dds, ddds
+        self.lat = torch.empty((Bn, cand_elems * 6), **f64)    # per candidate: [6][npad]  d, dd, ddd, dddd, x, y
         self.cost = torch.empty((4, Bn, Cc), **f64)
         self.cand_flags = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.curv_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
@@ -219,14 +218,14 @@ class FrenetEngine:
         Bf.coef_lon, Bf.coef_lat = self.coef_lon.data_ptr(), self.coef_lat.data_ptr()
         Bf.row_S, Bf.row_flags = self.row_S.data_ptr(), self.row_flags.data_ptr()
         Bf.lon, Bf.lat, Bf.cost, Bf.cand_flags = self.lon.data_ptr(), self.lat.data_ptr(), self.cost.data_ptr(), self.cand_flags.data_ptr()
-        Bf.xy, Bf.curv_ok = self.xy.data_ptr(), self.curv_ok.data_ptr()
+        Bf.curv_ok = self.curv_ok.data_ptr()
         Bf.coll_free, Bf.first_blocker = self.coll_free.data_ptr(), self.first_blocker.data_ptr()
         Bf.result = op + ooffs["result"]
         Bf.winner, Bf.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
         self._cap_key = key
 
     def hbm_bytes(self) -> int:
-        ts = [self.coef_lon, self.coef_lat, self.row_S, self.row_flags, self.lon, self.lat, self.xy, self.cost, self.cand_flags,
+        ts = [self.coef_lon, self.coef_lat, self.row_S, self.row_flags, self.lon, self.lat, self.cost, self.cand_flags,
               self.curv_ok, self.coll_free, self.first_blocker, self._in_dev, self._out_dev, self._geom_dev]
         return sum(t.numel() * t.element_size() for t in ts)
 
@@ -297,29 +296,30 @@ class FrenetEngine:
 
     # -- views of device data ------------------------------------------------------------------
     def cand_offsets(self, n_v: int):
-        """(offset into a lateral field, row offset into a longitudinal field, steps) per candidate in list order."""
+        """Per candidate in list order: offset of its [6][npad] block in a scenario's `lat` slab, offset of its row's
+        [4][npad] block in the `lon` slab, padded length, step count."""
         g = self.geom
         iv = np.repeat(np.arange(n_v), g.n_t * g.n_d)
         iT = np.tile(np.repeat(np.arange(g.n_t), g.n_d), n_v)
         idd = np.tile(np.arange(g.n_d), n_v * g.n_t)
         within = iv.astype(np.int64) * g.sum_pad + g.t_offset[iT]
-        return within * g.n_d + idd * g.n_pad[iT], within, g.n_steps[iT]
+        npad = g.n_pad[iT].astype(np.int64)
+        return (within * g.n_d + idd * npad) * 6, within * 4, npad, g.n_steps[iT]
 
     def fetch_scenario(self, b: int = 0, with_xy: bool | None = None, with_collision: bool | None = None) -> dict:
         """D2H of one scenario's full lattice state as NumPy arrays (raw padded layout + offsets)."""
         with_xy = self.has_xy if with_xy is None else with_xy
         with_collision = self.has_collision if with_collision is None else with_collision
         nv = int(self.n_v[b])
-        out = dict(n_v=nv, lon=self.lon[:, b].cpu().numpy(), lat=self.lat[:, b].cpu().numpy(),
+        out = dict(n_v=nv, lon=self.lon[b].cpu().numpy(), lat=self.lat[b].cpu().numpy(),
                    cost=self.cost[:, b].cpu().numpy(), cand_flags=self.cand_flags[b].cpu().numpy(),
                    coef_lon=self.coef_lon[b].cpu().numpy(), coef_lat=self.coef_lat[b].cpu().numpy(),
                    row_S=self.row_S[b].cpu().numpy(), row_flags=self.row_flags[b].cpu().numpy())
-        if with_xy:
-            out["xy"] = self.xy[:, b].cpu().numpy()
+        out["has_xy"] = bool(with_xy)
         if with_collision:
             out["coll_free"] = self.coll_free[b].cpu().numpy()
             out["first_blocker"] = self.first_blocker[b].cpu().numpy()
-        out["lat_off"], out["lon_off"], out["nsteps"] = self.cand_offsets(nv)
+        out["lat_off"], out["lon_off"], out["npad"], out["nsteps"] = self.cand_offsets(nv)
         return out
 
     def padded_fields(self, sc: dict) -> dict:
@@ -332,14 +332,13 @@ class FrenetEngine:
         valid = k[None, :] < n[:, None]
         il = np.where(valid, sc["lat_off"][:, None] + k[None, :], 0)
         io = np.where(valid, sc["lon_off"][:, None] + k[None, :], 0)
+        fstride = np.where(valid, sc["npad"][:, None], 0)
         res = {"nsteps": n.astype(np.int32)}
-        for j, name in enumerate(("d", "dot_d", "ddot_d", "dddot_d")):
-            res[name] = np.where(valid, sc["lat"][j][il], np.nan)
+        names = ("d", "dot_d", "ddot_d", "dddot_d") + (("x", "y") if sc.get("has_xy") else ())
+        for j, name in enumerate(names):
+            res[name] = np.where(valid, sc["lat"][il + j * fstride], np.nan)
         for j, name in enumerate(("s", "dot_s", "ddot_s", "dddot_s")):
-            res[name] = np.where(valid, sc["lon"][j][io], np.nan)
-        if "xy" in sc:
-            res["x"] = np.where(valid, sc["xy"][0][il], np.nan)
-            res["y"] = np.where(valid, sc["xy"][1][il], np.nan)
+            res[name] = np.where(valid, sc["lon"][io + j * fstride], np.nan)
         for j, name in enumerate(("cd", "cv", "ct", "ctot")):
             res[name] = sc["cost"][j][:C_]
         res["valid"] = (sc["cand_flags"][:C_] & nat.CAND_VALID) != 0

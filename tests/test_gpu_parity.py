@@ -427,7 +427,7 @@ def test_fused_kernel_equals_separate_launches():
         (fo.OracleParams.defaults("v1").with_(v_max=5.3, a_max=3.1), dict(p0=z["p0"][:64], s0=z["s0"][:64], t0=z["time"][:64],
                                                                          trajectory=Circle(8, 5, 2), use_mask=1)),
     ]
-    names = ("lon", "lat", "xy", "cost", "cand_flags", "coll_free", "first_blocker", "coef_lon", "coef_lat")
+    names = ("cost", "cand_flags", "coll_free", "first_blocker", "coef_lon", "coef_lat")
     for prm, kw in cases:
         kw = dict(kw)
         p0, s0, t0 = kw.pop("p0"), kw.pop("s0"), kw.pop("t0")
