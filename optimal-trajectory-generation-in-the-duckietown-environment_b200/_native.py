@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libfrenet_b200.so")
+# OTG_B200_LIB selects another build of the same library (A/B experiments with compile-time tuning knobs)
+LIB_PATH = os.environ.get("OTG_B200_LIB") or os.path.join(_PKG_DIR, "libfrenet_b200.so")
 
 ABI_VERSION = 1
 

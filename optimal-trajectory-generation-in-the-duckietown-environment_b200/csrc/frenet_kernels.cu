@@ -27,6 +27,9 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kRowThreads = 256;   // CTA size of the per-row kernels (8 warps)
 constexpr int kMaxSmem = 227 * 1024;
+#ifndef FRENET_K2_MIN_CTAS
+#define FRENET_K2_MIN_CTAS 3   // resident CTAs per SM the evaluate kernel is compiled for (register cap 65536 / (256 * n))
+#endif
 
 thread_local char g_err[256] = "";
 
@@ -304,28 +307,36 @@ __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ 
 constexpr int kNoBlocker = 0x7fffffff;
 
 // x, y: this lane's point (lanes beyond the candidate's last step carry a copy of a valid point and valid = false).
-// obs: obstacle table in shared memory as (x, y) pairs; obstacles the sensor did not report are parked at +inf.
+// obs: obstacle table in shared memory as (x, y) pairs; obsf: the same rounded to fp32 for the cull; obstacles the
+// sensor did not report are parked at +inf.
 // best: lowest blocking obstacle index found so far for this candidate (warp-uniform); returns the updated value.
-// Obstacles are culled per chunk with a lane-parallel test against the chunk's bounding circle (conservative:
-// radius rounded up, threshold inflated), then the exact reference test (lib/tests/test_obstacle_planner.py:48)
-// runs on the few survivors in ascending index order, so the first hit is the chunk's lowest blocker.
-__device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int nvalid, const double2* __restrict__ obs, int O,
-                                             double R, double radius_sq, int best, int lane) {
+//
+// Two stages.  (1) Cull, in fp32 on the FMA/ALU pipes: obstacles are tested lane-parallel against the bounding
+// circle of the chunk's 32 points.  It is conservative: the circle radius is rounded up and the reach is padded
+// by 2^-18 of the coordinate magnitude, three orders of magnitude above the fp32 rounding error of the
+// operands, so no obstacle within the robot radius of any point can be dropped.  (2) The exact reference test
+// (lib/tests/test_obstacle_planner.py:48) in fp64 on the few survivors, in ascending index order, so the first
+// hit is the chunk's lowest blocker and the masks are bit-identical to a brute-force fp64 sweep.
+__device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int nvalid, const double2* __restrict__ obs,
+                                             const float2* __restrict__ obsf, int O, float Rf, double radius_sq, int best,
+                                             int lane) {
     const int mid = (nvalid - 1) >> 1;
-    const double cx = __shfl_sync(kFull, x, mid), cy = __shfl_sync(kFull, y, mid);
-    const double ex = x - cx, ey = y - cy;
-    const float r2 = __double2float_ru(fma(ex, ex, ey * ey));
+    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
+    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
+    const float ex = xf - cx, ey = yf - cy;
+    const float r2 = fmaf(ex, ex, ey * ey);
     const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));   // r2 >= 0: uint order == float order
-    const double reach = R + (double)__fsqrt_ru(r2max);
-    const double thr = reach * reach * (1.0 + 1e-9);
+    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
+    // Chunks whose extent does not fit fp32 (ill-conditioned low-speed candidates reach |d| ~ 1e80) are not culled at all.
+    const float thr = (r2max < 1e30f) ? reach * reach : CUDART_INF_F;
     const int lim = min(O, best);   // only lower indices can still improve `best`
     for (int ob = 0; ob < lim; ob += kWarp) {
         const int o = ob + lane;
         bool near = false;
         if (o < lim) {
-            const double2 q = obs[o];
-            const double ux = q.x - cx, uy = q.y - cy;
-            near = fma(ux, ux, uy * uy) <= thr;
+            const float2 q = obsf[o];
+            const float ux = q.x - cx, uy = q.y - cy;
+            near = !(fmaf(ux, ux, uy * uy) > thr);   // NaN counts as near
         }
         unsigned m = __ballot_sync(kFull, near);
         while (m) {
@@ -341,12 +352,14 @@ __device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int
 }
 
 // Stage a scenario's obstacle snapshot in shared memory.
-__device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double2* obs) {
+__device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double2* obs, float2* obsf) {
     const int O = B.n_obs;
     const double2* src = reinterpret_cast<const double2*>(B.obs_xy) + (int64_t)b * O;
     for (int o = threadIdx.x; o < O; o += blockDim.x) {
         const bool on = B.obs_active == nullptr || B.obs_active[(int64_t)b * O + o] != 0;
-        obs[o] = on ? src[o] : make_double2(CUDART_INF, CUDART_INF);
+        const double2 q = on ? src[o] : make_double2(CUDART_INF, CUDART_INF);
+        obs[o] = q;
+        obsf[o] = make_float2(__double2float_rn(q.x), __double2float_rn(q.y));   // inf stays inf
     }
 }
 
@@ -359,15 +372,16 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 //          KINEMATIC_OK flag is set unconditionally, which is the reference's behaviour.
 // The fused variants write each candidate-timestep exactly once (48 B: d, d', d'', d''', x, y) and read
 // nothing back; the unfused sequence K2 -> K3 -> K4 moves 72 B for the same result.
-// Shared memory (doubles): [2 * n_obs] obstacles (kColl) | [n_pad_max][kFrame or 1] frame | [n_d][6] lateral
+// Shared memory (doubles): [3 * n_obs, rounded up to 4] obstacles in fp64 and fp32 (kColl) | [n_pad_max][kFrame or 1] frame | [n_d][6] lateral
 // coefficients | [n_knots][9] spline table (kXY).
 template <bool kXY, bool kColl, bool kLimits>
-__global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
+__global__ void __launch_bounds__(kRowThreads, FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
     extern __shared__ __align__(16) double sm[];
     constexpr int FS = kXY ? kFrame : 1;   // frame stride: (px, py, nx, ny, u, pad) or just u
     constexpr int FU = kXY ? 4 : 0;        // position of u inside a frame entry
     double2* obs = reinterpret_cast<double2*>(sm);
-    double* frame = sm + (kColl ? 2 * B.n_obs : 0);
+    float2* obsf = reinterpret_cast<float2*>(sm + 2 * B.n_obs);
+    double* frame = sm + (kColl ? 4 * ((3 * B.n_obs + 3) / 4) : 0);   // 3 doubles per obstacle, kept 32-byte aligned
     double* coef = frame + L.n_pad_max * FS;
     double* tab = coef + L.n_d * 6;
     __shared__ double red[3][kRowThreads / 32];
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
     {
         const double* cq = B.coef_lat + A.cand0 * 6;
         for (int i = tid; i < L.n_d * 6; i += blockDim.x) coef[i] = cq[i];
-        if (kColl) stage_obstacles(B, A.b, obs);
+        if (kColl) stage_obstacles(B, A.b, obs, obsf);
         if (kXY && path.kind == FRENET_PATH_SPLINE) {
             for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
             __syncthreads();   // phase A reads the table
@@ -414,7 +428,10 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
         pl.load(B.coef_lon + br * 6);
         double* lon = B.lon + A.lon_off;
         double acc = 0.0, vmax = 0.0, amax = 0.0;
-        for (int k = tid; k < A.N; k += blockDim.x) {
+        // Samples k in [N, npad) are padding: they are evaluated and stored like real samples so that every 32-byte
+        // sector of the output is written in full (a partially written sector costs a DRAM read-modify-write, which
+        // halves the achieved store bandwidth), but they take no part in costs, limits or collisions.
+        for (int k = tid; k < A.npad; k += blockDim.x) {
             const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
             double s, v, a, j;
             pl.eval(t, s, v, a, j);
@@ -423,10 +440,12 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
             lon[2 * A.npad + k] = a;
             lon[3 * A.npad + k] = j;
             frame[k * FS + FU] = low ? fabs(s - s0) : t;
-            acc = fma(j, j, acc);
-            if (kLimits) {
-                vmax = fmax(vmax, fabs(v));
-                amax = fmax(amax, fabs(a));
+            if (k < A.N) {
+                acc = fma(j, j, acc);
+                if (kLimits) {
+                    vmax = fmax(vmax, fabs(v));
+                    amax = fmax(amax, fabs(a));
+                }
             }
             if (kXY) {
                 double px, py, nx, ny;
@@ -470,27 +489,33 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
     }
     const double clong = sh_clong;
     const bool rowfeas = sh_rowfeas;
-    const double R = kColl ? sqrt(P.radius_sq) : 0.0;
+    const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
     const int npad = A.npad, N = A.N;
 
     // Phase B: a warp per candidate, lanes over time steps; no global loads in this loop.
     for (int id = warp; id < L.n_d; id += nwarps) {
         Poly pq;
         pq.load(coef + id * 6);
-        double* out = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + lane;   // [6][npad] block of this candidate
+        // [6][npad] block of this candidate; `out` walks along k, the fields sit `fs` bytes apart
+        char* out = reinterpret_cast<char*>(B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + lane);
+        const int64_t fs = (int64_t)npad * sizeof(double);
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
 #pragma unroll 1
         for (int kb = 0; kb < N; kb += kWarp) {
-            const bool valid = kb + lane < N;
-            const double* fr = frame + (valid ? kb + lane : kb) * FS;   // out-of-range lanes shadow the chunk's first step
+            const bool valid = kb + lane < N;       // a real sample
+            const bool store = kb + lane < npad;    // real or padding: stored so that whole sectors are written
+            const double* fr = frame + (store ? kb + lane : kb) * FS;   // lanes beyond the padding shadow the chunk's first step
             double d0, v1, a2, j;
             pq.eval(fr[FU], d0, v1, a2, j);
+            char* o = out;
+            if (store) {
+                *reinterpret_cast<double*>(o) = d0;
+                *reinterpret_cast<double*>(o += fs) = v1;
+                *reinterpret_cast<double*>(o += fs) = a2;
+                *reinterpret_cast<double*>(o += fs) = j;
+            }
             if (valid) {
-                out[kb] = d0;
-                out[npad + kb] = v1;
-                out[2 * npad + kb] = a2;
-                out[3 * npad + kb] = j;
                 acc = fma(j, j, acc);
                 if (kLimits) amax = fmax(amax, fabs(a2));
             }
@@ -499,12 +524,14 @@ __global__ void __launch_bounds__(kRowThreads, 3) k2_evaluate(FrenetLattice L, F
                 const double2 nn = *reinterpret_cast<const double2*>(fr + 2);
                 const double x = __dadd_rn(pp.x, __dmul_rn(nn.x, d0));   // pt + n * d, unfused like the reference
                 const double y = __dadd_rn(pp.y, __dmul_rn(nn.y, d0));
-                if (valid) {
-                    out[4 * npad + kb] = x;
-                    out[5 * npad + kb] = y;
+                if (store) {
+                    *reinterpret_cast<double*>(o += fs) = x;
+                    *reinterpret_cast<double*>(o += fs) = y;
                 }
-                if (kColl) best = collide_chunk(x, y, valid, min(kWarp, N - kb), obs, B.n_obs, R, P.radius_sq, best, lane);
+                // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
+                if (kColl) best = collide_chunk(x, y, valid, min(kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq, best, lane);
             }
+            out += kWarp * sizeof(double);
         }
         acc = warp_sum(acc);
         if (kLimits) amax = warp_max(amax);
@@ -548,7 +575,7 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
         __syncthreads();
     }
     const double* s_row = B.lon + A.lon_off;
-    for (int k = tid; k < A.N; k += blockDim.x) {
+    for (int k = tid; k < A.npad; k += blockDim.x) {   // padding samples included: whole sectors are written (see K2)
         double px, py, nx, ny;
         path_frame(path.kind, path.circle, tab, path.n_knots, s_row[k], px, py, nx, ny);
         frame[k * 4] = px; frame[k * 4 + 1] = py; frame[k * 4 + 2] = nx; frame[k * 4 + 3] = ny;
@@ -560,17 +587,17 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
         const double* d = blk;
         double* x = blk + 4 * npad;
         double* y = blk + 5 * npad;
-        for (int kb = 0; kb < A.N; kb += kWarp * kChunksInFlight) {
+        for (int kb = 0; kb < npad; kb += kWarp * kChunksInFlight) {
             double dv[kChunksInFlight];
 #pragma unroll
             for (int q = 0; q < kChunksInFlight; ++q) {
                 const int k = kb + q * kWarp + lane;
-                dv[q] = k < A.N ? d[k] : 0.0;
+                dv[q] = k < npad ? d[k] : 0.0;
             }
 #pragma unroll
             for (int q = 0; q < kChunksInFlight; ++q) {
                 const int k = kb + q * kWarp + lane;
-                if (k < A.N) {
+                if (k < npad) {
                     const double2 pp = *reinterpret_cast<const double2*>(frame + k * 4);
                     const double2 nn = *reinterpret_cast<const double2*>(frame + k * 4 + 2);
                     x[k] = __dadd_rn(pp.x, __dmul_rn(nn.x, dv[q]));   // pt + n * d, unfused like the reference
@@ -637,6 +664,7 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
     extern __shared__ __align__(16) double sm[];
     const int O = B.n_obs;
     double2* obs = reinterpret_cast<double2*>(sm);
+    float2* obsf = reinterpret_cast<float2*>(sm + 2 * O);
 
     const int64_t br = blockIdx.x;
     const RowAddr A = row_addr(L, br);
@@ -651,9 +679,9 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
     }
     // Obstacles the sensor did not report are parked at infinity so the cull never selects them
     // (check_paths tests sensed obstacles only).
-    stage_obstacles(B, A.b, obs);
+    stage_obstacles(B, A.b, obs, obsf);
     __syncthreads();
-    const double R = sqrt(P.radius_sq);
+    const float Rf = __double2float_ru(sqrt(P.radius_sq));
 
     for (int id = warp; id < L.n_d; id += nwarps) {
         const double* xs = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
@@ -673,7 +701,7 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
             for (int q = 0; q < kChunksInFlight; ++q) {
                 const int k0 = kb + q * kWarp;
                 if (k0 < A.N)
-                    best = collide_chunk(xv[q], yv[q], k0 + lane < A.N, min(kWarp, A.N - k0), obs, O, R, P.radius_sq, best, lane);
+                    best = collide_chunk(xv[q], yv[q], k0 + lane < A.N, min(kWarp, A.N - k0), obs, obsf, O, Rf, P.radius_sq, best, lane);
             }
         }
         if (lane == 0) {
@@ -851,7 +879,7 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
     const size_t smem = ((size_t)L->n_pad_max * (kXY ? kFrame : 1) + (size_t)L->n_d * 6 + (spline ? (size_t)9 * path->n_knots : 0) +
-                         (kColl ? (size_t)2 * B->n_obs : 0)) * sizeof(double);
+                         (kColl ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0)) * sizeof(double);
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
     if (limits) {
@@ -943,7 +971,7 @@ int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const Fre
     if (int rc = check_lattice(L)) return rc;
     if (!P || !B || !B->row_flags || !B->lat || !B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "k4: NULL buffer");
     if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "k4: obstacle table missing");
-    const size_t smem = (size_t)2 * B->n_obs * sizeof(double);
+    const size_t smem = (size_t)3 * B->n_obs * sizeof(double);
     if (int rc = set_smem(k4_collision, smem, "k4: too many obstacles for shared memory")) return rc;
     k4_collision<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
     FRENET_CHECK_LAUNCH("k4_collision");
