@@ -108,6 +108,10 @@ typedef struct FrenetLattice {
     const double* axis_t;    /* [n_t]   np.arange(*t_interval) */
     const int32_t* n_steps;  /* [n_t]   len(np.arange(0, T + dt, dt)) */
     const int32_t* t_offset; /* [n_t+1] prefix sum of the step counts rounded up to 4 */
+    const double* t_pow;     /* [n_pad_max][4] t_k^2 .. t_k^5 for t_k = k * sample_period, evaluated on the host with the
+                                reference's own `**` (C pow): the longitudinal polynomial is sampled in the reference's
+                                power form with these, so that its values - which become the next replan's initial state
+                                and sit on the low-speed threshold in converged runs - round the way the reference's do */
     const double* axis_v;    /* [n_scen][n_v_cap] target speeds (velocity keeping) or target offsets (follow) */
     const int32_t* n_v;      /* [n_scen] */
 } FrenetLattice;
@@ -229,6 +233,12 @@ int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetP
  * Point i is written to x[i * out_stride], y[i * out_stride] (out_stride 2 with y = x + 1 fills an [n][2] table). */
 int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
                                int64_t out_stride, frenet_stream_t stream);
+
+/* Generic form of K4 for polylines that are not in the lattice layout: path p owns points offsets[p] .. offsets[p+1]-1
+ * of x / y; obstacles are an [n_obs][2] table (all tested).  Replaces check_collisions on one path at a time
+ * (lib/tests/test_moving_obstacle_planner.py:42-52) for every path of a list at once. */
+int frenet_polyline_collision(const double* x, const double* y, const int64_t* offsets, int32_t n_paths, const double* obs_xy,
+                              int32_t n_obs, double radius_sq, uint8_t* coll_free, int32_t* first_blocker, frenet_stream_t stream);
 
 #ifdef __cplusplus
 }

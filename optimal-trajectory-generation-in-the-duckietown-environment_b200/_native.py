@@ -38,7 +38,7 @@ class FrenetLattice(C.Structure):
     _fields_ = [("n_scen", C.c_int32), ("n_v_cap", C.c_int32), ("n_t", C.c_int32), ("n_d", C.c_int32),
                 ("n_pad_max", C.c_int32), ("reserved", C.c_int32), ("row_elems", C.c_int64), ("cand_elems", C.c_int64),
                 ("axis_d", C.c_void_p), ("axis_t", C.c_void_p), ("n_steps", C.c_void_p), ("t_offset", C.c_void_p),
-                ("axis_v", C.c_void_p), ("n_v", C.c_void_p)]
+                ("t_pow", C.c_void_p), ("axis_v", C.c_void_p), ("n_v", C.c_void_p)]
 
 
 class FrenetPath(C.Structure):
@@ -99,6 +99,8 @@ def _load():
         "frenet_gather_winner": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_int32, C.c_int32, C.c_void_p]),
         "frenet_plan": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
+        "frenet_polyline_collision": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]),
         "frenet_points_to_cartesian": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                                  C.c_int64, C.c_void_p]),
     }

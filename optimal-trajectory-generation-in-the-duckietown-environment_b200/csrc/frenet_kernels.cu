@@ -27,8 +27,14 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kRowThreads = 256;   // CTA size of the per-row kernels (8 warps)
 constexpr int kMaxSmem = 227 * 1024;
+// Resident CTAs per SM the evaluate kernel is compiled for (register cap 65536 / (256 * n)).  Measured on B200: the
+// store-bound variants are fastest at 3 (80 registers, no rematerialisation), the collision variant at 4 (it is
+// latency-bound: dependent shuffle / vote / shared-memory chains want more warps).
 #ifndef FRENET_K2_MIN_CTAS
-#define FRENET_K2_MIN_CTAS 3   // resident CTAs per SM the evaluate kernel is compiled for (register cap 65536 / (256 * n))
+#define FRENET_K2_MIN_CTAS 3
+#endif
+#ifndef FRENET_K2_MIN_CTAS_COLL
+#define FRENET_K2_MIN_CTAS_COLL 4
 #endif
 
 thread_local char g_err[256] = "";
@@ -118,6 +124,22 @@ struct Poly {
     }
 };
 
+// The reference's own evaluation order (trajectory_1d.py:46,54,63,70): power form, every product and sum rounded
+// separately, powers of t taken from the host table (C pow, like the reference's `**`).  Used for the longitudinal
+// polynomial only (once per row and step): its samples become the next replan's initial state, and in converged
+// runs the sampled speed sits exactly on low_speed_threshold, so how it rounds decides which lateral mode the next
+// replan uses.  tp = {t^2, t^3, t^4, t^5}.
+__device__ __forceinline__ void eval_power_form(const Poly& p, double t, const double* __restrict__ tp, double& v0, double& v1,
+                                                double& v2, double& v3) {
+    const double t2 = tp[0], t3 = tp[1], t4 = tp[2], t5 = tp[3];
+    auto mul = [](double a, double b) { return __dmul_rn(a, b); };
+    auto add = [](double a, double b) { return __dadd_rn(a, b); };
+    v0 = add(add(add(add(add(p.a0, mul(p.a1, t)), mul(p.a2, t2)), mul(p.a3, t3)), mul(p.a4, t4)), mul(p.a5, t5));
+    v1 = add(add(add(add(p.a1, mul(mul(2.0, p.a2), t)), mul(mul(3.0, p.a3), t2)), mul(mul(4.0, p.a4), t3)), mul(mul(5.0, p.a5), t4));
+    v2 = add(add(add(mul(2.0, p.a2), mul(mul(6.0, p.a3), t)), mul(mul(12.0, p.a4), t2)), mul(mul(20.0, p.a5), t3));
+    v3 = add(add(mul(6.0, p.a3), mul(mul(24.0, p.a4), t)), mul(mul(60.0, p.a5), t2));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -202,8 +224,9 @@ __global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetPa
     // S: arc length at the last sample (:155; signed in the Optimal variant, trajectory_planner_optimal.py:151)
     Poly pl;
     pl.load(a);
-    const double t_last = (double)(L.n_steps[iT] - 1) * P.sample_period;
-    const double s_last = pl.val(t_last);
+    const int k_last = L.n_steps[iT] - 1;
+    double s_last, unused1, unused2, unused3;
+    eval_power_form(pl, (double)k_last * P.sample_period, L.t_pow + 4 * k_last, s_last, unused1, unused2, unused3);
     const double S = (P.lowspeed_rule == FRENET_LOWSPEED_OPTIMAL) ? (s_last - s0) : fabs(s_last - s0);
     bool low = false, dropped = false;
     if (P.lowspeed_rule == FRENET_LOWSPEED_V1) {
@@ -375,7 +398,7 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // Shared memory (doubles): [3 * n_obs, rounded up to 4] obstacles in fp64 and fp32 (kColl) | [n_pad_max][kFrame or 1] frame | [n_d][6] lateral
 // coefficients | [n_knots][9] spline table (kXY).
 template <bool kXY, bool kColl, bool kLimits>
-__global__ void __launch_bounds__(kRowThreads, FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
+__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
     extern __shared__ __align__(16) double sm[];
     constexpr int FS = kXY ? kFrame : 1;   // frame stride: (px, py, nx, ny, u, pad) or just u
     constexpr int FU = kXY ? 4 : 0;        // position of u inside a frame entry
@@ -434,7 +457,7 @@ __global__ void __launch_bounds__(kRowThreads, FRENET_K2_MIN_CTAS) k2_evaluate(F
         for (int k = tid; k < A.npad; k += blockDim.x) {
             const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
             double s, v, a, j;
-            pl.eval(t, s, v, a, j);
+            eval_power_form(pl, t, L.t_pow + 4 * k, s, v, a, j);
             lon[k] = s;
             lon[A.npad + k] = v;
             lon[2 * A.npad + k] = a;
@@ -473,13 +496,14 @@ __global__ void __launch_bounds__(kRowThreads, FRENET_K2_MIN_CTAS) k2_evaluate(F
                 am = fmax(am, red[2][w]);
             }
             const double T = L.axis_t[A.iT];
-            const double t_last = (double)(A.N - 1) * dt;
+            double s_last, v_last, a_last, j_last;
+            eval_power_form(pl, (double)(A.N - 1) * dt, L.t_pow + 4 * (A.N - 1), s_last, v_last, a_last, j_last);
             double term;
             if (P.follow) {
-                const double e = pl.val(t_last) - B.target[((int64_t)A.b * L.n_t + A.iT) * 3];
+                const double e = s_last - B.target[((int64_t)A.b * L.n_t + A.iT) * 3];
                 term = __dmul_rn(P.ks, __dmul_rn(e, e));
             } else {
-                const double e = pl.d1(t_last) - B.scal[(int64_t)A.b * 3 + 1];
+                const double e = v_last - B.scal[(int64_t)A.b * 3 + 1];
                 term = __dmul_rn(P.kdots, __dmul_rn(e, e));
             }
             sh_clong = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, jsum), __dmul_rn(P.kt, T)), term);
@@ -711,6 +735,38 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
     }
 }
 
+// Collision test of arbitrary polylines (one warp per path): the generic form of K4 for candidate lists that do not
+// live in the lattice layout (e.g. `Frenet` objects built elsewhere and passed to the driver-level check_paths).
+__global__ void __launch_bounds__(256) polyline_collision(const double* __restrict__ x, const double* __restrict__ y,
+                                                          const int64_t* __restrict__ offsets, int n_paths,
+                                                          const double* __restrict__ obs_xy, int O, double radius_sq,
+                                                          uint8_t* coll_free, int32_t* first_blocker) {
+    extern __shared__ __align__(16) double sm[];
+    double2* obs = reinterpret_cast<double2*>(sm);
+    float2* obsf = reinterpret_cast<float2*>(sm + 2 * O);
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+        const double2 q = reinterpret_cast<const double2*>(obs_xy)[o];
+        obs[o] = q;
+        obsf[o] = make_float2(__double2float_rn(q.x), __double2float_rn(q.y));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= n_paths) return;
+    const int64_t lo = offsets[p];
+    const int N = (int)(offsets[p + 1] - lo);
+    const float Rf = __double2float_ru(sqrt(radius_sq));
+    int best = kNoBlocker;
+    for (int kb = 0; kb < N; kb += kWarp) {
+        const int k = kb + lane < N ? kb + lane : kb;
+        best = collide_chunk(x[lo + k], y[lo + k], kb + lane < N, min(kWarp, N - kb), obs, obsf, O, Rf, radius_sq, best, lane);
+    }
+    if (lane == 0) {
+        coll_free[p] = best == kNoBlocker ? 1 : 0;
+        first_blocker[p] = best == kNoBlocker ? -1 : best;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: first-wins argmin, one CTA per scenario
 // ------------------------------------------------------------------------------------------------
@@ -843,7 +899,7 @@ int check_lattice(const FrenetLattice* L) {
     if (!L) return fail(FRENET_ERR_BAD_ARG, "lattice is NULL");
     if (L->n_scen <= 0 || L->n_v_cap <= 0 || L->n_t <= 0 || L->n_d <= 0 || L->n_pad_max <= 0)
         return fail(FRENET_ERR_BAD_ARG, "lattice sizes must be positive");
-    if (!L->axis_d || !L->axis_t || !L->n_steps || !L->t_offset || !L->axis_v || !L->n_v)
+    if (!L->axis_d || !L->axis_t || !L->n_steps || !L->t_offset || !L->t_pow || !L->axis_v || !L->n_v)
         return fail(FRENET_ERR_BAD_ARG, "lattice axis pointer is NULL");
     if (L->row_elems <= 0 || L->cand_elems != L->row_elems * L->n_d || (L->row_elems & 3))
         return fail(FRENET_ERR_BAD_ARG, "inconsistent lattice strides");
@@ -1016,9 +1072,23 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     if ((stages & FRENET_STAGE_CURVATURE) && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K4) && !fuse_k4 && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
-    if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, (stages & FRENET_STAGE_K3) ? 1 : 0, stream)))
+    if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, (stages & (FRENET_STAGE_K3 | FRENET_STAGE_K4)) ? 1 : 0, stream)))
         return rc;
     return rc;
+}
+
+int frenet_polyline_collision(const double* x, const double* y, const int64_t* offsets, int32_t n_paths, const double* obs_xy,
+                              int32_t n_obs, double radius_sq, uint8_t* coll_free, int32_t* first_blocker, frenet_stream_t stream) {
+    if (n_paths < 0 || n_obs < 0) return fail(FRENET_ERR_BAD_ARG, "polyline: negative size");
+    if (n_paths == 0) return FRENET_OK;
+    if (!x || !y || !offsets || !coll_free || !first_blocker || (n_obs > 0 && !obs_xy))
+        return fail(FRENET_ERR_BAD_ARG, "polyline: NULL buffer");
+    const size_t smem = (size_t)3 * n_obs * sizeof(double);
+    if (int rc = set_smem(polyline_collision, smem, "polyline: too many obstacles for shared memory")) return rc;
+    polyline_collision<<<(n_paths + 7) / 8, 256, smem, (cudaStream_t)stream>>>(x, y, offsets, n_paths, obs_xy, n_obs, radius_sq,
+                                                                              coll_free, first_blocker);
+    FRENET_CHECK_LAUNCH("polyline_collision");
+    return FRENET_OK;
 }
 
 int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,

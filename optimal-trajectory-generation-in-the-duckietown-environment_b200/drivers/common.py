@@ -1,0 +1,122 @@
+"""Driver-level pieces of the hot path: Frenet -> Cartesian (K3), collision filter (K4), masked argmin (K5).
+
+In the reference these live in the experiment modules, not in the planner:
+`frenet_to_glob`, `check_paths`, `check_collisions`, `compute_ortogonal_vect` and the constant
+`robot_radius` of lib/tests/test_obstacle_planner.py:16-56 and lib/tests/test_moving_obstacle_planner.py:15-57.
+The functions here keep those names and signatures.  When they are handed the planner's own candidate list
+(the `LatticePaths` view returned by `replanner`) they launch K3 / K4 on the lattice that is already in HBM;
+handed any other list of Frenet-like objects they pack it and run the generic point / polyline kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _native as nat
+from ..engine import FrenetEngine
+from ..planner.lattice_planner import LatticePaths
+
+robot_radius = 0.7
+
+_generic_engine = None
+
+
+def _engine_for_lists() -> FrenetEngine:
+    global _generic_engine
+    if _generic_engine is None:
+        _generic_engine = FrenetEngine(1)
+    return _generic_engine
+
+
+def compute_ortogonal_vect(traj, s):
+    """Unit normal of the reference path at arc length s (test_obstacle_planner.py:53-56): one point, host side."""
+    g = traj.compute_first_derivative(s)
+    th = np.arctan2(g[1], g[0])
+    return np.array([-np.sin(th), np.cos(th)])
+
+
+def _is_live(paths) -> bool:
+    return isinstance(paths, LatticePaths) and paths._engine.generation == paths._generation
+
+
+def frenet_to_glob(planner, trajectory, frenet_paths):
+    """Adds Cartesian x, y to every path (test_obstacle_planner.py:18-25): K3."""
+    if _is_live(frenet_paths):
+        eng = frenet_paths._engine
+        if not eng.has_xy:
+            eng.launch(planner._params, eng.path_handle(trajectory), nat.STAGE_K3)
+        return frenet_paths
+    eng = _engine_for_lists()
+    paths = list(frenet_paths)
+    if paths:
+        s = np.concatenate([np.asarray(p.s, dtype=np.float64) for p in paths])
+        d = np.concatenate([np.asarray(p.d, dtype=np.float64) for p in paths])
+        x, y = eng.points_to_cartesian(eng.path_handle(trajectory), s, d)
+        at = 0
+        for p in paths:
+            n = len(p.s)
+            p.x.extend(x[at:at + n].tolist())     # the reference appends
+            p.y.extend(y[at:at + n].tolist())
+            at += n
+    return frenet_paths
+
+
+def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
+    """Shared body of both `check_paths` flavours.
+
+    Returns (surviving paths, sensed obstacles, first-blocker index into the sensed list per BLOCKED path).
+    `rpose` is passed to `sensor.sense` positionally like the reference does, which means the sensor uses its
+    attached robot's pose (proximity_sensor.py:53-57)."""
+    sensed = sensor.sense(rpose)
+    if not sensed:
+        return frenet_paths, sensed, np.zeros(0, dtype=np.int64)
+    if _is_live(frenet_paths):
+        eng = frenet_paths._engine
+        planner = frenet_paths._planner
+        n = len(sensed)
+        if n > eng.n_obs:      # grow the obstacle capacity (keeps the lattice: only the small input block moves)
+            raise RuntimeError(f"{n} sensed obstacles exceed the planner's obstacle capacity {eng.n_obs}; "
+                               "construct the planner with _n_obs_cap >= the number of obstacles")
+        eng.obs_xy[0, :n] = np.array([ob.position for ob in sensed], dtype=np.float64)
+        eng.obs_active[0, :n] = 1
+        eng.upload()
+        # K4, then K5 with the collision mask and a gather of the masked winner: one call, one small copy back
+        eng.launch(planner._params, None, nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER, nat.MASK_COLLISION,
+                   nat.SEL_MASKED, n_obs=n)
+        eng.download(sync=True)
+        C_ = frenet_paths._n_all
+        winner = planner._frenet_from_winner("argmin_masked")
+        def fetch_mask():
+            frenet_paths._check_live()
+            return eng.coll_free[0, :C_].cpu().numpy() != 0
+
+        view = frenet_paths.masked_view(fetch_mask,
+int(eng.result[0]["n_survivors"]), {"ctot": winner})
+        first = np.zeros(0, dtype=np.int64)
+        if want_blockers:
+            free = eng.coll_free[0, :C_].cpu().numpy() != 0
+            valid = (eng.cand_flags[0, :C_].cpu().numpy() & nat.CAND_VALID) != 0
+            first = eng.first_blocker[0, :C_].cpu().numpy()[valid & ~free]
+        return view, sensed, first
+    paths = list(frenet_paths)
+    eng = _engine_for_lists()
+    free, first = eng.polyline_collision([p.x for p in paths], [p.y for p in paths],
+                                         np.array([ob.position for ob in sensed], dtype=np.float64), robot_radius ** 2)
+    return [p for p, ok in zip(paths, free) if ok], sensed, first[~free]
+
+
+def single_path_collision(path, obstacles):
+    """(collision_free, first blocking obstacle or None) for one path: one launch of the polyline kernel."""
+    if not obstacles:
+        return True, None
+    eng = _engine_for_lists()
+    free, first = eng.polyline_collision([path.x], [path.y], np.array([ob.position for ob in obstacles], dtype=np.float64),
+                                         robot_radius ** 2)
+    return bool(free[0]), (None if free[0] else obstacles[int(first[0])])
+
+
+def best_path(paths, key: str = "ctot"):
+    """`min(paths, key=attrgetter(key))`: first minimal element; ValueError when `paths` is empty."""
+    if isinstance(paths, LatticePaths):
+        return paths.argmin(key)
+    from operator import attrgetter
+    return min(paths, key=attrgetter(key))

@@ -57,6 +57,9 @@ class LatticeGeometry:
         self.n_t, self.n_d = len(self.T), len(self.D)
         self.n_pad_max = int(npad.max()) if self.n_t else 0
         self.sum_pad = int(self.t_offset[-1])
+        # t_k ** n exactly as the reference forms them (Python float pow), k = 0 .. n_pad_max - 1
+        self.t_pow = np.array([[float(np.float64(k) * np.float64(self.period)) ** n for n in (2, 3, 4, 5)]
+                               for k in range(self.n_pad_max)], dtype=np.float64).reshape(self.n_pad_max, 4)
         self.key = (self.D.tobytes(), self.T.tobytes(), self.period)
 
     @staticmethod
@@ -149,10 +152,13 @@ class FrenetEngine:
         self.row_elems, self.cand_elems = row_elems, cand_elems
 
         # geometry arrays (one small upload per geometry change)
-        g = np.zeros(_align(nD * 8) + _align(nT * 8) + _align(nT * 4) + _align((nT + 1) * 4), dtype=np.uint8)
+        g = np.zeros(_align(nD * 8) + _align(nT * 8) + _align(nT * 4) + _align((nT + 1) * 4) + _align(geom.n_pad_max * 32),
+                     dtype=np.uint8)
         o_d, o_t = 0, _align(nD * 8)
         o_n = o_t + _align(nT * 8)
         o_o = o_n + _align(nT * 4)
+        o_p = o_o + _align((nT + 1) * 4)
+        g[o_p:o_p + geom.n_pad_max * 32] = geom.t_pow.reshape(-1).view(np.uint8)
         g[o_d:o_d + nD * 8] = geom.D.view(np.uint8)
         g[o_t:o_t + nT * 8] = geom.T.view(np.uint8)
         g[o_n:o_n + nT * 4] = geom.n_steps.view(np.uint8)
@@ -217,7 +223,7 @@ class FrenetEngine:
         L = self.L
         L.n_scen, L.n_v_cap, L.n_t, L.n_d, L.n_pad_max = Bn, self.n_v_cap, nT, nD, geom.n_pad_max
         L.row_elems, L.cand_elems = row_elems, cand_elems
-        L.axis_d, L.axis_t, L.n_steps, L.t_offset = gp + o_d, gp + o_t, gp + o_n, gp + o_o
+        L.axis_d, L.axis_t, L.n_steps, L.t_offset, L.t_pow = gp + o_d, gp + o_t, gp + o_n, gp + o_o, gp + o_p
         L.axis_v, L.n_v = ip + offs["axis_v"], ip + offs["n_v"]
         Bf = self.B
         Bf.state, Bf.scal, Bf.target = ip + offs["state"], ip + offs["scal"], ip + offs["target"]
@@ -365,3 +371,20 @@ class FrenetEngine:
         nat.check(nat.lib.frenet_points_to_cartesian(C.byref(path.desc), s.data_ptr(), d.data_ptr(), s.numel(), x.data_ptr(),
                                                      y.data_ptr(), 1, C.c_void_p(stream)))
         return x.cpu().numpy(), y.cpu().numpy()
+
+    def polyline_collision(self, xs, ys, obstacles_xy, radius_sq: float):
+        """Generic K4: `xs`, `ys` are lists of per-path coordinate sequences; returns (coll_free bool[n], first_blocker int[n])."""
+        n = len(xs)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum([len(v) for v in xs])
+        x = np.concatenate([np.asarray(v, dtype=np.float64) for v in xs]) if n else np.zeros(0)
+        y = np.concatenate([np.asarray(v, dtype=np.float64) for v in ys]) if n else np.zeros(0)
+        obs = np.ascontiguousarray(obstacles_xy, dtype=np.float64).reshape(-1, 2)
+        dev = self.device
+        tx, ty, to, tb = (torch.from_numpy(a).to(dev) for a in (x, y, offsets, obs))
+        free = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        first = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nat.check(nat.lib.frenet_polyline_collision(tx.data_ptr(), ty.data_ptr(), to.data_ptr(), n, tb.data_ptr(), obs.shape[0],
+                                                    float(radius_sq), free.data_ptr(), first.data_ptr(), C.c_void_p(stream)))
+        return free.cpu().numpy()[:n] != 0, first.cpu().numpy()[:n]

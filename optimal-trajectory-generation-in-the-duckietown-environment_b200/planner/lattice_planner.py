@@ -52,6 +52,9 @@ class LatticePaths:
         self._t_initial = planner.t_initial
         self._n_all = n_v * self._engine.geom.n_t * self._engine.geom.n_d
         self._subset = None       # positions (into the valid list) kept by a filter, or None = all
+        self._pending_mask = None  # callable -> bool mask over ALL candidates, resolved on first element access
+        self._known_len = None    # length known from a K5 record without touching the candidate arrays
+        self._best = {}           # cost key -> Frenet already gathered on the device (e.g. the masked winner)
 
     # -- device -> host ---------------------------------------------------------------------------
     def _check_live(self):
@@ -77,10 +80,19 @@ class LatticePaths:
 
     def _positions(self):
         self.materialize()
+        if self._pending_mask is not None:
+            keep = np.asarray(self._pending_mask(), dtype=bool)[self._valid_idx]
+            base = np.arange(len(self._valid_idx)) if self._subset is None else self._subset
+            self._subset = base[keep[base]]
+            self._pending_mask = None
         return self._valid_idx if self._subset is None else self._valid_idx[self._subset]
 
     # -- sequence protocol -------------------------------------------------------------------------
     def __len__(self):
+        if self._known_len is not None:
+            return self._known_len
+        if self._pending_mask is not None:
+            return len(self._positions())
         if self._subset is not None:
             return len(self._subset)
         if self._fields is None and self._planner._rule != nat.LOWSPEED_OPTIMAL:
@@ -128,10 +140,23 @@ class LatticePaths:
         out.__dict__.update(self.__dict__)
         base = np.arange(len(self._valid_idx)) if self._subset is None else self._subset
         out._subset = base[np.asarray(keep_mask, dtype=bool)]
+        out._known_len, out._best = None, {}
+        return out
+
+    def masked_view(self, mask_fn, known_len: int, best: dict) -> "LatticePaths":
+        """A filtered view whose mask (over all candidates) is fetched from the device only if elements are
+        looked at; its length and its cheapest element are already known from the K5 record."""
+        out = LatticePaths.__new__(LatticePaths)
+        out.__dict__.update(self.__dict__)
+        out._pending_mask, out._known_len, out._best = mask_fn, int(known_len), dict(best)
         return out
 
     def argmin(self, key: str = "ctot"):
         """First minimal element by cost `key` (what `min(paths, key=attrgetter(key))` returns); ValueError if empty."""
+        if key in self._best:
+            if self._best[key] is None:
+                raise ValueError("min() arg is an empty sequence")
+            return self._best[key]
         pos = self._positions()
         if len(pos) == 0:
             raise ValueError("min() arg is an empty sequence")
@@ -238,7 +263,9 @@ class _LatticePlanner(Planner):
         self.__dict__["_params"] = P
         eng.run(P, None, nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER, 0, nat.SEL_CTOT)
         self.__dict__["_winner_cache"] = {"ctot": self._frenet_from_winner("argmin_ctot")}
-        return LatticePaths(self, len(V), follow)
+        paths = LatticePaths(self, len(V), follow)
+        paths._best["ctot"] = self._winner_cache["ctot"]     # None when the lattice is empty
+        return paths
 
     def _frenet_from_winner(self, result_field: str):
         """Frenet object from the engine's winner block (None if the selection is empty)."""

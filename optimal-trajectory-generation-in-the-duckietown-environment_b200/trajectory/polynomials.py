@@ -1,13 +1,16 @@
-"""Boundary-value polynomials used by the host side (targets, tests, lazy views).
+"""Boundary-value polynomials used by the host side (leading-vehicle targets, tests).
 
 Same class names / constructor signatures / method names as the reference's
-`lib/trajectory/trajectory_1d.py:12-130`.  The reference obtains the free coefficients
-with `np.linalg.solve` on a 3x3 (quintic) or 2x2 (quartic) system; here they come from
-the closed-form solution of those systems, which is also what the K1 CUDA kernel
-evaluates (csrc/frenet_kernels.cu, `quintic_bvp` / `quartic_bvp`).  The two agree to
-about 2e-14 relative (tests/test_oracle_golden.py pins this against the reference).
+`lib/trajectory/trajectory_1d.py:12-130`.  The classes obtain the free coefficients with
+`np.linalg.solve` like the reference, because host-side callers compare sampled values with
+`==` (`Target.get_frenet_stop_target` asserts an exactly zero end velocity).  `quintic_bvp` /
+`quartic_bvp` are the closed-form solutions of the same systems, i.e. what the K1 CUDA kernel
+evaluates (csrc/frenet_kernels.cu); the two agree to about 2e-14 relative
+(tests/test_host_logic.py).
 """
 from __future__ import annotations
+
+import numpy as np
 
 
 def quintic_bvp(p0, dp0, ddp0, p1, dp1, ddp1, T):
@@ -43,8 +46,16 @@ class QuinticPolynomial:
     """1-D quintic; mirrors `lib/trajectory/trajectory_1d.py:12-71`."""
 
     def __init__(self, p0, dot_p0, ddot_p0, p1, dot_p1, ddot_p1, T):
-        (self.a0, self.a1, self.a2,
-         self.a3, self.a4, self.a5) = quintic_bvp(p0, dot_p0, ddot_p0, p1, dot_p1, ddot_p1, T)
+        self.a0, self.a1, self.a2 = p0, dot_p0, ddot_p0 / 2
+        powers = np.array([T ** n for n in range(6)])
+        # rows: position, velocity, acceleration at T; columns: a3, a4, a5
+        M = np.array([[powers[3], powers[4], powers[5]],
+                      [3 * powers[2], 4 * powers[3], 5 * powers[4]],
+                      [6 * powers[1], 12 * powers[2], 20 * powers[3]]])
+        rhs = np.array([p1 - self.a0 - self.a1 * T - self.a2 * T ** 2,
+                        dot_p1 - self.a1 - 2 * self.a2 * T,
+                        ddot_p1 - 2 * self.a2])
+        self.a3, self.a4, self.a5 = np.linalg.solve(M, rhs)
 
     def compute_pt(self, t):
         return (self.a0 + self.a1 * t + self.a2 * t ** 2 + self.a3 * t ** 3
@@ -65,7 +76,10 @@ class QuarticPolynomial:
     """1-D quartic; mirrors `lib/trajectory/trajectory_1d.py:74-130`."""
 
     def __init__(self, s0, dot_s0, ddot_s0, dot_s1, ddot_s1, T):
-        self.a0, self.a1, self.a2, self.a3, self.a4 = quartic_bvp(s0, dot_s0, ddot_s0, dot_s1, ddot_s1, T)
+        self.a0, self.a1, self.a2 = s0, dot_s0, ddot_s0 / 2.0
+        M = np.array([[3 * T ** 2, 4 * T ** 3], [6 * T, 12 * T ** 2]])   # velocity and acceleration rows; columns a3, a4
+        rhs = np.array([dot_s1 - self.a1 - 2 * self.a2 * T, ddot_s1 - 2 * self.a2])
+        self.a3, self.a4 = np.linalg.solve(M, rhs)
 
     def compute_pt(self, t):
         return self.a0 + self.a1 * t + self.a2 * t ** 2 + self.a3 * t ** 3 + self.a4 * t ** 4

@@ -493,6 +493,35 @@ def gen_sensor_gate():
          range=np.array(3.5), aperture=np.array(np.pi / 6))
 
 
+def gen_dt_sequences():
+    """Replan gating of the DT variants (trajectory_planner_dt.py:229-233, trajectory_planner_obstacles.py:238-242):
+    a run of `replanner(t)` calls; records the returned states and whether a new lattice was generated."""
+    out = {}
+    for name, cls, pcls in (("dt", TrajectoryPlannerV1DT, TrajectoryPlannerParamsDT),
+                            ("dt_obstacles", TrajectoryPlannerV1DTObstacles, TrajectoryPlannerParamsDTObstacles)):
+        pl = cls(pcls())
+        pl.initialize(t0=0.1, p0=(0.05, 0.0, 0.0), s0=(1.0, 0.3, 0.0), dd=0.1)
+        times = np.arange(0.1, 4.0, 0.1)
+        ret_s, ret_p, replanned, argmin, nc = [], [], [], [], []
+        for i, t in enumerate(times):
+            before = pl.opt_path_tot
+            kw = dict(force=True) if (name == "dt_obstacles" and i == 20) else {}
+            s_, p_ = pl.replanner(t, **kw)
+            ret_s.append(s_)
+            ret_p.append(p_)
+            replanned.append(pl.opt_path_tot is not before)
+            argmin.append(pl.paths.index(pl.opt_path_tot))
+            nc.append(len(pl.paths))
+        out[f"{name}_times"] = times
+        out[f"{name}_ret_s"] = np.array(ret_s, dtype=np.float64)
+        out[f"{name}_ret_p"] = np.array(ret_p, dtype=np.float64)
+        out[f"{name}_replanned"] = np.array(replanned, dtype=np.uint8)
+        out[f"{name}_argmin"] = np.array(argmin, dtype=np.int32)
+        out[f"{name}_ncand"] = np.array(nc, dtype=np.int32)
+        print(f"  {name}: replanned {int(np.sum(replanned))} of {len(times)} calls")
+    save("dt_sequences", **out)
+
+
 GENERATORS = {
     "kat_variants": gen_kat_variants,
     "paths": gen_paths,
@@ -504,6 +533,7 @@ GENERATORS = {
     "sensor_gate": gen_sensor_gate,
     "dense_config4": gen_dense_config4,
     "config5_sample": gen_config5_sample,
+    "dt_sequences": gen_dt_sequences,
 }
 
 if __name__ == "__main__":
