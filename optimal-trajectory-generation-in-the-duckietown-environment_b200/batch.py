@@ -126,7 +126,8 @@ class BatchPlanner:
         nv = np.ceil((hi - lo) / q).astype(np.int32)
         if int(nv.max()) > e.n_v_cap:
             raise ValueError("longitudinal axis longer than the configured capacity")
-        e.axis_v[:] = lo[:, None] + np.arange(e.n_v_cap)[None, :] * q     # == np.arange(lo, hi, q) (start + i * step)
+        delta = (lo + q) - lo                                             # np.arange's own step: (start + step) - start
+        e.axis_v[:] = lo[:, None] + np.arange(e.n_v_cap)[None, :] * delta[:, None]     # == np.arange(lo, hi, q) element-wise
         e.n_v[:] = nv
         self._n_v_sum = int(nv.sum())
         self._obs_frenet = obs_s is not None

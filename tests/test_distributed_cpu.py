@@ -1,0 +1,55 @@
+"""world_size-2 gloo test of the multi-GPU host logic (scenario sharding + the single gather of result records).
+The compute itself needs a GPU; here each rank fabricates its shard's records so that the collective path, the
+ragged shard sizes and the scenario order are exercised on CPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, n_total, port, out):
+    sys.path.insert(0, ROOT)
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat
+    from otg_b200.batch import gather_results, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(n_total, rank, world)
+    rec = np.zeros(hi - lo, dtype=np.dtype(nat.RESULT_DTYPE))
+    rec["argmin_ctot"] = np.arange(lo, hi)
+    rec["argmin_masked"] = np.arange(lo, hi) * 2 - 1
+    rec["status"] = rank
+    rec["min_ctot"] = np.arange(lo, hi) * 0.5
+    allrec = gather_results(rec, n_total)
+    ok = (len(allrec) == n_total and np.array_equal(allrec["argmin_ctot"], np.arange(n_total))
+          and np.array_equal(allrec["argmin_masked"], np.arange(n_total) * 2 - 1)
+          and np.array_equal(allrec["min_ctot"], np.arange(n_total) * 0.5)
+          and all(np.all(allrec["status"][slice(*shard_range(n_total, r, world))] == r) for r in range(world)))
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [7, 64])
+def test_gather_results_world2_gloo(n_total):
+    world = 2
+    port = 29500 + (os.getpid() + n_total) % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, n_total, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_gather_without_process_group_is_identity():
+    sys.path.insert(0, ROOT)
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat
+    from otg_b200.batch import gather_results
+    rec = np.zeros(5, dtype=np.dtype(nat.RESULT_DTYPE))
+    assert gather_results(rec, 5) is rec
