@@ -216,3 +216,13 @@ def test_workload_generators_are_deterministic_and_sharded_consistently():
         assert parts[0][0] == 0 and parts[-1][1] == 4096 and all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
         assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
     assert shard_range(10, 3, 4) == (8, 10) and shard_range(2, 3, 4) == (2, 2)
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package, bench's GPU arm aside, may import or name it."""
+    pkg = os.path.join(ROOT, "optimal-trajectory-generation-in-the-duckietown-environment_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "frenet_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
