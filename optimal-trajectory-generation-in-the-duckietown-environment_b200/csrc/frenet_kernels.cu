@@ -154,7 +154,6 @@ __device__ __forceinline__ double warp_max(double v) {
 // Row addressing shared by the per-row kernels (layout: include/frenet_b200.h).
 constexpr int kLonFields = 4;    // s, ds, dds, ddds
 constexpr int kCandFields = 6;   // d, dd, ddd, dddd, x, y
-constexpr int kFrame = 6;        // doubles per step of the shared-memory path frame: px, py, nx, ny, u, (pad)
 
 struct RowAddr {
     int b, r, iv, iT, N, npad;
@@ -374,6 +373,44 @@ __device__ __forceinline__ int collide_chunk(double x, double y, bool valid, int
     return best;
 }
 
+// The same test for a lane that carries TWO consecutive samples (the fused kernel's layout: 64 steps per warp
+// iteration, 16-byte stores).  One bounding circle and one cull per 64 steps; a survivor is tested against both
+// of the lane's points.
+__device__ __forceinline__ int collide_pair(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int nvalid,
+                                            const double2* __restrict__ obs, const float2* __restrict__ obsf, int O, float Rf,
+                                            double radius_sq, int best, int lane) {
+    const int mid = (nvalid - 1) >> 2;   // lane holding the middle step
+    const float xf = __double2float_rn(xa), yf = __double2float_rn(ya);
+    const float xg = __double2float_rn(xb), yg = __double2float_rn(yb);
+    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
+    const float ex = xf - cx, ey = yf - cy, fx = xg - cx, fy = yg - cy;
+    const float r2 = fmaxf(fmaf(ex, ex, ey * ey), fmaf(fx, fx, fy * fy));
+    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
+    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
+    const float thr = (r2max < 1e30f) ? reach * reach : CUDART_INF_F;
+    const int lim = min(O, best);
+    for (int ob = 0; ob < lim; ob += kWarp) {
+        const int o = ob + lane;
+        bool near = false;
+        if (o < lim) {
+            const float2 q = obsf[o];
+            const float ux = q.x - cx, uy = q.y - cy;
+            near = !(fmaf(ux, ux, uy * uy) > thr);
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const double2 q = obs[ob + j];
+            const double dxa = xa - q.x, dya = ya - q.y, dxb = xb - q.x, dyb = yb - q.y;
+            const bool hit = (valid_a && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= radius_sq)) ||
+                             (valid_b && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= radius_sq));
+            if (__any_sync(kFull, hit)) return ob + j;
+        }
+    }
+    return best;
+}
+
 // Stage a scenario's obstacle snapshot in shared memory.
 __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double2* obs, float2* obsf) {
     const int O = B.n_obs;
@@ -395,18 +432,21 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 //          KINEMATIC_OK flag is set unconditionally, which is the reference's behaviour.
 // The fused variants write each candidate-timestep exactly once (48 B: d, d', d'', d''', x, y) and read
 // nothing back; the unfused sequence K2 -> K3 -> K4 moves 72 B for the same result.
-// Shared memory (doubles): [3 * n_obs, rounded up to 4] obstacles in fp64 and fp32 (kColl) | [n_pad_max][kFrame or 1] frame | [n_d][6] lateral
-// coefficients | [n_knots][9] spline table (kXY).
+// Shared memory (doubles): [3 * n_obs, rounded up to 4] obstacles in fp64 and fp32 (kColl) | [n_pad_max] lateral argument |
+// 4 x [n_pad_max] path frame (kXY) | [n_d][6] lateral coefficients | [n_knots][9] spline table (kXY).
 template <bool kXY, bool kColl, bool kLimits>
 __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int FS = kXY ? kFrame : 1;   // frame stride: (px, py, nx, ny, u, pad) or just u
-    constexpr int FU = kXY ? 4 : 0;        // position of u inside a frame entry
+    const int npm = L.n_pad_max;
     double2* obs = reinterpret_cast<double2*>(sm);
     float2* obsf = reinterpret_cast<float2*>(sm + 2 * B.n_obs);
-    double* frame = sm + (kColl ? 4 * ((3 * B.n_obs + 3) / 4) : 0);   // 3 doubles per obstacle, kept 32-byte aligned
-    double* coef = frame + L.n_pad_max * FS;
-    double* tab = coef + L.n_d * 6;
+    double* su = sm + (kColl ? 4 * ((3 * B.n_obs + 3) / 4) : 0);   // [npm] lateral argument: t_k, or |s_k - s0| in low-speed mode
+    double* fpx = su + npm;                                        // [npm] x 4 path frame (kXY): point and unit normal
+    double* fpy = fpx + (kXY ? npm : 0);
+    double* fnx = fpy + (kXY ? npm : 0);
+    double* fny = fnx + (kXY ? npm : 0);
+    double* coef = fny + (kXY ? npm : 0);                          // [n_d][6] lateral coefficients of this row (from K1)
+    double* tab = coef + L.n_d * 6;                                // [n_knots][9] spline table (kXY, spline path)
     __shared__ double red[3][kRowThreads / 32];
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
@@ -462,7 +502,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             lon[A.npad + k] = v;
             lon[2 * A.npad + k] = a;
             lon[3 * A.npad + k] = j;
-            frame[k * FS + FU] = low ? fabs(s - s0) : t;
+            su[k] = low ? fabs(s - s0) : t;
             if (k < A.N) {
                 acc = fma(j, j, acc);
                 if (kLimits) {
@@ -473,7 +513,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             if (kXY) {
                 double px, py, nx, ny;
                 path_frame(path.kind, path.circle, tab, path.n_knots, s, px, py, nx, ny);
-                frame[k * FS] = px; frame[k * FS + 1] = py; frame[k * FS + 2] = nx; frame[k * FS + 3] = ny;
+                fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
             }
         }
         // longitudinal jerk sum and limits: per-warp partials combined in a fixed order (deterministic)
@@ -516,46 +556,56 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
     const int npad = A.npad, N = A.N;
 
-    // Phase B: a warp per candidate, lanes over time steps; no global loads in this loop.
+    // Phase B: a warp per candidate; every lane owns TWO consecutive time steps per iteration (64 steps per warp
+    // iteration, 16-byte loads from shared memory and 16-byte stores to HBM); no global loads in this loop.
     for (int id = warp; id < L.n_d; id += nwarps) {
         Poly pq;
         pq.load(coef + id * 6);
         // [6][npad] block of this candidate; `out` walks along k, the fields sit `fs` bytes apart
-        char* out = reinterpret_cast<char*>(B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + lane);
+        char* out = reinterpret_cast<char*>(B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + 2 * lane);
         const int64_t fs = (int64_t)npad * sizeof(double);
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
 #pragma unroll 1
-        for (int kb = 0; kb < N; kb += kWarp) {
-            const bool valid = kb + lane < N;       // a real sample
-            const bool store = kb + lane < npad;    // real or padding: stored so that whole sectors are written
-            const double* fr = frame + (store ? kb + lane : kb) * FS;   // lanes beyond the padding shadow the chunk's first step
-            double d0, v1, a2, j;
-            pq.eval(fr[FU], d0, v1, a2, j);
+        for (int kb = 0; kb < N; kb += 2 * kWarp) {
+            const int k0 = kb + 2 * lane;
+            const bool store = k0 < npad;           // npad is even: a pair is stored whole or not at all
+            const bool valid_a = k0 < N, valid_b = k0 + 1 < N;   // real samples (the rest is padding)
+            const int kk = store ? k0 : kb;         // lanes beyond the padding shadow the chunk's first pair
+            const double2 u = *reinterpret_cast<const double2*>(su + kk);
+            double da, va, aa, ja, db, vb, ab, jb;
+            pq.eval(u.x, da, va, aa, ja);
+            pq.eval(u.y, db, vb, ab, jb);
             char* o = out;
             if (store) {
-                *reinterpret_cast<double*>(o) = d0;
-                *reinterpret_cast<double*>(o += fs) = v1;
-                *reinterpret_cast<double*>(o += fs) = a2;
-                *reinterpret_cast<double*>(o += fs) = j;
+                *reinterpret_cast<double2*>(o) = make_double2(da, db);
+                *reinterpret_cast<double2*>(o += fs) = make_double2(va, vb);
+                *reinterpret_cast<double2*>(o += fs) = make_double2(aa, ab);
+                *reinterpret_cast<double2*>(o += fs) = make_double2(ja, jb);
             }
-            if (valid) {
-                acc = fma(j, j, acc);
-                if (kLimits) amax = fmax(amax, fabs(a2));
+            if (valid_a) {
+                acc = fma(ja, ja, acc);
+                if (kLimits) amax = fmax(amax, fabs(aa));
+            }
+            if (valid_b) {
+                acc = fma(jb, jb, acc);
+                if (kLimits) amax = fmax(amax, fabs(ab));
             }
             if (kXY) {
-                const double2 pp = *reinterpret_cast<const double2*>(fr);
-                const double2 nn = *reinterpret_cast<const double2*>(fr + 2);
-                const double x = __dadd_rn(pp.x, __dmul_rn(nn.x, d0));   // pt + n * d, unfused like the reference
-                const double y = __dadd_rn(pp.y, __dmul_rn(nn.y, d0));
+                const double2 px = *reinterpret_cast<const double2*>(fpx + kk), py = *reinterpret_cast<const double2*>(fpy + kk);
+                const double2 nx = *reinterpret_cast<const double2*>(fnx + kk), ny = *reinterpret_cast<const double2*>(fny + kk);
+                const double xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)), xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));   // pt + n * d,
+                const double ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)), yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));   // unfused like the reference
                 if (store) {
-                    *reinterpret_cast<double*>(o += fs) = x;
-                    *reinterpret_cast<double*>(o += fs) = y;
+                    *reinterpret_cast<double2*>(o += fs) = make_double2(xa, xb);
+                    *reinterpret_cast<double2*>(o += fs) = make_double2(ya, yb);
                 }
                 // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
-                if (kColl) best = collide_chunk(x, y, valid, min(kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq, best, lane);
+                if (kColl)
+                    best = collide_pair(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq,
+                                        best, lane);
             }
-            out += kWarp * sizeof(double);
+            out += 2 * kWarp * sizeof(double);
         }
         acc = warp_sum(acc);
         if (kLimits) amax = warp_max(amax);
@@ -934,7 +984,7 @@ template <bool kXY, bool kColl>
 int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, cudaStream_t stream) {
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
-    const size_t smem = ((size_t)L->n_pad_max * (kXY ? kFrame : 1) + (size_t)L->n_d * 6 + (spline ? (size_t)9 * path->n_knots : 0) +
+    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 6 + (spline ? (size_t)9 * path->n_knots : 0) +
                          (kColl ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0)) * sizeof(double);
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
