@@ -125,7 +125,7 @@ class ClockSampler:
     def __init__(self, index):
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
@@ -181,6 +181,76 @@ def time_kernels(bp, reps):
             b.record()
         torch.cuda.synchronize()
         out[name] = float(np.mean([a.elapsed_time(b) for a, b in evs]))   # ms
+    return out
+
+
+def replan_latency(n_calls=200):
+    """Metric 2: wall time of ONE replan through the drop-in planner API, host perf_counter around
+    the Python calls (H2D of inputs, kernels, D2H of the result record + winner trajectory, Python return).
+    Reference figures measured in the survey container (1 CPU thread): 70.6 ms (config 1), ~122 ms (config 2), 14.3 s (dense)."""
+    import otg_b200  # noqa: F401
+    from otg_b200 import drivers, workloads as w
+    from otg_b200.drivers import moving_obstacle_planner as mv
+    from otg_b200.planner import TrajectoryPlannerV1, TrajectoryPlannerParams
+    from otg_b200.sensor import ProximitySensor, StaticObstacle
+    from otg_b200.sim import Unicycle
+    from otg_b200.trajectory import CircleTrajectory2D, SplineTrajectory2D
+
+    def pct(ts):
+        ts = np.sort(np.array(ts)) * 1e6
+        return {"p50_us": float(ts[len(ts) // 2]), "p90_us": float(ts[int(len(ts) * 0.9)]), "calls": len(ts)}
+
+    out = {}
+    # config 1: default lattice (320 candidates, 5920 cand-ts), planner.replanner only
+    pl = TrajectoryPlannerV1(TrajectoryPlannerParams())
+    pl.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(0.0, 0.0, 0.0))
+    ts = []
+    for i in range(n_calls + 20):
+        t = time.perf_counter()
+        pl.replanner(0.1 + 0.1 * (i + 1))
+        ts.append(time.perf_counter() - t)
+    out["config1_replanner"] = pct(ts[20:])
+    # config 2/3: + frenet_to_glob + check_paths (3 sensed obstacles) + masked pick
+    tr = CircleTrajectory2D(8, 5, 2)
+    robot = Unicycle()
+    robot.set_initial_pose(np.array([3.0, 0.0, 0.0]))
+    sensor = ProximitySensor(3.5, np.pi / 6)
+    sensor.attach(robot)
+    sensor.set_obstacle([StaticObstacle(np.array(p)) for p in ([5.0, 0.3], [6.0, -1.0], [4.5, 2.5])])
+    pl = TrajectoryPlannerV1(TrajectoryPlannerParams())
+    pl.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(3.0, 2.0, 0.0))
+    ts = []
+    for i in range(n_calls + 20):
+        t = time.perf_counter()
+        pl.replanner(0.2)
+        paths = drivers.frenet_to_glob(pl, tr, pl.paths)
+        pl.paths, _ = mv.check_paths(paths, sensor, robot.p)
+        pl.opt_path_tot = drivers.best_path(pl.paths)
+        ts.append(time.perf_counter() - t)
+    out["config3_replan_transform_collide_pick"] = pct(ts[20:])
+    # config 4: dense lattice (9600 candidates, 954720 cand-ts), spline path, 64 obstacles, one planner
+    sc = w.config4_scenario()
+    spl = SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY)
+    pl = TrajectoryPlannerV1(TrajectoryPlannerParams(**w.DENSE_PARAMS), _n_obs_cap=64)
+    pl.initialize(t0=sc["t0"], p0=sc["p0"], s0=sc["s0"], dd=sc["dd"])
+    eng = pl._engine
+    ox, oy = eng.points_to_cartesian(eng.path_handle(spl), sc["obs_s"], sc["obs_d"])
+
+    class AllSeeing:
+        obstacles = [StaticObstacle(np.array([x, y])) for x, y in zip(ox, oy)]
+
+        def sense(self, *a, **k):
+            return self.obstacles
+
+    ts = []
+    for i in range(n_calls // 2 + 10):
+        t = time.perf_counter()
+        pl.replanner(sc["t0"])
+        paths = drivers.frenet_to_glob(pl, spl, pl.paths)
+        pl.paths, _ = mv.check_paths(paths, AllSeeing(), None)
+        pl.opt_path_tot = drivers.best_path(pl.paths)
+        ts.append(time.perf_counter() - t)
+    out["config4_dense_64_obstacles"] = pct(ts[10:])
     return out
 
 
@@ -314,6 +384,7 @@ def run_gpu(args):
                 "gpu_launches": bp.launches_per_plan * args.steps,
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
+                "replan_latency": replan_latency() if world == 1 else None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
         print(json.dumps(line), flush=True)
     if world > 1:
