@@ -84,7 +84,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = 2 * cores   # scenarios per step: a bounded sample of the 512-scenario shard (about 1.5 s of work per core)
+    n = cores   # scenarios per step: a bounded sample of the 512-scenario shard (one scenario, about 1 s, per core)
     wl = workload(0, n)
     with mp.get_context("spawn").Pool(cores) as pool:
         for _ in range(args.warmup):
@@ -181,6 +181,40 @@ def time_kernels(bp, reps):
             b.record()
         torch.cuda.synchronize()
         out[name] = float(np.mean([a.elapsed_time(b) for a, b in evs]))   # ms
+    return out
+
+
+def predicted_mode(wl, steps, dev):
+    """EXTENSION leg: the same step with obstacles propagated over the horizon on the device (time-indexed table,
+    step k tested against the predicted position at t_initial + k * period) instead of the reference's snapshot."""
+    import torch
+    import otg_b200  # noqa: F401
+    from otg_b200 import workloads as w
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.trajectory import SplineTrajectory2D
+    n = len(wl["t0"])
+    sc = w.config5_scenarios()
+    bp = BatchPlanner(dense_params(), SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY), n, N_OBS, "v1", dev, predict_steps=150)
+    kw = dict(p0=wl["p0"], s0=wl["s0"], t0=wl["t0"], dd=wl["dd"], obs_s=sc["obs_s"][:n], obs_d=sc["obs_d"][:n] + sc["obs_offset"][:n],
+              obs_speed=sc["obs_speed"][:n])
+    bp.stage_inputs(**kw)
+    bp.engine.upload()
+    for _ in range(3):
+        bp.launch_resident()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        bp.launch_resident()
+        bp.engine.download(sync=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    feasible = int((bp.engine.result["status"] == 0).sum())
+    out = {"value": bp.cand_timesteps() / (ms * 1e-3), "unit": "candidate-timesteps/s", "ms_per_step": ms, "predict_steps": 150,
+           "gpu_launches_per_step": bp.launches_per_plan, "scenarios_with_feasible": feasible}
+    del bp
+    torch.cuda.empty_cache()
     return out
 
 
@@ -385,7 +419,12 @@ def run_gpu(args):
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
                 "replan_latency": replan_latency() if world == 1 else None,
+                "predicted_obstacles": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
+        if world == 1:
+            del bp
+            torch.cuda.empty_cache()
+            line["predicted_obstacles"] = predicted_mode(wl, max(3, args.steps // 3), dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

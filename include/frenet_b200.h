@@ -149,7 +149,10 @@ typedef struct FrenetBuffers {
     const double* obs_xy;      /* [n_scen][n_obs][2] obstacle snapshot, or NULL */
     const uint8_t* obs_active; /* [n_scen][n_obs] 1 = sensed (tested), or NULL = all */
     int32_t n_obs;
-    int32_t reserved;
+    int32_t n_obs_steps;       /* EXTENSION: 0 = snapshot table `obs_xy` (the reference: every step is tested against the obstacles'
+                                  CURRENT positions, lib/tests/test_moving_obstacle_planner.py:89-91); K > 0 = predicted table below */
+    const double* obs_xy_t;    /* [n_scen][n_obs][n_obs_steps][2] predicted positions: step k is tested against entry min(k, K-1) */
+    float* obs_bounds;         /* scratch [n_scen][ceil(n_pad_max/32)][n_obs][4] (per 32-step chunk bounding circles, K4 fills it) */
     /* K1 outputs */
     double* coef_lon;          /* [n_scen][R][6] a0..a5 (a5 = 0 for the velocity-keeping quartic) */
     double* coef_lat;          /* [n_scen][C][6] */
@@ -233,6 +236,14 @@ int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetP
  * Point i is written to x[i * out_stride], y[i * out_stride] (out_stride 2 with y = x + 1 fills an [n][2] table). */
 int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
                                int64_t out_stride, frenet_stream_t stream);
+
+/* EXTENSION - device-side obstacle prediction: fills a predicted table [n_scen][n_obs][n_steps][2] from the moving-obstacle
+ * time law of the reference (lib/sensor/dynamic_obstacle.py:43-56): at step k obstacle o of scenario b sits at arc length
+ * obs_s + ((t0[b] + k * period) * obs_speed) % 50 with lateral offset obs_d.  obs_s / obs_d / obs_speed: [n_scen][n_obs];
+ * t0: [n_scen] with stride t0_stride doubles (pass buf->scal + 2 and 3 to use the planners' t_initial). */
+int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const double* obs_d, const double* obs_speed,
+                             const double* t0, int64_t t0_stride, int32_t n_scen, int32_t n_obs, int32_t n_steps, double period,
+                             double* obs_xy_t, frenet_stream_t stream);
 
 /* Generic form of K4 for polylines that are not in the lattice layout: path p owns points offsets[p] .. offsets[p+1]-1
  * of x / y; obstacles are an [n_obs][2] table (all tested).  Replaces check_collisions on one path at a time

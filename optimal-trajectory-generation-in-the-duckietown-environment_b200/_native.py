@@ -60,7 +60,8 @@ RESULT_BYTES = 64
 
 class FrenetBuffers(C.Structure):
     _fields_ = [("state", C.c_void_p), ("scal", C.c_void_p), ("target", C.c_void_p), ("obs_xy", C.c_void_p),
-                ("obs_active", C.c_void_p), ("n_obs", C.c_int32), ("reserved", C.c_int32),
+                ("obs_active", C.c_void_p), ("n_obs", C.c_int32), ("n_obs_steps", C.c_int32),
+                ("obs_xy_t", C.c_void_p), ("obs_bounds", C.c_void_p),
                 ("coef_lon", C.c_void_p), ("coef_lat", C.c_void_p), ("row_S", C.c_void_p), ("row_flags", C.c_void_p),
                 ("lon", C.c_void_p), ("lat", C.c_void_p), ("cost", C.c_void_p), ("cand_flags", C.c_void_p),
                 ("curv_ok", C.c_void_p),
@@ -99,6 +100,8 @@ def _load():
         "frenet_gather_winner": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_int32, C.c_int32, C.c_void_p]),
         "frenet_plan": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
+        "frenet_predict_obstacles": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
         "frenet_polyline_collision": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double,
                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
         "frenet_points_to_cartesian": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -84,7 +84,7 @@ class BatchPlanner:
     """
 
     def __init__(self, params, trajectory, n_scen: int, n_obs: int = 0, variant: str = "v1", device=None,
-                 robot_radius: float = 0.7):
+                 robot_radius: float = 0.7, predict_steps: int = 0):
         self.p = params
         self.variant = variant
         self.n_scen = int(n_scen)
@@ -92,7 +92,11 @@ class BatchPlanner:
         self.engine = FrenetEngine(self.n_scen, device)
         self.period = lat.sample_period(params, variant)
         self.geom = LatticeGeometry.from_intervals(lat.di_interval(params, variant), lat.t_interval(params, variant), self.period)
-        self.engine.configure(self.geom, lat.max_long_axis_len(params), self.n_obs)
+        # predict_steps > 0 (EXTENSION): obstacles are propagated over the horizon on the device and step k of every
+        # candidate is tested against the obstacles' predicted positions at t_initial + k * period; 0 = the reference's
+        # snapshot semantics (every step against the positions at t_initial).
+        self.predict_steps = int(predict_steps)
+        self.engine.configure(self.geom, lat.max_long_axis_len(params), self.n_obs, self.predict_steps)
         self.path = self.engine.path_handle(trajectory)
         self.radius_sq = robot_radius ** 2
         self.params = make_params(params, lat.VARIANTS[variant]["rule"], self.period, False, self.radius_sq)
@@ -109,7 +113,8 @@ class BatchPlanner:
         self._n_v_sum = 0
 
     # -- host -> pinned staging ----------------------------------------------------------------
-    def stage_inputs(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None):
+    def stage_inputs(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None,
+                     obs_speed=None):
         """Write one batch of host inputs into the pinned staging block (no device work yet)."""
         e, B = self.engine, self.n_scen
         p0 = np.asarray(p0, dtype=np.float64).reshape(B, 3)
@@ -134,6 +139,7 @@ class BatchPlanner:
         if self.n_obs:
             if obs_s is not None:
                 e.obs_sd[0], e.obs_sd[1] = obs_s, obs_d
+                e.obs_speed[:] = 0.0 if obs_speed is None else obs_speed
             elif obs_xy is not None:
                 e.obs_xy[:] = obs_xy
             e.obs_active[:] = 1 if obs_active is None else obs_active
@@ -142,16 +148,22 @@ class BatchPlanner:
         """H2D of the staged inputs, the pipeline, D2H of records + winners; asynchronous on the current stream."""
         e = self.engine
         e.upload()
-        if self.n_obs and self._obs_frenet:
-            e.place_obstacles(self.path)
+        self._place()
         e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
         e.download(sync=False)
+
+    def _place(self):
+        e = self.engine
+        if self.n_obs and self._obs_frenet:
+            if self.predict_steps:
+                e.predict_obstacles(self.path, self.period)
+            else:
+                e.place_obstacles(self.path)
 
     def launch_resident(self):
         """The pipeline alone on inputs already in HBM (no host traffic)."""
         e = self.engine
-        if self.n_obs and self._obs_frenet:
-            e.place_obstacles(self.path)
+        self._place()
         e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
 
     @property
@@ -159,8 +171,10 @@ class BatchPlanner:
         n = bin(self.stages).count("1")
         if (self.stages & nat.STAGE_K2) and (self.stages & nat.STAGE_K3):     # frenet_plan fuses K2+K3 (+K4)
             n -= 1
-            if (self.stages & nat.STAGE_K4) and not (self.stages & nat.STAGE_CURVATURE):
+            if (self.stages & nat.STAGE_K4) and not (self.stages & nat.STAGE_CURVATURE) and not self.predict_steps:
                 n -= 1
+        if self.predict_steps and (self.stages & nat.STAGE_K4):
+            n += 1                                                            # per-chunk obstacle bounds
         return n + (1 if (self.n_obs and getattr(self, "_obs_frenet", False)) else 0)
 
     @property
@@ -179,9 +193,10 @@ class BatchPlanner:
         e = self.engine
         return BatchResult(e.result.copy(), e.winner.copy(), e.winner_steps.copy(), self.cand_timesteps())
 
-    def plan(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None) -> BatchResult:
+    def plan(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None,
+             obs_speed=None) -> BatchResult:
         """Host arrays in, per-scenario results out (synchronous)."""
-        self.stage_inputs(p0, s0, t0, dd, desired_speed, obs_s, obs_d, obs_xy, obs_active)
+        self.stage_inputs(p0, s0, t0, dd, desired_speed, obs_s, obs_d, obs_xy, obs_active, obs_speed)
         self.launch()
         return self.result()
 

@@ -785,6 +785,133 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXTENSION: predicted (time-indexed) obstacles.  The reference tests every step of a candidate against the
+// obstacles' CURRENT positions; here step k can be tested against the obstacle's predicted position at step k.
+// ------------------------------------------------------------------------------------------------
+// Per (scenario, 32-step chunk, obstacle): bounding circle of the obstacle's predicted positions in that chunk.
+__global__ void __launch_bounds__(128) obstacle_chunk_bounds(const double* __restrict__ obs_t, const uint8_t* __restrict__ active, int O,
+                                                             int K, int n_chunks, float4* __restrict__ bounds) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+        float4 out = make_float4(CUDART_INF_F, CUDART_INF_F, 0.0f, 0.0f);
+        if (active == nullptr || active[(int64_t)b * O + o] != 0) {
+            const double2* tbl = reinterpret_cast<const double2*>(obs_t) + ((int64_t)b * O + o) * K;
+            const int k0 = chunk * kWarp;
+            const double2 c = tbl[min(k0 + kWarp / 2, K - 1)];
+            double r2 = 0.0;
+            for (int k = k0; k < k0 + kWarp; ++k) {
+                const double2 q = tbl[min(k, K - 1)];
+                const double dx = q.x - c.x, dy = q.y - c.y;
+                r2 = fmax(r2, fma(dx, dx, dy * dy));
+            }
+            out = make_float4(__double2float_rn(c.x), __double2float_rn(c.y), __fsqrt_ru(__double2float_ru(r2)), 0.0f);
+        }
+        bounds[((int64_t)b * n_chunks + chunk) * O + o] = out;
+    }
+}
+
+// Collision test of one 32-step chunk against predicted obstacles.  k: this lane's step; tbl: the scenario's predicted table
+// [O][K] (global memory, L2 resident: the rows of a scenario share it); cb: this chunk's obstacle bounds in shared memory.
+__device__ __forceinline__ int collide_chunk_predicted(double x, double y, bool valid, int nvalid, int k, const double2* __restrict__ tbl,
+                                                       int K, const float4* __restrict__ cb, int O, float Rf, double radius_sq,
+                                                       int best, int lane) {
+    const int mid = (nvalid - 1) >> 1;
+    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
+    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
+    const float ex = xf - cx, ey = yf - cy;
+    const float r2 = fmaf(ex, ex, ey * ey);
+    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
+    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
+    const bool wide = !(r2max < 1e30f);
+    const int lim = min(O, best);
+    const int kk = min(k, K - 1);
+    for (int ob = 0; ob < lim; ob += kWarp) {
+        const int o = ob + lane;
+        bool near = false;
+        if (o < lim) {
+            const float4 q = cb[o];
+            const float ux = q.x - cx, uy = q.y - cy;
+            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
+            near = wide ? (q.x < CUDART_INF_F) : !(fmaf(ux, ux, uy * uy) > rr * rr);
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const double2 q = tbl[(int64_t)(ob + j) * K + kk];
+            const double dx = x - q.x, dy = y - q.y;
+            const bool hit = valid && (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= radius_sq);
+            if (__any_sync(kFull, hit)) return ob + j;
+        }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(kRowThreads) k4_collision_predicted(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+    extern __shared__ __align__(16) double sm[];
+    const int O = B.n_obs, K = B.n_obs_steps;
+    const int n_chunks = (L.n_pad_max + kWarp - 1) / kWarp;
+    float4* cb = reinterpret_cast<float4*>(sm);   // [n_chunks][O]
+
+    const int64_t br = blockIdx.x;
+    const RowAddr A = row_addr(L, br);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int flags = B.row_flags[br];
+    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
+        for (int id = tid; id < L.n_d; id += blockDim.x) {
+            B.coll_free[A.cand0 + id] = 0;
+            B.first_blocker[A.cand0 + id] = -1;
+        }
+        return;
+    }
+    const float4* src = reinterpret_cast<const float4*>(B.obs_bounds) + (int64_t)A.b * n_chunks * O;
+    for (int i = tid; i < n_chunks * O; i += blockDim.x) cb[i] = src[i];
+    __syncthreads();
+    const double2* tbl = reinterpret_cast<const double2*>(B.obs_xy_t) + (int64_t)A.b * O * K;
+    const float Rf = __double2float_ru(sqrt(P.radius_sq));
+
+    for (int id = warp; id < L.n_d; id += nwarps) {
+        const double* xs = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
+        const double* ys = xs + A.npad;
+        int best = kNoBlocker;
+        for (int kb = 0; kb < A.N; kb += kWarp) {
+            const int k = kb + lane < A.N ? kb + lane : kb;
+            best = collide_chunk_predicted(xs[k], ys[k], kb + lane < A.N, min(kWarp, A.N - kb), k, tbl, K, cb + (kb / kWarp) * O, O, Rf,
+                                           P.radius_sq, best, lane);
+        }
+        if (lane == 0) {
+            B.coll_free[A.cand0 + id] = best == kNoBlocker ? 1 : 0;
+            B.first_blocker[A.cand0 + id] = best == kNoBlocker ? -1 : best;
+        }
+    }
+}
+
+// Device-side obstacle prediction from the reference's time law (lib/sensor/dynamic_obstacle.py:43-56).
+__global__ void __launch_bounds__(256) predict_obstacles(FrenetPath path, const double* __restrict__ obs_s, const double* __restrict__ obs_d,
+                                                         const double* __restrict__ obs_speed, const double* __restrict__ t0,
+                                                         int64_t t0_stride, int n_scen, int O, int K, double period,
+                                                         double* __restrict__ out) {
+    extern __shared__ __align__(16) double tab[];
+    if (path.kind == FRENET_PATH_SPLINE) {
+        for (int i = threadIdx.x; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+        __syncthreads();
+    }
+    const int64_t total = (int64_t)n_scen * O * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        const int64_t bo = i / K;
+        const int b = (int)(bo / O);
+        const double t = t0[(int64_t)b * t0_stride] + (double)k * period;
+        const double tau = obs_s[bo] + fmod(t * obs_speed[bo], 50.0);   // time_offset + t * speed % 50
+        double px, py, nx, ny;
+        path_frame(path.kind, path.circle, tab, path.n_knots, tau, px, py, nx, ny);
+        const double d = obs_d[bo];
+        out[2 * i] = __dadd_rn(px, __dmul_rn(nx, d));
+        out[2 * i + 1] = __dadd_rn(py, __dmul_rn(ny, d));
+    }
+}
+
 // Collision test of arbitrary polylines (one warp per path): the generic form of K4 for candidate lists that do not
 // live in the lattice layout (e.g. `Frenet` objects built elsewhere and passed to the driver-level check_paths).
 __global__ void __launch_bounds__(256) polyline_collision(const double* __restrict__ x, const double* __restrict__ y,
@@ -1076,7 +1203,20 @@ int frenet_k3_curvature(const FrenetLattice* L, const FrenetParams* P, const Fre
 int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
     if (!P || !B || !B->row_flags || !B->lat || !B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "k4: NULL buffer");
-    if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "k4: obstacle table missing");
+    if (B->n_obs < 0 || B->n_obs_steps < 0) return fail(FRENET_ERR_BAD_ARG, "k4: negative obstacle count");
+    if (B->n_obs_steps > 0 && B->n_obs > 0) {   // predicted table
+        if (!B->obs_xy_t || !B->obs_bounds) return fail(FRENET_ERR_BAD_ARG, "k4: predicted obstacle table or bounds scratch missing");
+        const int n_chunks = (L->n_pad_max + kWarp - 1) / kWarp;
+        obstacle_chunk_bounds<<<dim3(n_chunks, L->n_scen), 128, 0, (cudaStream_t)stream>>>(
+            B->obs_xy_t, B->obs_active, B->n_obs, B->n_obs_steps, n_chunks, reinterpret_cast<float4*>(B->obs_bounds));
+        FRENET_CHECK_LAUNCH("obstacle_chunk_bounds");
+        const size_t smem = (size_t)n_chunks * B->n_obs * sizeof(float4);
+        if (int rc = set_smem(k4_collision_predicted, smem, "k4: too many obstacles for shared memory")) return rc;
+        k4_collision_predicted<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
+        FRENET_CHECK_LAUNCH("k4_collision_predicted");
+        return FRENET_OK;
+    }
+    if (B->n_obs > 0 && !B->obs_xy) return fail(FRENET_ERR_BAD_ARG, "k4: obstacle table missing");
     const size_t smem = (size_t)3 * B->n_obs * sizeof(double);
     if (int rc = set_smem(k4_collision, smem, "k4: too many obstacles for shared memory")) return rc;
     k4_collision<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
@@ -1112,7 +1252,7 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     // K2 and K3 (and K4 when nothing sits between them) run as ONE kernel unless the caller asks for separate launches:
     // same arithmetic, same outputs, but every sample is written once instead of being re-read by K3 and K4.
     const bool fuse = (stages & FRENET_STAGE_K2) && (stages & FRENET_STAGE_K3) && !(stages & FRENET_STAGE_NO_FUSE);
-    const bool fuse_k4 = fuse && (stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_CURVATURE);
+    const bool fuse_k4 = fuse && (stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_CURVATURE) && B && B->n_obs_steps == 0;
     if (fuse) {
         if ((rc = frenet_k2_fused(L, P, path, B, fuse_k4 ? 1 : 0, stream))) return rc;
     } else {
@@ -1125,6 +1265,24 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, (stages & (FRENET_STAGE_K3 | FRENET_STAGE_K4)) ? 1 : 0, stream)))
         return rc;
     return rc;
+}
+
+int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const double* obs_d, const double* obs_speed,
+                             const double* t0, int64_t t0_stride, int32_t n_scen, int32_t n_obs, int32_t n_steps, double period,
+                             double* obs_xy_t, frenet_stream_t stream) {
+    if (int rc = check_path(path)) return rc;
+    if (n_scen < 0 || n_obs < 0 || n_steps < 0) return fail(FRENET_ERR_BAD_ARG, "predict: negative size");
+    const int64_t total = (int64_t)n_scen * n_obs * n_steps;
+    if (total == 0) return FRENET_OK;
+    if (!obs_s || !obs_d || !obs_speed || !t0 || !obs_xy_t) return fail(FRENET_ERR_BAD_ARG, "predict: NULL buffer");
+    const size_t smem = (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0) * sizeof(double);
+    if (int rc = set_smem(predict_obstacles, smem, "predict: spline table too large for shared memory")) return rc;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    predict_obstacles<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*path, obs_s, obs_d, obs_speed, t0, t0_stride, n_scen, n_obs,
+                                                                             n_steps, period, obs_xy_t);
+    FRENET_CHECK_LAUNCH("predict_obstacles");
+    return FRENET_OK;
 }
 
 int frenet_polyline_collision(const double* x, const double* y, const int64_t* offsets, int32_t n_paths, const double* obs_xy,

@@ -135,10 +135,11 @@ class FrenetEngine:
         self.has_collision = False
 
     # -- allocation ---------------------------------------------------------------------------
-    def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0):
-        """(Re)allocate for a geometry / capacities; cheap when nothing changed."""
-        n_obs = int(n_obs)
-        key = (geom.key, int(n_v_cap), n_obs)
+    def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0, n_obs_steps: int = 0):
+        """(Re)allocate for a geometry / capacities; cheap when nothing changed.
+        n_obs_steps > 0 additionally allocates a predicted obstacle table [B][n_obs][n_obs_steps][2] (extension)."""
+        n_obs, n_obs_steps = int(n_obs), int(n_obs_steps)
+        key = (geom.key, int(n_v_cap), n_obs, n_obs_steps)
         if key == self._cap_key:
             return
         dev, Bn = self.device, self.n_scen
@@ -168,7 +169,8 @@ class FrenetEngine:
 
         # packed small inputs: one pinned host block, one device block
         sizes = [("state", Bn * 6 * 8), ("scal", Bn * 3 * 8), ("axis_v", Bn * self.n_v_cap * 8), ("target", Bn * nT * 3 * 8),
-                 ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("obs_sd", Bn * max(n_obs, 1) * 2 * 8), ("n_v", Bn * 4),
+                 ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("obs_sd", Bn * max(n_obs, 1) * 2 * 8),
+                 ("obs_speed", Bn * max(n_obs, 1) * 8), ("n_v", Bn * 4),
                  ("obs_active", Bn * max(n_obs, 1))]
         offs, tot = {}, 0
         for name, sz in sizes:
@@ -184,6 +186,7 @@ class FrenetEngine:
         no = max(n_obs, 1)
         self.obs_xy = hv[offs["obs_xy"]:offs["obs_xy"] + Bn * no * 16].view(np.float64).reshape(Bn, no, 2)
         self.obs_sd = hv[offs["obs_sd"]:offs["obs_sd"] + Bn * no * 16].view(np.float64).reshape(2, Bn, no)   # [s|d][B][O]
+        self.obs_speed = hv[offs["obs_speed"]:offs["obs_speed"] + Bn * no * 8].view(np.float64).reshape(Bn, no)
         self.n_v = hv[offs["n_v"]:offs["n_v"] + Bn * 4].view(np.int32)
         self.obs_active = hv[offs["obs_active"]:offs["obs_active"] + Bn * no].reshape(Bn, no)
         hv[:] = 0
@@ -219,6 +222,11 @@ class FrenetEngine:
         self.curv_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.coll_free = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.first_blocker = torch.empty((Bn, Cc), dtype=torch.int32, device=dev)
+        self.n_obs_steps = n_obs_steps
+        self.obs_xy_t = self.obs_bounds = None
+        if n_obs_steps > 0 and n_obs > 0:
+            self.obs_xy_t = torch.empty((Bn, n_obs, n_obs_steps, 2), **f64)
+            self.obs_bounds = torch.empty((Bn, (geom.n_pad_max + 31) // 32, n_obs, 4), dtype=torch.float32, device=dev)
 
         L = self.L
         L.n_scen, L.n_v_cap, L.n_t, L.n_d, L.n_pad_max = Bn, self.n_v_cap, nT, nD, geom.n_pad_max
@@ -233,13 +241,17 @@ class FrenetEngine:
         Bf.lon, Bf.lat, Bf.cost, Bf.cand_flags = self.lon.data_ptr(), self.lat.data_ptr(), self.cost.data_ptr(), self.cand_flags.data_ptr()
         Bf.curv_ok = self.curv_ok.data_ptr()
         Bf.coll_free, Bf.first_blocker = self.coll_free.data_ptr(), self.first_blocker.data_ptr()
+        Bf.n_obs_steps = n_obs_steps if self.obs_xy_t is not None else 0
+        Bf.obs_xy_t = self.obs_xy_t.data_ptr() if self.obs_xy_t is not None else None
+        Bf.obs_bounds = self.obs_bounds.data_ptr() if self.obs_bounds is not None else None
         Bf.result = op + ooffs["result"]
         Bf.winner, Bf.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
         self._cap_key = key
 
     def hbm_bytes(self) -> int:
         ts = [self.coef_lon, self.coef_lat, self.row_S, self.row_flags, self.lon, self.lat, self.cost, self.cand_flags,
-              self.curv_ok, self.coll_free, self.first_blocker, self._in_dev, self._out_dev, self._geom_dev]
+              self.curv_ok, self.coll_free, self.first_blocker, self._in_dev, self._out_dev, self._geom_dev] + [
+            t for t in (self.obs_xy_t, self.obs_bounds) if t is not None]
         return sum(t.numel() * t.element_size() for t in ts)
 
     @staticmethod
@@ -294,6 +306,19 @@ class FrenetEngine:
         xy = ip + self._in_offs["obs_xy"]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(nat.lib.frenet_points_to_cartesian(C.byref(path.desc), sd, sd + n * 8, n, xy, xy + 8, 2, C.c_void_p(stream)))
+
+    def predict_obstacles(self, path: PathHandle, period: float):
+        """EXTENSION: fill the predicted table from the uploaded `obs_sd` / `obs_speed` and each scenario's t_initial with the
+        reference's moving-obstacle time law (lib/sensor/dynamic_obstacle.py:43-56), one entry per sample period."""
+        if self.obs_xy_t is None:
+            raise RuntimeError("engine was configured without a predicted obstacle table (n_obs_steps = 0)")
+        ip = self._in_dev.data_ptr()
+        n = self.n_scen * self.n_obs
+        sd = ip + self._in_offs["obs_sd"]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_predict_obstacles(C.byref(path.desc), sd, sd + n * 8, ip + self._in_offs["obs_speed"],
+                                                   ip + self._in_offs["scal"] + 16, 3, self.n_scen, self.n_obs, self.n_obs_steps,
+                                                   float(period), self.obs_xy_t.data_ptr(), C.c_void_p(stream)))
 
     def download(self, sync: bool = True):
         """One D2H copy of the packed per-call outputs (result records, winner trajectories)."""

@@ -456,3 +456,57 @@ def test_fused_kernel_equals_separate_launches():
             fa = a2.padded_fields(a2.fetch_scenario(sidx))
             for n in ("d", "dot_d", "ddot_d", "dddot_d", "s", "dot_s", "ddot_s", "dddot_s", "x", "y"):
                 assert np.array_equal(fa[n], fb[n], equal_nan=True), (sidx, n)
+
+
+def test_predicted_obstacles_extension():
+    """EXTENSION (no reference code; the oracle's time-indexed table is the definition): obstacles propagated over the
+    horizon on the device.  (a) the predicted table equals the reference's time law evaluated by the oracle;
+    (b) collision masks / first blockers / masked argmin equal the oracle's time-indexed check; (c) with zero obstacle
+    speed the predicted mode reproduces the snapshot mode bit for bit (the reference's behaviour)."""
+    _gpu, nat, _, Spline = _imports()
+    from otg_b200 import workloads
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.planner import TrajectoryPlannerParams
+    sc = workloads.config5_scenarios()
+    B, O = 6, 128
+    sl = slice(40, 40 + B)
+    tr = Spline(workloads.SPLINE_WX, workloads.SPLINE_WY)
+    op = fo.SplinePath(workloads.SPLINE_WX, workloads.SPLINE_WY)
+    prm = _dense_prm()
+    params = TrajectoryPlannerParams(**workloads.DENSE_PARAMS)
+    d_tot = sc["obs_d"][sl] + sc["obs_offset"][sl]
+    K = 150
+    bp = BatchPlanner(params, tr, B, O, predict_steps=K)
+    res = bp.plan(sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], obs_s=sc["obs_s"][sl], obs_d=d_tot,
+                  obs_speed=sc["obs_speed"][sl])
+    table = bp.engine.obs_xy_t.cpu().numpy()                     # [B][O][K][2]
+    keep = bp.engine.coll_free.cpu().numpy()
+    first = bp.engine.first_blocker.cpu().numpy()
+    n_moved = 0
+    for b in range(B):
+        t = sc["t0"][sl][b] + np.arange(K) * prm.delta_t
+        tau = fo.obstacle_time_law(t[None, :], sc["obs_speed"][sl][b][:, None], sc["obs_s"][sl][b][:, None])
+        ox, oy = fo.frenet_to_cartesian(op, tau, d_tot[b][:, None])
+        ref = np.stack([ox, oy], 2)                              # [O][K][2]
+        assert_close(table[b], ref, GPU_RTOL, f"predicted table[{b}]", atol_scale=60.0)
+        L = fo.generate(prm, sc["p0"][sl][b], sc["s0"][sl][b], float(sc["t0"][sl][b]), dd=float(sc["dd"][sl][b]))
+        x, y = fo.lattice_to_cartesian(op, L)
+        ok, fb = fo.check_collisions(x, y, L.nsteps, np.transpose(ref, (1, 0, 2)))      # [K][O][2]
+        C_ = L.n_candidates
+        assert np.array_equal(keep[b, :C_] != 0, ok), f"predicted collision mask[{b}]"
+        assert np.array_equal(first[b, :C_], fb), f"predicted first blocker[{b}]"
+        _check_argmin(int(res.records["argmin_masked"][b]), fo.first_argmin(L.ctot, ok), L.ctot, f"predicted[{b}]")
+        ok0, _ = fo.check_collisions(x, y, L.nsteps, ref[:, 0, :])
+        n_moved += int((ok0 != ok).sum())
+    assert n_moved > 0                                           # the horizon prediction changes the outcome somewhere
+    # (c) standing obstacles: predicted == snapshot
+    snap = BatchPlanner(params, tr, B, O)
+    rs = snap.plan(sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], obs_s=sc["obs_s"][sl], obs_d=d_tot)
+    rp = bp.plan(sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], obs_s=sc["obs_s"][sl], obs_d=d_tot,
+                 obs_speed=np.zeros((B, O)))
+    assert np.array_equal(rs.records, rp.records)
+    assert np.array_equal(snap.engine.coll_free.cpu().numpy(), bp.engine.coll_free.cpu().numpy())
+    assert np.array_equal(snap.engine.first_blocker.cpu().numpy(), bp.engine.first_blocker.cpu().numpy())
+    for b in range(B):
+        n = int(rs.winner_steps[b])
+        assert np.array_equal(rs.winner[b, :, :n], rp.winner[b, :, :n], equal_nan=True)
