@@ -387,7 +387,10 @@ __device__ __forceinline__ int collide_pair(double xa, double ya, double xb, dou
     const float r2 = fmaxf(fmaf(ex, ex, ey * ey), fmaf(fx, fx, fy * fy));
     const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
     const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
-    const float thr = (r2max < 1e30f) ? reach * reach : CUDART_INF_F;
+    const bool finite = r2max < 1e30f;
+    const float thr = finite ? reach * reach : CUDART_INF_F;
+    const float rpt = Rf * 1.00001f + (fabsf(cx) + fabsf(cy) + reach) * 3.8147e-6f;   // every point of the chunk has |coord| <= |c| + reach
+    const float thr_pt = finite ? rpt * rpt : CUDART_INF_F;
     const int lim = min(O, best);
     for (int ob = 0; ob < lim; ob += kWarp) {
         const int o = ob + lane;
@@ -401,6 +404,12 @@ __device__ __forceinline__ int collide_pair(double xa, double ya, double xb, dou
         while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
+            // fp32 pre-test per lane (same conservative padding as the cull): most cull survivors touch no point at all,
+            // and the fp64 reference test below runs only when some lane may be within the robot radius.
+            const float2 qf = obsf[ob + j];
+            const float ax = xf - qf.x, ay = yf - qf.y, bx = xg - qf.x, by = yg - qf.y;
+            const bool maybe = !(fminf(fmaf(ax, ax, ay * ay), fmaf(bx, bx, by * by)) > thr_pt);   // NaN counts as maybe
+            if (!__any_sync(kFull, maybe)) continue;
             const double2 q = obs[ob + j];
             const double dxa = xa - q.x, dya = ya - q.y, dxb = xb - q.x, dyb = yb - q.y;
             const bool hit = (valid_a && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= radius_sq)) ||
@@ -433,7 +442,8 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // The fused variants write each candidate-timestep exactly once (48 B: d, d', d'', d''', x, y) and read
 // nothing back; the unfused sequence K2 -> K3 -> K4 moves 72 B for the same result.
 // Shared memory (doubles): [3 * n_obs, rounded up to 4] obstacles in fp64 and fp32 (kColl) | [n_pad_max] lateral argument |
-// 4 x [n_pad_max] path frame (kXY) | [n_d][6] lateral coefficients | [n_knots][9] spline table (kXY).
+// 4 x [n_pad_max] path frame (kXY) | [n_d][6] lateral coefficients | [n_d][5] per-candidate results | [n_knots][9] spline
+// table (kXY).
 template <bool kXY, bool kColl, bool kLimits>
 __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
     extern __shared__ __align__(16) double sm[];
@@ -446,7 +456,9 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     double* fnx = fpy + (kXY ? npm : 0);
     double* fny = fnx + (kXY ? npm : 0);
     double* coef = fny + (kXY ? npm : 0);                          // [n_d][6] lateral coefficients of this row (from K1)
-    double* tab = coef + L.n_d * 6;                                // [n_knots][9] spline table (kXY, spline path)
+    double* resc = coef + L.n_d * 6;                               // [n_d][4] cd, cv, ct, ctot of the row's candidates
+    int* resi = reinterpret_cast<int*>(resc + L.n_d * 4);          // [n_d][2] flags, first blocker
+    double* tab = resc + L.n_d * 5;                                // [n_knots][9] spline table (kXY, spline path)
     __shared__ double red[3][kRowThreads / 32];
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
@@ -609,21 +621,29 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         }
         acc = warp_sum(acc);
         if (kLimits) amax = warp_max(amax);
-        if (lane == 0) {   // :165-167 / :174-176
-            const int64_t c = A.cand0 + id;
+        if (lane == 0) {   // :165-167 / :174-176; staged in shared memory, written out coalesced below
             const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
             const double e = L.axis_d[id] - B.scal[(int64_t)A.b * 3];
             const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
-            B.cost[c] = clat;
-            B.cost[A.candF + c] = P.follow ? 0.0 : clong;
-            B.cost[2 * A.candF + c] = P.follow ? clong : 0.0;
-            B.cost[3 * A.candF + c] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
+            resc[id * 4] = clat;
+            resc[id * 4 + 1] = P.follow ? 0.0 : clong;
+            resc[id * 4 + 2] = P.follow ? clong : 0.0;
+            resc[id * 4 + 3] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
             const bool kin = kLimits ? (rowfeas && amax <= P.a_max) : true;
-            B.cand_flags[c] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0);
-            if (kColl) {
-                B.coll_free[c] = best == kNoBlocker ? 1 : 0;
-                B.first_blocker[c] = best == kNoBlocker ? -1 : best;
-            }
+            resi[id * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0);
+            resi[id * 2 + 1] = best;
+        }
+    }
+    __syncthreads();
+    for (int id = tid; id < L.n_d; id += blockDim.x) {
+        const int64_t c = A.cand0 + id;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = resc[id * 4 + f];
+        B.cand_flags[c] = (uint8_t)resi[id * 2];
+        if (kColl) {
+            const int best = resi[id * 2 + 1];
+            B.coll_free[c] = best == kNoBlocker ? 1 : 0;
+            B.first_blocker[c] = best == kNoBlocker ? -1 : best;
         }
     }
 }
@@ -1111,7 +1131,7 @@ template <bool kXY, bool kColl>
 int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, cudaStream_t stream) {
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
-    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 6 + (spline ? (size_t)9 * path->n_knots : 0) +
+    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 11 + (spline ? (size_t)9 * path->n_knots : 0) +
                          (kColl ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0)) * sizeof(double);
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
