@@ -510,3 +510,62 @@ def test_predicted_obstacles_extension():
     for b in range(B):
         n = int(rs.winner_steps[b])
         assert np.array_equal(rs.winner[b, :, :n], rp.winner[b, :, :n], equal_nan=True)
+
+
+def test_odd_sizes_all_kernels_and_no_stray_writes():
+    """Every kernel once on odd shapes (scripts/sanitize_case.py; compute-sanitizer is closed on this pool, so the
+    bounds evidence is our own): output buffers are pre-filled with a sentinel, and after a launch (a) every element a
+    kernel is responsible for - padding samples included - is overwritten, (b) everything else still holds the sentinel."""
+    import runpy, os
+    import torch
+    from _golden import ROOT
+    runpy.run_path(os.path.join(ROOT, "scripts", "sanitize_case.py"), run_name="__main__")
+
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200 import lattice as lat
+    from otg_b200.engine import FrenetEngine, LatticeGeometry, make_params
+    prm = fo.OracleParams.defaults("v1").with_(delta_t=0.07, d_road_width=0.7)      # N = 16, 23, 30, 37 -> npad 16, 24, 32, 40
+    a = _gpu.planner_attrs(prm)
+    B = 3
+    s0 = np.array([[1.0, 0.2, 0.0], [2.0, 1.6, 0.1], [3.0, 3.4, -0.2]])             # 5, 6 and 5 target speeds: ragged V axes
+    p0 = np.zeros((B, 3))
+    geom = LatticeGeometry.from_intervals(lat.di_interval(a, "v1"), lat.t_interval(a, "v1"), 0.07)
+    axes = [lat.long_axis(a, s0[b, 1], False) for b in range(B)]
+    eng = FrenetEngine(B)
+    eng.configure(geom, 7, 4)                                                      # one more V slot than any scenario uses
+    SENT = float(np.frombuffer(np.uint64(0x7ff8dead0000beef).tobytes(), dtype=np.float64)[0])
+    for t in (eng.lon, eng.lat, eng.cost, eng.coef_lon, eng.coef_lat, eng.row_S):
+        t.fill_(SENT)
+    eng.coll_free.fill_(77)
+    eng.first_blocker.fill_(-77)
+    eng.cand_flags.fill_(77)
+    eng.state[:, :3], eng.state[:, 3:] = p0, s0
+    eng.scal[:] = (0.0, 2.5, 0.1)
+    for b, x in enumerate(axes):
+        eng.axis_v[b, :len(x)] = x
+        eng.n_v[b] = len(x)
+    eng.obs_xy[:] = np.array([[4.0, 0.5], [6.0, -1.0], [9.0, 0.0], [50.0, 50.0]])
+    P = make_params(a, nat.LOWSPEED_V1, 0.07, False)
+    eng.run(P, eng.path_handle(Circle(8, 5, 2)), nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K3 | nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER,
+            nat.MASK_COLLISION, nat.SEL_MASKED)
+
+    def is_sent(x):
+        return x.view(np.uint64) == np.uint64(0x7ff8dead0000beef)
+
+    lon, latb = eng.lon.cpu().numpy(), eng.lat.cpu().numpy()
+    nT, nD = geom.n_t, geom.n_d
+    for b in range(B):
+        nv = len(axes[b])
+        used_lon = nv * geom.sum_pad * 4
+        used_lat = nv * geom.sum_pad * nD * 6
+        assert not is_sent(lon[b, :used_lon]).any(), "unwritten longitudinal sample (padding included)"
+        assert not is_sent(latb[b, :used_lat]).any(), "unwritten lateral / Cartesian sample (padding included)"
+        assert is_sent(lon[b, used_lon:]).all() and is_sent(latb[b, used_lat:]).all(), "write beyond the scenario's rows"
+        C_ = nv * nT * nD
+        cost = eng.cost[:, b].cpu().numpy()
+        assert not is_sent(cost[:, :C_]).any()
+        assert (cost[:, C_:] == 0.0).all()                      # rows beyond n_v are cleared by K2, not left undefined
+        assert (eng.cand_flags[b, C_:].cpu().numpy() == 0).all() and (eng.cand_flags[b, :C_].cpu().numpy() == 3).all()
+        assert (eng.coll_free[b, C_:].cpu().numpy() == 0).all() and (eng.first_blocker[b, C_:].cpu().numpy() == -1).all()
+        assert set(np.unique(eng.coll_free[b, :C_].cpu().numpy())) <= {0, 1}
+    torch.cuda.synchronize()
