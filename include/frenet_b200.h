@@ -245,6 +245,12 @@ int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const 
                              const double* t0, int64_t t0_stride, int32_t n_scen, int32_t n_obs, int32_t n_steps, double period,
                              double* obs_xy_t, frenet_stream_t stream);
 
+/* Device-side cone gate of the proximity sensor: active[b][o] = 1 iff obstacle o of scenario b lies inside the cone of
+ * length `range` and half-aperture `aperture` ahead of robot_pose[b] = (x, y, theta).
+ * Replaces ProximitySensor.sense (lib/sensor/proximity_sensor.py:41-75) for a whole batch; obs_xy: [n_scen][n_obs][2]. */
+int frenet_sensor_gate(const double* robot_pose, const double* obs_xy, int32_t n_scen, int32_t n_obs, double range, double aperture,
+                       uint8_t* active, frenet_stream_t stream);
+
 /* Generic form of K4 for polylines that are not in the lattice layout: path p owns points offsets[p] .. offsets[p+1]-1
  * of x / y; obstacles are an [n_obs][2] table (all tested).  Replaces check_collisions on one path at a time
  * (lib/tests/test_moving_obstacle_planner.py:42-52) for every path of a list at once. */

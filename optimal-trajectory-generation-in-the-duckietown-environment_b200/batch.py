@@ -114,8 +114,13 @@ class BatchPlanner:
 
     # -- host -> pinned staging ----------------------------------------------------------------
     def stage_inputs(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None,
-                     obs_speed=None):
-        """Write one batch of host inputs into the pinned staging block (no device work yet)."""
+                     obs_speed=None, robot_pose=None, sensor=None, targets=None):
+        """Write one batch of host inputs into the pinned staging block (no device work yet).
+
+        robot_pose [B][3] + sensor=(range, aperture): the obstacle mask is computed on the device by the cone gate
+        (snapshot obstacles only) instead of being passed in `obs_active`.
+        targets [B][n_t][3]: follow mode - quintic longitudinal to the (st, dst, ddst) triples, cost ct
+        (trajectory_planner.py:131-144); the V axis then holds the target offsets of `si_interval`."""
         e, B = self.engine, self.n_scen
         p0 = np.asarray(p0, dtype=np.float64).reshape(B, 3)
         s0 = np.asarray(s0, dtype=np.float64).reshape(B, 3)
@@ -126,8 +131,13 @@ class BatchPlanner:
         # per-scenario target-speed axis: the reference's rounding rule (trajectory_planner.py:120), vectorised.
         # np.round is round-half-to-even like Python's round() on floats.
         q, n = self.p.d_d_s, self.p.num_sample
-        lo = np.round(s0[:, 1] - q * n)
-        hi = np.round(s0[:, 1] + q * n + q)
+        follow = targets is not None
+        self.params.follow = 1 if follow else 0
+        if follow:
+            e.target[:] = np.asarray(targets, dtype=np.float64).reshape(B, self.geom.n_t, 3)
+        centre = np.zeros(B) if follow else s0[:, 1]            # follow: si_interval is centred on 0 (trajectory_planner.py:119)
+        lo = np.round(centre - q * n)
+        hi = np.round(centre + q * n + q)
         nv = np.ceil((hi - lo) / q).astype(np.int32)
         if int(nv.max()) > e.n_v_cap:
             raise ValueError("longitudinal axis longer than the configured capacity")
@@ -143,6 +153,10 @@ class BatchPlanner:
             elif obs_xy is not None:
                 e.obs_xy[:] = obs_xy
             e.obs_active[:] = 1 if obs_active is None else obs_active
+        self._gate = None
+        if robot_pose is not None and sensor is not None:
+            e.robot_pose[:] = robot_pose
+            self._gate = (float(sensor[0]), float(sensor[1]))
 
     def launch(self):
         """H2D of the staged inputs, the pipeline, D2H of records + winners; asynchronous on the current stream."""
@@ -159,6 +173,8 @@ class BatchPlanner:
                 e.predict_obstacles(self.path, self.period)
             else:
                 e.place_obstacles(self.path)
+        if self.n_obs and getattr(self, "_gate", None) and not self.predict_steps:
+            e.sensor_gate(*self._gate)
 
     def launch_resident(self):
         """The pipeline alone on inputs already in HBM (no host traffic)."""
@@ -194,9 +210,9 @@ class BatchPlanner:
         return BatchResult(e.result.copy(), e.winner.copy(), e.winner_steps.copy(), self.cand_timesteps())
 
     def plan(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None,
-             obs_speed=None) -> BatchResult:
+             obs_speed=None, robot_pose=None, sensor=None, targets=None) -> BatchResult:
         """Host arrays in, per-scenario results out (synchronous)."""
-        self.stage_inputs(p0, s0, t0, dd, desired_speed, obs_s, obs_d, obs_xy, obs_active, obs_speed)
+        self.stage_inputs(p0, s0, t0, dd, desired_speed, obs_s, obs_d, obs_xy, obs_active, obs_speed, robot_pose, sensor, targets)
         self.launch()
         return self.result()
 

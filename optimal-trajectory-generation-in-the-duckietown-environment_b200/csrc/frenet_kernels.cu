@@ -932,6 +932,26 @@ __global__ void __launch_bounds__(256) predict_obstacles(FrenetPath path, const 
     }
 }
 
+// Cone gate of the proximity sensor (lib/sensor/proximity_sensor.py:41-75), one thread per (scenario, obstacle).
+__global__ void __launch_bounds__(256) sensor_gate(const double* __restrict__ pose, const double* __restrict__ obs_xy, int n_scen, int O,
+                                                   double range, double aperture, uint8_t* __restrict__ active) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_scen * O) return;
+    const int b = (int)(i / O);
+    const double px = pose[3 * b], py = pose[3 * b + 1], th = pose[3 * b + 2];
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    const double rx = obs_xy[2 * i] - px, ry = obs_xy[2 * i + 1] - py;
+    const double along = __dadd_rn(__dmul_rn(rx, cs), __dmul_rn(ry, sn));          // np.dot(diff, dir)
+    bool on = !(along < 0.0 || along >= range);
+    if (on) {
+        const double cross = fabs(__dadd_rn(__dmul_rn(cs, ry), -__dmul_rn(sn, rx)));   // |dir x diff|
+        const double dotp = __dadd_rn(__dmul_rn(cs, rx), __dmul_rn(sn, ry));           // np.dot(dir, diff)
+        on = !(fabs(atan2(cross, dotp)) > aperture);
+    }
+    active[i] = on ? 1 : 0;
+}
+
 // Collision test of arbitrary polylines (one warp per path): the generic form of K4 for candidate lists that do not
 // live in the lattice layout (e.g. `Frenet` objects built elsewhere and passed to the driver-level check_paths).
 __global__ void __launch_bounds__(256) polyline_collision(const double* __restrict__ x, const double* __restrict__ y,
@@ -1302,6 +1322,17 @@ int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const 
     predict_obstacles<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*path, obs_s, obs_d, obs_speed, t0, t0_stride, n_scen, n_obs,
                                                                              n_steps, period, obs_xy_t);
     FRENET_CHECK_LAUNCH("predict_obstacles");
+    return FRENET_OK;
+}
+
+int frenet_sensor_gate(const double* robot_pose, const double* obs_xy, int32_t n_scen, int32_t n_obs, double range, double aperture,
+                       uint8_t* active, frenet_stream_t stream) {
+    if (n_scen < 0 || n_obs < 0) return fail(FRENET_ERR_BAD_ARG, "sensor gate: negative size");
+    const int64_t total = (int64_t)n_scen * n_obs;
+    if (total == 0) return FRENET_OK;
+    if (!robot_pose || !obs_xy || !active) return fail(FRENET_ERR_BAD_ARG, "sensor gate: NULL buffer");
+    sensor_gate<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(robot_pose, obs_xy, n_scen, n_obs, range, aperture, active);
+    FRENET_CHECK_LAUNCH("sensor_gate");
     return FRENET_OK;
 }
 

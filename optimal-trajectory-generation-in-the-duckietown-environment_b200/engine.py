@@ -170,7 +170,7 @@ class FrenetEngine:
         # packed small inputs: one pinned host block, one device block
         sizes = [("state", Bn * 6 * 8), ("scal", Bn * 3 * 8), ("axis_v", Bn * self.n_v_cap * 8), ("target", Bn * nT * 3 * 8),
                  ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("obs_sd", Bn * max(n_obs, 1) * 2 * 8),
-                 ("obs_speed", Bn * max(n_obs, 1) * 8), ("n_v", Bn * 4),
+                 ("obs_speed", Bn * max(n_obs, 1) * 8), ("robot_pose", Bn * 3 * 8), ("n_v", Bn * 4),
                  ("obs_active", Bn * max(n_obs, 1))]
         offs, tot = {}, 0
         for name, sz in sizes:
@@ -187,6 +187,7 @@ class FrenetEngine:
         self.obs_xy = hv[offs["obs_xy"]:offs["obs_xy"] + Bn * no * 16].view(np.float64).reshape(Bn, no, 2)
         self.obs_sd = hv[offs["obs_sd"]:offs["obs_sd"] + Bn * no * 16].view(np.float64).reshape(2, Bn, no)   # [s|d][B][O]
         self.obs_speed = hv[offs["obs_speed"]:offs["obs_speed"] + Bn * no * 8].view(np.float64).reshape(Bn, no)
+        self.robot_pose = hv[offs["robot_pose"]:offs["robot_pose"] + Bn * 24].view(np.float64).reshape(Bn, 3)
         self.n_v = hv[offs["n_v"]:offs["n_v"] + Bn * 4].view(np.int32)
         self.obs_active = hv[offs["obs_active"]:offs["obs_active"] + Bn * no].reshape(Bn, no)
         hv[:] = 0
@@ -306,6 +307,18 @@ class FrenetEngine:
         xy = ip + self._in_offs["obs_xy"]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(nat.lib.frenet_points_to_cartesian(C.byref(path.desc), sd, sd + n * 8, n, xy, xy + 8, 2, C.c_void_p(stream)))
+
+    def sensor_gate(self, rng: float, aperture: float):
+        """Device-side `ProximitySensor.sense` for the whole batch: fills the device `obs_active` mask from the uploaded
+        `robot_pose` and the device `obs_xy` table (lib/sensor/proximity_sensor.py:41-75)."""
+        ip = self._in_dev.data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_sensor_gate(ip + self._in_offs["robot_pose"], ip + self._in_offs["obs_xy"], self.n_scen, self.n_obs,
+                                             float(rng), float(aperture), ip + self._in_offs["obs_active"], C.c_void_p(stream)))
+
+    def device_obs_active(self) -> np.ndarray:
+        o = self._in_offs["obs_active"]
+        return self._in_dev[o:o + self.n_scen * max(self.n_obs, 1)].cpu().numpy().reshape(self.n_scen, max(self.n_obs, 1))
 
     def predict_obstacles(self, path: PathHandle, period: float):
         """EXTENSION: fill the predicted table from the uploaded `obs_sd` / `obs_speed` and each scenario's t_initial with the

@@ -569,3 +569,61 @@ def test_odd_sizes_all_kernels_and_no_stray_writes():
         assert (eng.coll_free[b, C_:].cpu().numpy() == 0).all() and (eng.first_blocker[b, C_:].cpu().numpy() == -1).all()
         assert set(np.unique(eng.coll_free[b, :C_].cpu().numpy())) <= {0, 1}
     torch.cuda.synchronize()
+
+
+def test_device_sensor_gate_and_batched_follow_mode():
+    """the cone gate of ProximitySensor.sense evaluated on the device for a batch, and follow
+    mode (target triples per horizon) through the batch API."""
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.engine import FrenetEngine, LatticeGeometry
+    from otg_b200.planner import TrajectoryPlannerParams
+    z = golden("sensor_gate")
+    B, O = z["obs_xy"].shape[:2]
+    eng = FrenetEngine(B)
+    eng.configure(LatticeGeometry.from_intervals((-1, 1, 1), (1, 2, 1), 0.5), 2, O)
+    eng.robot_pose[:] = z["pose"]
+    eng.obs_xy[:] = z["obs_xy"]
+    eng.upload()
+    eng.sensor_gate(float(z["range"]), float(z["aperture"]))
+    assert np.array_equal(eng.device_obs_active(), z["mask"])
+    # the recorded closed-loop runs: which obstacles the sensor reported at every step
+    for kind in ("static", "moving"):
+        s = golden(f"sim_planner_{kind}")
+        e2 = FrenetEngine(499)
+        e2.configure(LatticeGeometry.from_intervals((-1, 1, 1), (1, 2, 1), 0.5), 2, 10)
+        e2.robot_pose[:] = s["robot_pose_in"]
+        e2.obs_xy[:] = s["obs_all_xy"]
+        e2.upload()
+        e2.sensor_gate(3.5, np.pi / 6)
+        want = np.zeros((499, 10), dtype=np.uint8)
+        for i in range(499):
+            want[i, s["obs_idx"][i, :s["n_sensed"][i]]] = 1
+        assert np.array_equal(e2.device_obs_active(), want), kind
+    # gate inside the batch pipeline == passing the same mask explicitly
+    s = golden("sim_planner_moving")
+    idx = np.nonzero(s["n_sensed"] > 0)[0][:48]
+    want = np.zeros((len(idx), 10), dtype=np.uint8)
+    for j, i in enumerate(idx):
+        want[j, s["obs_idx"][i, :s["n_sensed"][i]]] = 1
+    bp = BatchPlanner(TrajectoryPlannerParams(), Circle(8, 5, 2), len(idx), 10)
+    r1 = bp.plan(s["p0"][idx], s["s0"][idx], s["time"][idx], obs_xy=s["obs_all_xy"][idx], obs_active=want)
+    r2 = bp.plan(s["p0"][idx], s["s0"][idx], s["time"][idx], obs_xy=s["obs_all_xy"][idx],
+                 robot_pose=s["robot_pose_in"][idx], sensor=(3.5, np.pi / 6))
+    assert np.array_equal(r1.records, r2.records)
+    assert np.array_equal(r1.records["argmin_masked"], s["argmin_masked"][idx])
+    # batched follow mode against the reference's follow-mode lattices
+    f = golden("follow_mode")
+    g = [prefixed(f, f"r{j}_") for j in range(3)]
+    bp = BatchPlanner(TrajectoryPlannerParams(), Circle(8, 5, 2), 3, 0)
+    r = bp.plan(np.stack([x["p0"] for x in g]), np.stack([x["s0"] for x in g]), np.array([float(x["time"]) for x in g]),
+                targets=np.stack([x["triples"] for x in g]))
+    cost = bp.engine.cost.cpu().numpy()
+    for j, x in enumerate(g):
+        C_ = len(x["nsteps"])
+        assert r.records["n_valid"][j] == C_ and r.records["argmin_ctot"][j] == int(x["argmin"])
+        assert_close(cost[2, j, :C_], x["ct"], GPU_RTOL, f"follow batch[{j}].ct")
+        assert_close(cost[3, j, :C_], x["ctot"], GPU_RTOL, f"follow batch[{j}].ctot")
+    # and back to velocity keeping on the same planner object
+    r = bp.plan(np.stack([x["p0"] for x in g]), np.stack([x["s0"] for x in g]), np.array([float(x["time"]) for x in g]))
+    assert (bp.engine.cost[2].cpu().numpy() == 0).all() and bp.params.follow == 0
