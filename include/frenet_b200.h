@@ -245,6 +245,16 @@ int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const 
                              const double* t0, int64_t t0_stride, int32_t n_scen, int32_t n_obs, int32_t n_steps, double period,
                              double* obs_xy_t, frenet_stream_t stream);
 
+/* Device-side `replan_ctot` bookkeeping for a batch (lib/planner/trajectory_planner.py:206-212 with optimal_at_time :183-195
+ * and the interval rule :120): for every scenario, the new initial state is the gathered winner (buf->winner) sampled at
+ * `time[b * time_stride]` - index 0 / last when the time is outside the winner's window, else round-half-even of
+ * (time - t[0]) / lookup_period - t_initial becomes that time, and the target-speed axis is rebuilt from the new speed
+ * (round(ds0 - d_d_s * num_sample), round(ds0 + d_d_s * num_sample + d_d_s), d_d_s) into lat->axis_v / lat->n_v.
+ * Scenarios without a winner keep their state and get status[b] = 1 (the reference raises there); status may be NULL.
+ * The buffers written are the `state`, `scal`, `axis_v`, `n_v` inputs themselves (cast away const: they are device memory). */
+int frenet_advance_state(const FrenetLattice* lat, const FrenetBuffers* buf, const double* time, int64_t time_stride,
+                         double lookup_period, double d_d_s, int32_t num_sample, int32_t* status, frenet_stream_t stream);
+
 /* Device-side cone gate of the proximity sensor: active[b][o] = 1 iff obstacle o of scenario b lies inside the cone of
  * length `range` and half-aperture `aperture` ahead of robot_pose[b] = (x, y, theta).
  * Replaces ProximitySensor.sense (lib/sensor/proximity_sensor.py:41-75) for a whole batch; obs_xy: [n_scen][n_obs][2]. */

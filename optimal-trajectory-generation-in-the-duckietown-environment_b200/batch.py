@@ -182,6 +182,31 @@ class BatchPlanner:
         self._place()
         e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
 
+    def replanner(self, time, robot_pose=None, sensor=None, obs_xy=None, sync: bool = True):
+        """One `planner.replanner(time)` for every scenario WITHOUT a host round trip for the planner state
+        (trajectory_planner.py:206-212, 223-234): the new initial state is the previous (masked) winner sampled at `time`,
+        taken on the device; then the pipeline runs again.  Call `plan(...)` once first (it plays the role of
+        `initialize`).  robot_pose + sensor=(range, aperture) re-evaluate the cone gate; obs_xy moves the obstacles."""
+        e = self.engine
+        regions = []
+        if robot_pose is not None:
+            e.robot_pose[:] = robot_pose
+            regions.append("robot_pose")
+        if obs_xy is not None:
+            e.obs_xy[:] = obs_xy
+            regions.append("obs_xy")
+        if regions:
+            e.upload_region(*regions)
+        lookup = getattr(self.p, "sampling_t", None) if self.variant == "dt_obstacles" else self.p.delta_t
+        e.advance_state(time, lookup, self.p.d_d_s, self.p.num_sample)
+        if self.n_obs and sensor is not None:
+            e.sensor_gate(float(sensor[0]), float(sensor[1]))
+        e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
+        e.download(sync=sync)
+        if sync:
+            self._n_v_sum = int(e.result["n_valid"].sum()) // max(self.geom.n_t * self.geom.n_d, 1)
+        return e.result
+
     @property
     def launches_per_plan(self) -> int:
         n = bin(self.stages).count("1")

@@ -932,6 +932,45 @@ __global__ void __launch_bounds__(256) predict_obstacles(FrenetPath path, const 
     }
 }
 
+// replan_ctot's bookkeeping on the device (trajectory_planner.py:183-195, 206-212, 120), one thread per scenario.
+__global__ void __launch_bounds__(128) advance_state(FrenetLattice L, FrenetBuffers B, const double* __restrict__ time, int64_t time_stride,
+                                                     double lookup_period, double q, int num_sample, int32_t* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.n_scen) return;
+    const int n = B.winner_steps[b];
+    if (n <= 0) {
+        if (status) status[b] = 1;
+        return;
+    }
+    const double* w = B.winner + (int64_t)b * FRENET_WINNER_ROWS * L.n_pad_max;
+    const double t = time[(int64_t)b * time_stride];
+    int k;
+    if (t <= w[0]) k = 0;
+    else if (t >= w[n - 1]) k = n - 1;
+    else {
+        k = (int)rint((t - w[0]) / lookup_period);      // Python round(): half to even
+        k = k < 0 ? k + n : k;                          // (a negative index would wrap like a Python list)
+        k = min(max(k, 0), n - 1);
+    }
+    double* st = const_cast<double*>(B.state) + (int64_t)b * 6;
+    const int npm = L.n_pad_max;
+    st[0] = w[1 * npm + k]; st[1] = w[2 * npm + k]; st[2] = w[3 * npm + k];     // d, dd, ddd
+    st[3] = w[5 * npm + k];
+    const double ds0 = w[6 * npm + k];
+    st[4] = ds0;
+    st[5] = w[7 * npm + k];                                                       // s, ds, dds
+    const_cast<double*>(B.scal)[(int64_t)b * 3 + 2] = t;
+    // np.arange(round(ds0 - q n), round(ds0 + q n + q), q): length ceil((stop - start) / step), values start + i * ((start + step) - start)
+    const double lo = rint(ds0 - q * num_sample), hi = rint(ds0 + q * num_sample + q);
+    int nv = (int)ceil((hi - lo) / q);
+    nv = min(max(nv, 0), L.n_v_cap);
+    const double delta = (lo + q) - lo;
+    double* av = const_cast<double*>(L.axis_v) + (int64_t)b * L.n_v_cap;
+    for (int i = 0; i < L.n_v_cap; ++i) av[i] = lo + (double)i * delta;
+    const_cast<int32_t*>(L.n_v)[b] = nv;
+    if (status) status[b] = 0;
+}
+
 // Cone gate of the proximity sensor (lib/sensor/proximity_sensor.py:41-75), one thread per (scenario, obstacle).
 __global__ void __launch_bounds__(256) sensor_gate(const double* __restrict__ pose, const double* __restrict__ obs_xy, int n_scen, int O,
                                                    double range, double aperture, uint8_t* __restrict__ active) {
@@ -1322,6 +1361,17 @@ int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const 
     predict_obstacles<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*path, obs_s, obs_d, obs_speed, t0, t0_stride, n_scen, n_obs,
                                                                              n_steps, period, obs_xy_t);
     FRENET_CHECK_LAUNCH("predict_obstacles");
+    return FRENET_OK;
+}
+
+int frenet_advance_state(const FrenetLattice* L, const FrenetBuffers* B, const double* time, int64_t time_stride, double lookup_period,
+                         double d_d_s, int32_t num_sample, int32_t* status, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!B || !B->winner || !B->winner_steps || !B->state || !B->scal || !time) return fail(FRENET_ERR_BAD_ARG, "advance: NULL buffer");
+    if (!(lookup_period > 0.0) || !(d_d_s > 0.0) || num_sample < 0) return fail(FRENET_ERR_BAD_ARG, "advance: bad interval parameters");
+    advance_state<<<(L->n_scen + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*L, *B, time, time_stride, lookup_period, d_d_s, num_sample,
+                                                                             status);
+    FRENET_CHECK_LAUNCH("advance_state");
     return FRENET_OK;
 }
 

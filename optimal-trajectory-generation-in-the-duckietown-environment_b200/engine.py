@@ -276,6 +276,38 @@ class FrenetEngine:
         """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles)."""
         self._in_dev.copy_(self._in_host, non_blocking=True)
 
+    def upload_region(self, *names):
+        """H2D of individual input arrays of the packed block (e.g. "robot_pose", "obs_xy") without touching the rest -
+        used when the planner state itself lives on the device between replans."""
+        sizes = {"state": self.n_scen * 48, "scal": self.n_scen * 24, "axis_v": self.n_scen * self.n_v_cap * 8,
+                 "target": self.n_scen * self.geom.n_t * 24, "obs_xy": self.n_scen * max(self.n_obs, 1) * 16,
+                 "obs_sd": self.n_scen * max(self.n_obs, 1) * 16, "obs_speed": self.n_scen * max(self.n_obs, 1) * 8,
+                 "robot_pose": self.n_scen * 24, "n_v": self.n_scen * 4, "obs_active": self.n_scen * max(self.n_obs, 1)}
+        for name in names:
+            o = self._in_offs[name]
+            self._in_dev[o:o + sizes[name]].copy_(self._in_host[o:o + sizes[name]], non_blocking=True)
+
+    def advance_state(self, time, lookup_period: float, d_d_s: float, num_sample: int):
+        """Device-side replan bookkeeping (frenet_advance_state): next state = gathered winner at `time`, new V axes."""
+        if not hasattr(self, "_time_dev") or self._time_dev.numel() != self.n_scen:
+            self._time_dev = torch.empty(self.n_scen, dtype=torch.float64, device=self.device)
+            self._adv_status = torch.zeros(self.n_scen, dtype=torch.int32, device=self.device)
+        if np.ndim(time) == 0:
+            self._time_dev.fill_(float(time))
+        else:
+            self._time_dev.copy_(torch.as_tensor(np.ascontiguousarray(time, dtype=np.float64)), non_blocking=True)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_advance_state(C.byref(self.L), C.byref(self.B), self._time_dev.data_ptr(), 1, float(lookup_period),
+                                               float(d_d_s), int(num_sample), self._adv_status.data_ptr(), C.c_void_p(stream)))
+
+    def device_state(self):
+        """(state [B][6], scal [B][3], n_v [B]) as they currently are ON THE DEVICE."""
+        o, B = self._in_offs, self.n_scen
+        st = self._in_dev[o["state"]:o["state"] + B * 48].cpu().numpy().view(np.float64).reshape(B, 6)
+        sc = self._in_dev[o["scal"]:o["scal"] + B * 24].cpu().numpy().view(np.float64).reshape(B, 3)
+        nv = self._in_dev[o["n_v"]:o["n_v"] + B * 4].cpu().numpy().view(np.int32)
+        return st, sc, nv
+
     def launch(self, params: nat.FrenetParams, path: PathHandle | None, stages: int, use_mask: int = 0,
                gather_sel: int = nat.SEL_CTOT, n_obs: int | None = None):
         """Enqueue the selected pipeline stages on torch's current stream (asynchronous)."""

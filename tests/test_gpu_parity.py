@@ -627,3 +627,37 @@ def test_device_sensor_gate_and_batched_follow_mode():
     # and back to velocity keeping on the same planner object
     r = bp.plan(np.stack([x["p0"] for x in g]), np.stack([x["s0"] for x in g]), np.array([float(x["time"]) for x in g]))
     assert (bp.engine.cost[2].cpu().numpy() == 0).all() and bp.params.follow == 0
+
+
+@pytest.mark.parametrize("kind", ["full", "static", "moving"])
+def test_device_resident_replan_chain_matches_reference_runs(kind):
+    """SURVEY section 8f row 1 (planner side): the replan loop of the reference's experiments with the planner state
+    kept on the device between replans (frenet_advance_state), for a batch of identical agents.  Driven with the
+    recorded robot poses / obstacle positions, every step's state and chosen candidate equal the reference run."""
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.planner import TrajectoryPlannerParams
+    z = golden(f"sim_planner_{kind}")
+    B = 3
+    n_obs = 0 if kind == "full" else 10
+    bp = BatchPlanner(TrajectoryPlannerParams(), Circle(8, 5, 2), B, n_obs)
+    rep = lambda a: np.repeat(np.asarray(a)[None], B, axis=0)
+    kw = {}
+    if n_obs:
+        kw = dict(obs_xy=rep(z["obs_all_xy"][0]), obs_active=np.zeros((B, 10), dtype=np.uint8))   # initialize(): nothing sensed yet
+    r = bp.plan(rep(z["init_p0"]), rep(z["init_s0"]), np.full(B, z["time"][0]), **kw)
+    assert (r.records["argmin_masked"] == int(z["init_argmin"])).all()
+    ref_pick = z["argmin"] if kind == "full" else z["argmin_masked"]
+    for i in range(499):
+        step_kw = {}
+        if n_obs:
+            step_kw = dict(robot_pose=rep(z["robot_pose_in"][i]), sensor=(3.5, np.pi / 6), obs_xy=rep(z["obs_all_xy"][i]))
+        rec = bp.replanner(float(z["time"][i]), **step_kw)
+        assert (rec["argmin_masked"] == ref_pick[i]).all(), f"{kind}: step {i}"
+        assert (rec["argmin_ctot"] == z["argmin"][i]).all() and (rec["n_valid"] == z["ncand"][i]).all()
+        if i % 25 == 0 or i == 498:
+            st, sc, nv = bp.engine.device_state()
+            assert_close(st[:, :3], rep(z["p0"][i]), GPU_RTOL, f"{kind}: p0 @ {i}", atol_scale=1.0)
+            assert_close(st[:, 3:], rep(z["s0"][i]), GPU_RTOL, f"{kind}: s0 @ {i}", atol_scale=1.0)
+            assert (sc[:, 2] == z["time"][i]).all() and (nv == len(np.arange(*z["dsi"][i]))).all()
+    assert bp.cand_timesteps() == B * (int(z["ncand"][498]) // 64) * 16 * (11 + 16 + 21 + 26)
