@@ -522,6 +522,57 @@ def gen_dt_sequences():
     save("dt_sequences", **out)
 
 
+def gen_follow_fallback():
+    """The branch of the moving-obstacle driver that the canned run never takes (test_moving_obstacle_planner.py:92-97):
+    every candidate is blocked, so the planner is re-run in follow mode behind the first blocking obstacle.  A slow
+    obstacle is parked on the track just ahead of the robot; the reference driver loop is run for a few steps."""
+    t_vect, robot, trajectory, transformer, controller, planner = _sim_objects()
+    np.random.seed(11)
+    ob = MovingObstacle(np.array([1.5, 0.0]), trajectory)
+    # the lattice is started at arc length 0.5 (below); the obstacle sits 0.5 m further on - inside the robot radius of the
+    # point every candidate starts from - and moves on at 0.3 m/s
+    ob.trajectory.offset, ob.trajectory.speed, ob.trajectory.time_offset = 0, 0.3, 1.0
+    ob.step(0)
+    sensor = ProximitySensor(3.5, np.pi / 6)
+    sensor.attach(robot)
+    sensor.set_obstacle([ob])
+    n = 12
+    rec = dict(time=t_vect[:n].copy(), fired=np.zeros(n, dtype=np.uint8), ret_s=np.zeros((n, 3)), ret_p=np.zeros((n, 3)),
+               ncand=np.zeros(n, dtype=np.int32), argmin=np.zeros(n, dtype=np.int32), ctot_min=np.zeros(n),
+               robot_pose=np.zeros((n, 3)), si=np.zeros((n, 3)), obs_xy=np.zeros((n, 2)))
+    robot_p = robot.p
+    transformer.estimatePosition(trajectory, robot_p)
+    f = transformer.transform(robot_p)
+    planner.initialize(t0=t_vect[0], p0=(f[1], 0.0, 0.0), s0=(0.5, 0.0, 0.0))
+    for i in range(n):
+        est_pt = transformer.estimatePosition(trajectory, robot_p)
+        robot_fpose = transformer.transform(robot_p)
+        pos_s, pos_d = planner.replanner(t_vect[i])
+        paths = ref_moving.frenet_to_glob(planner, trajectory, planner.paths)
+        sensor.step_obstacle(t_vect[i])
+        rec["obs_xy"][i] = ob.position
+        planner.paths, leading = ref_moving.check_paths(paths, sensor, robot_p)
+        if len(planner.paths) == 0:
+            rec["fired"][i] = 1
+            s_target = leading[0].trajectory
+            s_target.set_transformer(transformer)
+            pos_s, pos_d = planner.replanner(t_vect[i], s_target=s_target)
+            ref_moving.frenet_to_glob(planner, trajectory, planner.paths)
+        planner.opt_path_tot = min(planner.paths, key=attrgetter('ctot'))
+        rec["ret_s"][i], rec["ret_p"][i] = pos_s, pos_d
+        rec["ncand"][i] = len(planner.paths)
+        rec["argmin"][i] = planner.paths.index(planner.opt_path_tot)
+        rec["ctot_min"][i] = planner.opt_path_tot.ctot
+        rec["si"][i] = planner.si_interval
+        error = np.array([0, pos_d[0]]) - robot_fpose[0:2]
+        derror = np.array([pos_s[1], pos_d[1]])
+        u = controller.compute(robot_fpose, error, derror, trajectory.compute_curvature(est_pt))
+        robot_p, _ = robot.step(u, 0.1)
+        rec["robot_pose"][i] = robot_p
+    print(f"  follow fallback fired in {int(rec['fired'].sum())} of {n} steps; candidates {rec['ncand'].tolist()}")
+    save("follow_fallback", **rec)
+
+
 GENERATORS = {
     "kat_variants": gen_kat_variants,
     "paths": gen_paths,
@@ -534,6 +585,7 @@ GENERATORS = {
     "dense_config4": gen_dense_config4,
     "config5_sample": gen_config5_sample,
     "dt_sequences": gen_dt_sequences,
+    "follow_fallback": gen_follow_fallback,
 }
 
 if __name__ == "__main__":

@@ -280,3 +280,56 @@ def test_driver_functions_on_plain_lists_and_all_blocked():
     assert len(kept) == 0 and len(lead) == len(paths)
     with pytest.raises(ValueError):
         drivers.best_path(kept)
+
+
+def test_follow_mode_fallback_when_every_candidate_is_blocked():
+    """The branch the canned moving-obstacle run never takes (test_moving_obstacle_planner.py:92-97): all candidates
+    collide -> re-plan in follow mode behind the first blocking obstacle; recorded from the reference driver loop."""
+    import otg_b200  # noqa: F401
+    from otg_b200 import drivers
+    from otg_b200.drivers import moving_obstacle_planner as mv
+    from otg_b200.sensor import ProximitySensor, MovingObstacle
+    z = golden("follow_fallback")
+    el = mv.default_elements()
+    np.random.seed(11)
+    ob = MovingObstacle(np.array([1.5, 0.0]), el.trajectory)
+    ob.trajectory.offset, ob.trajectory.speed, ob.trajectory.time_offset = 0, 0.3, 1.0
+    ob.step(0)
+    sensor = ProximitySensor(3.5, np.pi / 6)
+    sensor.attach(el.robot)
+    sensor.set_obstacle([ob])
+    planner, trajectory, transformer, controller, robot = el.planner, el.trajectory, el.transformer, el.controller, el.robot
+    robot_p = robot.p
+    transformer.estimatePosition(trajectory, robot_p)
+    f = transformer.transform(robot_p)
+    planner.initialize(t0=el.t_vect[0], p0=(f[1], 0.0, 0.0), s0=(0.5, 0.0, 0.0))
+    fired = []
+    for i in range(len(z["time"])):
+        t = el.t_vect[i]
+        est_pt = transformer.estimatePosition(trajectory, robot_p)
+        robot_fpose = transformer.transform(robot_p)
+        pos_s, pos_d = planner.replanner(t)
+        paths = drivers.frenet_to_glob(planner, trajectory, planner.paths)
+        sensor.step_obstacle(t)
+        assert_close(ob.position, z["obs_xy"][i], 1e-12, f"obstacle @ {i}", atol_scale=10.0)
+        planner.paths, leading = mv.check_paths(paths, sensor, robot_p)
+        if len(planner.paths) == 0:
+            fired.append(i)
+            assert len(leading) == 320 and all(o is ob for o in leading)
+            s_target = leading[0].trajectory
+            s_target.set_transformer(transformer)
+            pos_s, pos_d = planner.replanner(t, s_target=s_target)
+            drivers.frenet_to_glob(planner, trajectory, planner.paths)
+        planner.opt_path_tot = drivers.best_path(planner.paths)
+        assert len(planner.paths) == int(z["ncand"][i]), i
+        assert planner.paths.index(planner.opt_path_tot) == int(z["argmin"][i]), i
+        assert planner.opt_path_tot.ctot == pytest.approx(float(z["ctot_min"][i]), rel=RT)
+        assert_close(np.array(pos_s), z["ret_s"][i], RT, f"ret_s @ {i}", atol_scale=1.0)
+        assert_close(np.array(pos_d), z["ret_p"][i], RT, f"ret_p @ {i}", atol_scale=1.0)
+        assert tuple(planner.si_interval) == tuple(z["si"][i])
+        error = np.array([0, pos_d[0]]) - robot_fpose[0:2]
+        derror = np.array([pos_s[1], pos_d[1]])
+        u = controller.compute(robot_fpose, error, derror, trajectory.compute_curvature(est_pt))
+        robot_p, _ = robot.step(u, 0.1)
+        assert_close(robot_p, z["robot_pose"][i], 1e-9, f"pose @ {i}", atol_scale=10.0)
+    assert fired == np.nonzero(z["fired"])[0].tolist() and len(fired) == 5
