@@ -255,6 +255,21 @@ int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const 
 int frenet_advance_state(const FrenetLattice* lat, const FrenetBuffers* buf, const double* time, int64_t time_stride,
                          double lookup_period, double d_d_s, int32_t num_sample, int32_t* status, frenet_stream_t stream);
 
+/* Robot side of the closed loop for a batch of agents; per-agent scalar work kept on the device so
+ * that a simulation step needs no host round trip.
+ *
+ * frenet_sim_project - FrenetGNTransformOld.estimatePosition + transform (lib/transform/gn_transform_old.py:18-76): `max_iter`
+ * damped Gauss-Newton steps on the arc length estimate (in/out, [n]), then the robot pose [n][3] expressed in the Frenet
+ * frame anchored there -> fpose [n][3]; curvature [n] = trajectory.compute_curvature(estimate).
+ *
+ * frenet_sim_control_step - FrenetIOLController.compute (lib/controller/ctrl_frenet_iol.py:63-103) with the planner's
+ * output (state [n][6] = p0, dp0, ddp0, s0, ds0, dds0 as returned by replanner) followed by Unicycle.step
+ * (lib/platform/unicycle.py:16-81): pose [n][3] is advanced in place, control [n][2] = (v, omega). */
+int frenet_sim_project(const FrenetPath* path, const double* pose, double* estimate, int32_t max_iter, double damping, double* fpose,
+                       double* curvature, int32_t n, frenet_stream_t stream);
+int frenet_sim_control_step(const double* fpose, const double* state, const double* curvature, double b, double kp_s, double kp_d,
+                            double dt, double* pose, double* control, int32_t n, frenet_stream_t stream);
+
 /* Device-side cone gate of the proximity sensor: active[b][o] = 1 iff obstacle o of scenario b lies inside the cone of
  * length `range` and half-aperture `aperture` ahead of robot_pose[b] = (x, y, theta).
  * Replaces ProximitySensor.sense (lib/sensor/proximity_sensor.py:41-75) for a whole batch; obs_xy: [n_scen][n_obs][2]. */

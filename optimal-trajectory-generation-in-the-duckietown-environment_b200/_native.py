@@ -104,6 +104,10 @@ def _load():
                                                C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
         "frenet_advance_state": (C.c_int, [P(FrenetLattice), P(FrenetBuffers), C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32,
                                            C.c_void_p, C.c_void_p]),
+        "frenet_sim_project": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p]),
+        "frenet_sim_control_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                              C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
         "frenet_sensor_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
         "frenet_polyline_collision": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double,
                                                 C.c_void_p, C.c_void_p, C.c_void_p]),

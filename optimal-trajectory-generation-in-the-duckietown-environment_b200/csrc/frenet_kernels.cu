@@ -971,6 +971,126 @@ __global__ void __launch_bounds__(128) advance_state(FrenetLattice L, FrenetBuff
     if (status) status[b] = 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Robot side of the closed loop (per-agent scalar work)
+// ------------------------------------------------------------------------------------------------
+// Path point and first derivative as the host classes give them (circle: forward chord over dt).
+__device__ __forceinline__ void path_pt_grad(int kind, const double* __restrict__ circle, const double* __restrict__ tab, int n_knots,
+                                             double s, double& px, double& py, double& gx, double& gy) {
+    if (kind == FRENET_PATH_CIRCLE) {
+        circle_pt(circle, s, px, py);
+        double qx, qy;
+        const double h = circle[3];
+        circle_pt(circle, s + h, qx, qy);
+        gx = (qx - px) / h;
+        gy = (qy - py) / h;
+    } else {
+        spline_eval(tab, n_knots, s, px, py, gx, gy);
+    }
+}
+
+// trajectory.compute_curvature (circle_trajectory.py:88-117: 1/r on the four arcs; spline_trajectory.py:173-181)
+__device__ __forceinline__ double path_curvature(int kind, const double* __restrict__ c, const double* __restrict__ tab, int n, double t) {
+    if (kind == FRENET_PATH_CIRCLE) {
+        const double r = c[2], period = c[4];
+        const double* b = c + 5;
+        if (t >= period) t = fmod(t, period);
+        const bool straight = (t >= 0.0 && t < b[0]) || (t >= b[1] && t < b[2]) || (t >= b[3] && t < b[4]) || (t >= b[5] && t < b[6]);
+        return straight ? 0.0 : 1.0 / r;
+    }
+    const double first = tab[0], last = tab[(n - 1) * 9];
+    double dx, dy, ddx, ddy;
+    if (t < first) { dx = dy = ddx = ddy = first; }
+    else if (t >= last) { dx = dy = ddx = ddy = last; }
+    else {
+        int lo = 0, hi = n - 1;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (tab[mid * 9] <= t) lo = mid; else hi = mid;
+        }
+        const double* q = tab + lo * 9;
+        const double u = t - q[0];
+        dx = q[2] + 2.0 * q[3] * u + 3.0 * q[4] * (u * u);
+        dy = q[6] + 2.0 * q[7] * u + 3.0 * q[8] * (u * u);
+        ddx = 2.0 * q[3] + 6.0 * q[4] * u;
+        ddy = 2.0 * q[7] + 6.0 * q[8] * u;
+    }
+    return (ddy * dx - ddx * dy) / (dx * dx + dy * dy);
+}
+
+__global__ void __launch_bounds__(128) sim_project(FrenetPath path, const double* __restrict__ pose, double* __restrict__ estimate,
+                                                   int max_iter, double damping, double* __restrict__ fpose,
+                                                   double* __restrict__ curvature, int n) {
+    extern __shared__ __align__(16) double tab[];
+    if (path.kind == FRENET_PATH_SPLINE) {
+        for (int i = threadIdx.x; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+        __syncthreads();
+    }
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const double x = pose[3 * a], y = pose[3 * a + 1], th = pose[3 * a + 2];
+    double s = estimate[a];
+    double px, py, gx, gy;
+    for (int it = 0; it < max_iter; ++it) {   // do_ls, gn_transform_old.py:93-106
+        path_pt_grad(path.kind, path.circle, tab, path.n_knots, s, px, py, gx, gy);
+        const double ex = px - x, ey = py - y;
+        const double H = __dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), damping);
+        const double bb = __dadd_rn(__dmul_rn(gx, ex), __dmul_rn(gy, ey));
+        s += -bb / H;
+    }
+    estimate[a] = s;
+    path_pt_grad(path.kind, path.circle, tab, path.n_knots, s, px, py, gx, gy);
+    const double tr = atan2(gy, gx);
+    double sn, cs;
+    sincos(tr, &sn, &cs);
+    // R^T p - R^T t with R = [[c, -s], [s, c]] (transform, :58-68)
+    const double fx = __dadd_rn(__dadd_rn(__dmul_rn(cs, x), __dmul_rn(sn, y)), -__dadd_rn(__dmul_rn(cs, px), __dmul_rn(sn, py)));
+    const double fy = __dadd_rn(__dadd_rn(__dmul_rn(-sn, x), __dmul_rn(cs, y)), -__dadd_rn(__dmul_rn(-sn, px), __dmul_rn(cs, py)));
+    fpose[3 * a] = fx;
+    fpose[3 * a + 1] = fy;
+    fpose[3 * a + 2] = th - tr;
+    curvature[a] = path_curvature(path.kind, path.circle, tab, path.n_knots, s);
+}
+
+__global__ void __launch_bounds__(128) sim_control_step(const double* __restrict__ fpose, const double* __restrict__ state,
+                                                        const double* __restrict__ curvature, double b, double kp_s, double kp_d, double dt,
+                                                        double* __restrict__ pose, double* __restrict__ control, int n) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const double* st = state + 6 * a;              // p0, dp0, ddp0, s0, ds0, dds0: what replanner returned
+    const double d = fpose[3 * a + 1], t = fpose[3 * a + 2], k = curvature[a];
+    // error = [0, pos_d[0]] - robot_fpose[:2]; the controller zeroes the s component (ctrl_frenet_iol.py:97-98)
+    const double pe0 = 0.0 * kp_s, pe1 = (st[0] - d) * kp_d;
+    (void)pe0;
+    const double r0 = st[4] + 0.0, r1 = st[1] + pe1;   // feed-forward (ds, dd) + proportional term
+    double sn, cs;
+    sincos(t, &sn, &cs);
+    const double m00 = cs * (1.0 + b * k * sn) / (1.0 - k * d), m01 = -b * sn;
+    const double m10 = sn - (k * cs) / (1.0 - k * d), m11 = b * cs;
+    const double det = m00 * m11 - m01 * m10;
+    const double v = (m11 * r0 - m01 * r1) / det, w = (-m10 * r0 + m00 * r1) / det;
+    control[2 * a] = v;
+    control[2 * a + 1] = w;
+    // Unicycle.step: closed-form pose increment with the reference's truncated series (unicycle.py:24-28, 52-66)
+    double* p = pose + 3 * a;
+    const double drho = dt * v, dth = dt * w;
+    const double t2 = dth * dth, t3 = t2 * dth, t4 = t2 * t2, t5 = t4 * dth, t6 = t3 * t3, t7 = t6 * dth;
+    const double Sin = 1.0 - 1.0 / 6 * t2 + 1.0 / 120 * t4 - 1.0 / 5040 * t6;
+    const double Cos = 1.0 / 2 * dth - 1.0 / 24 * t3 + 1.0 / 720 * t5 - 1.0 / 40320 * t7;
+    const double dx = drho * Sin, dy = drho * Cos;
+    double s0, c0, s1, c1;
+    sincos(p[2], &s0, &c0);
+    sincos(dth, &s1, &c1);
+    const double nx = __dadd_rn(__dadd_rn(__dmul_rn(c0, dx), __dmul_rn(-s0, dy)), p[0]);
+    const double ny = __dadd_rn(__dadd_rn(__dmul_rn(s0, dx), __dmul_rn(c0, dy)), p[1]);
+    const double nth = atan2(__dadd_rn(__dmul_rn(s0, c1), __dmul_rn(c0, s1)), __dadd_rn(__dmul_rn(c0, c1), __dmul_rn(-s0, s1)));
+    const double dpt = nth - p[2];
+    const double vx = (nx - p[0]) / dt, vy = (ny - p[1]) / dt, vt = atan2(sin(dpt), cos(dpt)) / dt;
+    p[0] += dt * vx;     // self.p += dt * vel
+    p[1] += dt * vy;
+    p[2] += dt * vt;
+}
+
 // Cone gate of the proximity sensor (lib/sensor/proximity_sensor.py:41-75), one thread per (scenario, obstacle).
 __global__ void __launch_bounds__(256) sensor_gate(const double* __restrict__ pose, const double* __restrict__ obs_xy, int n_scen, int O,
                                                    double range, double aperture, uint8_t* __restrict__ active) {
@@ -1372,6 +1492,29 @@ int frenet_advance_state(const FrenetLattice* L, const FrenetBuffers* B, const d
     advance_state<<<(L->n_scen + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*L, *B, time, time_stride, lookup_period, d_d_s, num_sample,
                                                                              status);
     FRENET_CHECK_LAUNCH("advance_state");
+    return FRENET_OK;
+}
+
+int frenet_sim_project(const FrenetPath* path, const double* pose, double* estimate, int32_t max_iter, double damping, double* fpose,
+                       double* curvature, int32_t n, frenet_stream_t stream) {
+    if (int rc = check_path(path)) return rc;
+    if (n < 0 || max_iter < 0) return fail(FRENET_ERR_BAD_ARG, "sim project: negative size");
+    if (n == 0) return FRENET_OK;
+    if (!pose || !estimate || !fpose || !curvature) return fail(FRENET_ERR_BAD_ARG, "sim project: NULL buffer");
+    const size_t smem = (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0) * sizeof(double);
+    if (int rc = set_smem(sim_project, smem, "sim project: spline table too large for shared memory")) return rc;
+    sim_project<<<(n + 127) / 128, 128, smem, (cudaStream_t)stream>>>(*path, pose, estimate, max_iter, damping, fpose, curvature, n);
+    FRENET_CHECK_LAUNCH("sim_project");
+    return FRENET_OK;
+}
+
+int frenet_sim_control_step(const double* fpose, const double* state, const double* curvature, double b, double kp_s, double kp_d,
+                            double dt, double* pose, double* control, int32_t n, frenet_stream_t stream) {
+    if (n < 0) return fail(FRENET_ERR_BAD_ARG, "sim control: negative size");
+    if (n == 0) return FRENET_OK;
+    if (!fpose || !state || !curvature || !pose || !control) return fail(FRENET_ERR_BAD_ARG, "sim control: NULL buffer");
+    sim_control_step<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(fpose, state, curvature, b, kp_s, kp_d, dt, pose, control, n);
+    FRENET_CHECK_LAUNCH("sim_control_step");
     return FRENET_OK;
 }
 

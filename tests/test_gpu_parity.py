@@ -661,3 +661,26 @@ def test_device_resident_replan_chain_matches_reference_runs(kind):
             assert_close(st[:, 3:], rep(z["s0"][i]), GPU_RTOL, f"{kind}: s0 @ {i}", atol_scale=1.0)
             assert (sc[:, 2] == z["time"][i]).all() and (nv == len(np.arange(*z["dsi"][i]))).all()
     assert bp.cand_timesteps() == B * (int(z["ncand"][498]) // 64) * 16 * (11 + 16 + 21 + 26)
+
+
+@pytest.mark.parametrize("kind", ["full", "static", "moving"])
+def test_device_resident_closed_loop_matches_reference_runs(kind):
+    """SURVEY section 8f row 1, whole loop: projection, replan, sensor gate, controller and unicycle on the device for a
+    batch of agents; robot trajectory and chosen candidates against the recorded reference experiments."""
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200.batch_sim import BatchSimulator
+    from otg_b200.planner import TrajectoryPlannerParams
+    z = golden(f"sim_planner_{kind}")
+    B = 2
+    n_obs = 0 if kind == "full" else 10
+    sim = BatchSimulator(TrajectoryPlannerParams(), Circle(8, 5, 2), B, n_obs)
+    rep = lambda a: np.repeat(np.asarray(a)[None], B, axis=0)
+    r = sim.reset(np.zeros((B, 3)), float(z["time"][0]), obs_xy=rep(z["obs_all_xy"][0]) if n_obs else None)
+    assert (r.records["argmin_masked"] == int(z["init_argmin"])).all()
+    ref_pick = z["argmin"] if kind == "full" else z["argmin_masked"]
+    for i in range(499):
+        moved = rep(z["obs_all_xy"][i]) if kind == "moving" else None
+        rec = sim.step(float(z["time"][i]), obs_xy=moved, sync=True)
+        assert (rec["argmin_masked"] == ref_pick[i]).all(), f"{kind}: step {i}"
+        if i % 20 == 0 or i == 498:
+            assert_close(sim.robot_pose(), rep(z["robot_pose"][i]), 1e-8, f"{kind}: robot pose @ {i}", atol_scale=20.0)
