@@ -218,6 +218,42 @@ def predicted_mode(wl, steps, dev):
     return out
 
 
+def closed_loop(dev, n_agents=8192, steps=30):
+    """SURVEY section 8f row 1 leg: whole closed-loop steps (projection, replan, cone gate, collision filter, controller,
+    unicycle) for `n_agents` agents of BASELINE config 2 (default lattice, circle path, 10 static obstacles) with all
+    per-step state on the device.  The reference runs one agent at ~122 ms per step on one CPU thread."""
+    import torch
+    import otg_b200  # noqa: F401
+    from otg_b200.batch_sim import BatchSimulator
+    from otg_b200.drivers.obstacle_planner import seeded_obstacles
+    from otg_b200.planner import TrajectoryPlannerParams
+    from otg_b200.trajectory import CircleTrajectory2D
+    tr = CircleTrajectory2D(8, 5, 2)
+    pts = seeded_obstacles(np.arange(0.1, 50, 0.1), tr).T
+    sim = BatchSimulator(TrajectoryPlannerParams(), tr, n_agents, 10)
+    rng = np.random.default_rng(1)
+    pose = np.stack([rng.uniform(0, 7, n_agents), rng.uniform(-0.3, 0.3, n_agents), rng.uniform(-0.1, 0.1, n_agents)], 1)
+    sim.reset(pose, 0.1, obs_xy=np.repeat(pts[None], n_agents, 0))
+    t_vect = np.arange(0.1, 50, 0.1)
+    for i in range(5):
+        sim.step(float(t_vect[i]))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(5, 5 + steps):
+        sim.step(float(t_vect[i]))
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    rec = sim.step(float(t_vect[5 + steps]), sync=True)
+    cts = float(rec["n_valid"].sum()) / 64 * 16 * (11 + 16 + 21 + 26)
+    out = {"agents": n_agents, "ms_per_step": ms, "agent_steps_per_s": n_agents / (ms * 1e-3), "candidate_timesteps_per_s": cts / (ms * 1e-3),
+           "agents_with_feasible": int((rec["status"] == 0).sum()), "kernel_launches_per_step": 9}
+    del sim
+    torch.cuda.empty_cache()
+    return out
+
+
 def replan_latency(n_calls=200):
     """Metric 2: wall time of ONE replan through the drop-in planner API, host perf_counter around
     the Python calls (H2D of inputs, kernels, D2H of the result record + winner trajectory, Python return).
@@ -340,11 +376,16 @@ def run_gpu(args):
     cts_step_local = bp.cand_timesteps()
 
     # ---- end-to-end arm: host buffers through the public API ----
+    # Every step copies its own inputs host -> device and its results device -> host; the host stages the NEXT step's
+    # inputs into the pinned block while the GPU works on the current one (the staging block is free again as soon as
+    # the H2D copy has been consumed - `wait_staging_free`).
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        bp.stage_inputs(**wl)
+    bp.stage_inputs(**wl)
+    for i in range(args.steps):
         bp.launch()
+        if i + 1 < args.steps:
+            bp.stage_inputs(**wl)
         res = bp.result()
         allrec = gather(res.records)
     barrier()
@@ -419,12 +460,13 @@ def run_gpu(args):
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
                 "replan_latency": replan_latency() if world == 1 else None,
-                "predicted_obstacles": None,
+                "predicted_obstacles": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
         if world == 1:
             del bp
             torch.cuda.empty_cache()
             line["predicted_obstacles"] = predicted_mode(wl, max(3, args.steps // 3), dev)
+            line["closed_loop"] = closed_loop(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -122,6 +122,7 @@ class BatchPlanner:
         targets [B][n_t][3]: follow mode - quintic longitudinal to the (st, dst, ddst) triples, cost ct
         (trajectory_planner.py:131-144); the V axis then holds the target offsets of `si_interval`."""
         e, B = self.engine, self.n_scen
+        e.wait_staging_free()      # the previous call's H2D copy may still be reading the pinned block
         p0 = np.asarray(p0, dtype=np.float64).reshape(B, 3)
         s0 = np.asarray(s0, dtype=np.float64).reshape(B, 3)
         e.state[:, :3], e.state[:, 3:] = p0, s0
@@ -229,17 +230,21 @@ class BatchPlanner:
     def cand_timesteps(self) -> int:
         return int(self.geom.n_steps.astype(np.int64).sum()) * self.geom.n_d * self._n_v_sum
 
-    def result(self) -> BatchResult:
+    def result(self, copy: bool = False) -> BatchResult:
+        """Wait for the last launch and hand out its results.  The arrays are views of the pinned block the device wrote
+        into - valid until the next launch of this planner; pass copy=True (or call `.copy()` on them) to keep them."""
         torch.cuda.current_stream(self.engine.device).synchronize()
         e = self.engine
-        return BatchResult(e.result.copy(), e.winner.copy(), e.winner_steps.copy(), self.cand_timesteps())
+        if copy:
+            return BatchResult(e.result.copy(), e.winner.copy(), e.winner_steps.copy(), self.cand_timesteps())
+        return BatchResult(e.result, e.winner, e.winner_steps, self.cand_timesteps())
 
     def plan(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None,
              obs_speed=None, robot_pose=None, sensor=None, targets=None) -> BatchResult:
         """Host arrays in, per-scenario results out (synchronous)."""
         self.stage_inputs(p0, s0, t0, dd, desired_speed, obs_s, obs_d, obs_xy, obs_active, obs_speed, robot_pose, sensor, targets)
         self.launch()
-        return self.result()
+        return self.result(copy=True)
 
 
 def plan_sharded(params, trajectory, scenarios: dict, variant: str = "v1", tile: int = 512, group=None):

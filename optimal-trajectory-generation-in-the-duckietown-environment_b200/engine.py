@@ -273,8 +273,19 @@ class FrenetEngine:
 
     # -- launches ------------------------------------------------------------------------------
     def upload(self, stream=None):
-        """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles)."""
+        """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles).  An event marks the
+        end of the copy so that the host may refill the pinned block for the NEXT call while this call's kernels run
+        (`wait_staging_free`)."""
         self._in_dev.copy_(self._in_host, non_blocking=True)
+        if not hasattr(self, "_h2d_done"):
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
+
+    def wait_staging_free(self):
+        """Block until the last `upload()` has finished reading the pinned staging block."""
+        ev = getattr(self, "_h2d_done", None)
+        if ev is not None:
+            ev.synchronize()
 
     def upload_region(self, *names):
         """H2D of individual input arrays of the packed block (e.g. "robot_pose", "obs_xy") without touching the rest -
