@@ -129,6 +129,7 @@ class FrenetEngine:
         self.L = nat.FrenetLattice()
         self.B = nat.FrenetBuffers()
         self._cap_key = None
+        self._graphs = {}
         self._paths = {}
         self.generation = 0
         self.has_xy = False
@@ -143,6 +144,7 @@ class FrenetEngine:
         if key == self._cap_key:
             return
         dev, Bn = self.device, self.n_scen
+        self._graphs.clear()          # captured graphs point into the buffers that are about to be replaced
         self.geom, self.n_v_cap, self.n_obs = geom, int(n_v_cap), n_obs
         nT, nD = geom.n_t, geom.n_d
         R = self.n_v_cap * nT
@@ -272,14 +274,15 @@ class FrenetEngine:
         return h[1]
 
     # -- launches ------------------------------------------------------------------------------
-    def upload(self, stream=None):
+    def upload(self, stream=None, record_event: bool = True):
         """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles).  An event marks the
         end of the copy so that the host may refill the pinned block for the NEXT call while this call's kernels run
         (`wait_staging_free`)."""
         self._in_dev.copy_(self._in_host, non_blocking=True)
-        if not hasattr(self, "_h2d_done"):
-            self._h2d_done = torch.cuda.Event()
-        self._h2d_done.record(torch.cuda.current_stream(self.device))
+        if record_event:
+            if not hasattr(self, "_h2d_done"):
+                self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.device))
 
     def wait_staging_free(self):
         """Block until the last `upload()` has finished reading the pinned staging block."""
@@ -387,6 +390,34 @@ class FrenetEngine:
         self.upload()
         self.launch(params, path, stages, use_mask, gather_sel, n_obs)
         self.download(sync=True)
+
+    def run_graph(self, params, path, stages, use_mask=0, gather_sel=nat.SEL_CTOT, n_obs=None):
+        """`run` replayed from a CUDA graph (H2D copy, kernels, D2H copy as one launch): the launch-bound single-replan
+        path.  The graph bakes in the kernel arguments (parameters, sizes, pointers), so it is keyed by them and
+        re-captured when any of them changes; the per-replan inputs travel through the pinned block, which the graph's
+        copy node reads at replay time."""
+        key = (bytes(params), id(path), int(stages), int(use_mask), int(gather_sel), self.B.n_obs if n_obs is None else int(n_obs),
+               self._cap_key)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) > 16:
+                self._graphs.clear()
+            self.run(params, path, stages, use_mask, gather_sel, n_obs)      # warm-up outside capture (lazy module load, attributes)
+            gen, has_xy, has_coll = self.generation, self.has_xy, self.has_collision
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.upload(record_event=False)
+                self.launch(params, path, stages, use_mask, gather_sel, n_obs)
+                self.download(sync=False)
+            self.generation, self.has_xy, self.has_collision = gen, has_xy, has_coll
+            self._graphs[key] = g
+            return                      # the warm-up run already produced this call's results
+        g.replay()
+        torch.cuda.current_stream(self.device).synchronize()
+        if stages & nat.STAGE_K2:
+            self.generation += 1
+            self.has_xy = bool(stages & nat.STAGE_K3)
+            self.has_collision = bool(stages & nat.STAGE_K4)
 
     # -- views of device data ------------------------------------------------------------------
     def cand_offsets(self, n_v: int):

@@ -261,7 +261,7 @@ class _LatticePlanner(Planner):
             eng.target[0] = self._target_triples(geom.T)
         P = make_params(self, self._rule, period, follow)
         self.__dict__["_params"] = P
-        eng.run(P, None, nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER, 0, nat.SEL_CTOT)
+        eng.run_graph(P, None, nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER, 0, nat.SEL_CTOT)
         self.__dict__["_winner_cache"] = {"ctot": self._frenet_from_winner("argmin_ctot")}
         paths = LatticePaths(self, len(V), follow)
         paths._best["ctot"] = self._winner_cache["ctot"]     # None when the lattice is empty
