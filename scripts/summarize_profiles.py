@@ -24,8 +24,8 @@ def short(n):
 
 seq = [(short(r[idx["Kernel Name"]]), float(r[idx["Metric Value"]]), r[idx["Grid Size"]]) for r in rows[1:]]
 # one pipeline step = points_to_cartesian, k1, fused k2, k5, gather (5 launches); the bench does 3 warm-up steps first
-step_names = ["points_to_cartesian", "k1_coefficients", "k2_evaluate<1, 1, 0>", "k5_argmin", "gather_winner"]
-starts = [i for i in range(len(seq) - 4) if [s[0] for s in seq[i:i + 5]] == step_names]
+step_names = ["points_to_cartesian", "k1_coefficients", "k2_evaluate<1, 1,", "k5_argmin", "gather_winner"]
+starts = [i for i in range(len(seq) - 4) if all(seq[i + j][0].startswith(step_names[j]) for j in range(5))]
 lines = [f"# ncu launch list summary ({tag})", "",
          f"Source: `{os.path.basename(launches)}` (`ncu --metrics gpu__time_duration.sum --clock-control none`, same command as the",
          "bench line: `python bench.py --steps 5 --warmup 3 --no-cpu`).  Per-launch times are cold-cache and serialised:",
@@ -36,12 +36,12 @@ use = starts[3:] if len(starts) > 3 else starts
 tot = collections.OrderedDict((n, 0.0) for n in step_names)
 grid = {}
 for i in use:
-    for n, t, g in seq[i:i + 5]:
-        tot[n] += t
-        grid[n] = g
+    for n0, (n, t, g) in zip(step_names, seq[i:i + 5]):
+        tot[n0] += t
+        grid[n0] = g
 step_total = sum(tot.values())
 for n in step_names:
-    lines.append(f"| `{n}` | {grid.get(n, '')} | {tot[n] / max(len(use), 1) / 1e3:.1f} | {100 * tot[n] / step_total:.1f} % |")
+    lines.append(f"| `{n.rstrip(',')}` | {grid.get(n, '')} | {tot[n] / max(len(use), 1) / 1e3:.1f} | {100 * tot[n] / max(step_total, 1e-9):.1f} % |")
 lines += ["", "All launches of the capture, by kernel:", "", "| kernel | launches | total ms | mean us |", "|---|---|---|---|"]
 agg = collections.OrderedDict()
 for n, t, g in seq:
