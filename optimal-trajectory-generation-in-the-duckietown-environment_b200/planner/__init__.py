@@ -1,5 +1,5 @@
 """Planner package: same exports as the reference's `lib/planner/__init__.py:5-10`."""
-from .planner import Planner
+from .base import Planner
 from .frenet import Frenet
 from .params import (TrajectoryPlannerDefaultParams, TrajectoryPlannerParams,
                      TrajectoryPlannerDefaultParamsDT, TrajectoryPlannerParamsDT,

@@ -22,7 +22,7 @@ from ..engine import FrenetEngine, LatticeGeometry, make_params
 from .frenet import Frenet
 from .params import (TrajectoryPlannerParams, TrajectoryPlannerParamsDT, TrajectoryPlannerParamsDTObstacles,
                      TrajectoryPlannerParamsOptimal)
-from .planner import Planner
+from .base import Planner
 
 logger = logging.getLogger(__name__)
 
