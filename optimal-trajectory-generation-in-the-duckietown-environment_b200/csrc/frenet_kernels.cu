@@ -718,12 +718,15 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 // ------------------------------------------------------------------------------------------------
 // K3: Frenet -> Cartesian, one CTA per row; the path frame is computed once per (row, step)
 // ------------------------------------------------------------------------------------------------
-constexpr int kChunksInFlight = 4;   // chunks whose loads are issued before the first use (latency hiding)
 
 __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, FrenetPath path, FrenetBuffers B) {
     extern __shared__ __align__(16) double sm[];
-    double* frame = sm;                        // [n_pad_max][4]: px, py, nx, ny
-    double* tab = sm + L.n_pad_max * 4;        // [n_knots][9] spline table staged in shared memory
+    const int npm = L.n_pad_max;
+    double* fpx = sm;                  // [n_pad_max] x 4: path point and unit normal per step
+    double* fpy = fpx + npm;
+    double* fnx = fpy + npm;
+    double* fny = fnx + npm;
+    double* tab = fny + npm;           // [n_knots][9] spline table staged in shared memory
 
     const int64_t br = blockIdx.x;
     const int flags = B.row_flags[br];
@@ -739,30 +742,43 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
     for (int k = tid; k < A.npad; k += blockDim.x) {   // padding samples included: whole sectors are written (see K2)
         double px, py, nx, ny;
         path_frame(path.kind, path.circle, tab, path.n_knots, s_row[k], px, py, nx, ny);
-        frame[k * 4] = px; frame[k * 4 + 1] = py; frame[k * 4 + 2] = nx; frame[k * 4 + 3] = ny;
+        fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
     }
     __syncthreads();
+    // A warp works on TWO candidates at a time and every lane on pairs of steps: four 16-byte loads are in flight per
+    // lane before the first use, which is what hides the HBM latency of this read-modify-write pass.
     const int npad = A.npad;
-    for (int id = warp; id < L.n_d; id += nwarps) {
-        double* blk = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad);
-        const double* d = blk;
-        double* x = blk + 4 * npad;
-        double* y = blk + 5 * npad;
-        for (int kb = 0; kb < npad; kb += kWarp * kChunksInFlight) {
-            double dv[kChunksInFlight];
+    constexpr int kSpan = 2 * kWarp;   // steps covered by one 16-byte access of a warp
+    for (int id = warp; id < L.n_d; id += 2 * nwarps) {
+        const bool two = id + nwarps < L.n_d;
+        double* blk1 = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad);
+        double* blk2 = two ? blk1 + (int64_t)nwarps * (kCandFields * npad) : blk1;
+        for (int kb = 0; kb < npad; kb += 2 * kSpan) {
+            double2 d1[2], d2[2];
 #pragma unroll
-            for (int q = 0; q < kChunksInFlight; ++q) {
-                const int k = kb + q * kWarp + lane;
-                dv[q] = k < npad ? d[k] : 0.0;
+            for (int q = 0; q < 2; ++q) {
+                const int k = kb + q * kSpan + 2 * lane;
+                const bool in = k < npad;
+                d1[q] = in ? *reinterpret_cast<const double2*>(blk1 + k) : make_double2(0.0, 0.0);
+                d2[q] = (in && two) ? *reinterpret_cast<const double2*>(blk2 + k) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int q = 0; q < kChunksInFlight; ++q) {
-                const int k = kb + q * kWarp + lane;
+            for (int q = 0; q < 2; ++q) {
+                const int k = kb + q * kSpan + 2 * lane;
                 if (k < npad) {
-                    const double2 pp = *reinterpret_cast<const double2*>(frame + k * 4);
-                    const double2 nn = *reinterpret_cast<const double2*>(frame + k * 4 + 2);
-                    x[k] = __dadd_rn(pp.x, __dmul_rn(nn.x, dv[q]));   // pt + n * d, unfused like the reference
-                    y[k] = __dadd_rn(pp.y, __dmul_rn(nn.y, dv[q]));
+                    const double2 px = *reinterpret_cast<const double2*>(fpx + k), py = *reinterpret_cast<const double2*>(fpy + k);
+                    const double2 nx = *reinterpret_cast<const double2*>(fnx + k), ny = *reinterpret_cast<const double2*>(fny + k);
+                    // pt + n * d, unfused like the reference
+                    *reinterpret_cast<double2*>(blk1 + 4 * npad + k) =
+                        make_double2(__dadd_rn(px.x, __dmul_rn(nx.x, d1[q].x)), __dadd_rn(px.y, __dmul_rn(nx.y, d1[q].y)));
+                    *reinterpret_cast<double2*>(blk1 + 5 * npad + k) =
+                        make_double2(__dadd_rn(py.x, __dmul_rn(ny.x, d1[q].x)), __dadd_rn(py.y, __dmul_rn(ny.y, d1[q].y)));
+                    if (two) {
+                        *reinterpret_cast<double2*>(blk2 + 4 * npad + k) =
+                            make_double2(__dadd_rn(px.x, __dmul_rn(nx.x, d2[q].x)), __dadd_rn(px.y, __dmul_rn(nx.y, d2[q].y)));
+                        *reinterpret_cast<double2*>(blk2 + 5 * npad + k) =
+                            make_double2(__dadd_rn(py.x, __dmul_rn(ny.x, d2[q].x)), __dadd_rn(py.y, __dmul_rn(ny.y, d2[q].y)));
+                    }
                 }
             }
         }
@@ -848,21 +864,24 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
         const double* xs = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
         const double* ys = xs + A.npad;
         int best = kNoBlocker;   // lowest blocking obstacle index found so far (warp-uniform)
-        for (int kb = 0; kb < A.N; kb += kWarp * kChunksInFlight) {
-            double xv[kChunksInFlight], yv[kChunksInFlight];
+        // two steps per lane, two 64-step spans loaded before the first test (latency hiding)
+        for (int kb = 0; kb < A.N; kb += 4 * kWarp) {
+            double2 xv[2], yv[2];
 #pragma unroll
-            for (int q = 0; q < kChunksInFlight; ++q) {
-                const int k0 = kb + q * kWarp;
-                const int k = k0 + lane;
-                const int kk = k < A.N ? k : (k0 < A.N ? k0 : kb);
-                xv[q] = xs[kk];
-                yv[q] = ys[kk];
+            for (int q = 0; q < 2; ++q) {
+                const int k0 = kb + q * 2 * kWarp;
+                const int k = k0 + 2 * lane;
+                const int kk = k < A.npad ? k : (k0 < A.npad ? k0 : kb);   // npad is even: a pair inside the padding is readable
+                xv[q] = *reinterpret_cast<const double2*>(xs + kk);
+                yv[q] = *reinterpret_cast<const double2*>(ys + kk);
             }
 #pragma unroll
-            for (int q = 0; q < kChunksInFlight; ++q) {
-                const int k0 = kb + q * kWarp;
+            for (int q = 0; q < 2; ++q) {
+                const int k0 = kb + q * 2 * kWarp;
+                const int k = k0 + 2 * lane;
                 if (k0 < A.N)
-                    best = collide_chunk(xv[q], yv[q], k0 + lane < A.N, min(kWarp, A.N - k0), obs, obsf, O, Rf, P.radius_sq, best, lane);
+                    best = collide_pair(xv[q].x, yv[q].x, xv[q].y, yv[q].y, k < A.N, k + 1 < A.N, min(2 * kWarp, A.N - k0), obs, obsf, O,
+                                        Rf, P.radius_sq, best, lane);
             }
         }
         if (lane == 0) {
