@@ -73,9 +73,16 @@ def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
         eng = frenet_paths._engine
         planner = frenet_paths._planner
         n = len(sensed)
-        if n > eng.n_obs:      # grow the obstacle capacity (keeps the lattice: only the small input block moves)
-            raise RuntimeError(f"{n} sensed obstacles exceed the planner's obstacle capacity {eng.n_obs}; "
-                               "construct the planner with _n_obs_cap >= the number of obstacles")
+        if n > eng.n_obs:
+            # more obstacles than the planner's staging capacity (constructor kwarg `_n_obs_cap`, default 64): test the
+            # lattice's Cartesian polylines with the generic kernel instead of re-allocating the lattice buffers
+            frenet_paths.materialize()
+            pos = frenet_paths._positions()
+            f = frenet_paths._fields
+            nst = f["nsteps"]
+            free, first = eng.polyline_collision([f["x"][c, :nst[c]] for c in pos], [f["y"][c, :nst[c]] for c in pos],
+                                                 np.array([ob.position for ob in sensed], dtype=np.float64), robot_radius ** 2)
+            return frenet_paths.filtered(free), sensed, first[~free]
         eng.obs_xy[0, :n] = np.array([ob.position for ob in sensed], dtype=np.float64)
         eng.obs_active[0, :n] = 1
         eng.upload()

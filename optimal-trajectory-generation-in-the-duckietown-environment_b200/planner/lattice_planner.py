@@ -188,7 +188,7 @@ class _LatticePlanner(Planner):
             self.__dict__["_engine_obj"] = e
             self.__dict__["_geom_cache"] = {}
             self.__dict__["_n_v_cap"] = 0
-            self.__dict__.setdefault("_n_obs_cap", 16)     # obstacle-table capacity of check_paths (constructor kwarg)
+            self.__dict__.setdefault("_n_obs_cap", 64)     # obstacle-table capacity of check_paths (constructor kwarg)
         return e
 
     def _sample_period(self):

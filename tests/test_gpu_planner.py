@@ -333,3 +333,30 @@ def test_follow_mode_fallback_when_every_candidate_is_blocked():
         robot_p, _ = robot.step(u, 0.1)
         assert_close(robot_p, z["robot_pose"][i], 1e-9, f"pose @ {i}", atol_scale=10.0)
     assert fired == np.nonzero(z["fired"])[0].tolist() and len(fired) == 5
+
+
+def test_more_obstacles_than_the_staging_capacity():
+    """check_paths with more sensed obstacles than the planner's obstacle staging capacity falls back to the generic
+    polyline kernel and gives the same survivors as the lattice kernel."""
+    import otg_b200  # noqa: F401
+    from otg_b200 import drivers
+    from otg_b200.drivers import moving_obstacle_planner as mv
+    from otg_b200.planner import TrajectoryPlannerV1, TrajectoryPlannerParams
+    from otg_b200.sensor import StaticObstacle
+    from otg_b200.trajectory import CircleTrajectory2D
+    tr = CircleTrajectory2D(8, 5, 2)
+    rng = np.random.default_rng(5)
+    obstacles = [StaticObstacle(np.array([rng.uniform(4, 12), rng.uniform(-3, 3)])) for _ in range(9)]
+
+    class Sees:
+        def sense(self, *a, **k):
+            return obstacles
+
+    out = []
+    for cap in (4, 64):
+        pl = TrajectoryPlannerV1(TrajectoryPlannerParams(), _n_obs_cap=cap)
+        pl.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(3.0, 2.0, 0.0))
+        paths = drivers.frenet_to_glob(pl, tr, pl.paths)
+        kept, lead = mv.check_paths(paths, Sees(), None)
+        out.append(([f.index for f in kept], [id(o) for o in lead], drivers.best_path(kept).index))
+    assert out[0] == out[1] and 0 < len(out[0][0]) < 320
