@@ -70,8 +70,12 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 md = [f"# ncu --set full summary ({tag})", "", f"Source: `{os.path.basename(rep)}` (`ncu --set full --clock-control none --import-source on -k regex:k2_evaluate -s 3 -c 1",
       "python bench.py --steps 2 --warmup 3 --no-cpu`, i.e. the bench's own 512-scenario launch).", ""]
 traffic = {}
+seen = set()
 for row in r[2:]:
     name = row[ix["Kernel Name"]]
+    if name in seen:        # one section per distinct kernel (the first captured launch)
+        continue
+    seen.add(name)
     md += [f"## `{name[:100]}`", "", "| metric | value | unit |", "|---|---|---|"]
     for w in want:
         if w in ix:
