@@ -25,7 +25,10 @@ namespace {
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kRowThreads = 256;   // CTA size of the per-row kernels (8 warps)
+#ifndef FRENET_ROW_THREADS
+#define FRENET_ROW_THREADS 256
+#endif
+constexpr int kRowThreads = FRENET_ROW_THREADS;   // CTA size of the per-row kernels (8 warps)
 constexpr int kMaxSmem = 227 * 1024;
 // Resident CTAs per SM the evaluate kernel is compiled for (register cap 65536 / (256 * n)).  Measured on B200: the
 // store-bound variants are fastest at 3 (80 registers, no rematerialisation), the collision variant at 4 (it is
