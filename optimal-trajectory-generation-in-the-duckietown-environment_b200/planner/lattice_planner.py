@@ -249,8 +249,8 @@ class _LatticePlanner(Planner):
         if geom is None:
             geom = LatticeGeometry.from_intervals(self.di_interval, self.t_interval, period)
             self._geom_cache[gkey] = geom
-        if len(V) > self._n_v_cap:
-            self.__dict__["_n_v_cap"] = max(len(V), lat.max_long_axis_len(self))
+        if len(V) > self._n_v_cap or self._n_v_cap == 0:      # an empty axis (no candidates at all) still needs a valid layout
+            self.__dict__["_n_v_cap"] = max(1, len(V), lat.max_long_axis_len(self))
         eng.configure(geom, self._n_v_cap, self._n_obs_cap)
         eng.state[0, :3] = self.p0
         eng.state[0, 3:] = self.s0

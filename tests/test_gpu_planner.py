@@ -360,3 +360,18 @@ def test_more_obstacles_than_the_staging_capacity():
         kept, lead = mv.check_paths(paths, Sees(), None)
         out.append(([f.index for f in kept], [id(o) for o in lead], drivers.best_path(kept).index))
     assert out[0] == out[1] and 0 < len(out[0][0]) < 320
+
+
+def test_empty_lattice_raises_like_min_of_empty_list():
+    """d_d_s = 0.2, num_sample = 1 at ds0 = 0: both ends of the target-speed interval round to 0, np.arange is empty, the
+    reference's initialize() dies in min([]) with ValueError - so does ours (no candidates, K5 reports EMPTY)."""
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat
+    from otg_b200.planner import TrajectoryPlannerV1, TrajectoryPlannerParams
+    pl = TrajectoryPlannerV1(TrajectoryPlannerParams(d_d_s=0.2, num_sample=1))
+    with pytest.raises(ValueError):
+        pl.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(0.0, 0.0, 0.0))
+    assert len(pl.paths) == 0 and pl._engine.result[0]["status"] == nat.STATUS_EMPTY
+    pl2 = TrajectoryPlannerV1(TrajectoryPlannerParams(d_d_s=0.2, num_sample=1))
+    pl2.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(0.0, 1.5, 0.0))       # a non-degenerate speed works with the same parameters
+    assert len(pl2.paths) == len(np.arange(round(1.5 - 0.2), round(1.5 + 0.2 + 0.2), 0.2)) * 4 * 16 == 5 * 64
