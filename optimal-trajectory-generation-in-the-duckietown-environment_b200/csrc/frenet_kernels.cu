@@ -47,6 +47,10 @@ constexpr int kMaxSmem = 227 * 1024;
 #ifndef FRENET_K2_DYNAMIC
 #define FRENET_K2_DYNAMIC 0
 #endif
+// 1: unit normal of the path as the normalised, rotated tangent; 0: through atan2 + sincos like the reference's code.
+#ifndef FRENET_FRAME_NORMALISE
+#define FRENET_FRAME_NORMALISE 0
+#endif
 
 thread_local char g_err[256] = "";
 
@@ -327,6 +331,18 @@ __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ 
     } else {
         spline_eval(tab, n_knots, s, px, py, gx, gy);
     }
+#if FRENET_FRAME_NORMALISE
+    // (-sin th, cos th) with th = atan2(gy, gx) is the tangent rotated by 90 degrees and normalised; computing it that
+    // way costs ~15 instructions instead of ~250 for atan2 + sincos and agrees to the last bit or two.  Degenerate
+    // tangents (zero, non-finite) take the reference's literal route so that atan2(0, 0) = 0 still gives n = (0, 1).
+    const double g2 = fma(gx, gx, gy * gy);
+    if (g2 > 1e-280 && g2 < 1e280) {
+        const double inv = 1.0 / sqrt(g2);
+        nx = -gy * inv;
+        ny = gx * inv;
+        return;
+    }
+#endif
     const double th = atan2(gy, gx);
     double sn, cs;
     sincos(th, &sn, &cs);
