@@ -469,7 +469,7 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // The fused variants write each candidate-timestep exactly once (48 B: d, d', d'', d''', x, y) and read
 // nothing back; the unfused sequence K2 -> K3 -> K4 moves 72 B for the same result.
 // Shared memory (doubles): [3 * n_obs, rounded up to 4] obstacles in fp64 and fp32 (kColl) | [n_pad_max] lateral argument |
-// 4 x [n_pad_max] path frame (kXY) | [n_d][6] lateral coefficients | [n_d][5] per-candidate results | [n_knots][9] spline
+// 4 x [n_pad_max] path frame (kXY) | [n_d][6] lateral coefficients | [n_d][5] per-candidate results | [n_d] lateral axis | [n_knots][9] spline
 // table (kXY).
 // kPair:   every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead) - the
 //          mapping for long horizons; short horizons (at most 32 padded samples, e.g. the reference's default lattice with
@@ -488,7 +488,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     double* coef = fny + (kXY ? npm : 0);                          // [n_d][6] lateral coefficients of this row (from K1)
     double* resc = coef + L.n_d * 6;                               // [n_d][4] cd, cv, ct, ctot of the row's candidates
     int* resi = reinterpret_cast<int*>(resc + L.n_d * 4);          // [n_d][2] flags, first blocker
-    double* tab = resc + L.n_d * 5;                                // [n_knots][9] spline table (kXY, spline path)
+    double* axd = resc + L.n_d * 5;                                // [n_d] lateral target axis
+    double* tab = axd + L.n_d;                                     // [n_knots][9] spline table (kXY, spline path)
     __shared__ double red[3][kRowThreads / 32];
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
@@ -521,6 +522,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     {
         const double* cq = B.coef_lat + A.cand0 * 6;
         for (int i = tid; i < L.n_d * 6; i += blockDim.x) coef[i] = cq[i];
+        for (int i = tid; i < L.n_d; i += blockDim.x) axd[i] = L.axis_d[i];
         if (kColl) stage_obstacles(B, A.b, obs, obsf);
         if (kXY && path.kind == FRENET_PATH_SPLINE) {
             for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
@@ -597,6 +599,9 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     }
     const double clong = sh_clong;
     const bool rowfeas = sh_rowfeas;
+    // row constants of the lateral cost, fetched once (not per candidate, where a global load would stall the warp's epilogue)
+    const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
+    const double dd_target = B.scal[(int64_t)A.b * 3];
     const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
     const int npad = A.npad, N = A.N;
 
@@ -703,8 +708,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         acc = warp_sum(acc);
         if (kLimits) amax = warp_max(amax);
         if (lane == 0) {   // :165-167 / :174-176; staged in shared memory, written out coalesced below
-            const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
-            const double e = L.axis_d[id] - B.scal[(int64_t)A.b * 3];
+            const double e = axd[id] - dd_target;
             const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
             resc[id * 4] = clat;
             resc[id * 4 + 1] = P.follow ? 0.0 : clong;
@@ -1415,7 +1419,7 @@ template <bool kXY, bool kColl>
 int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, cudaStream_t stream) {
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
-    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 11 + (spline ? (size_t)9 * path->n_knots : 0) +
+    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 12 + (spline ? (size_t)9 * path->n_knots : 0) +
                          (kColl ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0)) * sizeof(double);
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
