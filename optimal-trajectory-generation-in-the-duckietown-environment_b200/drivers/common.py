@@ -60,6 +60,45 @@ def frenet_to_glob(planner, trajectory, frenet_paths):
     return frenet_paths
 
 
+class LazyArray:
+    """An integer array that is fetched from the device the first time somebody looks at it; its length is known up front."""
+
+    def __init__(self, fetch, n):
+        self._fetch, self._n, self._data = fetch, int(n), None
+
+    def _get(self):
+        if self._data is None:
+            self._data = np.asarray(self._fetch())
+        return self._data
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+
+class LeadingObstacles:
+    """`leading_obstacles` of the moving-obstacle `check_paths`: one blocking obstacle per blocked candidate, resolved lazily."""
+
+    def __init__(self, sensed, first):
+        self._sensed, self._first = sensed, first
+
+    def __len__(self):
+        return len(self._first)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._sensed[int(j)] for j in np.asarray(self._first[:])[i]]
+        return self._sensed[int(self._first[i])]
+
+    def __iter__(self):
+        return (self._sensed[int(j)] for j in self._first)
+
+
 def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
     """Shared body of both `check_paths` flavours.
 
@@ -85,11 +124,10 @@ def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
             return frenet_paths.filtered(free), sensed, first[~free]
         eng.obs_xy[0, :n] = np.array([ob.position for ob in sensed], dtype=np.float64)
         eng.obs_active[0, :n] = 1
-        eng.upload()
-        # K4, then K5 with the collision mask and a gather of the masked winner: one call, one small copy back
-        eng.launch(planner._params, None, nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER, nat.MASK_COLLISION,
-                   nat.SEL_MASKED, n_obs=n)
-        eng.download(sync=True)
+        # K4, then K5 with the collision mask and a gather of the masked winner: one graph replay (H2D of the obstacle
+        # table, three kernels, D2H of the record + winner)
+        eng.run_graph(planner._params, None, nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER, nat.MASK_COLLISION,
+                      nat.SEL_MASKED, n_obs=n)
         C_ = frenet_paths._n_all
         winner = planner._frenet_from_winner("argmin_masked")
         def fetch_mask():
@@ -100,9 +138,16 @@ def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
 int(eng.result[0]["n_survivors"]), {"ctot": winner})
         first = np.zeros(0, dtype=np.int64)
         if want_blockers:
-            free = eng.coll_free[0, :C_].cpu().numpy() != 0
-            valid = (eng.cand_flags[0, :C_].cpu().numpy() & nat.CAND_VALID) != 0
-            first = eng.first_blocker[0, :C_].cpu().numpy()[valid & ~free]
+            gen = eng.generation
+
+            def fetch_blockers():      # only the all-blocked fallback of the moving-obstacle driver ever looks at these
+                if eng.generation != gen:
+                    raise RuntimeError("the blocking obstacles of an earlier replan are no longer on the device")
+                free = eng.coll_free[0, :C_].cpu().numpy() != 0
+                valid = (eng.cand_flags[0, :C_].cpu().numpy() & nat.CAND_VALID) != 0
+                return eng.first_blocker[0, :C_].cpu().numpy()[valid & ~free]
+
+            first = LazyArray(fetch_blockers, int(eng.result[0]["n_valid"]) - int(eng.result[0]["n_survivors"]))
         return view, sensed, first
     paths = list(frenet_paths)
     eng = _engine_for_lists()

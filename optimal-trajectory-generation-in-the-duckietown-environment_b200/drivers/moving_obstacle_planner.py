@@ -5,7 +5,7 @@ import numpy as np
 
 from ..sensor import ProximitySensor, MovingObstacle
 from .common import (robot_radius, compute_ortogonal_vect, frenet_to_glob, collision_filter, single_path_collision,
-                     best_path)
+                     best_path, LeadingObstacles)
 from .obstacle_planner import seeded_obstacles
 from .simulation import SimulationResult, default_elements, frenet_start
 
@@ -13,7 +13,7 @@ from .simulation import SimulationResult, default_elements, frenet_start
 def check_paths(frenet_paths, sensor, rpose):
     """(surviving candidates, one blocking obstacle per blocked candidate) - test_moving_obstacle_planner.py:26-39."""
     kept, sensed, first = collision_filter(frenet_paths, sensor, rpose, want_blockers=True)
-    return kept, [sensed[int(j)] for j in first]
+    return kept, LeadingObstacles(sensed, first)
 
 
 def check_collisions(path, obstacles):
