@@ -351,24 +351,25 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather(records):
-        return gather_results(records, n_total, None, dev) if world > 1 else records
+    def gather(records=None):
+        # the one collective of the path: all ranks' 64-byte result records, all-gathered on the device
+        return bp.gather_records(n_total) if world > 1 else (records if records is not None else bp.engine.result)
 
     # ---- resident arm: `value` ----
     bp.stage_inputs(**wl)
     bp.engine.upload()
     for _ in range(args.warmup):
         bp.launch_resident()
-        bp.engine.download(sync=True)
-        gather(bp.engine.result)
+        bp.engine.download(sync=world == 1)
+        gather()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         bp.launch_resident()
-        bp.engine.download(sync=True)     # records + winners leave the device every step
-        gather(bp.engine.result)           # the one collective of the path
+        bp.engine.download(sync=world == 1)   # records + winners leave the device every step
+        gather()                               # the one collective of the path (synchronises the stream)
     ev1.record()
     barrier()
     ms_dev = ev0.elapsed_time(ev1)
@@ -386,8 +387,10 @@ def run_gpu(args):
         bp.launch()
         if i + 1 < args.steps:
             bp.stage_inputs(**wl)
-        res = bp.result()
-        allrec = gather(res.records)
+        if world == 1:
+            allrec = bp.result().records
+        else:
+            allrec = gather()
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
 

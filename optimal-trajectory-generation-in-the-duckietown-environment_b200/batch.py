@@ -208,6 +208,30 @@ class BatchPlanner:
             self._n_v_sum = int(e.result["n_valid"].sum()) // max(self.geom.n_t * self.geom.n_d, 1)
         return e.result
 
+    def gather_records(self, n_total: int, group=None) -> np.ndarray:
+        """All ranks' result records of the last launch, in scenario order: ONE NCCL all-gather straight from the device
+        block K5 wrote (no host staging), then one copy to the host.  Must follow a launch on this stream; shard sizes
+        follow `shard_range`.  Without a process group it returns this planner's own records."""
+        import torch.distributed as dist
+        e = self.engine
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            torch.cuda.current_stream(e.device).synchronize()
+            return e.result
+        world = dist.get_world_size(group)
+        cap = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+        if cap != self.n_scen:      # ragged shards: go through the padded host path
+            torch.cuda.current_stream(e.device).synchronize()
+            return gather_results(e.result, n_total, group, e.device)
+        o = e._out_offs["result"]
+        local = e._out_dev[o:o + self.n_scen * nat.RESULT_BYTES]
+        if getattr(self, "_gather_buf", None) is None or self._gather_buf.numel() != world * local.numel():
+            self._gather_buf = torch.empty(world * local.numel(), dtype=torch.uint8, device=e.device)
+            self._gather_host = torch.empty(world * local.numel(), dtype=torch.uint8, pin_memory=True)
+        dist.all_gather_into_tensor(self._gather_buf, local, group=group)
+        self._gather_host.copy_(self._gather_buf, non_blocking=True)
+        torch.cuda.current_stream(e.device).synchronize()
+        return self._gather_host.numpy().view(np.dtype(nat.RESULT_DTYPE))
+
     @property
     def launches_per_plan(self) -> int:
         n = bin(self.stages).count("1")

@@ -203,6 +203,7 @@ class FrenetEngine:
         for name, sz in osz:
             ooffs[name] = otot
             otot += _align(sz)
+        self._out_offs = ooffs
         self._out_host = torch.empty(otot, dtype=torch.uint8, pin_memory=True)
         self._out_dev = torch.zeros(otot, dtype=torch.uint8, device=dev)
         ov = self._out_host.numpy()

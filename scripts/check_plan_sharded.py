@@ -30,6 +30,16 @@ tr = SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY)
 records, tiles = plan_sharded(params, tr, scen, tile=8)
 single = BatchPlanner(params, tr, n, 128).plan(**scen).records
 ok = np.array_equal(records, single)
+# equal shards: the on-device all-gather of BatchPlanner.gather_records
+from otg_b200.batch import shard_range  # noqa: E402
+m = 8 * world
+lo, hi = shard_range(m, rank, world)
+bp = BatchPlanner(params, tr, hi - lo, 128)
+sub = {k: v[lo:hi] for k, v in scen.items()}
+bp.stage_inputs(**sub)
+bp.launch()
+allrec = bp.gather_records(m).copy()
+ok = ok and np.array_equal(allrec, single[:m])
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
