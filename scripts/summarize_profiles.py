@@ -52,7 +52,11 @@ for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
     lines.append(f"| `{n[:80]}` | {c} | {t / 1e6:.3f} | {t / c / 1e3:.1f} |")
 open(os.path.join(out_dir, f"{tag}_launches_summary.md"), "w").write("\n".join(lines) + "\n")
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# `rep` is an .ncu-rep, or the CSV of `ncu -i <rep> --page raw --csv` when the report itself was too large to bring back
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"],
+                                                                     capture_output=True, text=True).stdout
+out_name = sys.argv[4] if len(sys.argv) > 4 else f"{tag}_fused_kernel_ncu_summary.md"
+note = sys.argv[5] if len(sys.argv) > 5 else "python bench.py --steps 2 --warmup 3 --no-cpu`, i.e. the bench's own 512-scenario launch"
 r = list(csv.reader(raw.splitlines()))
 h, units = r[0], r[1]
 ix = {k: i for i, k in enumerate(h)}
@@ -67,8 +71,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__grid_size", "launch__block_size"]
-md = [f"# ncu --set full summary ({tag})", "", f"Source: `{os.path.basename(rep)}` (`ncu --set full --clock-control none --import-source on -k regex:k2_evaluate -s 3 -c 1",
-      "python bench.py --steps 2 --warmup 3 --no-cpu`, i.e. the bench's own 512-scenario launch).", ""]
+md = [f"# ncu --set full summary ({tag})", "", f"Source: `{os.path.basename(rep)}` (`ncu --set full --clock-control none ...", note + ").", ""]
 traffic = {}
 seen = set()
 for row in r[2:]:
@@ -98,9 +101,10 @@ for row in r[2:]:
     key = "k2k3k4_fused" if "<1, 1," in name or "(bool)1, (bool)1" in name else ("k2k3_fused" if "<1, 0," in name else "k2_evaluate")
     traffic[key] = rd + wr
     md.append(f"DRAM traffic per launch: {rd / 1e9:.3f} GB read + {wr / 1e9:.3f} GB written = **{(rd + wr) / 1e9:.3f} GB**.")
-open(os.path.join(out_dir, f"{tag}_fused_kernel_ncu_summary.md"), "w").write("\n".join(md) + "\n")
-tpath = os.path.join(out_dir, "traffic.json")
-old = json.load(open(tpath)) if os.path.exists(tpath) else {}
-old.update(traffic)
-json.dump(old, open(tpath, "w"), indent=1)
+open(os.path.join(out_dir, out_name), "w").write("\n".join(md) + "\n")
+if len(sys.argv) <= 4:      # only the full-size capture feeds traffic.json (bytes per launch of the bench's own launch)
+    tpath = os.path.join(out_dir, "traffic.json")
+    old = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    old.update(traffic)
+    json.dump(old, open(tpath, "w"), indent=1)
 print(traffic)
