@@ -4,15 +4,25 @@
 // traffic (K2, K3), a candidate x step x obstacle distance test (K4) and a tiny reduction (K5).
 // Design rules used throughout (DESIGN.md has the numbers):
 //   * one CTA per lattice row (scenario, target speed, horizon): the longitudinal samples, the path
-//     frame (point + normal) and the obstacle table are produced / staged once per CTA in shared
-//     memory and reused by the n_d candidates of the row;
-//   * inside a CTA a warp owns a candidate and its lanes own consecutive time steps, so every
-//     global store is a contiguous run of doubles (k fastest, rows padded to 32-byte sectors);
+//     frame (point + normal), the row's lateral coefficients and the obstacle table are produced /
+//     staged once per CTA in shared memory and reused by the n_d candidates of the row;
+//   * inside a CTA a warp owns a candidate and its lanes own consecutive time steps (two per lane,
+//     16-byte accesses, for long horizons), so every global store is a contiguous, sector-aligned run
+//     of doubles; the six fields of a candidate sit next to each other ([candidate][6][npad]);
+//   * only whole 32-byte sectors are written (padding samples are stored too): a partially written
+//     sector costs a DRAM read-modify-write and halves the achieved store bandwidth;
+//   * K2, K3 and K4 run as ONE kernel in the pipeline: a sample is evaluated, transformed and
+//     collision-tested while it is in registers and written once (48 B instead of 72 B moved);
 //   * per-candidate sums (jerk integrals) and maxima are reduced with warp shuffles in a fixed
 //     butterfly order: results are deterministic and sign-symmetric, so the reference's exact
 //     cost ties between mirror candidates (+d / -d) survive and are broken by lowest index;
-//   * K4 culls obstacles per 32-step chunk with a lane-parallel bounding-circle test before the
-//     exact distance test, which keeps the fp64 pipe off the critical path.
+//   * collisions: per chunk of steps an fp32, lane-parallel bounding-circle cull over the obstacle
+//     table, an fp32 per-lane pre-test on the survivors, and only then the reference's fp64 test -
+//     conservative margins make the masks bit-identical to a brute-force fp64 sweep;
+//   * the longitudinal polynomial (once per row and step) is sampled in the reference's own power
+//     form with host-provided powers of t, because its values feed the next replan's state and sit
+//     exactly on the low-speed threshold in converged runs.
+// Compile-time knobs (FRENET_*) record measured alternatives; the defaults are the fastest on B200.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
