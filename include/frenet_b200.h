@@ -74,7 +74,10 @@ enum { FRENET_ROW_EXISTS = 1, FRENET_ROW_LOWSPEED = 2, FRENET_ROW_DROPPED = 4 };
 /* cand_flags bits (K2) */
 enum { FRENET_CAND_VALID = 1, FRENET_CAND_KINEMATIC_OK = 2 };
 
-enum { FRENET_PATH_CIRCLE = 0, FRENET_PATH_SPLINE = 1 };
+enum { FRENET_PATH_CIRCLE = 0, FRENET_PATH_SPLINE = 1, FRENET_PATH_PARABOLA = 2 };
+
+/* bits of `use_mask` (frenet_k5_argmin, frenet_plan): which filters the masked pick honours */
+enum { FRENET_MASK_KINEMATIC = 1, FRENET_MASK_CURVATURE = 2, FRENET_MASK_COLLISION = 4, FRENET_MASK_ROAD = 8 };
 
 /* selector for frenet_gather_winner */
 #define FRENET_WINNER_ROWS 12
@@ -116,11 +119,15 @@ typedef struct FrenetLattice {
     const int32_t* n_v;      /* [n_scen] */
 } FrenetLattice;
 
-/* Reference path descriptor (lib/trajectory/circle_trajectory.py:11-72, spline_trajectory.py:9-158). */
+/* Reference path descriptor (lib/trajectory/circle_trajectory.py:11-72, spline_trajectory.py:9-158).
+ * FRENET_PATH_PARABOLA is the lane-centre fit of the Duckietown runs (lib/mapper/mapper_obstacles.py:169-186):
+ * pt(x) = (x, a x^2 + b x + c) parameterised by x, normal from the chord over ds (compute_ortogonal_vect,
+ * lib/tests/test_mapper_planner_obstacles.py:137-142); circle[0..3] = a, b, c, ds. */
 typedef struct FrenetPath {
     int32_t kind;        /* FRENET_PATH_* */
     int32_t n_knots;     /* spline only */
-    double circle[16];   /* l, h, r, dt, period, 7 branch boundaries (host-evaluated in the reference's order) */
+    double circle[16];   /* circle: l, h, r, dt, period, 7 branch boundaries (host-evaluated in the reference's order);
+                            parabola: a, b, c, ds */
     const double* spline_table; /* device [n_knots][9]: knot, ax, bx, cx, dx, ay, by, cy, dy */
 } FrenetPath;
 
@@ -174,7 +181,20 @@ typedef struct FrenetBuffers {
     double* winner;            /* [n_scen][12][n_pad_max]: t, d, dd, ddd, dddd, s, ds, dds, ddds, x, y, then a row holding
                                   the winner's (cd, cv, ct, ctot) in its first four entries */
     int32_t* winner_steps;     /* [n_scen] number of valid samples, 0 if no winner */
+    /* Duckietown lane runs; both optional (NULL) */
+    const double* path_origin; /* [n_scen][2] (projection, planner.s0[0]): the lattice transform evaluates the path at
+                                  projection + (s - s0[0]) (frenet_to_glob_planner,
+                                  lib/tests/test_mapper_planner_obstacles.py:25-37); NULL: at s */
+    uint8_t* road_ok;          /* [n_scen][C] 1 = stays between the lane boundaries (frenet_k3_offroad) */
 } FrenetBuffers;
+
+/* Lane boundaries for frenet_k3_offroad: each a parabola in vertex form (h, k, a) =
+ * get_vertex_and_focus_distance(fit) (lib/tests/test_mapper_planner_obstacles.py:105-109). */
+typedef struct FrenetRoad {
+    double right[3];
+    double left[3];
+    int32_t has_right, has_left;   /* 0: that boundary was not detected (check_paths skips the test, :117-124) */
+} FrenetRoad;
 
 /* pipeline stage bits for frenet_plan */
 enum {
@@ -224,6 +244,11 @@ int frenet_k5_argmin(const FrenetLattice* lat, const FrenetBuffers* buf, int32_t
  * trajectory_planner.py:183-195).  sel: FRENET_SEL_*; has_xy: 0 leaves x, y rows untouched. */
 int frenet_gather_winner(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, int32_t sel, int32_t has_xy,
                          frenet_stream_t stream);
+
+/* Off-road filter of the Duckietown runs: check_offroad (lib/tests/test_mapper_planner_obstacles.py:62-70) for every candidate and
+ * both boundaries: road_ok = no sample with (y - k) - a (x - h)^2 < 0 on the right boundary nor > 0 on the left one.
+ * Needs K3 (x, y).  Honoured by K5 through FRENET_MASK_ROAD. */
+int frenet_k3_offroad(const FrenetLattice* lat, const FrenetRoad* road, const FrenetBuffers* buf, frenet_stream_t stream);
 
 /* The pipeline: launches the stages selected in `stages` in order K1, K2, K3, (curvature), K4, K5, gather;
  * K2+K3(+K4) are fused into one launch when selected together (FRENET_STAGE_NO_FUSE keeps them apart). */

@@ -20,10 +20,10 @@ STATUS_OK, STATUS_NO_FEASIBLE, STATUS_EMPTY = 0, 1, 2
 LOWSPEED_OFF, LOWSPEED_V1, LOWSPEED_OPTIMAL = 0, 1, 2
 ROW_EXISTS, ROW_LOWSPEED, ROW_DROPPED = 1, 2, 4
 CAND_VALID, CAND_KINEMATIC_OK = 1, 2
-PATH_CIRCLE, PATH_SPLINE = 0, 1
+PATH_CIRCLE, PATH_SPLINE, PATH_PARABOLA = 0, 1, 2
 SEL_CTOT, SEL_CD, SEL_CV, SEL_CT, SEL_MASKED = 0, 1, 2, 3, 4
 STAGE_K1, STAGE_K2, STAGE_K3, STAGE_K4, STAGE_K5, STAGE_GATHER, STAGE_CURVATURE, STAGE_NO_FUSE = 1, 2, 4, 8, 16, 32, 64, 128
-MASK_KINEMATIC, MASK_CURVATURE, MASK_COLLISION = 1, 2, 4
+MASK_KINEMATIC, MASK_CURVATURE, MASK_COLLISION, MASK_ROAD = 1, 2, 4, 8
 
 c_double_p = C.c_void_p   # device pointers are passed as integers (tensor.data_ptr())
 
@@ -67,7 +67,12 @@ class FrenetBuffers(C.Structure):
                 ("curv_ok", C.c_void_p),
                 ("coll_free", C.c_void_p), ("first_blocker", C.c_void_p),
                 ("result", C.c_void_p),
-                ("winner", C.c_void_p), ("winner_steps", C.c_void_p)]
+                ("winner", C.c_void_p), ("winner_steps", C.c_void_p),
+                ("path_origin", C.c_void_p), ("road_ok", C.c_void_p)]
+
+
+class FrenetRoad(C.Structure):
+    _fields_ = [("right", C.c_double * 3), ("left", C.c_double * 3), ("has_right", C.c_int32), ("has_left", C.c_int32)]
 
 
 assert C.sizeof(FrenetResult) == RESULT_BYTES
@@ -95,6 +100,7 @@ def _load():
         "frenet_k2_fused": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_void_p]),
         "frenet_k3_cartesian": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_void_p]),
         "frenet_k3_curvature": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_void_p]),
+        "frenet_k3_offroad": (C.c_int, [P(FrenetLattice), P(FrenetRoad), P(FrenetBuffers), C.c_void_p]),
         "frenet_k4_collision": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_void_p]),
         "frenet_k5_argmin": (C.c_int, [P(FrenetLattice), P(FrenetBuffers), C.c_int32, C.c_void_p]),
         "frenet_gather_winner": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_int32, C.c_int32, C.c_void_p]),

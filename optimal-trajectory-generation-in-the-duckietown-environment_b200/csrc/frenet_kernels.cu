@@ -325,6 +325,12 @@ __device__ __forceinline__ void spline_eval(const double* __restrict__ tab, int 
     gy = q[6] + 2.0 * q[7] * dx + 3.0 * q[8] * dx2;
 }
 
+// Lane-centre parabola of the Duckietown runs, a*x**2 + b*x + c in the reference's operation order, no contraction
+// (lib/mapper/mapper_obstacles.py:173).
+__device__ __forceinline__ double parabola_y(const double* __restrict__ q, double x) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(q[0], __dmul_rn(x, x)), __dmul_rn(q[1], x)), q[2]);
+}
+
 // Path point and unit normal at arc length s: n = (-sin th, cos th), th = arctan2 of the path's
 // first derivative (compute_ortogonal_vect, lib/tests/test_obstacle_planner.py:53-56).  The circle's
 // derivative is the reference's forward chord over dt (circle_trajectory.py:66-72).
@@ -338,6 +344,13 @@ __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ 
         circle_pt(circle, s + h, qx, qy);
         gx = (qx - px) / h;
         gy = (qy - py) / h;
+    } else if (kind == FRENET_PATH_PARABOLA) {
+        // Duckietown driver: chord over ds, not divided (lib/tests/test_mapper_planner_obstacles.py:137-142)
+        px = s;
+        py = parabola_y(circle, s);
+        const double s1 = s + circle[3];
+        gx = s1 - s;
+        gy = parabola_y(circle, s1) - py;
     } else {
         spline_eval(tab, n_knots, s, px, py, gx, gy);
     }
@@ -568,7 +581,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             }
             if (kXY) {
                 double px, py, nx, ny;
-                path_frame(path.kind, path.circle, tab, path.n_knots, s, px, py, nx, ny);
+                const double sp = B.path_origin ? B.path_origin[2 * A.b] + (s - B.path_origin[2 * A.b + 1]) : s;   // frenet_to_glob_planner
+                path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny);
                 fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
             }
         }
@@ -772,9 +786,12 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
         __syncthreads();
     }
     const double* s_row = B.lon + A.lon_off;
+    const bool relative = B.path_origin != nullptr;    // Duckietown runs: path evaluated at projection + (s - s0[0])
+    const double origin = relative ? B.path_origin[2 * A.b] : 0.0, s_start = relative ? B.path_origin[2 * A.b + 1] : 0.0;
     for (int k = tid; k < A.npad; k += blockDim.x) {   // padding samples included: whole sectors are written (see K2)
         double px, py, nx, ny;
-        path_frame(path.kind, path.circle, tab, path.n_knots, s_row[k], px, py, nx, ny);
+        const double sp = relative ? origin + (s_row[k] - s_start) : s_row[k];
+        path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny);
         fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
     }
     __syncthreads();
@@ -864,6 +881,37 @@ __global__ void __launch_bounds__(kRowThreads) k3_curvature(FrenetLattice L, Fre
         }
         bad = __any_sync(kFull, bad);
         if (lane == 0) B.curv_ok[A.cand0 + id] = bad ? 0 : 1;
+    }
+}
+
+// check_offroad for both lane boundaries (lib/tests/test_mapper_planner_obstacles.py:62-70, 117-124): a candidate is off the
+// road when any sample has (y - k) - a (x - h)^2 < 0 against the right boundary or > 0 against the left one.
+__global__ void __launch_bounds__(kRowThreads) k3_offroad(FrenetLattice L, FrenetRoad road, FrenetBuffers B) {
+    const int64_t br = blockIdx.x;
+    const RowAddr A = row_addr(L, br);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int flags = B.row_flags[br];
+    if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
+        for (int id = tid; id < L.n_d; id += blockDim.x) B.road_ok[A.cand0 + id] = 0;
+        return;
+    }
+    for (int id = warp; id < L.n_d; id += nwarps) {
+        const double* x = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
+        const double* y = x + A.npad;
+        bool off = false;
+        for (int k = lane; k < A.N; k += kWarp) {
+            const double xv = x[k], yv = y[k];
+            if (road.has_right) {
+                const double u = xv - road.right[0];
+                off |= __dadd_rn(yv - road.right[1], -__dmul_rn(road.right[2], __dmul_rn(u, u))) < 0.0;
+            }
+            if (road.has_left) {
+                const double u = xv - road.left[0];
+                off |= __dadd_rn(yv - road.left[1], -__dmul_rn(road.left[2], __dmul_rn(u, u))) > 0.0;
+            }
+        }
+        off = __any_sync(kFull, off);
+        if (lane == 0) B.road_ok[A.cand0 + id] = off ? 0 : 1;
     }
 }
 
@@ -1103,6 +1151,11 @@ __device__ __forceinline__ void path_pt_grad(int kind, const double* __restrict_
         circle_pt(circle, s + h, qx, qy);
         gx = (qx - px) / h;
         gy = (qy - py) / h;
+    } else if (kind == FRENET_PATH_PARABOLA) {   // analytic derivative (mapper_obstacles.py:174)
+        px = s;
+        py = parabola_y(circle, s);
+        gx = 1.0;
+        gy = __dadd_rn(__dmul_rn(__dmul_rn(2.0, circle[0]), s), circle[1]);
     } else {
         spline_eval(tab, n_knots, s, px, py, gx, gy);
     }
@@ -1116,6 +1169,15 @@ __device__ __forceinline__ double path_curvature(int kind, const double* __restr
         if (t >= period) t = fmod(t, period);
         const bool straight = (t >= 0.0 && t < b[0]) || (t >= b[1] && t < b[2]) || (t >= b[3] && t < b[4]) || (t >= b[5] && t < b[6]);
         return straight ? 0.0 : 1.0 / r;
+    }
+    if (kind == FRENET_PATH_PARABOLA) {   // the mapper's finite-difference form, verbatim (mapper_obstacles.py:176-184)
+        const double dt = 1.0 / 30.0;
+        const double x0 = t - dt, x1 = t, x2 = t + dt;
+        const double y0 = parabola_y(c, x0), y1 = parabola_y(c, x1), y2 = parabola_y(c, x2);
+        const double t1 = atan2(sin(y1 - y0), cos(x1 - x0));
+        const double t2 = atan2(sin(y2 - y1), cos(x2 - x1));
+        const double ex = x1 - x0, ey = y1 - y0;
+        return fabs(t2 - t1) / sqrt(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
     }
     const double first = tab[0], last = tab[(n - 1) * 9];
     double dx, dy, ddx, ddy;
@@ -1304,6 +1366,7 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
         if (use_mask & 1) pass = pass && (fl & FRENET_CAND_KINEMATIC_OK);
         if (use_mask & 2) pass = pass && B.curv_ok[base + c];
         if (use_mask & 4) pass = pass && B.coll_free[base + c];
+        if (use_mask & 8) pass = pass && B.road_ok[base + c];
         if (pass) {
             ++nsurv;
             best[4].take(ctot, c);
@@ -1419,7 +1482,7 @@ int check_path(const FrenetPath* path) {
     if (!path) return fail(FRENET_ERR_BAD_ARG, "path is NULL");
     if (path->kind == FRENET_PATH_SPLINE) {
         if (path->n_knots < 2 || !path->spline_table) return fail(FRENET_ERR_BAD_ARG, "spline path needs >= 2 knots and a table");
-    } else if (path->kind != FRENET_PATH_CIRCLE) {
+    } else if (path->kind != FRENET_PATH_CIRCLE && path->kind != FRENET_PATH_PARABOLA) {
         return fail(FRENET_ERR_BAD_ARG, "unknown path kind");
     }
     return FRENET_OK;
@@ -1547,11 +1610,22 @@ int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const Fre
     return FRENET_OK;
 }
 
+int frenet_k3_offroad(const FrenetLattice* L, const FrenetRoad* road, const FrenetBuffers* B, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!road || !B) return fail(FRENET_ERR_BAD_ARG, "k3_offroad: NULL argument");
+    if (!B->lat || !B->road_ok || !B->row_flags) return fail(FRENET_ERR_BAD_ARG, "k3_offroad: lat, road_ok and row_flags are required");
+    if (n_rows(L) == 0) return FRENET_OK;
+    k3_offroad<<<n_rows(L), kRowThreads, 0, (cudaStream_t)stream>>>(*L, *road, *B);
+    FRENET_CHECK_LAUNCH("k3_offroad");
+    return FRENET_OK;
+}
+
 int frenet_k5_argmin(const FrenetLattice* L, const FrenetBuffers* B, int32_t use_mask, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
     if (!B || !B->cost || !B->cand_flags || !B->result) return fail(FRENET_ERR_BAD_ARG, "k5: NULL buffer");
     if ((use_mask & 2) && !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "k5: curvature mask requested but curv_ok is NULL");
     if ((use_mask & 4) && !B->coll_free) return fail(FRENET_ERR_BAD_ARG, "k5: collision mask requested but coll_free is NULL");
+    if ((use_mask & 8) && !B->road_ok) return fail(FRENET_ERR_BAD_ARG, "k5: road mask requested but road_ok is NULL");
     k5_argmin<<<L->n_scen, kArgminThreads, 0, (cudaStream_t)stream>>>(*L, *B, use_mask);
     FRENET_CHECK_LAUNCH("k5_argmin");
     return FRENET_OK;
@@ -1585,7 +1659,10 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     if ((stages & FRENET_STAGE_CURVATURE) && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K4) && !fuse_k4 && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
-    if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, (stages & (FRENET_STAGE_K3 | FRENET_STAGE_K4)) ? 1 : 0, stream)))
+    // the winner block carries x, y when they exist: K3 / K4 ran in this call, or a mask computed from them is in use
+    const int winner_xy = ((stages & (FRENET_STAGE_K3 | FRENET_STAGE_K4)) ||
+                           (use_mask & (FRENET_MASK_CURVATURE | FRENET_MASK_COLLISION | FRENET_MASK_ROAD))) ? 1 : 0;
+    if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, winner_xy, stream)))
         return rc;
     return rc;
 }

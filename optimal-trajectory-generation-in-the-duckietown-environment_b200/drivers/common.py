@@ -134,8 +134,7 @@ def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
             frenet_paths._check_live()
             return eng.coll_free[0, :C_].cpu().numpy() != 0
 
-        view = frenet_paths.masked_view(fetch_mask,
-int(eng.result[0]["n_survivors"]), {"ctot": winner})
+        view = frenet_paths.masked_view(fetch_mask, int(eng.result[0]["n_survivors"]), {"ctot": winner})
         first = np.zeros(0, dtype=np.int64)
         if want_blockers:
             gen = eng.generation

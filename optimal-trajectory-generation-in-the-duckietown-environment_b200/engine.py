@@ -134,6 +134,7 @@ class FrenetEngine:
         self.generation = 0
         self.has_xy = False
         self.has_collision = False
+        self.relative_s = False       # Duckietown lane runs: the transform evaluates the path at path_origin + (s - s0[0])
 
     # -- allocation ---------------------------------------------------------------------------
     def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0, n_obs_steps: int = 0):
@@ -172,8 +173,8 @@ class FrenetEngine:
         # packed small inputs: one pinned host block, one device block
         sizes = [("state", Bn * 6 * 8), ("scal", Bn * 3 * 8), ("axis_v", Bn * self.n_v_cap * 8), ("target", Bn * nT * 3 * 8),
                  ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("obs_sd", Bn * max(n_obs, 1) * 2 * 8),
-                 ("obs_speed", Bn * max(n_obs, 1) * 8), ("robot_pose", Bn * 3 * 8), ("n_v", Bn * 4),
-                 ("obs_active", Bn * max(n_obs, 1))]
+                 ("obs_speed", Bn * max(n_obs, 1) * 8), ("robot_pose", Bn * 3 * 8), ("path_origin", Bn * 16),
+                 ("n_v", Bn * 4), ("obs_active", Bn * max(n_obs, 1))]
         offs, tot = {}, 0
         for name, sz in sizes:
             offs[name] = tot
@@ -190,6 +191,7 @@ class FrenetEngine:
         self.obs_sd = hv[offs["obs_sd"]:offs["obs_sd"] + Bn * no * 16].view(np.float64).reshape(2, Bn, no)   # [s|d][B][O]
         self.obs_speed = hv[offs["obs_speed"]:offs["obs_speed"] + Bn * no * 8].view(np.float64).reshape(Bn, no)
         self.robot_pose = hv[offs["robot_pose"]:offs["robot_pose"] + Bn * 24].view(np.float64).reshape(Bn, 3)
+        self.path_origin = hv[offs["path_origin"]:offs["path_origin"] + Bn * 16].view(np.float64).reshape(Bn, 2)
         self.n_v = hv[offs["n_v"]:offs["n_v"] + Bn * 4].view(np.int32)
         self.obs_active = hv[offs["obs_active"]:offs["obs_active"] + Bn * no].reshape(Bn, no)
         hv[:] = 0
@@ -226,6 +228,7 @@ class FrenetEngine:
         self.curv_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.coll_free = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.first_blocker = torch.empty((Bn, Cc), dtype=torch.int32, device=dev)
+        self.road_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.n_obs_steps = n_obs_steps
         self.obs_xy_t = self.obs_bounds = None
         if n_obs_steps > 0 and n_obs > 0:
@@ -250,11 +253,13 @@ class FrenetEngine:
         Bf.obs_bounds = self.obs_bounds.data_ptr() if self.obs_bounds is not None else None
         Bf.result = op + ooffs["result"]
         Bf.winner, Bf.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
+        Bf.road_ok = self.road_ok.data_ptr()
+        Bf.path_origin = ip + offs["path_origin"] if self.relative_s else None
         self._cap_key = key
 
     def hbm_bytes(self) -> int:
         ts = [self.coef_lon, self.coef_lat, self.row_S, self.row_flags, self.lon, self.lat, self.cost, self.cand_flags,
-              self.curv_ok, self.coll_free, self.first_blocker, self._in_dev, self._out_dev, self._geom_dev] + [
+              self.curv_ok, self.coll_free, self.first_blocker, self.road_ok, self._in_dev, self._out_dev, self._geom_dev] + [
             t for t in (self.obs_xy_t, self.obs_bounds) if t is not None]
         return sum(t.numel() * t.element_size() for t in ts)
 
@@ -264,6 +269,34 @@ class FrenetEngine:
         cand = row * geom.n_d
         C_ = n_v_cap * geom.n_t * geom.n_d
         return 8 * (4 * row + 6 * cand) + C_ * (6 * 8 + 4 * 8 + 3 + 4) + n_v_cap * geom.n_t * (6 * 8 + 8 + 4)
+
+    def set_relative_s(self, on: bool):
+        """Lattice transform at `path_origin[b, 0] + (s - path_origin[b, 1])` = projection + (s - s0[0]) (frenet_to_glob_planner of the Duckietown driver,
+        lib/tests/test_mapper_planner_obstacles.py:25-37) instead of at s.  `path_origin` is part of the packed inputs."""
+        on = bool(on)
+        if on != self.relative_s:
+            self.relative_s = on
+            self._graphs.clear()
+            if self.geom is not None:
+                self.B.path_origin = self._in_dev.data_ptr() + self._in_offs["path_origin"] if on else None
+
+    def offroad(self, right_fit=None, left_fit=None):
+        """road_ok for every candidate against the lane boundary fits (a, b, c) of y = a x^2 + b x + c; None = that boundary
+        was not detected (check_paths + check_offroad, lib/tests/test_mapper_planner_obstacles.py:62-70, 112-124)."""
+        if not self.has_xy:
+            raise RuntimeError("offroad(): the lattice has no Cartesian samples yet (run K3 first)")
+        road = nat.FrenetRoad()
+        for name, fit in (("right", right_fit), ("left", left_fit)):
+            if fit is None:
+                continue
+            a, b, c = (float(v) for v in fit)
+            vals = (-b / (2 * a), -(b ** 2 - 4 * a * c) / (4 * a), a)   # get_vertex_and_focus_distance (:105-109)
+            arr = getattr(road, name)
+            for i in range(3):
+                arr[i] = vals[i]
+            setattr(road, "has_" + name, 1)
+        nat.check(nat.lib.frenet_k3_offroad(C.byref(self.L), C.byref(road), C.byref(self.B),
+                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
     # -- path handles --------------------------------------------------------------------------
     def path_handle(self, trajectory) -> PathHandle:
@@ -297,7 +330,7 @@ class FrenetEngine:
         sizes = {"state": self.n_scen * 48, "scal": self.n_scen * 24, "axis_v": self.n_scen * self.n_v_cap * 8,
                  "target": self.n_scen * self.geom.n_t * 24, "obs_xy": self.n_scen * max(self.n_obs, 1) * 16,
                  "obs_sd": self.n_scen * max(self.n_obs, 1) * 16, "obs_speed": self.n_scen * max(self.n_obs, 1) * 8,
-                 "robot_pose": self.n_scen * 24, "n_v": self.n_scen * 4, "obs_active": self.n_scen * max(self.n_obs, 1)}
+                 "robot_pose": self.n_scen * 24, "path_origin": self.n_scen * 16, "n_v": self.n_scen * 4, "obs_active": self.n_scen * max(self.n_obs, 1)}
         for name in names:
             o = self._in_offs[name]
             self._in_dev[o:o + sizes[name]].copy_(self._in_host[o:o + sizes[name]], non_blocking=True)

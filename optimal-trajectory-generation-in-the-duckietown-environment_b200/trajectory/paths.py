@@ -23,6 +23,7 @@ import numpy as np
 
 PATH_KIND_CIRCLE = 0
 PATH_KIND_SPLINE = 1
+PATH_KIND_PARABOLA = 2
 
 # Layout of the double[16] block of a circle descriptor (see include/frenet_b200.h).
 _CIRC_L, _CIRC_H, _CIRC_R, _CIRC_DT, _CIRC_PERIOD, _CIRC_B0 = 0, 1, 2, 3, 4, 5
@@ -245,6 +246,43 @@ class SplineTrajectory2D(Trajectory, DifferentiableFunction):
         return PATH_KIND_SPLINE, n, np.zeros(16, dtype=np.float64), tab
 
 
+class ParabolaTrajectory2D(Trajectory, DifferentiableFunction):
+    """Lane-centre path of the Duckietown runs: y = a x^2 + b x + c in the robot frame, parameterised by x.  The reference
+    builds it as a bare `Trajectory()` carrying lambdas (`MapperSemanticObstacles.build_trajectory`,
+    lib/mapper/mapper_obstacles.py:169-186); this class has the same four callables plus a device descriptor."""
+    ds = 1 / 30     # chord of compute_ortogonal_vect in lib/tests/test_mapper_planner_obstacles.py:137-142
+
+    def __init__(self, a, b, c):
+        self.a, self.b, self.c = float(a), float(b), float(c)
+
+    @classmethod
+    def fit(cls, x, y):
+        """Quadratic least-squares fit through lane-centre points (mapper_obstacles.py:172)."""
+        return cls(*np.polyfit(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64), 2))
+
+    def compute_pt(self, x):
+        return np.array([x, self.a * x ** 2 + self.b * x + self.c])
+
+    def compute_first_derivative(self, x):
+        return np.array([1, 2 * self.a * x + self.b])
+
+    def compute_second_derivative(self, x):
+        return np.array([0, 2 * self.a])
+
+    def compute_curvature(self, t):
+        dt = 1 / 30
+        x0, x1, x2 = t - dt, t, t + dt
+        y0, y1, y2 = (self.compute_pt(x)[1] for x in (x0, x1, x2))
+        t1 = np.arctan2(np.sin(y1 - y0), np.cos(x1 - x0))
+        t2 = np.arctan2(np.sin(y2 - y1), np.cos(x2 - x1))
+        return np.abs(t2 - t1) / np.linalg.norm(np.array([x1 - x0, y1 - y0]))
+
+    def path_descriptor(self):
+        block = np.zeros(16, dtype=np.float64)
+        block[:4] = (self.a, self.b, self.c, self.ds)
+        return PATH_KIND_PARABOLA, 0, block, None
+
+
 def path_descriptor_of(trajectory):
     """Descriptor for one of our path objects or a duck-typed reference path object
     (anything exposing `l, h, r` or `s, sx, sy` the way the reference classes do).
@@ -261,4 +299,4 @@ def path_descriptor_of(trajectory):
         return proxy.path_descriptor()
     raise TypeError(
         f"reference path of type {type(trajectory).__name__} has no device descriptor "
-        "(supported: CircleTrajectory2D, SplineTrajectory2D)")
+        "(supported: CircleTrajectory2D, SplineTrajectory2D, ParabolaTrajectory2D)")

@@ -561,3 +561,45 @@ def optimal_target_triples(tg, T: np.ndarray, t_initial: float, delta_t: float) 
         k = round((t_initial + Tj - tg["t"][0]) / delta_t)
         out[j] = (tg["s"][k], tg["dot_s"][k], tg["ddot_s"][k])
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# Duckietown lane runs: parabola reference path, off-road filter
+# --------------------------------------------------------------------------------------------
+AGENT_SAFETY_RAD = (max(0.18, 0.13 + 0.02) / 2) * 1.8      # lib/video/constants.py:27-33
+
+
+@dataclass
+class ParabolaPath:
+    """The lane-centre path the mapper fits in the robot frame (lib/mapper/mapper_obstacles.py:169-186):
+    pt(x) = (x, a x^2 + b x + c), parameterised by x.  `tangent` is the chord over ds = 1/30 that the Duckietown
+    driver's compute_ortogonal_vect uses (lib/tests/test_mapper_planner_obstacles.py:137-142), NOT divided by ds."""
+    a: float
+    b: float
+    c: float
+    ds: float = 1 / 30
+
+    def pt(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return x, self.a * x ** 2 + self.b * x + self.c
+
+    def tangent(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        x1 = x + self.ds
+        return x1 - x, (self.a * x1 ** 2 + self.b * x1 + self.c) - (self.a * x ** 2 + self.b * x + self.c)
+
+
+def vertex_form(fit):
+    """get_vertex_and_focus_distance (test_mapper_planner_obstacles.py:105-109): (h, k, a) of a x^2 + b x + c."""
+    a, b, c = fit
+    return -b / (2 * a), -(b ** 2 - 4 * a * c) / (4 * a), a
+
+
+def offroad(x: np.ndarray, y: np.ndarray, nsteps: np.ndarray, fit, side: str) -> np.ndarray:
+    """check_offroad (test_mapper_planner_obstacles.py:62-70) for every candidate: True = leaves the road on `side`."""
+    h, k, a = vertex_form(fit)
+    valid = np.arange(x.shape[1])[None, :] < nsteps[:, None]
+    with np.errstate(invalid="ignore"):
+        dist = (y - k) - a * (x - h) ** 2
+        bad = (dist < 0) if side == "right" else (dist > 0)
+    return (bad & valid).any(axis=1)

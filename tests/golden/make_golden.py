@@ -573,6 +573,85 @@ def gen_follow_fallback():
     save("follow_fallback", **rec)
 
 
+def gen_dt_lane():
+    """Duckietown lane run pieces with the reference's own functions
+    (lib/tests/test_mapper_planner_obstacles.py:25-135): V1DTObstacles lattice, parabola path built like
+    MapperSemanticObstacles.build_trajectory (lib/mapper/mapper_obstacles.py:169-186), projection-relative
+    frenet_to_glob_planner, check_paths with off-road parabolas and two obstacle point sets.  The camera -> robot
+    mapping is perception (out of scope): obstacles are given in the robot frame through an identity `cam2rob`."""
+    import lib.tests.test_mapper_planner_obstacles as dtm
+    from lib.trajectory import Trajectory
+
+    class IdentityMapper:
+        def cam2rob(self, pts):
+            return np.asarray(pts, dtype=np.float64)
+
+    out = {}
+    cases = [  # (a, b, c) of the lane centre, right / left boundary fits (or None), projection, state, obstacles (r, lat)
+        dict(fit=(0.3, 0.05, 0.01), rw=(0.32, 0.05, -0.29), lw=(0.28, 0.05, 0.33), proj=0.07, s0=(0.0, 0.2, 0.0), p0=(0.01, 0.0, 0.0),
+             obs=[((0.60, 0.05), (0.58, 0.12))]),
+        dict(fit=(-0.4, 0.3, -0.02), rw=None, lw=(-0.4, 0.3, 0.25), proj=0.05, s0=(0.03, 0.45, 0.1), p0=(-0.03, 0.02, 0.0),
+             obs=[((0.50, -0.27), (0.48, -0.21)), ((0.95, -0.45), (0.92, -0.38))]),
+        dict(fit=(0.3, -0.1, 0.0), rw=(0.3, -0.1, -0.22), lw=None, proj=0.1, s0=(0.0, 0.0, 0.0), p0=(0.0, 0.0, 0.0), obs=[]),
+    ]
+    out["n_cases"] = np.array(len(cases))
+    for i, cs in enumerate(cases):
+        a, b, c = cs["fit"]
+        trajectory = Trajectory()
+        trajectory.compute_pt = lambda x, a=a, b=b, c=c: np.array([x, a * x ** 2 + b * x + c])
+        trajectory.compute_first_derivative = lambda x, a=a, b=b: np.array([1, 2 * a * x + b])
+        pl = TrajectoryPlannerV1DTObstacles(TrajectoryPlannerParamsDTObstacles())
+        pl.initialize(t0=0, p0=cs["p0"], s0=cs["s0"])
+        pl.replanner(time=1 / 30, force=True)
+        paths = dtm.frenet_to_glob_planner(pl, trajectory, pl.paths, cs["proj"])
+        obstacles = [{"end_point": r, "center": r, "end_right": r, "end_lat": l, "end_top": l} for r, l in cs["obs"]]
+        rw = None if cs["rw"] is None else np.array(cs["rw"])
+        lw = None if cs["lw"] is None else np.array(cs["lw"])
+        if not obstacles:
+            kept = dtm.check_paths(paths, obstacles, np.array([0.07, 0.0, 0.0]), IdentityMapper(), rw, lw)
+        else:
+            # check_paths (:112-135) tests `measure_obst != []` on an ndarray, which NumPy >= 2 refuses to broadcast (older
+            # NumPy warned and took the branch).  Same composition from the reference's own piece functions, branch taken:
+            _, _, obs_r, obs_lat, _ = dtm.obstacles_coordinates(obstacles, IdentityMapper())
+            kept = []
+            for f in paths:
+                if rw is not None and dtm.check_offroad(f, dtm.get_vertex_and_focus_distance(rw), 'right'):
+                    continue
+                if lw is not None and dtm.check_offroad(f, dtm.get_vertex_and_focus_distance(lw), 'left'):
+                    continue
+                if not dtm.check_collisions(f, obs_r) or not dtm.check_collisions(f, obs_lat):
+                    continue
+                kept.append(f)
+        kept_ids = {id(f) for f in kept}
+        pk = pack_paths(paths, with_xy=True)
+        for k, v in pk.items():
+            out[f"c{i}_{k}"] = v
+        out[f"c{i}_keep"] = np.array([1 if id(f) in kept_ids else 0 for f in paths], dtype=np.uint8)
+        out[f"c{i}_offroad_right"] = np.array([0 if rw is None else int(dtm.check_offroad(f, dtm.get_vertex_and_focus_distance(rw), 'right'))
+                                               for f in paths], dtype=np.uint8)
+        out[f"c{i}_offroad_left"] = np.array([0 if lw is None else int(dtm.check_offroad(f, dtm.get_vertex_and_focus_distance(lw), 'left'))
+                                              for f in paths], dtype=np.uint8)
+        out[f"c{i}_fit"] = np.array(cs["fit"], dtype=np.float64)
+        out[f"c{i}_rw"] = np.array(cs["rw"] if cs["rw"] else [np.nan] * 3, dtype=np.float64)
+        out[f"c{i}_lw"] = np.array(cs["lw"] if cs["lw"] else [np.nan] * 3, dtype=np.float64)
+        out[f"c{i}_proj"] = np.array(cs["proj"])
+        out[f"c{i}_init_p0"] = np.array(cs["p0"], dtype=np.float64)
+        out[f"c{i}_init_s0"] = np.array(cs["s0"], dtype=np.float64)
+        out[f"c{i}_p0"] = np.array(pl.p0, dtype=np.float64)          # state after the forced replan = the lattice's start state
+        out[f"c{i}_s0"] = np.array(pl.s0, dtype=np.float64)
+        out[f"c{i}_obs_r"] = np.array([r for r, _ in cs["obs"]], dtype=np.float64).reshape(-1, 2)
+        out[f"c{i}_obs_lat"] = np.array([l for _, l in cs["obs"]], dtype=np.float64).reshape(-1, 2)
+        out[f"c{i}_argmin"] = np.array(pl.paths.index(pl.opt_path_tot))
+        out[f"c{i}_argmin_kept"] = np.array(paths.index(min(kept, key=attrgetter('ctot'))) if kept else -1)
+        win = dtm.frenet_to_glob(trajectory, pl, cs["proj"])
+        out[f"c{i}_winner_xy"] = win
+        out[f"c{i}_normal"] = np.array([dtm.compute_ortogonal_vect(trajectory, s) for s in (0.0, 0.1, 0.37, -0.05)])
+        print(f"  dt lane case {i}: {len(paths)} candidates, kept {len(kept)}, off-road right {int(out[f'c{i}_offroad_right'].sum())} "
+              f"left {int(out[f'c{i}_offroad_left'].sum())}")
+    out["agent_safety_rad"] = np.array(dtm.dp.AGENT_SAFETY_RAD)
+    save("dt_lane", **out)
+
+
 GENERATORS = {
     "kat_variants": gen_kat_variants,
     "paths": gen_paths,
@@ -586,6 +665,7 @@ GENERATORS = {
     "config5_sample": gen_config5_sample,
     "dt_sequences": gen_dt_sequences,
     "follow_fallback": gen_follow_fallback,
+    "dt_lane": gen_dt_lane,
 }
 
 if __name__ == "__main__":

@@ -375,3 +375,106 @@ def test_empty_lattice_raises_like_min_of_empty_list():
     pl2 = TrajectoryPlannerV1(TrajectoryPlannerParams(d_d_s=0.2, num_sample=1))
     pl2.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(0.0, 1.5, 0.0))       # a non-degenerate speed works with the same parameters
     assert len(pl2.paths) == len(np.arange(round(1.5 - 0.2), round(1.5 + 0.2 + 0.2), 0.2)) * 4 * 16 == 5 * 64
+
+
+def test_duckietown_lane_filter_matches_reference():
+    """projection-relative transform on a parabola lane path, off-road + two-point-set collision
+    filter and cheapest survivor, against the reference's lib/tests/test_mapper_planner_obstacles.py functions."""
+    from operator import attrgetter
+    from otg_b200.drivers import dt_lane as dl
+    from otg_b200.trajectory import ParabolaTrajectory2D
+
+    class IdentityMapper:
+        def cam2rob(self, pts):
+            return np.asarray(pts, dtype=np.float64)
+
+    z = golden("dt_lane")
+    assert dl.AGENT_SAFETY_RAD == float(z["agent_safety_rad"])
+    K, Pm = _classes()["dt_obstacles"]
+    for i in range(int(z["n_cases"])):
+        g = prefixed(z, f"c{i}_")
+        lane = ParabolaTrajectory2D(*g["fit"])
+        for s, ref in zip((0.0, 0.1, 0.37, -0.05), g["normal"]):
+            assert_close(dl.compute_ortogonal_vect(lane, s), ref, 1e-15, "normal")
+        pl = K(Pm())
+        pl.initialize(t0=0, p0=tuple(g["init_p0"]), s0=tuple(g["init_s0"]))
+        pl.replanner(time=1 / 30, force=True)
+        assert_close(np.array(pl.s0), g["s0"], 1e-12, "s0")
+        proj = float(g["proj"])
+        paths = dl.frenet_to_glob_planner(pl, lane, pl.paths, proj)
+        C = len(paths)
+        assert C == len(g["nsteps"])
+        for c in (0, C // 2, C - 1):
+            n = int(g["nsteps"][c])
+            assert_close(np.array(paths[c].x), g["x"][c, :n], 1e-12, "x", atol_scale=1.0)
+            assert_close(np.array(paths[c].y), g["y"][c, :n], 1e-12, "y", atol_scale=1.0)
+        obstacles = [{"end_point": r, "center": r, "end_right": r, "end_lat": l, "end_top": l}
+                     for r, l in zip(g["obs_r"], g["obs_lat"])]
+        rw = None if np.isnan(g["rw"]).any() else g["rw"]
+        lw = None if np.isnan(g["lw"]).any() else g["lw"]
+        kept = dl.check_paths(paths, obstacles, np.array([0.07, 0.0, 0.0]), IdentityMapper(), rw, lw)
+        ref_keep = g["keep"].astype(bool)
+        assert len(kept) == int(ref_keep.sum())
+        assert [f.index for f in kept] == np.flatnonzero(ref_keep).tolist()
+        if ref_keep.any():
+            best = min(kept, key=attrgetter("ctot"))
+            assert best.index == int(g["argmin_kept"])
+            n = int(g["nsteps"][best.index])
+            assert_close(np.array(best.x), g["x"][best.index, :n], 1e-12, "best.x", atol_scale=1.0)
+        else:
+            with pytest.raises(ValueError):
+                min(kept, key=attrgetter("ctot"))
+        # off-road masks alone, straight from the device buffers
+        eng = pl._engine
+        eng.offroad(rw, None)
+        right = eng.road_ok[0, :C].cpu().numpy() == 0
+        eng.offroad(None, lw)
+        left = eng.road_ok[0, :C].cpu().numpy() == 0
+        assert (right == g["offroad_right"].astype(bool)).all() and (left == g["offroad_left"].astype(bool)).all()
+        # the unfiltered optimum in Cartesian coordinates (frenet_to_glob of the Duckietown driver)
+        assert pl.paths.index(pl.opt_path_tot) == int(g["argmin"])
+        assert_close(dl.frenet_to_glob(lane, pl, proj), g["winner_xy"], 1e-12, "winner_xy", atol_scale=1.0)
+        # same filter on plain lists (any list of Frenet-like objects, like the reference accepts)
+        plain = [paths[c] for c in range(C)]
+        for f in plain:
+            f.x, f.y = [], []
+        dl.frenet_to_glob_planner(pl, lane, plain, proj)
+        kept2 = dl.check_paths(plain, obstacles, np.array([0.07, 0.0, 0.0]), IdentityMapper(), rw, lw)
+        assert [f.index for f in kept2] == np.flatnonzero(ref_keep).tolist()
+
+
+def test_duckietown_lane_reference_style_trajectory_and_step():
+    """A bare object carrying the mapper's lambdas (lib/mapper/mapper_obstacles.py:169-186) is accepted, and lane_step chains
+    replan -> transform -> filter -> pick like the reference's per-frame loop (:222-238)."""
+    from otg_b200.drivers import dt_lane as dl
+
+    class Bare:
+        pass
+
+    a, b, c = 0.3, 0.05, 0.01
+    tr = Bare()
+    tr.compute_pt = lambda x: np.array([x, a * x ** 2 + b * x + c])
+    tr.compute_first_derivative = lambda x: np.array([1, 2 * a * x + b])
+    tr.compute_second_derivative = lambda x: np.array([0, 2 * a])
+    lane = dl.lane_trajectory(tr)
+    assert (lane.a, lane.b, lane.c) == (a, b, c)
+
+    class IdentityMapper:
+        def cam2rob(self, pts):
+            return np.asarray(pts, dtype=np.float64)
+
+    K, Pm = _classes()["dt_obstacles"]
+    pl = K(Pm())
+    pl.initialize(t0=0, p0=(0.01, 0.0, 0.0), s0=(0.0, 0.2, 0.0))
+    obstacles = [{"end_point": (0.6, 0.05), "center": (0.6, 0.05), "end_right": (0.6, 0.05), "end_lat": (0.58, 0.12), "end_top": (0.58, 0.12)}]
+    pos_s, pos_d, kept, xy = dl.lane_step(pl, tr, 0.07, 1 / 30, obstacles, IdentityMapper(), np.array([0.32, 0.05, -0.29]),
+                                          np.array([0.28, 0.05, 0.33]))
+    assert 0 < len(kept) < len(pl.paths)
+    assert xy.shape == (len(pl.opt_path_tot.t), 2)
+    # the pick is collision free and on the road: oracle check on the winner's own samples
+    x, y = xy[:, 0][None, :], xy[:, 1][None, :]
+    n = np.array([xy.shape[0]])
+    pts = np.array([(0.6, 0.05), (0.58, 0.12)])
+    assert fo.check_collisions(x, y, n, pts, fo.AGENT_SAFETY_RAD ** 2)[0][0]
+    assert not fo.offroad(x, y, n, (0.32, 0.05, -0.29), "right")[0] and not fo.offroad(x, y, n, (0.28, 0.05, 0.33), "left")[0]
+    assert pl.opt_path_tot.ctot == min(f.ctot for f in kept)

@@ -38,7 +38,7 @@ def test_struct_layouts_match_the_header():
     """Field order of the ctypes mirrors == field order in the header (a silent mismatch would corrupt launches)."""
     text = open(HEADER).read()
     for cname, ctype in (("FrenetParams", nat.FrenetParams), ("FrenetLattice", nat.FrenetLattice), ("FrenetPath", nat.FrenetPath),
-                         ("FrenetResult", nat.FrenetResult), ("FrenetBuffers", nat.FrenetBuffers)):
+                         ("FrenetResult", nat.FrenetResult), ("FrenetBuffers", nat.FrenetBuffers), ("FrenetRoad", nat.FrenetRoad)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []

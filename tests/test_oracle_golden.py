@@ -307,3 +307,43 @@ def test_config5_sample():
         assert np.array_equal(ok.astype(np.uint8), z["keep"][i, :C])
         assert np.array_equal(first.astype(np.int16), z["first_blocker"][i, :C])
         assert fo.first_argmin(L.ctot, ok) == int(z["argmin_masked"][i])
+
+
+# ------------------------------------------------------------------------------------------------
+def test_dt_lane():
+    """parabola path + projection-relative transform + off-road / two-set collision filter
+    against the reference's Duckietown driver functions (lib/tests/test_mapper_planner_obstacles.py:25-135)."""
+    z = golden("dt_lane")
+    assert fo.AGENT_SAFETY_RAD == float(z["agent_safety_rad"])
+    prm = fo.OracleParams.defaults(fo.VARIANT_DTOBS)
+    for i in range(int(z["n_cases"])):
+        c = prefixed(z, f"c{i}_")
+        L = fo.generate(prm, c["p0"], c["s0"], 1 / 30)
+        compare_packed(pack_lattice(L), c, ORACLE_RTOL, f"dt_lane{i}")
+        path = fo.ParabolaPath(*c["fit"])
+        nx, ny = path.tangent(np.array([0.0, 0.1, 0.37, -0.05]))
+        th = np.arctan2(ny, nx)
+        assert_close(np.stack([-np.sin(th), np.cos(th)], axis=1), c["normal"], 1e-15, "dt normal")
+        kept = L.kept_indices()
+        s = L.lon[L.row_of[kept], 0, :]
+        x, y = fo.frenet_to_cartesian(path, np.where(np.isnan(s), 0.0, float(c["proj"]) + (s - float(c["s0"][0]))), L.lat[kept, 0, :])
+        n = L.nsteps[kept]
+        for j in range(len(kept)):
+            assert_close(x[j, :n[j]], c["x"][j, :n[j]], 1e-13, "dt x", atol_scale=1.0)
+            assert_close(y[j, :n[j]], c["y"][j, :n[j]], 1e-13, "dt y", atol_scale=1.0)
+        keep = np.ones(len(kept), dtype=bool)
+        for fit, side in ((c["rw"], "right"), (c["lw"], "left")):
+            if np.isnan(fit).any():
+                assert not c[f"offroad_{side}"].any()
+                continue
+            off = fo.offroad(x, y, n, fit, side)
+            assert (off == c[f"offroad_{side}"].astype(bool)).all(), (i, side)
+            keep &= ~off
+        obs = np.concatenate([c["obs_r"], c["obs_lat"]])
+        ok, _ = fo.check_collisions(x, y, n, obs, fo.AGENT_SAFETY_RAD ** 2)
+        keep &= ok
+        assert (keep == c["keep"].astype(bool)).all(), i
+        am = fo.first_argmin(L.ctot[kept], keep) if keep.any() else -1
+        assert am == int(c["argmin_kept"])
+        w = int(c["argmin"])
+        assert_close(np.stack([x[w, :n[w]], y[w, :n[w]]], axis=1), c["winner_xy"], 1e-13, "dt winner", atol_scale=1.0)
