@@ -26,7 +26,7 @@ def planner_attrs(prm: fo.OracleParams) -> Attr:
 
 def run_batch(prm: fo.OracleParams, p0, s0, t0, dd=None, desired=None, targets=None, trajectory=None, obstacles=None,
               active=None, use_mask=0, di_interval=None, t_interval=None, gather_sel=nat.SEL_CTOT, curvature=False,
-              engine=None, no_fuse=False):
+              engine=None, no_fuse=False, projection=None, radius_sq=0.7 ** 2):
     """Runs B scenarios through K1..K5 (+K3/K4 when a path / obstacles are given).  Returns the engine."""
     a = planner_attrs(prm)
     p0 = np.atleast_2d(np.asarray(p0, dtype=np.float64))
@@ -44,6 +44,9 @@ def run_batch(prm: fo.OracleParams, p0, s0, t0, dd=None, desired=None, targets=N
     n_obs = 0 if obstacles is None else np.asarray(obstacles).shape[1]
     eng = engine or FrenetEngine(B)
     eng.configure(geom, n_v_cap, n_obs)
+    eng.set_relative_s(projection is not None)       # Duckietown lane runs: path evaluated at projection + (s - s0[0])
+    if projection is not None:
+        eng.path_origin[:, 0], eng.path_origin[:, 1] = np.broadcast_to(np.asarray(projection, dtype=np.float64), (B,)), s0[:, 0]
     eng.state[:, :3], eng.state[:, 3:] = p0, s0
     eng.scal[:, 0], eng.scal[:, 1], eng.scal[:, 2] = dd, desired, t0
     eng.axis_v[:] = 0
@@ -67,7 +70,7 @@ def run_batch(prm: fo.OracleParams, p0, s0, t0, dd=None, desired=None, targets=N
         use_mask |= nat.MASK_COLLISION
     if no_fuse:
         stages |= nat.STAGE_NO_FUSE
-    P = make_params(a, lat.VARIANTS[prm.variant]["rule"], lat.sample_period(a, prm.variant), follow)
+    P = make_params(a, lat.VARIANTS[prm.variant]["rule"], lat.sample_period(a, prm.variant), follow, radius_sq=radius_sq)
     eng.run(P, path, stages, use_mask, gather_sel)
     return eng
 

@@ -806,3 +806,61 @@ def test_randomised_shapes_and_parameters_against_oracle():
             _check_argmin(int(eng.result[b]["argmin_ctot"]), fo.first_argmin(L.ctot, L.keep), L.ctot, f"fuzz[{case},{b}]")
             n_cases += 1
     assert n_cases > 30
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("no_fuse", [False, True])
+def test_lane_parabola_batch_against_oracle(no_fuse):
+    """SURVEY.md section 8f row 2 at kernel level: a batch on the parabola lane path with the projection-relative transform
+    (fused and separate launches), obstacle points at the Duckiebot safety radius, the off-road kernel for both boundaries
+    and the masked pick honouring both filters."""
+    _gpu, nat, _, _ = _imports()
+    from otg_b200.trajectory import ParabolaTrajectory2D
+    rng = np.random.default_rng(2024)
+    B, O = 12, 6
+    fit = (0.35, -0.08, 0.02)
+    rw, lw = (0.37, -0.08, -0.26), (0.33, -0.08, 0.31)
+    prm = fo.OracleParams.defaults(fo.VARIANT_DTOBS)
+    p0 = np.stack([rng.uniform(-.1, .1, B), rng.uniform(-.05, .05, B), rng.uniform(-.05, .05, B)], 1)
+    s0 = np.stack([rng.uniform(0, 0.3, B), rng.uniform(0.05, 0.6, B), rng.uniform(-.1, .1, B)], 1)
+    t0 = rng.uniform(0, 2, B)
+    proj = rng.uniform(0.02, 0.15, B)
+    obs = np.stack([rng.uniform(0.3, 1.2, (B, O)), rng.uniform(-0.4, 0.6, (B, O))], 2)
+    r2 = fo.AGENT_SAFETY_RAD ** 2
+    eng = _gpu.run_batch(prm, p0, s0, t0, trajectory=ParabolaTrajectory2D(*fit), obstacles=obs, projection=proj, radius_sq=r2,
+                         no_fuse=no_fuse)
+    eng.offroad(rw, lw)
+    P = _gpu.make_params(_gpu.planner_attrs(prm), _gpu.lat.VARIANTS[prm.variant]["rule"], _gpu.lat.sample_period(_gpu.planner_attrs(prm), prm.variant),
+                         False, radius_sq=r2)
+    eng.launch(P, None, nat.STAGE_K5 | nat.STAGE_GATHER, nat.MASK_COLLISION | nat.MASK_ROAD, nat.SEL_MASKED)
+    eng.download(sync=True)
+    road = eng.road_ok.cpu().numpy()
+    path = fo.ParabolaPath(*fit)
+    n_off = n_hit = n_keep = 0
+    for b in range(B):
+        L = fo.generate(prm, p0[b], s0[b], t0[b])
+        f = eng.padded_fields(eng.fetch_scenario(b))
+        compare_packed(f, pack_lattice(L, t_field=False), GPU_RTOL, f"lane[{b}]")
+        s = L.lon[L.row_of, 0, :]
+        with np.errstate(invalid="ignore"):
+            x, y = fo.frenet_to_cartesian(path, np.where(np.isnan(s), 0.0, proj[b] + (s - s0[b, 0])), L.lat[:, 0, :])
+        nmax = f["x"].shape[1]
+        valid = np.arange(nmax)[None, :] < L.nsteps[:, None]
+        assert_close(f["x"], np.where(valid, x[:, :nmax], np.nan), GPU_RTOL, f"lane[{b}].x", atol_scale=1.0)
+        assert_close(f["y"], np.where(valid, y[:, :nmax], np.nan), GPU_RTOL, f"lane[{b}].y", atol_scale=1.0)
+        ok, first = fo.check_collisions(x, y, L.nsteps, obs[b], r2)
+        assert np.array_equal(f["coll_free"], ok)
+        assert np.array_equal(f["first_blocker"], first)
+        off = fo.offroad(x, y, L.nsteps, rw, "right") | fo.offroad(x, y, L.nsteps, lw, "left")
+        C_ = L.n_candidates
+        assert np.array_equal(road[b, :C_] == 0, off), f"lane[{b}] off-road mask"
+        mask = ok & ~off
+        n_off, n_hit, n_keep = n_off + int(off.sum()), n_hit + int((~ok).sum()), n_keep + int(mask.sum())
+        _check_argmin(int(eng.result[b]["argmin_masked"]), fo.first_argmin(L.ctot, mask), L.ctot, f"lane[{b}] masked")
+        assert eng.result[b]["n_survivors"] == int(mask.sum())
+        w = int(eng.result[b]["argmin_masked"])
+        if w >= 0:
+            n = int(eng.winner_steps[b])
+            assert n == L.nsteps[w]
+            assert_close(eng.winner[b, 9, :n], x[w, :n], GPU_RTOL, "winner x", atol_scale=1.0)
+    assert n_off > 0 and n_hit > 0 and n_keep > 0
