@@ -470,6 +470,124 @@ __device__ __forceinline__ int collide_pair(double xa, double ya, double xb, dou
     return best;
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXTENSION: predicted (time-indexed) obstacles.  The reference tests every step of a candidate against the
+// obstacles' CURRENT positions; here step k can be tested against the obstacle's predicted position at step k.
+// ------------------------------------------------------------------------------------------------
+// Per (scenario, chunk of `span` steps, obstacle): bounding circle of the obstacle's predicted positions in that chunk.
+// span: steps per chunk (32 for one step per lane, 64 where a lane carries two).
+__global__ void __launch_bounds__(128) obstacle_chunk_bounds(const double* __restrict__ obs_t, const uint8_t* __restrict__ active, int O,
+                                                             int K, int n_chunks, int span, float4* __restrict__ bounds) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+        float4 out = make_float4(CUDART_INF_F, CUDART_INF_F, 0.0f, 0.0f);
+        if (active == nullptr || active[(int64_t)b * O + o] != 0) {
+            const double2* tbl = reinterpret_cast<const double2*>(obs_t) + ((int64_t)b * O + o) * K;
+            const int k0 = chunk * span;
+            const double2 c = tbl[min(k0 + span / 2, K - 1)];
+            double r2 = 0.0;
+            for (int k = k0; k < k0 + span; ++k) {
+                const double2 q = tbl[min(k, K - 1)];
+                const double dx = q.x - c.x, dy = q.y - c.y;
+                r2 = fmax(r2, fma(dx, dx, dy * dy));
+            }
+            out = make_float4(__double2float_rn(c.x), __double2float_rn(c.y), __fsqrt_ru(__double2float_ru(r2)), 0.0f);
+        }
+        bounds[((int64_t)b * n_chunks + chunk) * O + o] = out;
+    }
+}
+
+// Collision test of one 32-step chunk against predicted obstacles.  k: this lane's step; tbl: the scenario's predicted table
+// [O][K] (global memory, L2 resident: the rows of a scenario share it); cb: this chunk's obstacle bounds in shared memory.
+__device__ __forceinline__ int collide_chunk_predicted(double x, double y, bool valid, int nvalid, int k, const double2* __restrict__ tbl,
+                                                       int K, const float4* __restrict__ cb, int O, float Rf, double radius_sq,
+                                                       int best, int lane) {
+    const int mid = (nvalid - 1) >> 1;
+    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
+    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
+    const float ex = xf - cx, ey = yf - cy;
+    const float r2 = fmaf(ex, ex, ey * ey);
+    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
+    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
+    const bool wide = !(r2max < 1e30f);
+    const float rpt = Rf * 1.00001f + (fabsf(cx) + fabsf(cy) + reach) * 3.8147e-6f;   // every point of the chunk has |coord| <= |c| + reach
+    const int lim = min(O, best);
+    const int kk = min(k, K - 1);
+    for (int ob = 0; ob < lim; ob += kWarp) {
+        const int o = ob + lane;
+        bool near = false;
+        if (o < lim) {
+            const float4 q = cb[o];
+            const float ux = q.x - cx, uy = q.y - cy;
+            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
+            // obstacles the sensor did not report are parked at +inf by the bounds kernel: never near
+            near = (q.x < CUDART_INF_F) && (wide || !(fmaf(ux, ux, uy * uy) > rr * rr));
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            // fp32 pre-test per lane against the obstacle's bounding circle over this chunk: the predicted position is
+            // fetched from the table (global memory) only when some lane may be within the robot radius of it
+            const float4 qc = cb[ob + j];
+            const float px = xf - qc.x, py = yf - qc.y;
+            const float rp = rpt + qc.z * 1.00001f + (fabsf(qc.x) + fabsf(qc.y)) * 3.8147e-6f;
+            if (!__any_sync(kFull, wide || !(fmaf(px, px, py * py) > rp * rp))) continue;
+            const double2 q = tbl[(int64_t)(ob + j) * K + kk];
+            const double dx = x - q.x, dy = y - q.y;
+            const bool hit = valid && (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= radius_sq);
+            if (__any_sync(kFull, hit)) return ob + j;
+        }
+    }
+    return best;
+}
+
+// The same for a lane that carries two consecutive samples (steps k0, k0 + 1): one cull per 64 steps against bounds
+// computed over 64-step chunks; a survivor's two predicted positions are adjacent in the table (one 32-byte read per lane).
+__device__ __forceinline__ int collide_pair_predicted(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int nvalid,
+                                                      int k0, const double2* __restrict__ tbl, int K, const float4* __restrict__ cb, int O,
+                                                      float Rf, double radius_sq, int best, int lane) {
+    const int mid = (nvalid - 1) >> 2;
+    const float xf = __double2float_rn(xa), yf = __double2float_rn(ya);
+    const float xg = __double2float_rn(xb), yg = __double2float_rn(yb);
+    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
+    const float ex = xf - cx, ey = yf - cy, fx = xg - cx, fy = yg - cy;
+    const float r2 = fmaxf(fmaf(ex, ex, ey * ey), fmaf(fx, fx, fy * fy));
+    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
+    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
+    const bool wide = !(r2max < 1e30f);
+    const float rpt = Rf * 1.00001f + (fabsf(cx) + fabsf(cy) + reach) * 3.8147e-6f;
+    const int lim = min(O, best);
+    const int ka = min(k0, K - 1), kb = min(k0 + 1, K - 1);
+    for (int ob = 0; ob < lim; ob += kWarp) {
+        const int o = ob + lane;
+        bool near = false;
+        if (o < lim) {
+            const float4 q = cb[o];
+            const float ux = q.x - cx, uy = q.y - cy;
+            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
+            // obstacles the sensor did not report are parked at +inf by the bounds kernel: never near
+            near = (q.x < CUDART_INF_F) && (wide || !(fmaf(ux, ux, uy * uy) > rr * rr));
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float4 qc = cb[ob + j];
+            const float pax = xf - qc.x, pay = yf - qc.y, pbx = xg - qc.x, pby = yg - qc.y;
+            const float rp = rpt + qc.z * 1.00001f + (fabsf(qc.x) + fabsf(qc.y)) * 3.8147e-6f;
+            if (!__any_sync(kFull, wide || !(fminf(fmaf(pax, pax, pay * pay), fmaf(pbx, pbx, pby * pby)) > rp * rp))) continue;
+            const double2* row = tbl + (int64_t)(ob + j) * K;
+            const double2 qa = row[ka], qb = row[kb];
+            const double dxa = xa - qa.x, dya = ya - qa.y, dxb = xb - qb.x, dyb = yb - qb.y;
+            const bool hit = (valid_a && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= radius_sq)) ||
+                             (valid_b && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= radius_sq));
+            if (__any_sync(kFull, hit)) return ob + j;
+        }
+    }
+    return best;
+}
+
 // Stage a scenario's obstacle snapshot in shared memory.
 __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double2* obs, float2* obsf) {
     const int O = B.n_obs;
@@ -486,7 +604,8 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // K2 (+K3 +K4 fused): evaluate / cost / feasibility, one CTA per row
 // ------------------------------------------------------------------------------------------------
 // kXY:     also transform every sample to Cartesian (K3) while it is in registers and store x, y.
-// kColl:   also run the collision test (K4) on the Cartesian point while it is in registers.
+// kColl:   also run the collision test (K4) on the Cartesian point while it is in registers: 1 = against the obstacle snapshot
+//          (the reference's test), 2 = against the predicted, time-indexed table (extension).
 // kLimits: track max |acceleration| / |speed| for the (extension) kinematic limits; without it the
 //          KINEMATIC_OK flag is set unconditionally, which is the reference's behaviour.
 // The fused variants write each candidate-timestep exactly once (48 B: d, d', d'', d''', x, y) and read
@@ -497,13 +616,16 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // kPair:   every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead) - the
 //          mapping for long horizons; short horizons (at most 32 padded samples, e.g. the reference's default lattice with
 //          11..26 steps) use one step per lane so that the warp's lanes are not left idle.
-template <bool kXY, bool kColl, bool kLimits, bool kPair>
+template <bool kXY, int kColl, bool kLimits, bool kPair>
 __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
     extern __shared__ __align__(16) double sm[];
     const int npm = L.n_pad_max;
     double2* obs = reinterpret_cast<double2*>(sm);
     float2* obsf = reinterpret_cast<float2*>(sm + 2 * B.n_obs);
-    double* su = sm + (kColl ? 4 * ((3 * B.n_obs + 3) / 4) : 0);   // [npm] lateral argument: t_k, or |s_k - s0| in low-speed mode
+    constexpr int kSpanSteps = kPair ? 2 * kWarp : kWarp;          // steps covered by one warp iteration
+    const int n_chunks = (npm + kSpanSteps - 1) / kSpanSteps;
+    const float4* cbs = reinterpret_cast<const float4*>(sm);       // kColl == 2: [n_chunks][n_obs] per-chunk obstacle bounds
+    double* su = sm + (kColl == 1 ? 4 * ((3 * B.n_obs + 3) / 4) : kColl == 2 ? 2 * n_chunks * B.n_obs : 0);   // [npm] lateral argument: t_k, or |s_k - s0| in low-speed mode
     double* fpx = su + npm;                                        // [npm] x 4 path frame (kXY): point and unit normal
     double* fpy = fpx + (kXY ? npm : 0);
     double* fnx = fpy + (kXY ? npm : 0);
@@ -546,7 +668,12 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         const double* cq = B.coef_lat + A.cand0 * 6;
         for (int i = tid; i < L.n_d * 6; i += blockDim.x) coef[i] = cq[i];
         for (int i = tid; i < L.n_d; i += blockDim.x) axd[i] = L.axis_d[i];
-        if (kColl) stage_obstacles(B, A.b, obs, obsf);
+        if (kColl == 1) stage_obstacles(B, A.b, obs, obsf);
+        if (kColl == 2) {
+            const float4* src = reinterpret_cast<const float4*>(B.obs_bounds) + (int64_t)A.b * n_chunks * B.n_obs;
+            float4* dst = reinterpret_cast<float4*>(sm);
+            for (int i = tid; i < n_chunks * B.n_obs; i += blockDim.x) dst[i] = src[i];
+        }
         if (kXY && path.kind == FRENET_PATH_SPLINE) {
             for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
             __syncthreads();   // phase A reads the table
@@ -627,6 +754,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
     const double dd_target = B.scal[(int64_t)A.b * 3];
     const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
+    // predicted mode: the scenario's table [n_obs][n_obs_steps] stays in global memory (L2 resident: every row of a scenario reads it)
+    const double2* tblp = kColl == 2 ? reinterpret_cast<const double2*>(B.obs_xy_t) + (int64_t)A.b * B.n_obs * B.n_obs_steps : nullptr;
     const int npad = A.npad, N = A.N;
 
     // Phase B: a warp per candidate; every lane owns TWO consecutive time steps per iteration (64 steps per warp
@@ -691,9 +820,12 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                         *reinterpret_cast<double2*>(o += fs) = make_double2(ya, yb);
                     }
                     // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
-                    if (kColl)
+                    if (kColl == 1)
                         best = collide_pair(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq,
                                             best, lane);
+                    if (kColl == 2)
+                        best = collide_pair_predicted(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), kk, tblp, B.n_obs_steps,
+                                                      cbs + (kb / (2 * kWarp)) * B.n_obs, B.n_obs, Rf, P.radius_sq, best, lane);
                 }
                 out += 2 * kWarp * sizeof(double);
             }
@@ -724,7 +856,10 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                         *reinterpret_cast<double*>(o += fs) = x;
                         *reinterpret_cast<double*>(o += fs) = y;
                     }
-                    if (kColl) best = collide_chunk(x, y, valid, min(kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq, best, lane);
+                    if (kColl == 1) best = collide_chunk(x, y, valid, min(kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq, best, lane);
+                    if (kColl == 2)
+                        best = collide_chunk_predicted(x, y, valid, min(kWarp, N - kb), kk, tblp, B.n_obs_steps, cbs + (kb / kWarp) * B.n_obs,
+                                                       B.n_obs, Rf, P.radius_sq, best, lane);
                 }
                 out1 += kWarp * sizeof(double);
             }
@@ -970,69 +1105,6 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
             B.first_blocker[A.cand0 + id] = best == kNoBlocker ? -1 : best;
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// EXTENSION: predicted (time-indexed) obstacles.  The reference tests every step of a candidate against the
-// obstacles' CURRENT positions; here step k can be tested against the obstacle's predicted position at step k.
-// ------------------------------------------------------------------------------------------------
-// Per (scenario, 32-step chunk, obstacle): bounding circle of the obstacle's predicted positions in that chunk.
-__global__ void __launch_bounds__(128) obstacle_chunk_bounds(const double* __restrict__ obs_t, const uint8_t* __restrict__ active, int O,
-                                                             int K, int n_chunks, float4* __restrict__ bounds) {
-    const int b = blockIdx.y, chunk = blockIdx.x;
-    for (int o = threadIdx.x; o < O; o += blockDim.x) {
-        float4 out = make_float4(CUDART_INF_F, CUDART_INF_F, 0.0f, 0.0f);
-        if (active == nullptr || active[(int64_t)b * O + o] != 0) {
-            const double2* tbl = reinterpret_cast<const double2*>(obs_t) + ((int64_t)b * O + o) * K;
-            const int k0 = chunk * kWarp;
-            const double2 c = tbl[min(k0 + kWarp / 2, K - 1)];
-            double r2 = 0.0;
-            for (int k = k0; k < k0 + kWarp; ++k) {
-                const double2 q = tbl[min(k, K - 1)];
-                const double dx = q.x - c.x, dy = q.y - c.y;
-                r2 = fmax(r2, fma(dx, dx, dy * dy));
-            }
-            out = make_float4(__double2float_rn(c.x), __double2float_rn(c.y), __fsqrt_ru(__double2float_ru(r2)), 0.0f);
-        }
-        bounds[((int64_t)b * n_chunks + chunk) * O + o] = out;
-    }
-}
-
-// Collision test of one 32-step chunk against predicted obstacles.  k: this lane's step; tbl: the scenario's predicted table
-// [O][K] (global memory, L2 resident: the rows of a scenario share it); cb: this chunk's obstacle bounds in shared memory.
-__device__ __forceinline__ int collide_chunk_predicted(double x, double y, bool valid, int nvalid, int k, const double2* __restrict__ tbl,
-                                                       int K, const float4* __restrict__ cb, int O, float Rf, double radius_sq,
-                                                       int best, int lane) {
-    const int mid = (nvalid - 1) >> 1;
-    const float xf = __double2float_rn(x), yf = __double2float_rn(y);
-    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
-    const float ex = xf - cx, ey = yf - cy;
-    const float r2 = fmaf(ex, ex, ey * ey);
-    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
-    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
-    const bool wide = !(r2max < 1e30f);
-    const int lim = min(O, best);
-    const int kk = min(k, K - 1);
-    for (int ob = 0; ob < lim; ob += kWarp) {
-        const int o = ob + lane;
-        bool near = false;
-        if (o < lim) {
-            const float4 q = cb[o];
-            const float ux = q.x - cx, uy = q.y - cy;
-            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
-            near = wide ? (q.x < CUDART_INF_F) : !(fmaf(ux, ux, uy * uy) > rr * rr);
-        }
-        unsigned m = __ballot_sync(kFull, near);
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const double2 q = tbl[(int64_t)(ob + j) * K + kk];
-            const double dx = x - q.x, dy = y - q.y;
-            const bool hit = valid && (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= radius_sq);
-            if (__any_sync(kFull, hit)) return ob + j;
-        }
-    }
-    return best;
 }
 
 __global__ void __launch_bounds__(kRowThreads) k4_collision_predicted(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
@@ -1488,12 +1560,27 @@ int check_path(const FrenetPath* path) {
     return FRENET_OK;
 }
 
-template <bool kXY, bool kColl>
+// predicted mode: chunk granularity of the obstacle bounds the fused kernel uses (it follows the kernel's lane mapping)
+inline int predicted_span(const FrenetLattice* L) { return L->n_pad_max > kWarp ? 2 * kWarp : kWarp; }
+inline int predicted_chunks(const FrenetLattice* L) { return (L->n_pad_max + predicted_span(L) - 1) / predicted_span(L); }
+
+int launch_obstacle_bounds(const FrenetLattice* L, const FrenetBuffers* B, int span, cudaStream_t stream) {
+    if (!B->obs_xy_t || !B->obs_bounds) return fail(FRENET_ERR_BAD_ARG, "predicted obstacle table or bounds scratch missing");
+    const int n_chunks = (L->n_pad_max + span - 1) / span;
+    if (n_chunks == 0 || L->n_scen == 0 || B->n_obs == 0) return FRENET_OK;
+    obstacle_chunk_bounds<<<dim3(n_chunks, L->n_scen), 128, 0, stream>>>(B->obs_xy_t, B->obs_active, B->n_obs, B->n_obs_steps, n_chunks, span,
+                                                                         reinterpret_cast<float4*>(B->obs_bounds));
+    FRENET_CHECK_LAUNCH("obstacle_chunk_bounds");
+    return FRENET_OK;
+}
+
+template <bool kXY, int kColl>
 int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, cudaStream_t stream) {
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
     const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 12 + (spline ? (size_t)9 * path->n_knots : 0) +
-                         (kColl ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0)) * sizeof(double);
+                         (kColl == 1 ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0) +
+                         (kColl == 2 ? (size_t)2 * predicted_chunks(L) * B->n_obs : 0)) * sizeof(double);
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
     const bool pair = L->n_pad_max > kWarp;   // long horizons: two steps per lane
@@ -1552,17 +1639,21 @@ int frenet_k1_coefficients(const FrenetLattice* L, const FrenetParams* P, const 
 
 int frenet_k2_evaluate(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_k2(L, P, B)) return rc;
-    return launch_k2<false, false>(L, P, nullptr, B, (cudaStream_t)stream);
+    return launch_k2<false, 0>(L, P, nullptr, B, (cudaStream_t)stream);
 }
 
 int frenet_k2_fused(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B,
                     int32_t with_collision, frenet_stream_t stream) {
     if (int rc = check_k2(L, P, B)) return rc;
     if (int rc = check_path(path)) return rc;
-    if (!with_collision) return launch_k2<true, false>(L, P, path, B, (cudaStream_t)stream);
+    if (!with_collision) return launch_k2<true, 0>(L, P, path, B, (cudaStream_t)stream);
     if (!B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "fused: collision output is NULL");
     if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "fused: obstacle table missing");
-    return launch_k2<true, true>(L, P, path, B, (cudaStream_t)stream);
+    if (B->n_obs_steps > 0 && B->n_obs > 0) {   // predicted obstacles: per-chunk bounds first, then the fused kernel reads the table
+        if (int rc = launch_obstacle_bounds(L, B, predicted_span(L), (cudaStream_t)stream)) return rc;
+        return launch_k2<true, 2>(L, P, path, B, (cudaStream_t)stream);
+    }
+    return launch_k2<true, 1>(L, P, path, B, (cudaStream_t)stream);
 }
 
 int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B,
@@ -1591,11 +1682,8 @@ int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const Fre
     if (!P || !B || !B->row_flags || !B->lat || !B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "k4: NULL buffer");
     if (B->n_obs < 0 || B->n_obs_steps < 0) return fail(FRENET_ERR_BAD_ARG, "k4: negative obstacle count");
     if (B->n_obs_steps > 0 && B->n_obs > 0) {   // predicted table
-        if (!B->obs_xy_t || !B->obs_bounds) return fail(FRENET_ERR_BAD_ARG, "k4: predicted obstacle table or bounds scratch missing");
         const int n_chunks = (L->n_pad_max + kWarp - 1) / kWarp;
-        obstacle_chunk_bounds<<<dim3(n_chunks, L->n_scen), 128, 0, (cudaStream_t)stream>>>(
-            B->obs_xy_t, B->obs_active, B->n_obs, B->n_obs_steps, n_chunks, reinterpret_cast<float4*>(B->obs_bounds));
-        FRENET_CHECK_LAUNCH("obstacle_chunk_bounds");
+        if (int rc = launch_obstacle_bounds(L, B, kWarp, (cudaStream_t)stream)) return rc;
         const size_t smem = (size_t)n_chunks * B->n_obs * sizeof(float4);
         if (int rc = set_smem(k4_collision_predicted, smem, "k4: too many obstacles for shared memory")) return rc;
         k4_collision_predicted<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
@@ -1649,7 +1737,7 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     // K2 and K3 (and K4 when nothing sits between them) run as ONE kernel unless the caller asks for separate launches:
     // same arithmetic, same outputs, but every sample is written once instead of being re-read by K3 and K4.
     const bool fuse = (stages & FRENET_STAGE_K2) && (stages & FRENET_STAGE_K3) && !(stages & FRENET_STAGE_NO_FUSE);
-    const bool fuse_k4 = fuse && (stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_CURVATURE) && B && B->n_obs_steps == 0;
+    const bool fuse_k4 = fuse && (stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_CURVATURE);
     if (fuse) {
         if ((rc = frenet_k2_fused(L, P, path, B, fuse_k4 ? 1 : 0, stream))) return rc;
     } else {

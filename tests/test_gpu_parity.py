@@ -458,7 +458,8 @@ def test_fused_kernel_equals_separate_launches():
                 assert np.array_equal(fa[n], fb[n], equal_nan=True), (sidx, n)
 
 
-def test_predicted_obstacles_extension():
+@pytest.mark.parametrize("no_fuse", [False, True])
+def test_predicted_obstacles_extension(no_fuse):
     """EXTENSION (no reference code; the oracle's time-indexed table is the definition): obstacles propagated over the
     horizon on the device.  (a) the predicted table equals the reference's time law evaluated by the oracle;
     (b) collision masks / first blockers / masked argmin equal the oracle's time-indexed check; (c) with zero obstacle
@@ -477,6 +478,8 @@ def test_predicted_obstacles_extension():
     d_tot = sc["obs_d"][sl] + sc["obs_offset"][sl]
     K = 150
     bp = BatchPlanner(params, tr, B, O, predict_steps=K)
+    if no_fuse:
+        bp.stages |= nat.STAGE_NO_FUSE       # K2, K3 and the standalone predicted K4 as separate launches
     res = bp.plan(sc["p0"][sl], sc["s0"][sl], sc["t0"][sl], dd=sc["dd"][sl], obs_s=sc["obs_s"][sl], obs_d=d_tot,
                   obs_speed=sc["obs_speed"][sl])
     table = bp.engine.obs_xy_t.cpu().numpy()                     # [B][O][K][2]
@@ -864,3 +867,48 @@ def test_lane_parabola_batch_against_oracle(no_fuse):
             assert n == L.nsteps[w]
             assert_close(eng.winner[b, 9, :n], x[w, :n], GPU_RTOL, "winner x", atol_scale=1.0)
     assert n_off > 0 and n_hit > 0 and n_keep > 0
+
+
+@pytest.mark.parametrize("no_fuse", [False, True])
+def test_predicted_obstacles_short_horizon_and_short_table(no_fuse):
+    """Predicted mode on the reference's default lattice (11..26 steps: one step per lane in the fused kernel) with a table
+    SHORTER than the horizon (steps beyond it reuse the last entry) and some obstacles switched off."""
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.planner import TrajectoryPlannerParams
+    rng = np.random.default_rng(77)
+    B, O, K = 10, 20, 9
+    prm = fo.OracleParams.defaults("v1")
+    params = TrajectoryPlannerParams()
+    tr, op = Circle(8, 5, 2), fo.CirclePath(8, 5, 2)
+    p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.3, .3, B), rng.uniform(-.3, .3, B)], 1)
+    s0 = np.stack([rng.uniform(0, 30, B), rng.uniform(2.2, 5, B), rng.uniform(-.3, .3, B)], 1)
+    t0 = rng.uniform(0, 3, B)
+    obs_s = s0[:, 0:1] + rng.uniform(1.5, 14, (B, O))
+    obs_d = rng.uniform(-3, 3, (B, O))
+    speed = rng.uniform(0, 3, (B, O))
+    active = (rng.uniform(size=(B, O)) < 0.8).astype(np.uint8)
+    bp = BatchPlanner(params, tr, B, O, predict_steps=K)
+    if no_fuse:
+        bp.stages |= nat.STAGE_NO_FUSE
+    res = bp.plan(p0, s0, t0, obs_s=obs_s, obs_d=obs_d, obs_speed=speed, obs_active=active)
+    keep = bp.engine.coll_free.cpu().numpy()
+    first = bp.engine.first_blocker.cpu().numpy()
+    n_hit = n_free = 0
+    for b in range(B):
+        t = t0[b] + np.arange(K) * prm.delta_t
+        tau = fo.obstacle_time_law(t[None, :], speed[b][:, None], obs_s[b][:, None])
+        ox, oy = fo.frenet_to_cartesian(op, tau, obs_d[b][:, None])
+        act = np.nonzero(active[b])[0]
+        ref = np.stack([ox, oy], 2)[act]                                        # [O_active][K][2]
+        L = fo.generate(prm, p0[b], s0[b], float(t0[b]))
+        x, y = fo.lattice_to_cartesian(op, L)
+        ok, fb = fo.check_collisions(x, y, L.nsteps, np.transpose(ref, (1, 0, 2)))
+        C_ = L.n_candidates
+        assert np.array_equal(keep[b, :C_] != 0, ok), f"short predicted mask[{b}]"
+        want = np.where(fb >= 0, act[np.maximum(fb, 0)], -1)
+        bad = np.nonzero(first[b, :C_] != want)[0]
+        assert len(bad) == 0, f"short predicted blocker[{b}]: candidates {bad[:5].tolist()} got {first[b, bad[:5]].tolist()} want {want[bad[:5]].tolist()}"
+        _check_argmin(int(res.records["argmin_masked"][b]), fo.first_argmin(L.ctot, ok), L.ctot, f"short predicted[{b}]")
+        n_hit, n_free = n_hit + int((~ok).sum()), n_free + int(ok.sum())
+    assert n_hit > 0 and n_free > 0
