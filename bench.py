@@ -71,6 +71,32 @@ def _cpu_one(args):
     return int(L.nsteps.sum())
 
 
+def cpu_replan_latency(n_calls=30):
+    """Metric 2 on the host: one replan of the reference's default lattice (320 candidates, 5920 cand-ts) through the CPU port,
+    single thread - (a) generate + argmin (config 1), (b) + Frenet -> Cartesian + collision filter against 3 obstacles +
+    masked pick (configs 2/3).  The unmodified reference measured in the survey container: 70.6 ms and ~122 ms."""
+    from oracle import frenet_oracle as fo
+    prm = fo.OracleParams.defaults("v1")
+    path = fo.CirclePath(8, 5, 2)
+    obs = np.array([[5.0, 0.3], [6.0, -1.0], [4.5, 2.5]])
+    t1, t3 = [], []
+    for i in range(n_calls + 3):
+        s0 = (3.0 + 0.01 * i, 2.0, 0.0)
+        t = time.perf_counter()
+        L = fo.generate(prm, (0.0, 0.0, 0.0), s0, 0.2)
+        fo.first_argmin(L.ctot, L.keep)
+        ta = time.perf_counter()
+        x, y = fo.lattice_to_cartesian(path, L)
+        ok, _ = fo.check_collisions(x, y, L.nsteps, obs)
+        fo.first_argmin(L.ctot, ok & L.keep)
+        tb = time.perf_counter()
+        t1.append(ta - t)
+        t3.append(tb - t)
+    med = lambda v: float(np.median(np.array(v[3:])) * 1e6)   # noqa: E731
+    return {"config1_replanner_p50_us": med(t1), "config3_replan_transform_collide_pick_p50_us": med(t3), "cores": 1, "kind": "port",
+            "calls": n_calls}
+
+
 def cpu_pass(pool, wl, n):
     jobs = [(wl["p0"][i], wl["s0"][i], float(wl["t0"][i]), float(wl["dd"][i]), wl["obs_s"][i], wl["obs_d"][i]) for i in range(n)]
     t = time.perf_counter()
@@ -211,8 +237,27 @@ def predicted_mode(wl, steps, dev):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
     feasible = int((bp.engine.result["status"] == 0).sum())
+    # the two launches that differ from the snapshot step, each alone
+    import ctypes as C
+    from otg_b200 import _native as nat
+    e = bp.engine
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    parts = {"predict_obstacles": lambda: e.predict_obstacles(bp.path, bp.period),
+             "bounds_plus_fused_kernel": lambda: nat.check(nat.lib.frenet_k2_fused(C.byref(e.L), C.byref(bp.params), C.byref(bp.path.desc),
+                                                                                   C.byref(e.B), 1, stream))}
+    kernels = {}
+    for name, fn in parts.items():
+        fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for x, y in evs:
+            x.record()
+            fn()
+            y.record()
+        torch.cuda.synchronize()
+        kernels[name] = {"ms": float(np.mean([x.elapsed_time(y) for x, y in evs]))}
     out = {"value": bp.cand_timesteps() / (ms * 1e-3), "unit": "candidate-timesteps/s", "ms_per_step": ms, "predict_steps": 150,
-           "gpu_launches_per_step": bp.launches_per_plan, "scenarios_with_feasible": feasible}
+           "gpu_launches_per_step": bp.launches_per_plan, "scenarios_with_feasible": feasible, "kernels": kernels}
     del bp
     torch.cuda.empty_cache()
     return out
@@ -450,7 +495,8 @@ def run_gpu(args):
                 cpu_pass(pool, wl, min(cores, n))   # warm the workers
                 c, tcpu = cpu_pass(pool, wl, n)
             cpu = {"value": c / tcpu, "unit": "candidate-timesteps/s", "cores": cores, "kind": "port",
-                   "sample": f"first {n} of the {SCEN_PER_GPU} scenarios of the step, oracle (NumPy port) in {cores} processes, {tcpu:.1f} s"}
+                   "sample": f"first {n} of the {SCEN_PER_GPU} scenarios of the step, oracle (NumPy port) in {cores} processes, {tcpu:.1f} s",
+                   "replan_latency": cpu_replan_latency()}
 
         line = {"metric": METRIC, "value": cts_step * args.steps / (ms_dev * 1e-3), "unit": "candidate-timesteps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
