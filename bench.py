@@ -476,6 +476,16 @@ def run_gpu(args):
             if name in algo:
                 kernels[name].update(algorithmic_gb=algo[name] / 1e9, gbs=algo[name] / (ms * 1e-3) / 1e9,
                                      frac_of_hbm_peak=algo[name] / (ms * 1e-3) / 1e9 / peak)
+        # the collision stage is read against the measured non-tensor FMA peak (scripts/alu_peak.cu, stored in
+        # profiles/measured_alu_peaks.json).  A brute-force sweep costs 5 flop per (candidate-timestep, obstacle); the kernel's
+        # cull skips most of it, so its brute-force-equivalent rate may exceed the fp64 peak.
+        ap_path = os.path.join(ROOT, "profiles", "measured_alu_peaks.json")
+        if os.path.exists(ap_path) and "k4_collision" in kernels:
+            alu = json.load(open(ap_path))
+            flops = 5.0 * N_OBS * cts
+            eq = flops / (kern["k4_collision"] * 1e-3) / 1e12
+            kernels["k4_collision"].update(brute_force_equiv_tflops=eq, fp64_fma_peak_tflops=alu["fp64_tflops"],
+                                           fp32_fma_peak_tflops=alu["fp32_tflops"], equiv_over_fp64_peak=eq / alu["fp64_tflops"])
         in_pipeline = ("k1_coefficients", "k2k3k4_fused", "k5_argmin", "gather_winner")   # what frenet_plan launches
         dom = max((k for k in algo if k in in_pipeline), key=lambda k: kern[k])
         pipeline_ms = sum(kern[k] for k in in_pipeline)
