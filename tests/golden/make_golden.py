@@ -343,7 +343,7 @@ def gen_dense_config4():
          obs_s=sc["obs_s"], obs_d=sc["obs_d"], obs_xy=obs_xy, **out)
 
 
-def gen_config5_sample(n_sample=8):
+def gen_config5_sample(n_sample=16):
     sys.path.insert(0, os.path.join(HERE, "..", ".."))
     import otg_b200  # noqa: F401
     from otg_b200 import workloads
