@@ -898,6 +898,206 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 (+K3 +K4 fused) for SHORT horizons: at most 32 padded samples per candidate (the reference's default lattice has 11..26)
+// ------------------------------------------------------------------------------------------------
+// A row of such a lattice is too little work for a CTA of its own (16 candidates x 26 steps against a path-frame phase that is a
+// few hundred dependent fp64 instructions deep), so a CTA takes `G` consecutive rows of one scenario: a WARP per row for the
+// longitudinal phase (lanes = time steps; the jerk sum and the limits are warp reductions), then the G x n_d candidates of the
+// group round-robin over the warps, one time step per lane.  Same arithmetic and the same reduction trees as k2_evaluate, so the
+// two kernels agree bit for bit where both apply.
+// Shared memory (doubles): obstacles as in k2_evaluate | [G][n_pad_max] lateral argument | 4 x [G][n_pad_max] path frame (kXY) |
+// [G n_d][6] lateral coefficients | [G n_d][5] per-candidate results | [n_d] lateral axis | [G][2] row cost and horizon |
+// [G] candidate block offsets | [G][4] ints: N, npad, usable, feasible | spline table (kXY).
+template <bool kXY, int kColl, bool kLimits>
+__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_short(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int G) {
+    extern __shared__ __align__(16) double sm[];
+    const int npm = L.n_pad_max, nd = L.n_d;
+    const int R = L.n_v_cap * L.n_t;
+    const int groups = (R + G - 1) / G;
+    const int b = blockIdx.x / groups;
+    const int row0 = (blockIdx.x % groups) * G;
+    const int Ga = min(G, R - row0);                               // rows of this group
+    const int GC = G * nd;
+    double2* obs = reinterpret_cast<double2*>(sm);
+    float2* obsf = reinterpret_cast<float2*>(sm + 2 * B.n_obs);
+    const float4* cbs = reinterpret_cast<const float4*>(sm);       // kColl == 2: [n_obs] bounds of the only chunk
+    double* su = sm + (kColl == 1 ? 4 * ((3 * B.n_obs + 3) / 4) : kColl == 2 ? 2 * B.n_obs : 0);
+    double* fpx = su + G * npm;
+    double* fpy = fpx + (kXY ? G * npm : 0);
+    double* fnx = fpy + (kXY ? G * npm : 0);
+    double* fny = fnx + (kXY ? G * npm : 0);
+    double* coef = fny + (kXY ? G * npm : 0);
+    double* resc = coef + GC * 6;
+    int* resi = reinterpret_cast<int*>(resc + GC * 4);
+    double* axd = resc + GC * 5;
+    double* rowd = axd + nd;
+    int64_t* rowo = reinterpret_cast<int64_t*>(rowd + 2 * G);
+    int* rowi = reinterpret_cast<int*>(rowo + G);
+    double* tab = rowd + 5 * G;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t br0 = (int64_t)b * R + row0;
+    const int64_t cand0 = br0 * nd;                                // the group's candidates are contiguous in every per-candidate array
+    const int64_t candF = (int64_t)L.n_scen * R * nd;
+    const double dt = P.sample_period;
+    const double s0 = B.state[(int64_t)b * 6 + 3];
+
+    // Phase 0: lateral coefficients of the whole group, lateral axis, obstacles, spline table.
+    {
+        const double* cq = B.coef_lat + cand0 * 6;
+        for (int i = tid; i < Ga * nd * 6; i += blockDim.x) coef[i] = cq[i];
+        for (int i = tid; i < nd; i += blockDim.x) axd[i] = L.axis_d[i];
+        if (kColl == 1) stage_obstacles(B, b, obs, obsf);
+        if (kColl == 2) {
+            const float4* src = reinterpret_cast<const float4*>(B.obs_bounds) + (int64_t)b * B.n_obs;   // one chunk per scenario
+            float4* dst = reinterpret_cast<float4*>(sm);
+            for (int i = tid; i < B.n_obs; i += blockDim.x) dst[i] = src[i];
+        }
+        if (kXY && path.kind == FRENET_PATH_SPLINE) {
+            for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+            __syncthreads();
+        }
+    }
+
+    // Phase A: a warp per row.
+    for (int g = warp; g < Ga; g += nwarps) {
+        const int64_t br = br0 + g;
+        const int flags = B.row_flags[br];
+        const RowAddr A = row_addr(L, br);
+        const bool usable = (flags & FRENET_ROW_EXISTS) && !(flags & FRENET_ROW_DROPPED);
+        if (lane == 0) {
+            rowi[4 * g] = A.N;
+            rowi[4 * g + 1] = A.npad;
+            rowi[4 * g + 2] = usable ? 1 : 0;
+            rowo[g] = A.cand_off;
+        }
+        if (!usable) continue;
+        const bool low = flags & FRENET_ROW_LOWSPEED;
+        Poly pl;
+        pl.load(B.coef_lon + br * 6);
+        double* lon = B.lon + A.lon_off;
+        double acc = 0.0, vmax = 0.0, amax = 0.0;
+        const int k = lane;
+        if (k < A.npad) {   // padding samples are evaluated and stored like real ones (whole sectors, see k2_evaluate)
+            const double t = (double)k * dt;
+            double s, v, a, j;
+            eval_power_form(pl, t, L.t_pow + 4 * k, s, v, a, j);
+            lon[k] = s;
+            lon[A.npad + k] = v;
+            lon[2 * A.npad + k] = a;
+            lon[3 * A.npad + k] = j;
+            su[g * npm + k] = low ? fabs(s - s0) : t;
+            if (k < A.N) {
+                acc = fma(j, j, acc);
+                if (kLimits) {
+                    vmax = fmax(vmax, fabs(v));
+                    amax = fmax(amax, fabs(a));
+                }
+            }
+            if (kXY) {
+                double px, py, nx, ny;
+                const double sp = B.path_origin ? B.path_origin[2 * b] + (s - B.path_origin[2 * b + 1]) : s;
+                path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny);
+                fpx[g * npm + k] = px; fpy[g * npm + k] = py; fnx[g * npm + k] = nx; fny[g * npm + k] = ny;
+            }
+        }
+        acc = warp_sum(acc);
+        if (kLimits) {
+            vmax = warp_max(vmax);
+            amax = warp_max(amax);
+        }
+        if (lane == 0) {   // trajectory_planner.py:143-144, 153-154
+            const double jsum = 0.0 + acc;
+            const double T = L.axis_t[A.iT];
+            double s_last, v_last, a_last, j_last;
+            eval_power_form(pl, (double)(A.N - 1) * dt, L.t_pow + 4 * (A.N - 1), s_last, v_last, a_last, j_last);
+            double term;
+            if (P.follow) {
+                const double e = s_last - B.target[((int64_t)b * L.n_t + A.iT) * 3];
+                term = __dmul_rn(P.ks, __dmul_rn(e, e));
+            } else {
+                const double e = v_last - B.scal[(int64_t)b * 3 + 1];
+                term = __dmul_rn(P.kdots, __dmul_rn(e, e));
+            }
+            rowd[2 * g] = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, jsum), __dmul_rn(P.kt, T)), term);
+            rowd[2 * g + 1] = low ? B.row_S[br] : T;
+            rowi[4 * g + 3] = kLimits ? ((vmax <= P.v_max) && (amax <= P.a_max)) : 1;
+        }
+    }
+    __syncthreads();
+
+    const double dd_target = B.scal[(int64_t)b * 3];
+    const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
+    const double2* tblp = kColl == 2 ? reinterpret_cast<const double2*>(B.obs_xy_t) + (int64_t)b * B.n_obs * B.n_obs_steps : nullptr;
+
+    // Phase B: a warp per candidate, one time step per lane.
+    for (int c = warp; c < Ga * nd; c += nwarps) {
+        const int g = c / nd, id = c - g * nd;
+        if (!rowi[4 * g + 2]) continue;
+        const int N = rowi[4 * g], npad = rowi[4 * g + 1];
+        Poly pq;
+        pq.load(coef + c * 6);
+        double* out = B.lat + rowo[g] + (int64_t)id * (kCandFields * npad) + lane;
+        const bool valid = lane < N;        // a real sample
+        const bool store = lane < npad;     // real or padding: stored so that whole sectors are written
+        const int kk = store ? lane : 0;    // lanes beyond the padding shadow the first step
+        double d0, v1, a2, j;
+        pq.eval(su[g * npm + kk], d0, v1, a2, j);
+        if (store) {
+            out[0] = d0;
+            out[npad] = v1;
+            out[2 * npad] = a2;
+            out[3 * npad] = j;
+        }
+        double acc = 0.0, amax = 0.0;
+        int best = kNoBlocker;
+        if (valid) {
+            acc = fma(j, j, acc);
+            if (kLimits) amax = fmax(amax, fabs(a2));
+        }
+        if (kXY) {
+            const int f = g * npm + kk;
+            const double x = __dadd_rn(fpx[f], __dmul_rn(fnx[f], d0));   // pt + n * d, unfused like the reference
+            const double y = __dadd_rn(fpy[f], __dmul_rn(fny[f], d0));
+            if (store) {
+                out[4 * npad] = x;
+                out[5 * npad] = y;
+            }
+            if (kColl == 1) best = collide_chunk(x, y, valid, N, obs, obsf, B.n_obs, Rf, P.radius_sq, best, lane);
+            if (kColl == 2) best = collide_chunk_predicted(x, y, valid, N, kk, tblp, B.n_obs_steps, cbs, B.n_obs, Rf, P.radius_sq, best, lane);
+        }
+        acc = warp_sum(acc);
+        if (kLimits) amax = warp_max(amax);
+        if (lane == 0) {   // :165-167 / :174-176
+            const double clong = rowd[2 * g], horizon = rowd[2 * g + 1];
+            const double e = axd[id] - dd_target;
+            const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
+            resc[c * 4] = clat;
+            resc[c * 4 + 1] = P.follow ? 0.0 : clong;
+            resc[c * 4 + 2] = P.follow ? clong : 0.0;
+            resc[c * 4 + 3] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
+            const bool kin = kLimits ? (rowi[4 * g + 3] && amax <= P.a_max) : true;
+            resi[c * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0);
+            resi[c * 2 + 1] = best;
+        }
+    }
+    __syncthreads();
+    // per-candidate results of the whole group, written coalesced; candidates of rows that do not exist get the neutral record
+    for (int c = tid; c < Ga * nd; c += blockDim.x) {
+        const bool usable = rowi[4 * (c / nd) + 2];
+        const int64_t gc = cand0 + c;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) B.cost[f * candF + gc] = usable ? resc[c * 4 + f] : 0.0;
+        B.cand_flags[gc] = usable ? (uint8_t)resi[c * 2] : 0;
+        if (kColl) {
+            const int best = usable ? resi[c * 2 + 1] : 0;
+            B.coll_free[gc] = (usable && best == kNoBlocker) ? 1 : 0;
+            B.first_blocker[gc] = (!usable || best == kNoBlocker) ? -1 : best;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: Frenet -> Cartesian, one CTA per row; the path frame is computed once per (row, step)
 // ------------------------------------------------------------------------------------------------
 
@@ -1584,16 +1784,37 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
     const bool pair = L->n_pad_max > kWarp;   // long horizons: two steps per lane
+    if (!pair) {
+        // short horizons: G consecutive rows of a scenario per CTA - as many as fit 48 KB of shared memory while the grid still
+        // fills the GPU a few times over (a single planner keeps one row per CTA: its latency is what matters)
+        const int R = L->n_v_cap * L->n_t;
+        const size_t fixed = (size_t)L->n_d + (spline ? (size_t)9 * path->n_knots : 0) +
+                             (kColl == 1 ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0) + (kColl == 2 ? (size_t)2 * B->n_obs : 0);
+        auto bytes = [&](int g) { return (fixed + (size_t)g * ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 11 + 5)) * sizeof(double); };
+        int G = R;
+        while (G > 1 && (bytes(G) > 48 * 1024 || (int64_t)L->n_scen * ((R + G - 1) / G) < 8 * 148)) G = (G + 1) / 2;
+        const size_t sm_short = bytes(G);
+        const unsigned grid_short = (unsigned)((int64_t)L->n_scen * ((R + G - 1) / G));
+        if (grid_short == 0) return FRENET_OK;
+#define FRENET_LAUNCH_SHORT(LIM)                                                                                             \
+    do {                                                                                                                     \
+        if (int rc = set_smem(k2_short<kXY, kColl, LIM>, sm_short, "k2: row group does not fit shared memory")) return rc;   \
+        k2_short<kXY, kColl, LIM><<<grid_short, kRowThreads, sm_short, stream>>>(*L, *P, pd, *B, G);                         \
+    } while (0)
+        if (limits) FRENET_LAUNCH_SHORT(true);
+        else FRENET_LAUNCH_SHORT(false);
+#undef FRENET_LAUNCH_SHORT
+        FRENET_CHECK_LAUNCH("k2_short");
+        return FRENET_OK;
+    }
     const unsigned grid = n_rows(L);
 #define FRENET_LAUNCH_K2(LIM, PAIR)                                                                                           \
     do {                                                                                                                      \
         if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, PAIR>, smem, "k2: row does not fit shared memory")) return rc;     \
         k2_evaluate<kXY, kColl, LIM, PAIR><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B);                              \
     } while (0)
-    if (limits && pair) FRENET_LAUNCH_K2(true, true);
-    else if (limits) FRENET_LAUNCH_K2(true, false);
-    else if (pair) FRENET_LAUNCH_K2(false, true);
-    else FRENET_LAUNCH_K2(false, false);
+    if (limits) FRENET_LAUNCH_K2(true, true);
+    else FRENET_LAUNCH_K2(false, true);
 #undef FRENET_LAUNCH_K2
     FRENET_CHECK_LAUNCH("k2_evaluate");
     return FRENET_OK;
@@ -1714,7 +1935,11 @@ int frenet_k5_argmin(const FrenetLattice* L, const FrenetBuffers* B, int32_t use
     if ((use_mask & 2) && !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "k5: curvature mask requested but curv_ok is NULL");
     if ((use_mask & 4) && !B->coll_free) return fail(FRENET_ERR_BAD_ARG, "k5: collision mask requested but coll_free is NULL");
     if ((use_mask & 8) && !B->road_ok) return fail(FRENET_ERR_BAD_ARG, "k5: road mask requested but road_ok is NULL");
-    k5_argmin<<<L->n_scen, kArgminThreads, 0, (cudaStream_t)stream>>>(*L, *B, use_mask);
+    // small lattices (the reference's default has 320-384 candidates) leave most of a 512-thread CTA idle: a narrower CTA lets
+    // more scenarios be resident per SM (the lexicographic minimum does not depend on the block size)
+    const int64_t C = (int64_t)L->n_v_cap * L->n_t * L->n_d;
+    const int threads = C <= 1024 ? 128 : kArgminThreads;
+    k5_argmin<<<L->n_scen, threads, 0, (cudaStream_t)stream>>>(*L, *B, use_mask);
     FRENET_CHECK_LAUNCH("k5_argmin");
     return FRENET_OK;
 }
