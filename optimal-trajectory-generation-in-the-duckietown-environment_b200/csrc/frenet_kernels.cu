@@ -5,9 +5,11 @@
 // Design rules used throughout (DESIGN.md has the numbers):
 //   * one CTA per lattice row (scenario, target speed, horizon): the longitudinal samples, the path
 //     frame (point + normal), the row's lateral coefficients and the obstacle table are produced /
-//     staged once per CTA in shared memory and reused by the n_d candidates of the row;
-//   * inside a CTA a warp owns a candidate and its lanes own consecutive time steps (two per lane,
-//     16-byte accesses, for long horizons), so every global store is a contiguous, sector-aligned run
+//     staged once per CTA in shared memory and reused by the n_d candidates of the row; lattices with short horizons
+//     (at most 32 padded samples, the reference's default) take several rows of a scenario per CTA, a warp per row
+//     for the longitudinal phase (k2_short), because one such row is too little work for a CTA;
+//   * inside a CTA a warp owns a candidate and its lanes own consecutive time steps (two per lane and
+//     16-byte accesses for long horizons, one per lane in k2_short), so every global store is a contiguous, sector-aligned run
 //     of doubles; the six fields of a candidate sit next to each other ([candidate][6][npad]);
 //   * only whole 32-byte sectors are written (padding samples are stored too): a partially written
 //     sector costs a DRAM read-modify-write and halves the achieved store bandwidth;
@@ -613,16 +615,15 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // Shared memory (doubles): [3 * n_obs, rounded up to 4] obstacles in fp64 and fp32 (kColl) | [n_pad_max] lateral argument |
 // 4 x [n_pad_max] path frame (kXY) | [n_d][6] lateral coefficients | [n_d][5] per-candidate results | [n_d] lateral axis | [n_knots][9] spline
 // table (kXY).
-// kPair:   every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead) - the
-//          mapping for long horizons; short horizons (at most 32 padded samples, e.g. the reference's default lattice with
-//          11..26 steps) use one step per lane so that the warp's lanes are not left idle.
-template <bool kXY, int kColl, bool kLimits, bool kPair>
+// Every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead): the mapping for long
+// horizons.  Lattices of at most 32 padded samples go through k2_short below instead.
+template <bool kXY, int kColl, bool kLimits>
 __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
     extern __shared__ __align__(16) double sm[];
     const int npm = L.n_pad_max;
     double2* obs = reinterpret_cast<double2*>(sm);
     float2* obsf = reinterpret_cast<float2*>(sm + 2 * B.n_obs);
-    constexpr int kSpanSteps = kPair ? 2 * kWarp : kWarp;          // steps covered by one warp iteration
+    constexpr int kSpanSteps = 2 * kWarp;                          // steps covered by one warp iteration
     const int n_chunks = (npm + kSpanSteps - 1) / kSpanSteps;
     const float4* cbs = reinterpret_cast<const float4*>(sm);       // kColl == 2: [n_chunks][n_obs] per-chunk obstacle bounds
     double* su = sm + (kColl == 1 ? 4 * ((3 * B.n_obs + 3) / 4) : kColl == 2 ? 2 * n_chunks * B.n_obs : 0);   // [npm] lateral argument: t_k, or |s_k - s0| in low-speed mode
@@ -784,85 +785,49 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         const int64_t fs = (int64_t)npad * sizeof(double);
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
-        if constexpr (kPair) {
 #pragma unroll 1
-            for (int kb = 0; kb < N; kb += 2 * kWarp) {
-                const int k0 = kb + 2 * lane;
-                const bool store = k0 < npad;           // npad is even: a pair is stored whole or not at all
-                const bool valid_a = k0 < N, valid_b = k0 + 1 < N;   // real samples (the rest is padding)
-                const int kk = store ? k0 : kb;         // lanes beyond the padding shadow the chunk's first pair
-                const double2 u = *reinterpret_cast<const double2*>(su + kk);
-                double da, va, aa, ja, db, vb, ab, jb;
-                pq.eval(u.x, da, va, aa, ja);
-                pq.eval(u.y, db, vb, ab, jb);
-                char* o = out;
-                if (store) {
-                    *reinterpret_cast<double2*>(o) = make_double2(da, db);
-                    *reinterpret_cast<double2*>(o += fs) = make_double2(va, vb);
-                    *reinterpret_cast<double2*>(o += fs) = make_double2(aa, ab);
-                    *reinterpret_cast<double2*>(o += fs) = make_double2(ja, jb);
-                }
-                if (valid_a) {
-                    acc = fma(ja, ja, acc);
-                    if (kLimits) amax = fmax(amax, fabs(aa));
-                }
-                if (valid_b) {
-                    acc = fma(jb, jb, acc);
-                    if (kLimits) amax = fmax(amax, fabs(ab));
-                }
-                if (kXY) {
-                    const double2 px = *reinterpret_cast<const double2*>(fpx + kk), py = *reinterpret_cast<const double2*>(fpy + kk);
-                    const double2 nx = *reinterpret_cast<const double2*>(fnx + kk), ny = *reinterpret_cast<const double2*>(fny + kk);
-                    const double xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)), xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));   // pt + n * d,
-                    const double ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)), yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));   // unfused like the reference
-                    if (store) {
-                        *reinterpret_cast<double2*>(o += fs) = make_double2(xa, xb);
-                        *reinterpret_cast<double2*>(o += fs) = make_double2(ya, yb);
-                    }
-                    // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
-                    if (kColl == 1)
-                        best = collide_pair(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq,
-                                            best, lane);
-                    if (kColl == 2)
-                        best = collide_pair_predicted(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), kk, tblp, B.n_obs_steps,
-                                                      cbs + (kb / (2 * kWarp)) * B.n_obs, B.n_obs, Rf, P.radius_sq, best, lane);
-                }
-                out += 2 * kWarp * sizeof(double);
+        for (int kb = 0; kb < N; kb += 2 * kWarp) {
+            const int k0 = kb + 2 * lane;
+            const bool store = k0 < npad;           // npad is even: a pair is stored whole or not at all
+            const bool valid_a = k0 < N, valid_b = k0 + 1 < N;   // real samples (the rest is padding)
+            const int kk = store ? k0 : kb;         // lanes beyond the padding shadow the chunk's first pair
+            const double2 u = *reinterpret_cast<const double2*>(su + kk);
+            double da, va, aa, ja, db, vb, ab, jb;
+            pq.eval(u.x, da, va, aa, ja);
+            pq.eval(u.y, db, vb, ab, jb);
+            char* o = out;
+            if (store) {
+                *reinterpret_cast<double2*>(o) = make_double2(da, db);
+                *reinterpret_cast<double2*>(o += fs) = make_double2(va, vb);
+                *reinterpret_cast<double2*>(o += fs) = make_double2(aa, ab);
+                *reinterpret_cast<double2*>(o += fs) = make_double2(ja, jb);
             }
-        } else {
-            char* out1 = out - lane * sizeof(double);   // `out` was set up for pairs (2 * lane); one step per lane here
-#pragma unroll 1
-            for (int kb = 0; kb < N; kb += kWarp) {
-                const bool valid = kb + lane < N;       // a real sample
-                const bool store = kb + lane < npad;    // real or padding: stored so that whole sectors are written
-                const int kk = store ? kb + lane : kb;  // lanes beyond the padding shadow the chunk's first step
-                double d0, v1, a2, j;
-                pq.eval(su[kk], d0, v1, a2, j);
-                char* o = out1;
-                if (store) {
-                    *reinterpret_cast<double*>(o) = d0;
-                    *reinterpret_cast<double*>(o += fs) = v1;
-                    *reinterpret_cast<double*>(o += fs) = a2;
-                    *reinterpret_cast<double*>(o += fs) = j;
-                }
-                if (valid) {
-                    acc = fma(j, j, acc);
-                    if (kLimits) amax = fmax(amax, fabs(a2));
-                }
-                if (kXY) {
-                    const double x = __dadd_rn(fpx[kk], __dmul_rn(fnx[kk], d0));   // pt + n * d, unfused like the reference
-                    const double y = __dadd_rn(fpy[kk], __dmul_rn(fny[kk], d0));
-                    if (store) {
-                        *reinterpret_cast<double*>(o += fs) = x;
-                        *reinterpret_cast<double*>(o += fs) = y;
-                    }
-                    if (kColl == 1) best = collide_chunk(x, y, valid, min(kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq, best, lane);
-                    if (kColl == 2)
-                        best = collide_chunk_predicted(x, y, valid, min(kWarp, N - kb), kk, tblp, B.n_obs_steps, cbs + (kb / kWarp) * B.n_obs,
-                                                       B.n_obs, Rf, P.radius_sq, best, lane);
-                }
-                out1 += kWarp * sizeof(double);
+            if (valid_a) {
+                acc = fma(ja, ja, acc);
+                if (kLimits) amax = fmax(amax, fabs(aa));
             }
+            if (valid_b) {
+                acc = fma(jb, jb, acc);
+                if (kLimits) amax = fmax(amax, fabs(ab));
+            }
+            if (kXY) {
+                const double2 px = *reinterpret_cast<const double2*>(fpx + kk), py = *reinterpret_cast<const double2*>(fpy + kk);
+                const double2 nx = *reinterpret_cast<const double2*>(fnx + kk), ny = *reinterpret_cast<const double2*>(fny + kk);
+                const double xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)), xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));   // pt + n * d,
+                const double ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)), yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));   // unfused like the reference
+                if (store) {
+                    *reinterpret_cast<double2*>(o += fs) = make_double2(xa, xb);
+                    *reinterpret_cast<double2*>(o += fs) = make_double2(ya, yb);
+                }
+                // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
+                if (kColl == 1)
+                    best = collide_pair(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq,
+                                        best, lane);
+                if (kColl == 2)
+                    best = collide_pair_predicted(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), kk, tblp, B.n_obs_steps,
+                                                  cbs + (kb / (2 * kWarp)) * B.n_obs, B.n_obs, Rf, P.radius_sq, best, lane);
+            }
+            out += 2 * kWarp * sizeof(double);
         }
         acc = warp_sum(acc);
         if (kLimits) amax = warp_max(amax);
@@ -1808,13 +1773,13 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
         return FRENET_OK;
     }
     const unsigned grid = n_rows(L);
-#define FRENET_LAUNCH_K2(LIM, PAIR)                                                                                           \
-    do {                                                                                                                      \
-        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, PAIR>, smem, "k2: row does not fit shared memory")) return rc;     \
-        k2_evaluate<kXY, kColl, LIM, PAIR><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B);                              \
+#define FRENET_LAUNCH_K2(LIM)                                                                                           \
+    do {                                                                                                                \
+        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM>, smem, "k2: row does not fit shared memory")) return rc;     \
+        k2_evaluate<kXY, kColl, LIM><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B);                              \
     } while (0)
-    if (limits) FRENET_LAUNCH_K2(true, true);
-    else FRENET_LAUNCH_K2(false, true);
+    if (limits) FRENET_LAUNCH_K2(true);
+    else FRENET_LAUNCH_K2(false);
 #undef FRENET_LAUNCH_K2
     FRENET_CHECK_LAUNCH("k2_evaluate");
     return FRENET_OK;
