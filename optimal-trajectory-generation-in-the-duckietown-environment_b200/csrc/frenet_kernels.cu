@@ -178,6 +178,18 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// the same over each half of the warp (lanes 0..15 / 16..31): two candidates per warp in k2_short
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double half_max(double v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
 // Row addressing shared by the per-row kernels (layout: include/frenet_b200.h).
 constexpr int kLonFields = 4;    // s, ds, dds, ddds
 constexpr int kCandFields = 6;   // d, dd, ddd, dddd, x, y
@@ -590,6 +602,101 @@ __device__ __forceinline__ int collide_pair_predicted(double xa, double ya, doub
     return best;
 }
 
+// Two candidates per warp (k2_short): lanes 0..15 carry candidate A, lanes 16..31 candidate B, two consecutive samples each, the
+// whole horizon in one go (at most 32 steps).  One bounding circle and one cull for the 64 points of both candidates (neighbours in
+// the lattice, so their trajectories lie close together); the exact test attributes a hit to the half it occurred in.  Obstacles are
+// visited in ascending order, so the first hit of a half is its lowest blocker; the sweep ends when both halves have one.
+// Returns this lane's candidate's lowest blocker (kNoBlocker if none).  mid: a lane holding a point near the middle.
+__device__ __forceinline__ int collide_halves(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int mid,
+                                              const double2* __restrict__ obs, const float2* __restrict__ obsf, int O, float Rf,
+                                              double radius_sq, int lane) {
+    const float xf = __double2float_rn(xa), yf = __double2float_rn(ya);
+    const float xg = __double2float_rn(xb), yg = __double2float_rn(yb);
+    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
+    const float ex = xf - cx, ey = yf - cy, fx = xg - cx, fy = yg - cy;
+    const float r2 = fmaxf(fmaf(ex, ex, ey * ey), fmaf(fx, fx, fy * fy));
+    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
+    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
+    const bool finite = r2max < 1e30f;
+    const float thr = finite ? reach * reach : CUDART_INF_F;
+    const float rpt = Rf * 1.00001f + (fabsf(cx) + fabsf(cy) + reach) * 3.8147e-6f;
+    const float thr_pt = finite ? rpt * rpt : CUDART_INF_F;
+    int best_lo = kNoBlocker, best_hi = kNoBlocker;   // lowest blocker of lanes 0..15 / 16..31 (warp-uniform)
+    for (int ob = 0; ob < O; ob += kWarp) {
+        const int o = ob + lane;
+        bool near = false;
+        if (o < O) {
+            const float2 q = obsf[o];
+            const float ux = q.x - cx, uy = q.y - cy;
+            near = !(fmaf(ux, ux, uy * uy) > thr);
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float2 qf = obsf[ob + j];
+            const float ax = xf - qf.x, ay = yf - qf.y, bx = xg - qf.x, by = yg - qf.y;
+            const bool maybe = !(fminf(fmaf(ax, ax, ay * ay), fmaf(bx, bx, by * by)) > thr_pt);
+            if (!__any_sync(kFull, maybe)) continue;
+            const double2 q = obs[ob + j];
+            const double dxa = xa - q.x, dya = ya - q.y, dxb = xb - q.x, dyb = yb - q.y;
+            const bool hit = (valid_a && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= radius_sq)) ||
+                             (valid_b && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= radius_sq));
+            const unsigned hb = __ballot_sync(kFull, hit);
+            if ((hb & 0xffffu) && best_lo == kNoBlocker) best_lo = ob + j;
+            if ((hb >> 16) && best_hi == kNoBlocker) best_hi = ob + j;
+            if (best_lo != kNoBlocker && best_hi != kNoBlocker) return lane < 16 ? best_lo : best_hi;
+        }
+    }
+    return lane < 16 ? best_lo : best_hi;
+}
+
+// The same against predicted obstacles: k0 is this lane's first step, cb the bounds of the only chunk (32 steps).
+__device__ __forceinline__ int collide_halves_predicted(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int mid,
+                                                        int k0, const double2* __restrict__ tbl, int K, const float4* __restrict__ cb,
+                                                        int O, float Rf, double radius_sq, int lane) {
+    const float xf = __double2float_rn(xa), yf = __double2float_rn(ya);
+    const float xg = __double2float_rn(xb), yg = __double2float_rn(yb);
+    const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
+    const float ex = xf - cx, ey = yf - cy, fx = xg - cx, fy = yg - cy;
+    const float r2 = fmaxf(fmaf(ex, ex, ey * ey), fmaf(fx, fx, fy * fy));
+    const float r2max = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(r2)));
+    const float reach = (Rf + __fsqrt_ru(r2max)) * 1.00001f + (fabsf(cx) + fabsf(cy)) * 3.8147e-6f;
+    const bool wide = !(r2max < 1e30f);
+    const float rpt = Rf * 1.00001f + (fabsf(cx) + fabsf(cy) + reach) * 3.8147e-6f;
+    const int ka = min(k0, K - 1), kb = min(k0 + 1, K - 1);
+    int best_lo = kNoBlocker, best_hi = kNoBlocker;
+    for (int ob = 0; ob < O; ob += kWarp) {
+        const int o = ob + lane;
+        bool near = false;
+        if (o < O) {
+            const float4 q = cb[o];
+            const float ux = q.x - cx, uy = q.y - cy;
+            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
+            near = (q.x < CUDART_INF_F) && (wide || !(fmaf(ux, ux, uy * uy) > rr * rr));
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float4 qc = cb[ob + j];
+            const float pax = xf - qc.x, pay = yf - qc.y, pbx = xg - qc.x, pby = yg - qc.y;
+            const float rp = rpt + qc.z * 1.00001f + (fabsf(qc.x) + fabsf(qc.y)) * 3.8147e-6f;
+            if (!__any_sync(kFull, wide || !(fminf(fmaf(pax, pax, pay * pay), fmaf(pbx, pbx, pby * pby)) > rp * rp))) continue;
+            const double2* row = tbl + (int64_t)(ob + j) * K;
+            const double2 qa = row[ka], qb = row[kb];
+            const double dxa = xa - qa.x, dya = ya - qa.y, dxb = xb - qb.x, dyb = yb - qb.y;
+            const bool hit = (valid_a && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= radius_sq)) ||
+                             (valid_b && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= radius_sq));
+            const unsigned hb = __ballot_sync(kFull, hit);
+            if ((hb & 0xffffu) && best_lo == kNoBlocker) best_lo = ob + j;
+            if ((hb >> 16) && best_hi == kNoBlocker) best_hi = ob + j;
+            if (best_lo != kNoBlocker && best_hi != kNoBlocker) return lane < 16 ? best_lo : best_hi;
+        }
+    }
+    return lane < 16 ? best_lo : best_hi;
+}
+
 // Stage a scenario's obstacle snapshot in shared memory.
 __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double2* obs, float2* obsf) {
     const int O = B.n_obs;
@@ -868,8 +975,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 // A row of such a lattice is too little work for a CTA of its own (16 candidates x 26 steps against a path-frame phase that is a
 // few hundred dependent fp64 instructions deep), so a CTA takes `G` consecutive rows of one scenario: a WARP per row for the
 // longitudinal phase (lanes = time steps; the jerk sum and the limits are warp reductions), then the G x n_d candidates of the
-// group round-robin over the warps, one time step per lane.  Same arithmetic and the same reduction trees as k2_evaluate, so the
-// two kernels agree bit for bit where both apply.
+// group two per warp (16 lanes each, two time steps per lane).  Same arithmetic and the same pairwise reduction tree as k2_evaluate.
 // Shared memory (doubles): obstacles as in k2_evaluate | [G][n_pad_max] lateral argument | 4 x [G][n_pad_max] path frame (kXY) |
 // [G n_d][6] lateral coefficients | [G n_d][5] per-candidate results | [n_d] lateral axis | [G][2] row cost and horizon |
 // [G] candidate block offsets | [G][4] ints: N, npad, usable, feasible | spline table (kXY).
@@ -995,45 +1101,73 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
     const double2* tblp = kColl == 2 ? reinterpret_cast<const double2*>(B.obs_xy_t) + (int64_t)b * B.n_obs * B.n_obs_steps : nullptr;
 
-    // Phase B: a warp per candidate, one time step per lane.
-    for (int c = warp; c < Ga * nd; c += nwarps) {
-        const int g = c / nd, id = c - g * nd;
-        if (!rowi[4 * g + 2]) continue;
+    // Phase B: TWO candidates per warp - lanes 0..15 / 16..31 - and two consecutive time steps per lane (16-byte accesses): a
+    // horizon of at most 32 padded samples fits 16 lanes, and the per-candidate overhead (coefficients, reductions, cost
+    // arithmetic, collision set-up) is paid once per pair of candidates.
+    const int total = Ga * nd;
+    const int half = lane >> 4, hl = lane & 15;
+    for (int pr = warp; 2 * pr < total; pr += nwarps) {
+        const int c = 2 * pr + half;
+        const int cc = min(c, total - 1);               // the odd one out at the end of the group: lanes 16..31 idle along
+        const int g = cc / nd, id = cc - g * nd;
+        const bool act = c < total && rowi[4 * g + 2];
+        const unsigned actmask = __ballot_sync(kFull, act);
+        if (!actmask) continue;
         const int N = rowi[4 * g], npad = rowi[4 * g + 1];
+        const int k0 = 2 * hl;
+        const bool store = act && k0 < npad;            // npad is even: a pair is stored whole or not at all
+        const bool valid_a = act && k0 < N, valid_b = act && k0 + 1 < N;
+        const int kk = k0 < npad ? k0 : 0;              // lanes beyond the padding shadow the first pair
         Poly pq;
-        pq.load(coef + c * 6);
-        double* out = B.lat + rowo[g] + (int64_t)id * (kCandFields * npad) + lane;
-        const bool valid = lane < N;        // a real sample
-        const bool store = lane < npad;     // real or padding: stored so that whole sectors are written
-        const int kk = store ? lane : 0;    // lanes beyond the padding shadow the first step
-        double d0, v1, a2, j;
-        pq.eval(su[g * npm + kk], d0, v1, a2, j);
+        pq.load(coef + cc * 6);
+        const double2 u = *reinterpret_cast<const double2*>(su + g * npm + kk);
+        double da, va, aa, ja, db, vb, ab, jb;
+        pq.eval(u.x, da, va, aa, ja);
+        pq.eval(u.y, db, vb, ab, jb);
+        double* out = B.lat + rowo[g] + (int64_t)id * (kCandFields * npad) + k0;
         if (store) {
-            out[0] = d0;
-            out[npad] = v1;
-            out[2 * npad] = a2;
-            out[3 * npad] = j;
+            *reinterpret_cast<double2*>(out) = make_double2(da, db);
+            *reinterpret_cast<double2*>(out + npad) = make_double2(va, vb);
+            *reinterpret_cast<double2*>(out + 2 * npad) = make_double2(aa, ab);
+            *reinterpret_cast<double2*>(out + 3 * npad) = make_double2(ja, jb);
         }
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
-        if (valid) {
-            acc = fma(j, j, acc);
-            if (kLimits) amax = fmax(amax, fabs(a2));
+        if (valid_a) {
+            acc = fma(ja, ja, acc);
+            if (kLimits) amax = fmax(amax, fabs(aa));
+        }
+        if (valid_b) {
+            acc = fma(jb, jb, acc);
+            if (kLimits) amax = fmax(amax, fabs(ab));
         }
         if (kXY) {
             const int f = g * npm + kk;
-            const double x = __dadd_rn(fpx[f], __dmul_rn(fnx[f], d0));   // pt + n * d, unfused like the reference
-            const double y = __dadd_rn(fpy[f], __dmul_rn(fny[f], d0));
+            const double2 px = *reinterpret_cast<const double2*>(fpx + f), py = *reinterpret_cast<const double2*>(fpy + f);
+            const double2 nx = *reinterpret_cast<const double2*>(fnx + f), ny = *reinterpret_cast<const double2*>(fny + f);
+            double xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)), xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));   // pt + n * d,
+            double ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)), yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));   // unfused like the reference
             if (store) {
-                out[4 * npad] = x;
-                out[5 * npad] = y;
+                *reinterpret_cast<double2*>(out + 4 * npad) = make_double2(xa, xb);
+                *reinterpret_cast<double2*>(out + 5 * npad) = make_double2(ya, yb);
             }
-            if (kColl == 1) best = collide_chunk(x, y, valid, N, obs, obsf, B.n_obs, Rf, P.radius_sq, best, lane);
-            if (kColl == 2) best = collide_chunk_predicted(x, y, valid, N, kk, tblp, B.n_obs_steps, cbs, B.n_obs, Rf, P.radius_sq, best, lane);
+            if (kColl) {
+                if (actmask != kFull) {   // one half has no candidate: it mirrors the other's points (and hits nothing)
+                    const double oxa = __shfl_xor_sync(kFull, xa, 16), oya = __shfl_xor_sync(kFull, ya, 16);
+                    const double oxb = __shfl_xor_sync(kFull, xb, 16), oyb = __shfl_xor_sync(kFull, yb, 16);
+                    if (!act) { xa = oxa; ya = oya; xb = oxb; yb = oyb; }
+                }
+                const int hsel = (actmask & 0xffffu) ? 0 : 16;
+                const int mid = hsel + ((__shfl_sync(kFull, N, hsel) - 1) >> 2);
+                if (kColl == 1) best = collide_halves(xa, ya, xb, yb, valid_a, valid_b, mid, obs, obsf, B.n_obs, Rf, P.radius_sq, lane);
+                if (kColl == 2)
+                    best = collide_halves_predicted(xa, ya, xb, yb, valid_a, valid_b, mid, kk, tblp, B.n_obs_steps, cbs, B.n_obs, Rf,
+                                                    P.radius_sq, lane);
+            }
         }
-        acc = warp_sum(acc);
-        if (kLimits) amax = warp_max(amax);
-        if (lane == 0) {   // :165-167 / :174-176
+        acc = half_sum(acc);
+        if (kLimits) amax = half_max(amax);
+        if (hl == 0 && act) {   // :165-167 / :174-176
             const double clong = rowd[2 * g], horizon = rowd[2 * g + 1];
             const double e = axd[id] - dd_target;
             const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
