@@ -263,6 +263,45 @@ def predicted_mode(wl, steps, dev):
     return out
 
 
+def all_checks_mode(wl, steps, dev):
+    """EXTENSION leg: the same step with FINITE kinematic and curvature limits (v_max, a_max, kappa_max), i.e. every feasibility
+    check of the evaluate kernel switched on next to the collision test - all in the one pipeline kernel.  The reference has no
+    such limits (the headline step runs with +inf, where every candidate is feasible by definition)."""
+    import torch
+    import otg_b200  # noqa: F401
+    from otg_b200 import workloads as w
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.planner import TrajectoryPlannerParams
+    from otg_b200.trajectory import SplineTrajectory2D
+    n = len(wl["t0"])
+    limits = dict(v_max=6.3, a_max=2.6, kappa_max=1.2)
+    bp = BatchPlanner(TrajectoryPlannerParams(**w.DENSE_PARAMS, **limits), SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY), n, N_OBS, "v1", dev)
+    bp.stage_inputs(**wl)
+    bp.engine.upload()
+    for _ in range(3):
+        bp.launch_resident()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        bp.launch_resident()
+        bp.engine.download(sync=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    e = bp.engine
+    C_ = float(e.result["n_valid"].sum())
+    kin = float(((e.cand_flags & 2) != 0).sum().item())
+    curv = float(e.curv_ok.sum().item())
+    out = {"value": bp.cand_timesteps() / (ms * 1e-3), "unit": "candidate-timesteps/s", "ms_per_step": ms, "limits": limits,
+           "gpu_launches_per_step": bp.launches_per_plan, "kinematic_ok_fraction": kin / max(C_, 1.0),
+           "curvature_ok_fraction": curv / max(C_, 1.0), "survivor_fraction": float(e.result["n_survivors"].sum()) / max(C_, 1.0),
+           "scenarios_with_feasible": int((e.result["status"] == 0).sum())}
+    del bp
+    torch.cuda.empty_cache()
+    return out
+
+
 def closed_loop(dev, n_agents=8192, steps=30):
     """SURVEY section 8f row 1 leg: whole closed-loop steps (projection, replan, cone gate, collision filter, controller,
     unicycle) for `n_agents` agents of BASELINE config 2 (default lattice, circle path, 10 static obstacles) with all
@@ -519,12 +558,13 @@ def run_gpu(args):
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
                 "replan_latency": replan_latency() if world == 1 else None,
-                "predicted_obstacles": None, "closed_loop": None,
+                "predicted_obstacles": None, "all_feasibility_checks": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
         if world == 1:
             del bp
             torch.cuda.empty_cache()
             line["predicted_obstacles"] = predicted_mode(wl, max(3, args.steps // 3), dev)
+            line["all_feasibility_checks"] = all_checks_mode(wl, max(3, args.steps // 3), dev)
             line["closed_loop"] = closed_loop(dev)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -218,8 +218,10 @@ int frenet_k1_coefficients(const FrenetLattice* lat, const FrenetParams* prm, co
  * Replaces the sampling and cost lines of generate_range_polynomials (trajectory_planner.py:139-176). */
 int frenet_k2_evaluate(const FrenetLattice* lat, const FrenetParams* prm, const FrenetBuffers* buf, frenet_stream_t stream);
 
-/* K2 + K3 (+ K4) as one kernel: every sample is evaluated, transformed (and collision-tested) while it is in
- * registers and written to HBM once.  Outputs are identical to the separate launches. */
+/* K2 + K3 (+ K4, + the curvature limit) as one kernel: every sample is evaluated, transformed (and collision- / curvature-tested)
+ * while it is in registers and written to HBM once.  Outputs are identical to the separate launches.
+ * with_collision: bit set of FRENET_FUSE_* (1 = the historical "with collision"). */
+enum { FRENET_FUSE_COLLISION = 1, FRENET_FUSE_CURVATURE = 2 };
 int frenet_k2_fused(const FrenetLattice* lat, const FrenetParams* prm, const FrenetPath* path, const FrenetBuffers* buf,
                     int32_t with_collision, frenet_stream_t stream);
 
@@ -251,7 +253,7 @@ int frenet_gather_winner(const FrenetLattice* lat, const FrenetParams* prm, cons
 int frenet_k3_offroad(const FrenetLattice* lat, const FrenetRoad* road, const FrenetBuffers* buf, frenet_stream_t stream);
 
 /* The pipeline: launches the stages selected in `stages` in order K1, K2, K3, (curvature), K4, K5, gather;
- * K2+K3(+K4) are fused into one launch when selected together (FRENET_STAGE_NO_FUSE keeps them apart). */
+ * K2+K3(+K4, +curvature) are fused into one launch when selected together (FRENET_STAGE_NO_FUSE keeps them apart). */
 int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetPath* path, const FrenetBuffers* buf,
                 int32_t stages, int32_t use_mask, int32_t gather_sel, frenet_stream_t stream);
 

@@ -237,7 +237,9 @@ class BatchPlanner:
         n = bin(self.stages).count("1")
         if (self.stages & nat.STAGE_K2) and (self.stages & nat.STAGE_K3):     # frenet_plan fuses K2+K3 (+K4)
             n -= 1
-            if (self.stages & nat.STAGE_K4) and not (self.stages & nat.STAGE_CURVATURE):
+            if self.stages & nat.STAGE_K4:
+                n -= 1
+            if self.stages & nat.STAGE_CURVATURE:
                 n -= 1
         if self.predict_steps and (self.stages & nat.STAGE_K4):
             n += 1                                                            # per-chunk obstacle bounds

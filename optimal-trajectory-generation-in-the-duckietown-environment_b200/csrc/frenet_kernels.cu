@@ -387,10 +387,26 @@ __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ 
     ny = cs;
 }
 
+// Menger curvature of three consecutive samples against kappa_max, squared and division-free:
+// kappa = 2 |a x b| / (|a| |b| |a + b|)  >  kappa_max   <=>   4 (a x b)^2  >  kappa_max^2 |a|^2 |b|^2 |a + b|^2.
+__device__ __forceinline__ bool menger_exceeds(double x0, double y0, double x1, double y1, double x2, double y2, double k2max) {
+    const double ax = x1 - x0, ay = y1 - y0;
+    const double bx = x2 - x1, by = y2 - y1;
+    const double cx = x2 - x0, cy = y2 - y0;
+    const double cr = __dadd_rn(__dmul_rn(ax, by), -__dmul_rn(ay, bx));
+    const double lhs = __dmul_rn(4.0, __dmul_rn(cr, cr));
+    const double la = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+    const double lb = __dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by));
+    const double lc = __dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy));
+    const double rhs = __dmul_rn(k2max, __dmul_rn(__dmul_rn(la, lb), lc));
+    return lhs > rhs;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Collision test of one 32-step chunk of one candidate (shared by K4 and the fused kernel)
 // ------------------------------------------------------------------------------------------------
 constexpr int kNoBlocker = 0x7fffffff;
+constexpr int kCurvOkBit = 0x100;   // staged next to the candidate flags in shared memory (not part of the stored flag byte)
 
 // x, y: this lane's point (lanes beyond the candidate's last step carry a copy of a valid point and valid = false).
 // obs: obstacle table in shared memory as (x, y) pairs; obsf: the same rounded to fp32 for the cull; obstacles the
@@ -725,7 +741,7 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // Every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead): the mapping for long
 // horizons.  Lattices of at most 32 padded samples go through k2_short below instead.
 template <bool kXY, int kColl, bool kLimits>
-__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B) {
+__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts) {
     extern __shared__ __align__(16) double sm[];
     const int npm = L.n_pad_max;
     double2* obs = reinterpret_cast<double2*>(sm);
@@ -764,6 +780,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                 B.coll_free[c] = 0;
                 B.first_blocker[c] = -1;
             }
+            if (kLimits && kXY && (opts & 1)) B.curv_ok[c] = 0;
         }
         return;
     }
@@ -865,6 +882,10 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     // predicted mode: the scenario's table [n_obs][n_obs_steps] stays in global memory (L2 resident: every row of a scenario reads it)
     const double2* tblp = kColl == 2 ? reinterpret_cast<const double2*>(B.obs_xy_t) + (int64_t)A.b * B.n_obs * B.n_obs_steps : nullptr;
     const int npad = A.npad, N = A.N;
+    // curvature limit (extension, with the kinematic limits): Menger curvature of every interior sample, tested while the
+    // samples are in registers - a lane needs its left neighbour's pair, lane 0 the last pair of the previous iteration
+    const bool do_curv = kLimits && kXY && (opts & 1);
+    const double k2max = P.kappa_max * P.kappa_max;
 
     // Phase B: a warp per candidate; every lane owns TWO consecutive time steps per iteration (64 steps per warp
     // iteration, 16-byte loads from shared memory and 16-byte stores to HBM); no global loads in this loop.
@@ -892,6 +913,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         const int64_t fs = (int64_t)npad * sizeof(double);
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
+        bool curv_bad = false;
+        double cxa = 0.0, cya = 0.0, cxb = 0.0, cyb = 0.0;   // lane 31's pair of the previous iteration
 #pragma unroll 1
         for (int kb = 0; kb < N; kb += 2 * kWarp) {
             const int k0 = kb + 2 * lane;
@@ -926,6 +949,18 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                     *reinterpret_cast<double2*>(o += fs) = make_double2(xa, xb);
                     *reinterpret_cast<double2*>(o += fs) = make_double2(ya, yb);
                 }
+                if (kLimits) {
+                    if (do_curv) {
+                        double qxa = __shfl_up_sync(kFull, xa, 1), qya = __shfl_up_sync(kFull, ya, 1);
+                        double qxb = __shfl_up_sync(kFull, xb, 1), qyb = __shfl_up_sync(kFull, yb, 1);
+                        if (lane == 0) { qxa = cxa; qya = cya; qxb = cxb; qyb = cyb; }
+                        // centres k0 - 1 (the neighbour's second sample) and k0 (this lane's first); interior means 1 <= k <= N - 2
+                        if (k0 >= 2 && k0 <= N - 1) curv_bad |= menger_exceeds(qxa, qya, qxb, qyb, xa, ya, k2max);
+                        if (k0 >= 1 && k0 <= N - 2) curv_bad |= menger_exceeds(qxb, qyb, xa, ya, xb, yb, k2max);
+                        cxa = __shfl_sync(kFull, xa, kWarp - 1); cya = __shfl_sync(kFull, ya, kWarp - 1);
+                        cxb = __shfl_sync(kFull, xb, kWarp - 1); cyb = __shfl_sync(kFull, yb, kWarp - 1);
+                    }
+                }
                 // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
                 if (kColl == 1)
                     best = collide_pair(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq,
@@ -937,7 +972,10 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             out += 2 * kWarp * sizeof(double);
         }
         acc = warp_sum(acc);
-        if (kLimits) amax = warp_max(amax);
+        if (kLimits) {
+            amax = warp_max(amax);
+            curv_bad = __any_sync(kFull, curv_bad);
+        }
         if (lane == 0) {   // :165-167 / :174-176; staged in shared memory, written out coalesced below
             const double e = axd[id] - dd_target;
             const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
@@ -946,7 +984,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             resc[id * 4 + 2] = P.follow ? clong : 0.0;
             resc[id * 4 + 3] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
             const bool kin = kLimits ? (rowfeas && amax <= P.a_max) : true;
-            resi[id * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0);
+            resi[id * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0) | (curv_bad ? 0 : kCurvOkBit);
             resi[id * 2 + 1] = best;
         }
     }
@@ -961,6 +999,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 #pragma unroll
         for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = resc[id * 4 + f];
         B.cand_flags[c] = (uint8_t)resi[id * 2];
+        if (do_curv) B.curv_ok[c] = (resi[id * 2] & kCurvOkBit) ? 1 : 0;
         if (kColl) {
             const int best = resi[id * 2 + 1];
             B.coll_free[c] = best == kNoBlocker ? 1 : 0;
@@ -980,7 +1019,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 // [G n_d][6] lateral coefficients | [G n_d][5] per-candidate results | [n_d] lateral axis | [G][2] row cost and horizon |
 // [G] candidate block offsets | [G][4] ints: N, npad, usable, feasible | spline table (kXY).
 template <bool kXY, int kColl, bool kLimits>
-__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_short(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int G) {
+__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_short(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int G, int opts) {
     extern __shared__ __align__(16) double sm[];
     const int npm = L.n_pad_max, nd = L.n_d;
     const int R = L.n_v_cap * L.n_t;
@@ -1101,6 +1140,9 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
     const double2* tblp = kColl == 2 ? reinterpret_cast<const double2*>(B.obs_xy_t) + (int64_t)b * B.n_obs * B.n_obs_steps : nullptr;
 
+    const bool do_curv = kLimits && kXY && (opts & 1);   // curvature limit, see k2_evaluate
+    const double k2max = P.kappa_max * P.kappa_max;
+
     // Phase B: TWO candidates per warp - lanes 0..15 / 16..31 - and two consecutive time steps per lane (16-byte accesses): a
     // horizon of at most 32 padded samples fits 16 lanes, and the per-candidate overhead (coefficients, reductions, cost
     // arithmetic, collision set-up) is paid once per pair of candidates.
@@ -1133,6 +1175,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         }
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
+        bool curv_bad = false;
         if (valid_a) {
             acc = fma(ja, ja, acc);
             if (kLimits) amax = fmax(amax, fabs(aa));
@@ -1150,6 +1193,17 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             if (store) {
                 *reinterpret_cast<double2*>(out + 4 * npad) = make_double2(xa, xb);
                 *reinterpret_cast<double2*>(out + 5 * npad) = make_double2(ya, yb);
+            }
+            if (kLimits) {
+                if (do_curv) {   // the whole horizon is in the half-warp: the left neighbour's pair is all a lane needs
+                    const double qxa = __shfl_up_sync(kFull, xa, 1), qya = __shfl_up_sync(kFull, ya, 1);
+                    const double qxb = __shfl_up_sync(kFull, xb, 1), qyb = __shfl_up_sync(kFull, yb, 1);
+                    bool bad = false;
+                    if (act && k0 >= 2 && k0 <= N - 1) bad |= menger_exceeds(qxa, qya, qxb, qyb, xa, ya, k2max);
+                    if (act && k0 >= 1 && k0 <= N - 2) bad |= menger_exceeds(qxb, qyb, xa, ya, xb, yb, k2max);
+                    const unsigned bb = __ballot_sync(kFull, bad);
+                    curv_bad = half ? (bb >> 16) != 0 : (bb & 0xffffu) != 0;
+                }
             }
             if (kColl) {
                 if (actmask != kFull) {   // one half has no candidate: it mirrors the other's points (and hits nothing)
@@ -1176,7 +1230,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             resc[c * 4 + 2] = P.follow ? clong : 0.0;
             resc[c * 4 + 3] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
             const bool kin = kLimits ? (rowi[4 * g + 3] && amax <= P.a_max) : true;
-            resi[c * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0);
+            resi[c * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0) | (curv_bad ? 0 : kCurvOkBit);
             resi[c * 2 + 1] = best;
         }
     }
@@ -1188,6 +1242,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 #pragma unroll
         for (int f = 0; f < 4; ++f) B.cost[f * candF + gc] = usable ? resc[c * 4 + f] : 0.0;
         B.cand_flags[gc] = usable ? (uint8_t)resi[c * 2] : 0;
+        if (do_curv) B.curv_ok[gc] = (usable && (resi[c * 2] & kCurvOkBit)) ? 1 : 0;
         if (kColl) {
             const int best = usable ? resi[c * 2 + 1] : 0;
             B.coll_free[gc] = (usable && best == kNoBlocker) ? 1 : 0;
@@ -1302,16 +1357,7 @@ __global__ void __launch_bounds__(kRowThreads) k3_curvature(FrenetLattice L, Fre
         const double* y = x + A.npad;
         bool bad = false;
         for (int k = 1 + lane; k + 1 < A.N; k += kWarp) {
-            const double ax = x[k] - x[k - 1], ay = y[k] - y[k - 1];
-            const double bx = x[k + 1] - x[k], by = y[k + 1] - y[k];
-            const double cx = x[k + 1] - x[k - 1], cy = y[k + 1] - y[k - 1];
-            const double cr = __dadd_rn(__dmul_rn(ax, by), -__dmul_rn(ay, bx));
-            const double lhs = __dmul_rn(4.0, __dmul_rn(cr, cr));
-            const double la = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
-            const double lb = __dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by));
-            const double lc = __dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy));
-            const double rhs = __dmul_rn(k2max, __dmul_rn(__dmul_rn(la, lb), lc));
-            bad |= lhs > rhs;
+            bad |= menger_exceeds(x[k - 1], y[k - 1], x[k], y[k], x[k + 1], y[k + 1], k2max);
         }
         bad = __any_sync(kFull, bad);
         if (lane == 0) B.curv_ok[A.cand0 + id] = bad ? 0 : 1;
@@ -1874,8 +1920,9 @@ int launch_obstacle_bounds(const FrenetLattice* L, const FrenetBuffers* B, int s
 }
 
 template <bool kXY, int kColl>
-int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, cudaStream_t stream) {
-    const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0);
+int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int opts, cudaStream_t stream) {
+    // opts bit 0: also test the curvature limit in the kernel (needs kXY; selects the limits variant)
+    const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0) || (kXY && (opts & 1));
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
     const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 12 + (spline ? (size_t)9 * path->n_knots : 0) +
                          (kColl == 1 ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0) +
@@ -1898,7 +1945,7 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
 #define FRENET_LAUNCH_SHORT(LIM)                                                                                             \
     do {                                                                                                                     \
         if (int rc = set_smem(k2_short<kXY, kColl, LIM>, sm_short, "k2: row group does not fit shared memory")) return rc;   \
-        k2_short<kXY, kColl, LIM><<<grid_short, kRowThreads, sm_short, stream>>>(*L, *P, pd, *B, G);                         \
+        k2_short<kXY, kColl, LIM><<<grid_short, kRowThreads, sm_short, stream>>>(*L, *P, pd, *B, G, opts);                         \
     } while (0)
         if (limits) FRENET_LAUNCH_SHORT(true);
         else FRENET_LAUNCH_SHORT(false);
@@ -1910,7 +1957,7 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
 #define FRENET_LAUNCH_K2(LIM)                                                                                           \
     do {                                                                                                                \
         if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM>, smem, "k2: row does not fit shared memory")) return rc;     \
-        k2_evaluate<kXY, kColl, LIM><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B);                              \
+        k2_evaluate<kXY, kColl, LIM><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B, opts);                              \
     } while (0)
     if (limits) FRENET_LAUNCH_K2(true);
     else FRENET_LAUNCH_K2(false);
@@ -1959,21 +2006,23 @@ int frenet_k1_coefficients(const FrenetLattice* L, const FrenetParams* P, const 
 
 int frenet_k2_evaluate(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_k2(L, P, B)) return rc;
-    return launch_k2<false, 0>(L, P, nullptr, B, (cudaStream_t)stream);
+    return launch_k2<false, 0>(L, P, nullptr, B, 0, (cudaStream_t)stream);
 }
 
 int frenet_k2_fused(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B,
                     int32_t with_collision, frenet_stream_t stream) {
     if (int rc = check_k2(L, P, B)) return rc;
     if (int rc = check_path(path)) return rc;
-    if (!with_collision) return launch_k2<true, 0>(L, P, path, B, (cudaStream_t)stream);
+    const int opts = (with_collision & FRENET_FUSE_CURVATURE) ? 1 : 0;
+    if (opts && !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "fused: curvature output is NULL");
+    if (!(with_collision & FRENET_FUSE_COLLISION)) return launch_k2<true, 0>(L, P, path, B, opts, (cudaStream_t)stream);
     if (!B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "fused: collision output is NULL");
     if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "fused: obstacle table missing");
     if (B->n_obs_steps > 0 && B->n_obs > 0) {   // predicted obstacles: per-chunk bounds first, then the fused kernel reads the table
         if (int rc = launch_obstacle_bounds(L, B, predicted_span(L), (cudaStream_t)stream)) return rc;
-        return launch_k2<true, 2>(L, P, path, B, (cudaStream_t)stream);
+        return launch_k2<true, 2>(L, P, path, B, opts, (cudaStream_t)stream);
     }
-    return launch_k2<true, 1>(L, P, path, B, (cudaStream_t)stream);
+    return launch_k2<true, 1>(L, P, path, B, opts, (cudaStream_t)stream);
 }
 
 int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B,
@@ -2061,14 +2110,15 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     // K2 and K3 (and K4 when nothing sits between them) run as ONE kernel unless the caller asks for separate launches:
     // same arithmetic, same outputs, but every sample is written once instead of being re-read by K3 and K4.
     const bool fuse = (stages & FRENET_STAGE_K2) && (stages & FRENET_STAGE_K3) && !(stages & FRENET_STAGE_NO_FUSE);
-    const bool fuse_k4 = fuse && (stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_CURVATURE);
+    const bool fuse_k4 = fuse && (stages & FRENET_STAGE_K4);
+    const bool fuse_curv = fuse && (stages & FRENET_STAGE_CURVATURE);
     if (fuse) {
-        if ((rc = frenet_k2_fused(L, P, path, B, fuse_k4 ? 1 : 0, stream))) return rc;
+        if ((rc = frenet_k2_fused(L, P, path, B, (fuse_k4 ? FRENET_FUSE_COLLISION : 0) | (fuse_curv ? FRENET_FUSE_CURVATURE : 0), stream))) return rc;
     } else {
         if ((stages & FRENET_STAGE_K2) && (rc = frenet_k2_evaluate(L, P, B, stream))) return rc;
         if ((stages & FRENET_STAGE_K3) && (rc = frenet_k3_cartesian(L, P, path, B, stream))) return rc;
     }
-    if ((stages & FRENET_STAGE_CURVATURE) && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_CURVATURE) && !fuse_curv && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K4) && !fuse_k4 && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
     // the winner block carries x, y when they exist: K3 / K4 ran in this call, or a mask computed from them is in use

@@ -277,18 +277,23 @@ def test_config5_sample_matches_reference():
 
 
 # ------------------------------------------------------------------------------------------------
-def test_batch_against_oracle_with_limits_and_curvature():
+@pytest.mark.parametrize("lattice,no_fuse", [("default", False), ("default", True), ("long", False), ("long", True)])
+def test_batch_against_oracle_with_limits_and_curvature(lattice, no_fuse):
     """Random batch on both paths vs the oracle, with FINITE kinematic / curvature limits (extension: the oracle
-    is the definition) and a partially active obstacle table."""
+    is the definition) and a partially active obstacle table.  "default": the reference's lattice (short-horizon kernel);
+    "long": 51..147 samples per candidate (two steps per lane, curvature triples across iteration boundaries).  Fused into the
+    pipeline kernel, and as separate K2 / K3 / curvature / K4 launches."""
     _gpu, nat, Circle, Spline = _imports()
     from otg_b200 import workloads
     rng = np.random.default_rng(123)
-    B = 24
+    B = 24 if lattice == "default" else 6
     p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.5, .5, B), rng.uniform(-.5, .5, B)], 1)
     s0 = np.stack([rng.uniform(0, 25, B), rng.uniform(0, 4, B), rng.uniform(-.5, .5, B)], 1)
     dd = rng.uniform(-1, 1, B)
     t0 = rng.uniform(0, 5, B)
     prm = fo.OracleParams.defaults("v1").with_(v_max=5.3, a_max=3.1, kappa_max=1.5)   # off the integer target speeds: no exact ties at the limit
+    if lattice == "long":
+        prm = prm.with_(delta_t=0.02, dt=0.25, d_road_width=1.0)
     for tr, op in ((Circle(8, 5, 2), fo.CirclePath(8, 5, 2)),
                    (Spline(workloads.SPLINE_WX, workloads.SPLINE_WY), fo.SplinePath(workloads.SPLINE_WX, workloads.SPLINE_WY))):
         so = s0[:, 0:1] + rng.uniform(1, 12, (B, 12))
@@ -296,8 +301,8 @@ def test_batch_against_oracle_with_limits_and_curvature():
         ox, oy = fo.frenet_to_cartesian(op, so, do)
         obs = np.stack([ox, oy], 2)
         active = (rng.uniform(size=(B, 12)) < 0.7).astype(np.uint8)
-        eng = _gpu.run_batch(prm, p0, s0, t0, dd=dd, trajectory=tr, obstacles=obs, active=active,
-                             use_mask=nat.MASK_KINEMATIC, curvature=True)
+        eng = _gpu.run_batch(prm, p0[:B], s0[:B], t0[:B], dd=dd[:B], trajectory=tr, obstacles=obs, active=active,
+                             use_mask=nat.MASK_KINEMATIC, curvature=True, no_fuse=no_fuse)
         curv = eng.curv_ok.cpu().numpy()
         n_infeasible = 0
         for b in range(B):
