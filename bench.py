@@ -302,6 +302,41 @@ def all_checks_mode(wl, steps, dev):
     return out
 
 
+def default_lattice_batch(dev, n_scen=32768, steps=10):
+    """The reference's OWN lattice (configs 1-3: 320-384 candidates x 11..26 steps, circle path, 10 obstacles) as a batch of
+    independent planners - the short-horizon form of the pipeline kernel."""
+    import torch
+    import otg_b200  # noqa: F401
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.planner import TrajectoryPlannerParams
+    from otg_b200.trajectory import CircleTrajectory2D
+    rng = np.random.default_rng(1)
+    B, O = n_scen, 10
+    p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.3, .3, B), rng.uniform(-.3, .3, B)], 1)
+    s0 = np.stack([rng.uniform(0, 30, B), rng.uniform(0, 4, B), rng.uniform(-.3, .3, B)], 1)
+    bp = BatchPlanner(TrajectoryPlannerParams(), CircleTrajectory2D(8, 5, 2), B, O, "v1", dev)
+    bp.stage_inputs(p0=p0, s0=s0, t0=np.full(B, 0.1), obs_s=s0[:, 0:1] + rng.uniform(2, 12, (B, O)), obs_d=rng.uniform(-3, 3, (B, O)))
+    bp.engine.upload()
+    for _ in range(3):
+        bp.launch_resident()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        bp.launch_resident()
+        bp.engine.download(sync=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    cts = bp.cand_timesteps()
+    out = {"planners": B, "ms_per_step": ms, "replans_per_s": B / (ms * 1e-3), "candidate_timesteps_per_s": cts / (ms * 1e-3),
+           "candidate_timesteps_per_step": cts, "gpu_launches_per_step": bp.launches_per_plan,
+           "planners_with_feasible": int((bp.engine.result["status"] == 0).sum())}
+    del bp
+    torch.cuda.empty_cache()
+    return out
+
+
 def closed_loop(dev, n_agents=8192, steps=30):
     """SURVEY section 8f row 1 leg: whole closed-loop steps (projection, replan, cone gate, collision filter, controller,
     unicycle) for `n_agents` agents of BASELINE config 2 (default lattice, circle path, 10 static obstacles) with all
@@ -558,13 +593,14 @@ def run_gpu(args):
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
                 "replan_latency": replan_latency() if world == 1 else None,
-                "predicted_obstacles": None, "all_feasibility_checks": None, "closed_loop": None,
+                "predicted_obstacles": None, "all_feasibility_checks": None, "default_lattice_batch": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
         if world == 1:
             del bp
             torch.cuda.empty_cache()
             line["predicted_obstacles"] = predicted_mode(wl, max(3, args.steps // 3), dev)
             line["all_feasibility_checks"] = all_checks_mode(wl, max(3, args.steps // 3), dev)
+            line["default_lattice_batch"] = default_lattice_batch(dev)
             line["closed_loop"] = closed_loop(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
