@@ -328,9 +328,16 @@ def default_lattice_batch(dev, n_scen=32768, steps=10):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
+    a.record()
+    for _ in range(steps):
+        bp.launch_resident()
+    b.record()
+    torch.cuda.synchronize()
+    ms_dev = a.elapsed_time(b) / steps
     cts = bp.cand_timesteps()
     out = {"planners": B, "ms_per_step": ms, "replans_per_s": B / (ms * 1e-3), "candidate_timesteps_per_s": cts / (ms * 1e-3),
-           "candidate_timesteps_per_step": cts, "gpu_launches_per_step": bp.launches_per_plan,
+           "ms_per_step_results_left_on_device": ms_dev, "candidate_timesteps_per_s_results_left_on_device": cts / (ms_dev * 1e-3),
+           "d2h_bytes_per_step": bp.d2h_bytes, "candidate_timesteps_per_step": cts, "gpu_launches_per_step": bp.launches_per_plan,
            "planners_with_feasible": int((bp.engine.result["status"] == 0).sum())}
     del bp
     torch.cuda.empty_cache()
