@@ -191,15 +191,17 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// the same over each half of the warp (lanes 0..15 / 16..31): two candidates per warp in k2_short
-__device__ __forceinline__ double half_sum(double v) {
+// the same over each aligned group of `lpc` lanes (16 or 8, warp-uniform): several candidates per warp in k2_short
+__device__ __forceinline__ double group_sum(double v, int lpc) {
+    if (lpc == 16) v += __shfl_xor_sync(kFull, v, 8);
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
 }
-__device__ __forceinline__ double half_max(double v) {
+__device__ __forceinline__ double group_max(double v, int lpc) {
+    if (lpc == 16) v = fmax(v, __shfl_xor_sync(kFull, v, 8));
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    for (int o = 4; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
     return v;
 }
 
@@ -631,14 +633,16 @@ __device__ __forceinline__ int collide_pair_predicted(double xa, double ya, doub
     return best;
 }
 
-// Two candidates per warp (k2_short): lanes 0..15 carry candidate A, lanes 16..31 candidate B, two consecutive samples each, the
-// whole horizon in one go (at most 32 steps).  One bounding circle and one cull for the 64 points of both candidates (neighbours in
-// the lattice, so their trajectories lie close together); the exact test attributes a hit to the half it occurred in.  Obstacles are
-// visited in ascending order, so the first hit of a half is its lowest blocker; the sweep ends when both halves have one.
-// Returns this lane's candidate's lowest blocker (kNoBlocker if none).  mid: a lane holding a point near the middle.
-__device__ __forceinline__ int collide_halves(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int mid,
+// Several candidates per warp (k2_short): the warp is split into groups of `lpc` lanes (16 or 8), one candidate per group, two
+// consecutive samples per lane, the whole horizon in one go.  One bounding circle and one cull for the 64 points of all groups
+// (neighbours in the lattice, so their trajectories lie close together); the exact test attributes a hit to the group it occurred in.
+// Obstacles are visited in ascending order, so a group's first hit is its lowest blocker; the sweep ends when every group has one.
+// base / gm: first lane and lane mask (shifted down) of this lane's group; act: the group carries a candidate.
+// Returns this lane's group's lowest blocker (kNoBlocker if none).  mid: a lane holding a point near the middle.
+__device__ __forceinline__ int collide_groups(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int mid,
                                               const double2* __restrict__ obs, const float2* __restrict__ obsf, int O, float Rf,
-                                              double radius_sq, int lane) {
+                                              double radius_sq, bool act, int base, unsigned gm) {
+    const int lane = threadIdx.x & 31;
     const float xf = __double2float_rn(xa), yf = __double2float_rn(ya);
     const float xg = __double2float_rn(xb), yg = __double2float_rn(yb);
     const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
@@ -650,7 +654,7 @@ __device__ __forceinline__ int collide_halves(double xa, double ya, double xb, d
     const float thr = finite ? reach * reach : CUDART_INF_F;
     const float rpt = Rf * 1.00001f + (fabsf(cx) + fabsf(cy) + reach) * 3.8147e-6f;
     const float thr_pt = finite ? rpt * rpt : CUDART_INF_F;
-    int best_lo = kNoBlocker, best_hi = kNoBlocker;   // lowest blocker of lanes 0..15 / 16..31 (warp-uniform)
+    int mine = act ? kNoBlocker : -1;   // this group's lowest blocker; a group without a candidate never extends the sweep
     for (int ob = 0; ob < O; ob += kWarp) {
         const int o = ob + lane;
         bool near = false;
@@ -672,18 +676,19 @@ __device__ __forceinline__ int collide_halves(double xa, double ya, double xb, d
             const bool hit = (valid_a && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= radius_sq)) ||
                              (valid_b && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= radius_sq));
             const unsigned hb = __ballot_sync(kFull, hit);
-            if ((hb & 0xffffu) && best_lo == kNoBlocker) best_lo = ob + j;
-            if ((hb >> 16) && best_hi == kNoBlocker) best_hi = ob + j;
-            if (best_lo != kNoBlocker && best_hi != kNoBlocker) return lane < 16 ? best_lo : best_hi;
+            if (!hb) continue;
+            if (((hb >> base) & gm) && mine == kNoBlocker) mine = ob + j;
+            if (__all_sync(kFull, mine != kNoBlocker)) return mine;
         }
     }
-    return lane < 16 ? best_lo : best_hi;
+    return mine;
 }
 
 // The same against predicted obstacles: k0 is this lane's first step, cb the bounds of the only chunk (32 steps).
-__device__ __forceinline__ int collide_halves_predicted(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int mid,
+__device__ __forceinline__ int collide_groups_predicted(double xa, double ya, double xb, double yb, bool valid_a, bool valid_b, int mid,
                                                         int k0, const double2* __restrict__ tbl, int K, const float4* __restrict__ cb,
-                                                        int O, float Rf, double radius_sq, int lane) {
+                                                        int O, float Rf, double radius_sq, bool act, int base, unsigned gm) {
+    const int lane = threadIdx.x & 31;
     const float xf = __double2float_rn(xa), yf = __double2float_rn(ya);
     const float xg = __double2float_rn(xb), yg = __double2float_rn(yb);
     const float cx = __shfl_sync(kFull, xf, mid), cy = __shfl_sync(kFull, yf, mid);
@@ -694,7 +699,7 @@ __device__ __forceinline__ int collide_halves_predicted(double xa, double ya, do
     const bool wide = !(r2max < 1e30f);
     const float rpt = Rf * 1.00001f + (fabsf(cx) + fabsf(cy) + reach) * 3.8147e-6f;
     const int ka = min(k0, K - 1), kb = min(k0 + 1, K - 1);
-    int best_lo = kNoBlocker, best_hi = kNoBlocker;
+    int mine = act ? kNoBlocker : -1;
     for (int ob = 0; ob < O; ob += kWarp) {
         const int o = ob + lane;
         bool near = false;
@@ -718,12 +723,12 @@ __device__ __forceinline__ int collide_halves_predicted(double xa, double ya, do
             const bool hit = (valid_a && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= radius_sq)) ||
                              (valid_b && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= radius_sq));
             const unsigned hb = __ballot_sync(kFull, hit);
-            if ((hb & 0xffffu) && best_lo == kNoBlocker) best_lo = ob + j;
-            if ((hb >> 16) && best_hi == kNoBlocker) best_hi = ob + j;
-            if (best_lo != kNoBlocker && best_hi != kNoBlocker) return lane < 16 ? best_lo : best_hi;
+            if (!hb) continue;
+            if (((hb >> base) & gm) && mine == kNoBlocker) mine = ob + j;
+            if (__all_sync(kFull, mine != kNoBlocker)) return mine;
         }
     }
-    return lane < 16 ? best_lo : best_hi;
+    return mine;
 }
 
 // Stage a scenario's obstacle snapshot in shared memory.
@@ -1030,7 +1035,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 // A row of such a lattice is too little work for a CTA of its own (16 candidates x 26 steps against a path-frame phase that is a
 // few hundred dependent fp64 instructions deep), so a CTA takes `G` consecutive rows of one scenario: a WARP per row for the
 // longitudinal phase (lanes = time steps; the jerk sum and the limits are warp reductions), then the G x n_d candidates of the
-// group two per warp (16 lanes each, two time steps per lane).  Same arithmetic and the same pairwise reduction tree as k2_evaluate.
+// group two or four per warp (16 or 8 lanes each, two time steps per lane).  Same arithmetic as k2_evaluate.
 // Shared memory (doubles): obstacles as in k2_evaluate | [G][n_pad_max] lateral argument | 4 x [G][n_pad_max] path frame (kXY) |
 // [G n_d][6] lateral coefficients | [G n_d][5] per-candidate results | [n_d] lateral axis | [G][2] row cost and horizon |
 // [G] candidate block offsets | [G][4] ints: N, npad, usable, feasible | spline table (kXY).
@@ -1159,25 +1164,39 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const bool do_curv = kLimits && kXY && (opts & 1);   // curvature limit, see k2_evaluate
     const double k2max = P.kappa_max * P.kappa_max;
 
-    // Phase B: TWO candidates per warp - lanes 0..15 / 16..31 - and two consecutive time steps per lane (16-byte accesses): a
-    // horizon of at most 32 padded samples fits 16 lanes, and the per-candidate overhead (coefficients, reductions, cost
-    // arithmetic, collision set-up) is paid once per pair of candidates.
-    const int total = Ga * nd;
-    const int half = lane >> 4, hl = lane & 15;
-    for (int pr = warp; 2 * pr < total; pr += nwarps) {
-        const int c = 2 * pr + half;
-        const int cc = min(c, total - 1);               // the odd one out at the end of the group: lanes 16..31 idle along
-        const int g = cc / nd, id = cc - g * nd;
-        const bool act = c < total && rowi[4 * g + 2];
-        const unsigned actmask = __ballot_sync(kFull, act);
-        if (!actmask) continue;
+    // Phase B: SEVERAL candidates per warp, two consecutive time steps per lane (16-byte accesses).  A horizon of at most 32 padded
+    // samples fits 16 lanes, one of at most 16 fits 8: a row's candidates are taken two or four at a time, and the per-candidate
+    // overhead (coefficients, reductions, cost arithmetic, collision set-up) is paid once per group of candidates.
+    // Work items = (row, group of 32 / lpc candidates), numbered row by row; lane g keeps row g's first item (the host keeps G <= 32).
+    const int lpc_l = (lane < Ga && rowi[4 * lane + 1] <= 16) ? 8 : 16;
+    const int items_l = lane < Ga ? (nd * lpc_l + kWarp - 1) / kWarp : 0;
+    int first_item = items_l;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, first_item, o);
+        if (lane >= o) first_item += v;
+    }
+    const int total_items = __shfl_sync(kFull, first_item, kWarp - 1);
+    first_item -= items_l;                                  // exclusive prefix: row `lane` starts at this item
+    for (int it = warp; it < total_items; it += nwarps) {
+        const int g = __popc(__ballot_sync(kFull, lane < Ga && first_item <= it)) - 1;
+        if (!rowi[4 * g + 2]) continue;                     // row does not exist / was dropped
+        const int lpc = __shfl_sync(kFull, lpc_l, g);
+        const int local = it - __shfl_sync(kFull, first_item, g);
+        const int shift = lpc == 16 ? 4 : 3;
+        const int sub = lane >> shift, hl = lane & (lpc - 1);
+        const int per = kWarp >> shift;                     // candidates per warp: 2 or 4
+        const int id_raw = local * per + sub;
+        const bool act = id_raw < nd;                       // the last group of a row may be short: idle groups shadow its first candidate
+        const int id = act ? id_raw : local * per;
+        const int c = g * nd + id;
         const int N = rowi[4 * g], npad = rowi[4 * g + 1];
         const int k0 = 2 * hl;
-        const bool store = act && k0 < npad;            // npad is even: a pair is stored whole or not at all
+        const bool store = act && k0 < npad;                // npad is even: a pair is stored whole or not at all
         const bool valid_a = act && k0 < N, valid_b = act && k0 + 1 < N;
-        const int kk = k0 < npad ? k0 : 0;              // lanes beyond the padding shadow the first pair
+        const int kk = k0 < npad ? k0 : 0;                  // lanes beyond the padding shadow the first pair
         Poly pq;
-        pq.load(coef + cc * 6);
+        pq.load(coef + c * 6);
         const double2 u = *reinterpret_cast<const double2*>(su + g * npm + kk);
         double da, va, aa, ja, db, vb, ab, jb;
         pq.eval(u.x, da, va, aa, ja);
@@ -1204,39 +1223,36 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             const int f = g * npm + kk;
             const double2 px = *reinterpret_cast<const double2*>(fpx + f), py = *reinterpret_cast<const double2*>(fpy + f);
             const double2 nx = *reinterpret_cast<const double2*>(fnx + f), ny = *reinterpret_cast<const double2*>(fny + f);
-            double xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)), xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));   // pt + n * d,
-            double ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)), yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));   // unfused like the reference
+            const double xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)), xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));   // pt + n * d,
+            const double ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)), yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));   // unfused like the reference
             if (store) {
                 *reinterpret_cast<double2*>(out + 4 * npad) = make_double2(xa, xb);
                 *reinterpret_cast<double2*>(out + 5 * npad) = make_double2(ya, yb);
             }
+            const int base = sub << shift;
+            const unsigned gm = lpc == 16 ? 0xffffu : 0xffu;
             if (kLimits) {
-                if (do_curv) {   // the whole horizon is in the half-warp: the left neighbour's pair is all a lane needs
+                if (do_curv) {   // the whole horizon is in the group: the left neighbour's pair is all a lane needs
                     const double qxa = __shfl_up_sync(kFull, xa, 1), qya = __shfl_up_sync(kFull, ya, 1);
                     const double qxb = __shfl_up_sync(kFull, xb, 1), qyb = __shfl_up_sync(kFull, yb, 1);
                     bool bad = false;
                     if (act && k0 >= 2 && k0 <= N - 1) bad |= menger_exceeds(qxa, qya, qxb, qyb, xa, ya, k2max);
                     if (act && k0 >= 1 && k0 <= N - 2) bad |= menger_exceeds(qxb, qyb, xa, ya, xb, yb, k2max);
-                    const unsigned bb = __ballot_sync(kFull, bad);
-                    curv_bad = half ? (bb >> 16) != 0 : (bb & 0xffffu) != 0;
+                    curv_bad = ((__ballot_sync(kFull, bad) >> base) & gm) != 0;
                 }
             }
+            // (an idle group evaluated its row-mate's candidate again: the same points, and valid_* are false there)
             if (kColl) {
-                if (actmask != kFull) {   // one half has no candidate: it mirrors the other's points (and hits nothing)
-                    const double oxa = __shfl_xor_sync(kFull, xa, 16), oya = __shfl_xor_sync(kFull, ya, 16);
-                    const double oxb = __shfl_xor_sync(kFull, xb, 16), oyb = __shfl_xor_sync(kFull, yb, 16);
-                    if (!act) { xa = oxa; ya = oya; xb = oxb; yb = oyb; }
-                }
-                const int hsel = (actmask & 0xffffu) ? 0 : 16;
-                const int mid = hsel + ((__shfl_sync(kFull, N, hsel) - 1) >> 2);
-                if (kColl == 1) best = collide_halves(xa, ya, xb, yb, valid_a, valid_b, mid, obs, obsf, B.n_obs, Rf, P.radius_sq, lane);
+                const int mid = (N - 1) >> 2;   // group 0 always carries a candidate
+                if (kColl == 1)
+                    best = collide_groups(xa, ya, xb, yb, valid_a, valid_b, mid, obs, obsf, B.n_obs, Rf, P.radius_sq, act, base, gm);
                 if (kColl == 2)
-                    best = collide_halves_predicted(xa, ya, xb, yb, valid_a, valid_b, mid, kk, tblp, B.n_obs_steps, cbs, B.n_obs, Rf,
-                                                    P.radius_sq, lane);
+                    best = collide_groups_predicted(xa, ya, xb, yb, valid_a, valid_b, mid, kk, tblp, B.n_obs_steps, cbs, B.n_obs, Rf,
+                                                    P.radius_sq, act, base, gm);
             }
         }
-        acc = half_sum(acc);
-        if (kLimits) amax = half_max(amax);
+        acc = group_sum(acc, lpc);
+        if (kLimits) amax = group_max(amax, lpc);
         if (hl == 0 && act) {   // :165-167 / :174-176
             const double clong = rowd[2 * g], horizon = rowd[2 * g + 1];
             const double e = axd[id] - dd_target;
@@ -1953,7 +1969,7 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
         const size_t fixed = (size_t)L->n_d + (spline ? (size_t)9 * path->n_knots : 0) +
                              (kColl == 1 ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0) + (kColl == 2 ? (size_t)2 * B->n_obs : 0);
         auto bytes = [&](int g) { return (fixed + (size_t)g * ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 11 + 5)) * sizeof(double); };
-        int G = R;
+        int G = R < kWarp ? R : kWarp;   // (phase B keeps one row per lane)
         while (G > 1 && (bytes(G) > 48 * 1024 || (int64_t)L->n_scen * ((R + G - 1) / G) < 8 * 148)) G = (G + 1) / 2;
         const size_t sm_short = bytes(G);
         const unsigned grid_short = (unsigned)((int64_t)L->n_scen * ((R + G - 1) / G));
