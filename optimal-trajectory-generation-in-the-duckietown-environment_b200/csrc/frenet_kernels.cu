@@ -24,7 +24,8 @@
 //   * the longitudinal polynomial (once per row and step) is sampled in the reference's own power
 //     form with host-provided powers of t, because its values feed the next replan's state and sit
 //     exactly on the low-speed threshold in converged runs.
-// Compile-time knobs (FRENET_*) record measured alternatives; the defaults are the fastest on B200.
+// Compile-time knobs (FRENET_*) record measured alternatives; the defaults are the fastest on B200 (profiles/r1_history.md lists
+// the alternatives that were measured and removed again).
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -50,14 +51,6 @@ constexpr int kMaxSmem = 227 * 1024;
 #endif
 #ifndef FRENET_K2_MIN_CTAS_COLL
 #define FRENET_K2_MIN_CTAS_COLL 4
-#endif
-// 1: each warp owns a contiguous range of a row's candidates and publishes their results itself (no barrier at the end
-// of the row); 0: candidates are dealt round-robin to the warps and the CTA publishes them after a barrier.
-#ifndef FRENET_K2_CONTIG
-#define FRENET_K2_CONTIG 0
-#endif
-#ifndef FRENET_K2_DYNAMIC
-#define FRENET_K2_DYNAMIC 0
 #endif
 // 1: the collision variants of the long-horizon kernel reload the candidate's coefficients from shared memory in every iteration instead of
 // keeping them in twelve registers across the collision test: no spills at the 64-register cap, fused kernel 6.2 -> 5.8 ms on B200
@@ -153,14 +146,6 @@ struct Poly {
         v2 = 2.0 * fma(d3, t, c2);
         const double e4 = fma(a5, t, d4);
         v3 = 6.0 * fma(e4, t, d3);
-    }
-    __device__ __forceinline__ double val(double t) const {
-        return fma(fma(fma(fma(fma(a5, t, a4), t, a3), t, a2), t, a1), t, a0);
-    }
-    __device__ __forceinline__ double d1(double t) const {
-        double v0, v1, v2, v3;
-        eval(t, v0, v1, v2, v3);
-        return v1;
     }
 };
 
@@ -780,13 +765,11 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     __shared__ double red[3][kRowThreads / 32];
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
-    __shared__ int sh_next;
 
     const int64_t br = blockIdx.x;
     const RowAddr A = row_addr(L, br);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int flags = B.row_flags[br];
-    if (tid == 0) sh_next = 0;      // published by the barriers of phase A
 
     if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
         for (int id = tid; id < L.n_d; id += blockDim.x) {
@@ -907,23 +890,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 
     // Phase B: a warp per candidate; every lane owns TWO consecutive time steps per iteration (64 steps per warp
     // iteration, 16-byte loads from shared memory and 16-byte stores to HBM); no global loads in this loop.
-    // Each warp owns a contiguous range of candidates, so it can publish their results itself (below) without a
-    // CTA-wide barrier at the end of the row.
-#if FRENET_K2_CONTIG
-    const int per_warp = (L.n_d + nwarps - 1) / nwarps;
-    const int id_begin = min(warp * per_warp, L.n_d), id_end = min(id_begin + per_warp, L.n_d);
-    for (int id = id_begin; id < id_end; ++id) {
-#elif FRENET_K2_DYNAMIC
-    // candidates are handed out one at a time from a shared counter: a warp whose candidate was blocked early (the
-    // collision test stops at the first blocker) immediately takes the next one
-    for (;;) {
-        int id = 0;
-        if (lane == 0) id = atomicAdd(&sh_next, 1);
-        id = __shfl_sync(kFull, id, 0);
-        if (id >= L.n_d) break;
-#else
+    // Candidates are dealt round-robin to the warps; their results are staged in shared memory and published after a barrier.
     for (int id = warp; id < L.n_d; id += nwarps) {
-#endif
         Poly pq;
         pq.load(coef + id * 6);
         // [6][npad] block of this candidate; `out` walks along k, the fields sit `fs` bytes apart
@@ -1009,13 +977,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             resi[id * 2 + 1] = best;
         }
     }
-#if FRENET_K2_CONTIG
-    __syncwarp();
-    for (int id = id_begin + lane; id < id_end; id += kWarp) {
-#else
     __syncthreads();
     for (int id = tid; id < L.n_d; id += blockDim.x) {
-#endif
         const int64_t c = A.cand0 + id;
 #pragma unroll
         for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = resc[id * 4 + f];
