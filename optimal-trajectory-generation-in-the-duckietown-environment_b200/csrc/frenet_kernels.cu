@@ -763,6 +763,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     double* axd = resc + L.n_d * 5;                                // [n_d] lateral target axis
     double* tab = axd + L.n_d;                                     // [n_knots][9] spline table (kXY, spline path)
     __shared__ double red[3][kRowThreads / 32];
+    __shared__ double sh_carry[kLimits ? kRowThreads / 32 : 1][4];   // curvature: the last pair of a warp's previous iteration
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
 
@@ -900,7 +901,6 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
         bool curv_bad = false;
-        double cxa = 0.0, cya = 0.0, cxb = 0.0, cyb = 0.0;   // lane 31's pair of the previous iteration
 #pragma unroll 1
         for (int kb = 0; kb < N; kb += 2 * kWarp) {
             const int k0 = kb + 2 * lane;
@@ -942,12 +942,15 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                     if (do_curv) {
                         double qxa = __shfl_up_sync(kFull, xa, 1), qya = __shfl_up_sync(kFull, ya, 1);
                         double qxb = __shfl_up_sync(kFull, xb, 1), qyb = __shfl_up_sync(kFull, yb, 1);
-                        if (lane == 0) { qxa = cxa; qya = cya; qxb = cxb; qyb = cyb; }
+                        if (lane == 0 && kb > 0) {   // lane 31's pair of the previous iteration, parked in shared memory
+                            qxa = sh_carry[warp][0]; qya = sh_carry[warp][1]; qxb = sh_carry[warp][2]; qyb = sh_carry[warp][3];
+                        }
                         // centres k0 - 1 (the neighbour's second sample) and k0 (this lane's first); interior means 1 <= k <= N - 2
                         if (k0 >= 2 && k0 <= N - 1) curv_bad |= menger_exceeds(qxa, qya, qxb, qyb, xa, ya, k2max);
                         if (k0 >= 1 && k0 <= N - 2) curv_bad |= menger_exceeds(qxb, qyb, xa, ya, xb, yb, k2max);
-                        cxa = __shfl_sync(kFull, xa, kWarp - 1); cya = __shfl_sync(kFull, ya, kWarp - 1);
-                        cxb = __shfl_sync(kFull, xb, kWarp - 1); cyb = __shfl_sync(kFull, yb, kWarp - 1);
+                        __syncwarp();
+                        if (lane == kWarp - 1) { sh_carry[warp][0] = xa; sh_carry[warp][1] = ya; sh_carry[warp][2] = xb; sh_carry[warp][3] = yb; }
+                        __syncwarp();
                     }
                 }
                 // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
