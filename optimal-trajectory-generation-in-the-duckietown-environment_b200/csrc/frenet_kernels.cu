@@ -521,7 +521,9 @@ __global__ void __launch_bounds__(128) obstacle_chunk_bounds(const double* __res
                 const double dx = q.x - c.x, dy = q.y - c.y;
                 r2 = fmax(r2, fma(dx, dx, dy * dy));
             }
-            out = make_float4(__double2float_rn(c.x), __double2float_rn(c.y), __fsqrt_ru(__double2float_ru(r2)), 0.0f);
+            // .w: the obstacle's share of every cull / pre-test radius (its own extent, rounded up, plus the fp32 rounding pad of its centre)
+            const float cxf = __double2float_rn(c.x), cyf = __double2float_rn(c.y), rad = __fsqrt_ru(__double2float_ru(r2));
+            out = make_float4(cxf, cyf, rad, __fadd_ru(__fmul_ru(rad, 1.00001f), __fmul_ru(fabsf(cxf) + fabsf(cyf), 3.8147e-6f)));
         }
         bounds[((int64_t)b * n_chunks + chunk) * O + o] = out;
     }
@@ -549,7 +551,7 @@ __device__ __forceinline__ int collide_chunk_predicted(double x, double y, bool 
         if (o < lim) {
             const float4 q = cb[o];
             const float ux = q.x - cx, uy = q.y - cy;
-            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
+            const float rr = reach + q.w;
             // obstacles the sensor did not report are parked at +inf by the bounds kernel: never near
             near = (q.x < CUDART_INF_F) && (wide || !(fmaf(ux, ux, uy * uy) > rr * rr));
         }
@@ -561,7 +563,7 @@ __device__ __forceinline__ int collide_chunk_predicted(double x, double y, bool 
             // fetched from the table (global memory) only when some lane may be within the robot radius of it
             const float4 qc = cb[ob + j];
             const float px = xf - qc.x, py = yf - qc.y;
-            const float rp = rpt + qc.z * 1.00001f + (fabsf(qc.x) + fabsf(qc.y)) * 3.8147e-6f;
+            const float rp = rpt + qc.w;
             if (!__any_sync(kFull, wide || !(fmaf(px, px, py * py) > rp * rp))) continue;
             const double2 q = tbl[(int64_t)(ob + j) * K + kk];
             const double dx = x - q.x, dy = y - q.y;
@@ -595,7 +597,7 @@ __device__ __forceinline__ int collide_pair_predicted(double xa, double ya, doub
         if (o < lim) {
             const float4 q = cb[o];
             const float ux = q.x - cx, uy = q.y - cy;
-            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
+            const float rr = reach + q.w;
             // obstacles the sensor did not report are parked at +inf by the bounds kernel: never near
             near = (q.x < CUDART_INF_F) && (wide || !(fmaf(ux, ux, uy * uy) > rr * rr));
         }
@@ -605,7 +607,7 @@ __device__ __forceinline__ int collide_pair_predicted(double xa, double ya, doub
             m &= m - 1;
             const float4 qc = cb[ob + j];
             const float pax = xf - qc.x, pay = yf - qc.y, pbx = xg - qc.x, pby = yg - qc.y;
-            const float rp = rpt + qc.z * 1.00001f + (fabsf(qc.x) + fabsf(qc.y)) * 3.8147e-6f;
+            const float rp = rpt + qc.w;
             if (!__any_sync(kFull, wide || !(fminf(fmaf(pax, pax, pay * pay), fmaf(pbx, pbx, pby * pby)) > rp * rp))) continue;
             const double2* row = tbl + (int64_t)(ob + j) * K;
             const double2 qa = row[ka], qb = row[kb];
@@ -691,7 +693,7 @@ __device__ __forceinline__ int collide_groups_predicted(double xa, double ya, do
         if (o < O) {
             const float4 q = cb[o];
             const float ux = q.x - cx, uy = q.y - cy;
-            const float rr = reach + q.z * 1.00001f + (fabsf(q.x) + fabsf(q.y)) * 3.8147e-6f;
+            const float rr = reach + q.w;
             near = (q.x < CUDART_INF_F) && (wide || !(fmaf(ux, ux, uy * uy) > rr * rr));
         }
         unsigned m = __ballot_sync(kFull, near);
@@ -700,7 +702,7 @@ __device__ __forceinline__ int collide_groups_predicted(double xa, double ya, do
             m &= m - 1;
             const float4 qc = cb[ob + j];
             const float pax = xf - qc.x, pay = yf - qc.y, pbx = xg - qc.x, pby = yg - qc.y;
-            const float rp = rpt + qc.z * 1.00001f + (fabsf(qc.x) + fabsf(qc.y)) * 3.8147e-6f;
+            const float rp = rpt + qc.w;
             if (!__any_sync(kFull, wide || !(fminf(fmaf(pax, pax, pay * pay), fmaf(pbx, pbx, pby * pby)) > rp * rp))) continue;
             const double2* row = tbl + (int64_t)(ob + j) * K;
             const double2 qa = row[ka], qb = row[kb];
