@@ -186,6 +186,9 @@ typedef struct FrenetBuffers {
                                   projection + (s - s0[0]) (frenet_to_glob_planner,
                                   lib/tests/test_mapper_planner_obstacles.py:25-37); NULL: at s */
     uint8_t* road_ok;          /* [n_scen][C] 1 = stays between the lane boundaries (frenet_k3_offroad) */
+    /* batched lane runs: every scenario has its own lane fit (both optional, NULL = the shared FrenetPath / FrenetRoad) */
+    const double* lane_params; /* [n_scen][4] a, b, c, ds of the scenario's lane-centre parabola (path kind FRENET_PATH_PARABOLA) */
+    const double* road_params; /* [n_scen][8] right boundary (h, k, a, given != 0), left boundary (h, k, a, given != 0) */
 } FrenetBuffers;
 
 /* Lane boundaries for frenet_k3_offroad: each a parabola in vertex form (h, k, a) =
@@ -200,7 +203,8 @@ typedef struct FrenetRoad {
 enum {
     FRENET_STAGE_K1 = 1, FRENET_STAGE_K2 = 2, FRENET_STAGE_K3 = 4, FRENET_STAGE_K4 = 8,
     FRENET_STAGE_K5 = 16, FRENET_STAGE_GATHER = 32, FRENET_STAGE_CURVATURE = 64,
-    FRENET_STAGE_NO_FUSE = 128 /* launch K2, K3, K4 separately even when frenet_plan could fuse them */
+    FRENET_STAGE_NO_FUSE = 128, /* launch K2, K3, K4 separately even when frenet_plan could fuse them */
+    FRENET_STAGE_OFFROAD = 256  /* lane-boundary filter from buf->road_params (per scenario), between K4 and K5 */
 };
 
 int frenet_abi_version(void);
@@ -251,6 +255,7 @@ int frenet_gather_winner(const FrenetLattice* lat, const FrenetParams* prm, cons
  * both boundaries: road_ok = no sample with (y - k) - a (x - h)^2 < 0 on the right boundary nor > 0 on the left one.
  * Needs K3 (x, y).  Honoured by K5 through FRENET_MASK_ROAD. */
 int frenet_k3_offroad(const FrenetLattice* lat, const FrenetRoad* road, const FrenetBuffers* buf, frenet_stream_t stream);
+/* (road may be NULL when buf->road_params holds per-scenario boundaries, which take precedence) */
 
 /* The pipeline: launches the stages selected in `stages` in order K1, K2, K3, (curvature), K4, K5, gather;
  * K2+K3(+K4, +curvature) are fused into one launch when selected together (FRENET_STAGE_NO_FUSE keeps them apart). */

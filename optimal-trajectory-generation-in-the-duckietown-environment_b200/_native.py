@@ -23,6 +23,7 @@ CAND_VALID, CAND_KINEMATIC_OK = 1, 2
 PATH_CIRCLE, PATH_SPLINE, PATH_PARABOLA = 0, 1, 2
 SEL_CTOT, SEL_CD, SEL_CV, SEL_CT, SEL_MASKED = 0, 1, 2, 3, 4
 STAGE_K1, STAGE_K2, STAGE_K3, STAGE_K4, STAGE_K5, STAGE_GATHER, STAGE_CURVATURE, STAGE_NO_FUSE = 1, 2, 4, 8, 16, 32, 64, 128
+STAGE_OFFROAD = 256
 MASK_KINEMATIC, MASK_CURVATURE, MASK_COLLISION, MASK_ROAD = 1, 2, 4, 8
 
 c_double_p = C.c_void_p   # device pointers are passed as integers (tensor.data_ptr())
@@ -68,7 +69,8 @@ class FrenetBuffers(C.Structure):
                 ("coll_free", C.c_void_p), ("first_blocker", C.c_void_p),
                 ("result", C.c_void_p),
                 ("winner", C.c_void_p), ("winner_steps", C.c_void_p),
-                ("path_origin", C.c_void_p), ("road_ok", C.c_void_p)]
+                ("path_origin", C.c_void_p), ("road_ok", C.c_void_p),
+                ("lane_params", C.c_void_p), ("road_params", C.c_void_p)]
 
 
 class FrenetRoad(C.Structure):

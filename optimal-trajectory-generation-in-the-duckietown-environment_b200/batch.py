@@ -113,6 +113,38 @@ class BatchPlanner:
         self._n_v_sum = 0
 
     # -- host -> pinned staging ----------------------------------------------------------------
+    def stage_lanes(self, lane_fits, projection, road_right=None, road_left=None, ds: float = 1 / 30):
+        """Batched Duckietown lane runs (SURVEY section 8f row 2 for many agents): every scenario has its own lane-centre parabola
+        `lane_fits[b] = (a, b, c)`, its own projection (the transform evaluates the path at projection + (s - s0[0])) and optionally
+        its own lane boundaries `road_right / road_left [B][3]` (rows of NaN = that boundary was not detected).  Call after
+        `stage_inputs` (it needs the staged s0); the planner's trajectory must be a ParabolaTrajectory2D (it fixes the path kind)."""
+        e, B = self.engine, self.n_scen
+        e.set_relative_s(True)
+        e.set_per_scenario_lanes(True)
+        e.lane_params[:, :3] = np.asarray(lane_fits, dtype=np.float64).reshape(B, 3)
+        e.lane_params[:, 3] = ds
+        e.path_origin[:, 0] = projection
+        e.path_origin[:, 1] = e.state[:, 3]
+        e.road_params[:] = 0.0
+        any_road = False
+        for col, fits in ((0, road_right), (4, road_left)):
+            if fits is None:
+                continue
+            f = np.asarray(fits, dtype=np.float64).reshape(B, 3)
+            given = ~np.isnan(f).any(axis=1)
+            a, b, c = (np.where(given, f[:, i], 1.0) for i in range(3))
+            e.road_params[:, col] = -b / (2 * a)                       # get_vertex_and_focus_distance (test_mapper_planner_obstacles.py:105-109)
+            e.road_params[:, col + 1] = -(b ** 2 - 4 * a * c) / (4 * a)
+            e.road_params[:, col + 2] = a
+            e.road_params[:, col + 3] = given
+            any_road = any_road or bool(given.any())
+        if any_road:
+            self.stages |= nat.STAGE_OFFROAD
+            self.use_mask |= nat.MASK_ROAD
+        else:
+            self.stages &= ~nat.STAGE_OFFROAD
+            self.use_mask &= ~nat.MASK_ROAD
+
     def stage_inputs(self, p0, s0, t0, dd=None, desired_speed=None, obs_s=None, obs_d=None, obs_xy=None, obs_active=None,
                      obs_speed=None, robot_pose=None, sensor=None, targets=None):
         """Write one batch of host inputs into the pinned staging block (no device work yet).
@@ -241,6 +273,7 @@ class BatchPlanner:
                 n -= 1
             if self.stages & nat.STAGE_CURVATURE:
                 n -= 1
+        # (STAGE_OFFROAD is one launch of its own)
         if self.predict_steps and (self.stages & nat.STAGE_K4):
             n += 1                                                            # per-chunk obstacle bounds
         return n + (1 if (self.n_obs and getattr(self, "_obs_frenet", False)) else 0)

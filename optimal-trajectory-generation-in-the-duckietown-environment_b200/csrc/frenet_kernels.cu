@@ -348,8 +348,10 @@ __device__ __forceinline__ double parabola_y(const double* __restrict__ q, doubl
 // Path point and unit normal at arc length s: n = (-sin th, cos th), th = arctan2 of the path's
 // first derivative (compute_ortogonal_vect, lib/tests/test_obstacle_planner.py:53-56).  The circle's
 // derivative is the reference's forward chord over dt (circle_trajectory.py:66-72).
+// lane: optional per-scenario parabola (a, b, c, ds) in global memory that replaces the descriptor's (batched Duckietown agents, each
+// with its own lane fit); read element-wise so that the descriptor stays in the kernel's parameter space.
 __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ circle, const double* __restrict__ tab, int n_knots,
-                                           double s, double& px, double& py, double& nx, double& ny) {
+                                           double s, double& px, double& py, double& nx, double& ny, const double* __restrict__ lane = nullptr) {
     double gx, gy;
     if (kind == FRENET_PATH_CIRCLE) {
         circle_pt(circle, s, px, py);
@@ -360,11 +362,12 @@ __device__ __forceinline__ void path_frame(int kind, const double* __restrict__ 
         gy = (qy - py) / h;
     } else if (kind == FRENET_PATH_PARABOLA) {
         // Duckietown driver: chord over ds, not divided (lib/tests/test_mapper_planner_obstacles.py:137-142)
+        const double q[3] = {lane ? lane[0] : circle[0], lane ? lane[1] : circle[1], lane ? lane[2] : circle[2]};
         px = s;
-        py = parabola_y(circle, s);
-        const double s1 = s + circle[3];
+        py = parabola_y(q, s);
+        const double s1 = s + (lane ? lane[3] : circle[3]);
         gx = s1 - s;
-        gy = parabola_y(circle, s1) - py;
+        gy = parabola_y(q, s1) - py;
     } else {
         spline_eval(tab, n_knots, s, px, py, gx, gy);
     }
@@ -791,6 +794,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const bool low = flags & FRENET_ROW_LOWSPEED;
     const double dt = P.sample_period;
     const double s0 = B.state[(int64_t)A.b * 6 + 3];
+    const double* lane_q = (kXY && B.lane_params) ? B.lane_params + 4 * (int64_t)A.b : nullptr;   // per-scenario lane parabola
 
     // Phase 0: stage the row's lateral coefficients, the spline table and the obstacle snapshot.
     {
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             if (kXY) {
                 double px, py, nx, ny;
                 const double sp = B.path_origin ? B.path_origin[2 * A.b] + (s - B.path_origin[2 * A.b + 1]) : s;   // frenet_to_glob_planner
-                path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny);
+                path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny, lane_q);
                 fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
             }
         }
@@ -1040,6 +1044,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const int64_t candF = (int64_t)L.n_scen * R * nd;
     const double dt = P.sample_period;
     const double s0 = B.state[(int64_t)b * 6 + 3];
+    const double* lane_q = (kXY && B.lane_params) ? B.lane_params + 4 * (int64_t)b : nullptr;
 
     // Phase 0: lateral coefficients of the whole group, lateral axis, obstacles, spline table.
     {
@@ -1096,7 +1101,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             if (kXY) {
                 double px, py, nx, ny;
                 const double sp = B.path_origin ? B.path_origin[2 * b] + (s - B.path_origin[2 * b + 1]) : s;
-                path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny);
+                path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny, lane_q);
                 fpx[g * npm + k] = px; fpy[g * npm + k] = py; fnx[g * npm + k] = nx; fny[g * npm + k] = ny;
             }
         }
@@ -1275,12 +1280,13 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
         __syncthreads();
     }
     const double* s_row = B.lon + A.lon_off;
+    const double* lane_q = B.lane_params ? B.lane_params + 4 * (int64_t)A.b : nullptr;
     const bool relative = B.path_origin != nullptr;    // Duckietown runs: path evaluated at projection + (s - s0[0])
     const double origin = relative ? B.path_origin[2 * A.b] : 0.0, s_start = relative ? B.path_origin[2 * A.b + 1] : 0.0;
     for (int k = tid; k < A.npad; k += blockDim.x) {   // padding samples included: whole sectors are written (see K2)
         double px, py, nx, ny;
         const double sp = relative ? origin + (s_row[k] - s_start) : s_row[k];
-        path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny);
+        path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny, lane_q);
         fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
     }
     __syncthreads();
@@ -1374,6 +1380,11 @@ __global__ void __launch_bounds__(kRowThreads) k3_offroad(FrenetLattice L, Frene
     if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
         for (int id = tid; id < L.n_d; id += blockDim.x) B.road_ok[A.cand0 + id] = 0;
         return;
+    }
+    if (B.road_params) {   // per-scenario boundaries: [n_scen][8] = right (h, k, a, given), left (h, k, a, given)
+        const double* q = B.road_params + 8 * (int64_t)A.b;
+        road.right[0] = q[0]; road.right[1] = q[1]; road.right[2] = q[2]; road.has_right = q[3] != 0.0;
+        road.left[0] = q[4]; road.left[1] = q[5]; road.left[2] = q[6]; road.has_left = q[7] != 0.0;
     }
     for (int id = warp; id < L.n_d; id += nwarps) {
         const double* x = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
@@ -2069,7 +2080,9 @@ int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const Fre
 
 int frenet_k3_offroad(const FrenetLattice* L, const FrenetRoad* road, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
-    if (!road || !B) return fail(FRENET_ERR_BAD_ARG, "k3_offroad: NULL argument");
+    if (!B || (!road && !B->road_params)) return fail(FRENET_ERR_BAD_ARG, "k3_offroad: NULL argument");
+    static const FrenetRoad no_road = {};
+    if (!road) road = &no_road;        // per-scenario boundaries come from buf->road_params
     if (!B->lat || !B->road_ok || !B->row_flags) return fail(FRENET_ERR_BAD_ARG, "k3_offroad: lat, road_ok and row_flags are required");
     if (n_rows(L) == 0) return FRENET_OK;
     k3_offroad<<<n_rows(L), kRowThreads, 0, (cudaStream_t)stream>>>(*L, *road, *B);
@@ -2120,6 +2133,7 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     }
     if ((stages & FRENET_STAGE_CURVATURE) && !fuse_curv && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K4) && !fuse_k4 && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
+    if ((stages & FRENET_STAGE_OFFROAD) && (rc = frenet_k3_offroad(L, nullptr, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
     // the winner block carries x, y when they exist: K3 / K4 ran in this call, or a mask computed from them is in use
     const int winner_xy = ((stages & (FRENET_STAGE_K3 | FRENET_STAGE_K4)) ||

@@ -135,6 +135,7 @@ class FrenetEngine:
         self.has_xy = False
         self.has_collision = False
         self.relative_s = False       # Duckietown lane runs: the transform evaluates the path at path_origin + (s - s0[0])
+        self.per_scenario_lanes = False   # every scenario has its own lane-centre parabola and lane boundaries (lane_params, road_params)
 
     # -- allocation ---------------------------------------------------------------------------
     def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0, n_obs_steps: int = 0):
@@ -173,7 +174,7 @@ class FrenetEngine:
         # packed small inputs: one pinned host block, one device block
         sizes = [("state", Bn * 6 * 8), ("scal", Bn * 3 * 8), ("axis_v", Bn * self.n_v_cap * 8), ("target", Bn * nT * 3 * 8),
                  ("obs_xy", Bn * max(n_obs, 1) * 2 * 8), ("obs_sd", Bn * max(n_obs, 1) * 2 * 8),
-                 ("obs_speed", Bn * max(n_obs, 1) * 8), ("robot_pose", Bn * 3 * 8), ("path_origin", Bn * 16),
+                 ("obs_speed", Bn * max(n_obs, 1) * 8), ("robot_pose", Bn * 3 * 8), ("path_origin", Bn * 16), ("lane_params", Bn * 32), ("road_params", Bn * 64),
                  ("n_v", Bn * 4), ("obs_active", Bn * max(n_obs, 1))]
         offs, tot = {}, 0
         for name, sz in sizes:
@@ -192,6 +193,8 @@ class FrenetEngine:
         self.obs_speed = hv[offs["obs_speed"]:offs["obs_speed"] + Bn * no * 8].view(np.float64).reshape(Bn, no)
         self.robot_pose = hv[offs["robot_pose"]:offs["robot_pose"] + Bn * 24].view(np.float64).reshape(Bn, 3)
         self.path_origin = hv[offs["path_origin"]:offs["path_origin"] + Bn * 16].view(np.float64).reshape(Bn, 2)
+        self.lane_params = hv[offs["lane_params"]:offs["lane_params"] + Bn * 32].view(np.float64).reshape(Bn, 4)
+        self.road_params = hv[offs["road_params"]:offs["road_params"] + Bn * 64].view(np.float64).reshape(Bn, 8)
         self.n_v = hv[offs["n_v"]:offs["n_v"] + Bn * 4].view(np.int32)
         self.obs_active = hv[offs["obs_active"]:offs["obs_active"] + Bn * no].reshape(Bn, no)
         hv[:] = 0
@@ -255,6 +258,8 @@ class FrenetEngine:
         Bf.winner, Bf.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
         Bf.road_ok = self.road_ok.data_ptr()
         Bf.path_origin = ip + offs["path_origin"] if self.relative_s else None
+        Bf.lane_params = ip + offs["lane_params"] if self.per_scenario_lanes else None
+        Bf.road_params = ip + offs["road_params"] if self.per_scenario_lanes else None
         self._cap_key = key
 
     def hbm_bytes(self) -> int:
@@ -279,6 +284,18 @@ class FrenetEngine:
             self._graphs.clear()
             if self.geom is not None:
                 self.B.path_origin = self._in_dev.data_ptr() + self._in_offs["path_origin"] if on else None
+
+    def set_per_scenario_lanes(self, on: bool):
+        """Batched lane runs: the parabola path and the lane boundaries are read per scenario from `lane_params` ([B][4]: a, b, c, ds)
+        and `road_params` ([B][8]: right h, k, a, given; left h, k, a, given) of the packed inputs instead of the shared descriptors."""
+        on = bool(on)
+        if on != self.per_scenario_lanes:
+            self.per_scenario_lanes = on
+            self._graphs.clear()
+            if self.geom is not None:
+                ip = self._in_dev.data_ptr()
+                self.B.lane_params = ip + self._in_offs["lane_params"] if on else None
+                self.B.road_params = ip + self._in_offs["road_params"] if on else None
 
     def offroad(self, right_fit=None, left_fit=None):
         """road_ok for every candidate against the lane boundary fits (a, b, c) of y = a x^2 + b x + c; None = that boundary
@@ -330,7 +347,8 @@ class FrenetEngine:
         sizes = {"state": self.n_scen * 48, "scal": self.n_scen * 24, "axis_v": self.n_scen * self.n_v_cap * 8,
                  "target": self.n_scen * self.geom.n_t * 24, "obs_xy": self.n_scen * max(self.n_obs, 1) * 16,
                  "obs_sd": self.n_scen * max(self.n_obs, 1) * 16, "obs_speed": self.n_scen * max(self.n_obs, 1) * 8,
-                 "robot_pose": self.n_scen * 24, "path_origin": self.n_scen * 16, "n_v": self.n_scen * 4, "obs_active": self.n_scen * max(self.n_obs, 1)}
+                 "robot_pose": self.n_scen * 24, "path_origin": self.n_scen * 16, "lane_params": self.n_scen * 32,
+                 "road_params": self.n_scen * 64, "n_v": self.n_scen * 4, "obs_active": self.n_scen * max(self.n_obs, 1)}
         for name in names:
             o = self._in_offs[name]
             self._in_dev[o:o + sizes[name]].copy_(self._in_host[o:o + sizes[name]], non_blocking=True)

@@ -917,3 +917,64 @@ def test_predicted_obstacles_short_horizon_and_short_table(no_fuse):
         _check_argmin(int(res.records["argmin_masked"][b]), fo.first_argmin(L.ctot, ok), L.ctot, f"short predicted[{b}]")
         n_hit, n_free = n_hit + int((~ok).sum()), n_free + int(ok.sum())
     assert n_hit > 0 and n_free > 0
+
+
+def test_batched_lane_runs_with_per_scenario_fits():
+    """SURVEY.md section 8f row 2 for a batch of agents: every scenario has its OWN lane-centre parabola, projection, lane boundaries
+    and obstacle points (`BatchPlanner.stage_lanes`); transform, off-road mask, collision mask and masked pick against the oracle."""
+    _gpu, nat, _, _ = _imports()
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.planner import TrajectoryPlannerParamsDTObstacles
+    from otg_b200.trajectory import ParabolaTrajectory2D
+    rng = np.random.default_rng(404)
+    B, O = 14, 4
+    prm = fo.OracleParams.defaults(fo.VARIANT_DTOBS)
+    fits = np.stack([rng.uniform(-0.5, 0.5, B), rng.uniform(-0.15, 0.15, B), rng.uniform(-0.03, 0.03, B)], 1)
+    fits[np.abs(fits[:, 0]) < 0.05, 0] = 0.2
+    right = fits + np.array([0.02, 0.0, -0.28])
+    left = fits + np.array([-0.02, 0.0, 0.3])
+    right[3] = np.nan                                   # boundary not detected in some scenes
+    left[5] = np.nan
+    right[9] = left[9] = np.nan
+    proj = rng.uniform(0.02, 0.15, B)
+    p0 = np.stack([rng.uniform(-.1, .1, B), rng.uniform(-.05, .05, B), rng.uniform(-.05, .05, B)], 1)
+    s0 = np.stack([rng.uniform(0, 0.3, B), rng.uniform(0.05, 0.6, B), rng.uniform(-.1, .1, B)], 1)
+    t0 = rng.uniform(0, 2, B)
+    obs = np.stack([rng.uniform(0.3, 1.2, (B, O)), rng.uniform(-0.4, 0.6, (B, O))], 2)
+    r2 = fo.AGENT_SAFETY_RAD ** 2
+    bp = BatchPlanner(TrajectoryPlannerParamsDTObstacles(), ParabolaTrajectory2D(0.0, 0.0, 0.0), B, O, "dt_obstacles",
+                      robot_radius=fo.AGENT_SAFETY_RAD)
+    bp.stage_inputs(p0, s0, t0, obs_xy=obs)
+    bp.stage_lanes(fits, proj, road_right=right, road_left=left)
+    bp.launch()
+    res = bp.result(copy=True)
+    eng = bp.engine
+    road = eng.road_ok.cpu().numpy()
+    n_off = n_hit = n_keep = 0
+    for b in range(B):
+        L = fo.generate(prm, p0[b], s0[b], t0[b])
+        f = eng.padded_fields(eng.fetch_scenario(b))
+        path = fo.ParabolaPath(*fits[b])
+        s = L.lon[L.row_of, 0, :]
+        with np.errstate(invalid="ignore"):
+            x, y = fo.frenet_to_cartesian(path, np.where(np.isnan(s), 0.0, proj[b] + (s - s0[b, 0])), L.lat[:, 0, :])
+        nmax = f["x"].shape[1]
+        valid = np.arange(nmax)[None, :] < L.nsteps[:, None]
+        assert_close(f["x"], np.where(valid, x[:, :nmax], np.nan), GPU_RTOL, f"lanes[{b}].x", atol_scale=1.0)
+        assert_close(f["y"], np.where(valid, y[:, :nmax], np.nan), GPU_RTOL, f"lanes[{b}].y", atol_scale=1.0)
+        ok, first = fo.check_collisions(x, y, L.nsteps, obs[b], r2)
+        assert np.array_equal(f["coll_free"], ok) and np.array_equal(f["first_blocker"], first)
+        off = np.zeros(L.n_candidates, dtype=bool)
+        if not np.isnan(right[b]).any():
+            off |= fo.offroad(x, y, L.nsteps, right[b], "right")
+        if not np.isnan(left[b]).any():
+            off |= fo.offroad(x, y, L.nsteps, left[b], "left")
+        C_ = L.n_candidates
+        if np.isnan(right[b]).any() and np.isnan(left[b]).any():
+            assert (road[b, :C_] == 1).all()
+        assert np.array_equal(road[b, :C_] == 0, off), f"lanes[{b}] off-road mask"
+        mask = ok & ~off
+        n_off, n_hit, n_keep = n_off + int(off.sum()), n_hit + int((~ok).sum()), n_keep + int(mask.sum())
+        _check_argmin(int(res.records["argmin_masked"][b]), fo.first_argmin(L.ctot, mask), L.ctot, f"lanes[{b}] masked")
+        assert res.records["n_survivors"][b] == int(mask.sum())
+    assert n_off > 0 and n_hit > 0 and n_keep > 0
