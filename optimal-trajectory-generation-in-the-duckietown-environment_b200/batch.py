@@ -266,16 +266,17 @@ class BatchPlanner:
 
     @property
     def launches_per_plan(self) -> int:
-        n = bin(self.stages).count("1")
-        if (self.stages & nat.STAGE_K2) and (self.stages & nat.STAGE_K3):     # frenet_plan fuses K2+K3 (+K4)
-            n -= 1
-            if self.stages & nat.STAGE_K4:
+        """Kernel launches of one `launch()` (what bench.py reports as gpu_launches)."""
+        st = self.stages
+        kernels = [nat.STAGE_K1, nat.STAGE_K2, nat.STAGE_K3, nat.STAGE_CURVATURE, nat.STAGE_K4, nat.STAGE_OFFROAD, nat.STAGE_K5, nat.STAGE_GATHER]
+        n = sum(1 for k in kernels if st & k)
+        if not (st & nat.STAGE_NO_FUSE):
+            if (st & nat.STAGE_K2) and (st & nat.STAGE_K3):     # frenet_plan fuses K2 + K3 (+ K4, + curvature)
+                n -= 1 + (1 if st & nat.STAGE_K4 else 0) + (1 if st & nat.STAGE_CURVATURE else 0)
+            if (st & nat.STAGE_K5) and (st & nat.STAGE_GATHER):  # argmin + winner gather
                 n -= 1
-            if self.stages & nat.STAGE_CURVATURE:
-                n -= 1
-        # (STAGE_OFFROAD is one launch of its own)
-        if self.predict_steps and (self.stages & nat.STAGE_K4):
-            n += 1                                                            # per-chunk obstacle bounds
+        if self.predict_steps and (st & nat.STAGE_K4):
+            n += 1                                               # per-chunk obstacle bounds
         return n + (1 if (self.n_obs and getattr(self, "_obs_frenet", False)) else 0)
 
     @property

@@ -772,7 +772,10 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
 
-    const int64_t br = blockIdx.x;
+    // opts bits 8..: a row is split over `parts` CTAs (small batches, where one CTA per row would leave most of the GPU idle): every
+    // part repeats the row's longitudinal phase and takes every parts-th round of candidates
+    const int parts = max(1, opts >> 8), part = blockIdx.x % parts;
+    const int64_t br = blockIdx.x / parts;
     const RowAddr A = row_addr(L, br);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int flags = B.row_flags[br];
@@ -827,10 +830,12 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
             double s, v, a, j;
             eval_power_form(pl, t, L.t_pow + 4 * k, s, v, a, j);
-            lon[k] = s;
-            lon[A.npad + k] = v;
-            lon[2 * A.npad + k] = a;
-            lon[3 * A.npad + k] = j;
+            if (part == 0) {
+                lon[k] = s;
+                lon[A.npad + k] = v;
+                lon[2 * A.npad + k] = a;
+                lon[3 * A.npad + k] = j;
+            }
             su[k] = low ? fabs(s - s0) : t;
             if (k < A.N) {
                 acc = fma(j, j, acc);
@@ -898,7 +903,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     // Phase B: a warp per candidate; every lane owns TWO consecutive time steps per iteration (64 steps per warp
     // iteration, 16-byte loads from shared memory and 16-byte stores to HBM); no global loads in this loop.
     // Candidates are dealt round-robin to the warps; their results are staged in shared memory and published after a barrier.
-    for (int id = warp; id < L.n_d; id += nwarps) {
+    for (int id = warp + nwarps * part; id < L.n_d; id += nwarps * parts) {
         Poly pq;
         pq.load(coef + id * 6);
         // [6][npad] block of this candidate; `out` walks along k, the fields sit `fs` bytes apart
@@ -988,6 +993,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     }
     __syncthreads();
     for (int id = tid; id < L.n_d; id += blockDim.x) {
+        if ((id / nwarps) % parts != part) continue;   // another part's candidate
         const int64_t c = A.cand0 + id;
 #pragma unroll
         for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = resc[id * 4 + f];
@@ -1260,7 +1266,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 // K3: Frenet -> Cartesian, one CTA per row; the path frame is computed once per (row, step)
 // ------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, FrenetPath path, FrenetBuffers B) {
+__global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, FrenetPath path, FrenetBuffers B, int parts) {
     extern __shared__ __align__(16) double sm[];
     const int npm = L.n_pad_max;
     double* fpx = sm;                  // [n_pad_max] x 4: path point and unit normal per step
@@ -1269,7 +1275,8 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
     double* fny = fnx + npm;
     double* tab = fny + npm;           // [n_knots][9] spline table staged in shared memory
 
-    const int64_t br = blockIdx.x;
+    const int part = blockIdx.x % parts;   // small batches: a row's candidates are split over `parts` CTAs
+    const int64_t br = blockIdx.x / parts;
     const int flags = B.row_flags[br];
     if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) return;
     const RowAddr A = row_addr(L, br);
@@ -1294,7 +1301,7 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
     // lane before the first use, which is what hides the HBM latency of this read-modify-write pass.
     const int npad = A.npad;
     constexpr int kSpan = 2 * kWarp;   // steps covered by one 16-byte access of a warp
-    for (int id = warp; id < L.n_d; id += 2 * nwarps) {
+    for (int id = warp + 2 * nwarps * part; id < L.n_d; id += 2 * nwarps * parts) {
         const bool two = id + nwarps < L.n_d;
         double* blk1 = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad);
         double* blk2 = two ? blk1 + (int64_t)nwarps * (kCandFields * npad) : blk1;
@@ -1409,13 +1416,14 @@ __global__ void __launch_bounds__(kRowThreads) k3_offroad(FrenetLattice L, Frene
 // ------------------------------------------------------------------------------------------------
 // K4: collision, one CTA per row; obstacles staged in shared memory
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+__global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, FrenetParams P, FrenetBuffers B, int parts) {
     extern __shared__ __align__(16) double sm[];
     const int O = B.n_obs;
     double2* obs = reinterpret_cast<double2*>(sm);
     float2* obsf = reinterpret_cast<float2*>(sm + 2 * O);
 
-    const int64_t br = blockIdx.x;
+    const int part = blockIdx.x % parts;   // small batches: a row's candidates are split over `parts` CTAs
+    const int64_t br = blockIdx.x / parts;
     const RowAddr A = row_addr(L, br);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int flags = B.row_flags[br];
@@ -1432,7 +1440,7 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
     __syncthreads();
     const float Rf = __double2float_ru(sqrt(P.radius_sq));
 
-    for (int id = warp; id < L.n_d; id += nwarps) {
+    for (int id = warp + nwarps * part; id < L.n_d; id += nwarps * parts) {
         const double* xs = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad) + 4 * A.npad;
         const double* ys = xs + A.npad;
         int best = kNoBlocker;   // lowest blocking obstacle index found so far (warp-uniform)
@@ -1764,10 +1772,50 @@ struct Best {
     }
 };
 
+// The winner block of one scenario (the arrays `optimal_at_time` indexes, trajectory_planner.py:183-195), copied by all threads of the CTA.
+__device__ __forceinline__ int winner_index(const FrenetResult& res, int sel) {
+    return sel == FRENET_SEL_CTOT ? res.argmin_ctot
+         : sel == FRENET_SEL_CD   ? res.argmin_cd
+         : sel == FRENET_SEL_CV   ? res.argmin_cv
+         : sel == FRENET_SEL_CT   ? res.argmin_ct
+                                  : res.argmin_masked;
+}
+
+__device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int c, int has_xy) {
+    if (c < 0) {
+        if (threadIdx.x == 0) B.winner_steps[b] = 0;
+        return;
+    }
+    const int r = c / L.n_d, id = c % L.n_d;
+    const RowAddr A = row_addr(L, (int64_t)b * L.n_v_cap * L.n_t + r);
+    double* w = B.winner + (int64_t)b * FRENET_WINNER_ROWS * L.n_pad_max;
+    const double t0 = B.scal[(int64_t)b * 3 + 2];
+    const double* cand = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad);
+    const double* lon = B.lon + A.lon_off;
+    for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
+        w[k] = (double)k * P.sample_period + t0;   // f.t[i] += t_initial (:178-179)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            w[(1 + f) * L.n_pad_max + k] = cand[f * A.npad + k];
+            w[(5 + f) * L.n_pad_max + k] = lon[f * A.npad + k];
+        }
+        if (has_xy) {
+            w[9 * L.n_pad_max + k] = cand[4 * A.npad + k];
+            w[10 * L.n_pad_max + k] = cand[5 * A.npad + k];
+        }
+    }
+    if (threadIdx.x < 4) w[11 * L.n_pad_max + threadIdx.x] = B.cost[threadIdx.x * A.candF + A.cand0 + id];
+    if (threadIdx.x == 0) B.winner_steps[b] = A.N;
+}
+
 constexpr int kKeys = 5;   // ctot, cd, cv, ct, masked ctot
 constexpr int kArgminThreads = 512;
 
-__global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, FrenetBuffers B, int use_mask) {
+// gather_sel >= 0: the CTA also copies that selection's winner block (gather_winner) once the record is known - one launch less
+// in every pipeline that wants both.
+__global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, FrenetParams P, FrenetBuffers B, int use_mask, int gather_sel,
+                                                            int has_xy) {
+    __shared__ int sh_winner;
     __shared__ double sv[kKeys][kArgminThreads / 32];
     __shared__ int si[kKeys][kArgminThreads / 32];
     __shared__ int scount[2][kArgminThreads / 32];
@@ -1781,23 +1829,43 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
 #pragma unroll
     for (int q = 0; q < kKeys; ++q) best[q].init();
     int nvalid = 0, nsurv = 0;
-    for (int c = tid; c < C; c += blockDim.x) {
-        const int fl = B.cand_flags[base + c];
-        if (!(fl & FRENET_CAND_VALID)) continue;
-        ++nvalid;
-        const double ctot = B.cost[3 * candF + base + c];
-        best[0].take(ctot, c);
-        best[1].take(B.cost[base + c], c);
-        best[2].take(B.cost[candF + base + c], c);
-        best[3].take(B.cost[2 * candF + base + c], c);
-        bool pass = true;
-        if (use_mask & 1) pass = pass && (fl & FRENET_CAND_KINEMATIC_OK);
-        if (use_mask & 2) pass = pass && B.curv_ok[base + c];
-        if (use_mask & 4) pass = pass && B.coll_free[base + c];
-        if (use_mask & 8) pass = pass && B.road_ok[base + c];
-        if (pass) {
-            ++nsurv;
-            best[4].take(ctot, c);
+    // Every load of an iteration is issued before anything depends on one (a single planner is one CTA here: its latency is a chain
+    // of memory round trips), and four candidates are in flight per thread.
+    constexpr int kUnroll = 4;
+    for (int c0 = tid; c0 < C; c0 += kUnroll * blockDim.x) {
+        int fl[kUnroll];
+        double cd[kUnroll], cv[kUnroll], ct[kUnroll], ctot[kUnroll];
+        uint8_t m_curv[kUnroll], m_coll[kUnroll], m_road[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int c = c0 + u * blockDim.x;
+            const bool in = c < C;
+            const int64_t g = base + (in ? c : c0);
+            fl[u] = in ? B.cand_flags[g] : 0;
+            cd[u] = B.cost[g];
+            cv[u] = B.cost[candF + g];
+            ct[u] = B.cost[2 * candF + g];
+            ctot[u] = B.cost[3 * candF + g];
+            m_curv[u] = (use_mask & 2) ? B.curv_ok[g] : 1;
+            m_coll[u] = (use_mask & 4) ? B.coll_free[g] : 1;
+            m_road[u] = (use_mask & 8) ? B.road_ok[g] : 1;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int c = c0 + u * blockDim.x;
+            if (!(fl[u] & FRENET_CAND_VALID)) continue;
+            ++nvalid;
+            best[0].take(ctot[u], c);
+            best[1].take(cd[u], c);
+            best[2].take(cv[u], c);
+            best[3].take(ct[u], c);
+            bool pass = true;
+            if (use_mask & 1) pass = pass && (fl[u] & FRENET_CAND_KINEMATIC_OK);
+            pass = pass && m_curv[u] && m_coll[u] && m_road[u];
+            if (pass) {
+                ++nsurv;
+                best[4].take(ctot[u], c);
+            }
         }
     }
 #pragma unroll
@@ -1840,42 +1908,18 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
         res.min_masked_ctot = out[4].v;
         res.reserved[0] = res.reserved[1] = 0.0;
         B.result[b] = res;
+        sh_winner = gather_sel >= 0 ? winner_index(res, gather_sel) : -1;
+    }
+    if (gather_sel >= 0) {
+        __syncthreads();
+        gather_one(L, P, B, b, sh_winner, has_xy);
     }
 }
 
 // Winner gather: the sampled state optimal_at_time indexes (trajectory_planner.py:183-195), 11 rows + a cost row.
 __global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetParams P, FrenetBuffers B, int sel, int has_xy) {
     const int b = blockIdx.x;
-    const FrenetResult& res = B.result[b];
-    const int c = sel == FRENET_SEL_CTOT ? res.argmin_ctot
-                : sel == FRENET_SEL_CD   ? res.argmin_cd
-                : sel == FRENET_SEL_CV   ? res.argmin_cv
-                : sel == FRENET_SEL_CT   ? res.argmin_ct
-                                         : res.argmin_masked;
-    if (c < 0) {
-        if (threadIdx.x == 0) B.winner_steps[b] = 0;
-        return;
-    }
-    const int r = c / L.n_d, id = c % L.n_d;
-    const RowAddr A = row_addr(L, (int64_t)b * L.n_v_cap * L.n_t + r);
-    double* w = B.winner + (int64_t)b * FRENET_WINNER_ROWS * L.n_pad_max;
-    const double t0 = B.scal[(int64_t)b * 3 + 2];
-    const double* cand = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad);
-    const double* lon = B.lon + A.lon_off;
-    for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
-        w[k] = (double)k * P.sample_period + t0;   // f.t[i] += t_initial (:178-179)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            w[(1 + f) * L.n_pad_max + k] = cand[f * A.npad + k];
-            w[(5 + f) * L.n_pad_max + k] = lon[f * A.npad + k];
-        }
-        if (has_xy) {
-            w[9 * L.n_pad_max + k] = cand[4 * A.npad + k];
-            w[10 * L.n_pad_max + k] = cand[5 * A.npad + k];
-        }
-    }
-    if (threadIdx.x < 4) w[11 * L.n_pad_max + threadIdx.x] = B.cost[threadIdx.x * A.candF + A.cand0 + id];
-    if (threadIdx.x == 0) B.winner_steps[b] = A.N;
+    gather_one(L, P, B, b, winner_index(B.result[b], sel), has_xy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1964,7 +2008,11 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
         FRENET_CHECK_LAUNCH("k2_short");
         return FRENET_OK;
     }
-    const unsigned grid = n_rows(L);
+    // a single planner (or a handful) has too few rows to fill the GPU with one CTA each: split the rows' candidates over several CTAs
+    int parts = 1;
+    while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * (kRowThreads / kWarp) < L->n_d) parts *= 2;
+    opts |= parts << 8;
+    const unsigned grid = n_rows(L) * parts;
 #define FRENET_LAUNCH_K2(LIM)                                                                                           \
     do {                                                                                                                \
         if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM>, smem, "k2: row does not fit shared memory")) return rc;     \
@@ -1983,6 +2031,25 @@ int check_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers*
         !B->cost || !B->cand_flags)
         return fail(FRENET_ERR_BAD_ARG, "k2: NULL buffer");
     if (P->follow && !B->target) return fail(FRENET_ERR_BAD_ARG, "k2: follow mode needs target triples");
+    return FRENET_OK;
+}
+
+int launch_k5(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, int32_t use_mask, int gather_sel, int has_xy,
+              cudaStream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!B || !B->cost || !B->cand_flags || !B->result) return fail(FRENET_ERR_BAD_ARG, "k5: NULL buffer");
+    if ((use_mask & 2) && !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "k5: curvature mask requested but curv_ok is NULL");
+    if ((use_mask & 4) && !B->coll_free) return fail(FRENET_ERR_BAD_ARG, "k5: collision mask requested but coll_free is NULL");
+    if ((use_mask & 8) && !B->road_ok) return fail(FRENET_ERR_BAD_ARG, "k5: road mask requested but road_ok is NULL");
+    if (gather_sel >= 0 && (!P || !B->winner || !B->winner_steps || !B->lat || !B->lon || !B->scal))
+        return fail(FRENET_ERR_BAD_ARG, "k5 + gather: NULL buffer");
+    // small lattices (the reference's default has 320-384 candidates) leave most of a 512-thread CTA idle: a narrower CTA lets
+    // more scenarios be resident per SM (the lexicographic minimum does not depend on the block size)
+    const int64_t C = (int64_t)L->n_v_cap * L->n_t * L->n_d;
+    const int threads = C <= 1024 ? 128 : kArgminThreads;
+    static const FrenetParams no_params = {};
+    k5_argmin<<<L->n_scen, threads, 0, stream>>>(*L, P ? *P : no_params, *B, use_mask, gather_sel, has_xy);
+    FRENET_CHECK_LAUNCH("k5_argmin");
     return FRENET_OK;
 }
 
@@ -2044,7 +2111,9 @@ int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const Fre
     if (!B || !B->row_flags || !B->lon || !B->lat) return fail(FRENET_ERR_BAD_ARG, "k3: NULL buffer");
     const size_t smem = ((size_t)4 * L->n_pad_max + (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0)) * sizeof(double);
     if (int rc = set_smem(k3_cartesian, smem, "k3: horizon / spline table too large for shared memory")) return rc;
-    k3_cartesian<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *path, *B);
+    int parts = 1;
+    while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * 2 * (kRowThreads / kWarp) < L->n_d) parts *= 2;
+    k3_cartesian<<<n_rows(L) * parts, kRowThreads, smem, (cudaStream_t)stream>>>(*L, *path, *B, parts);
     FRENET_CHECK_LAUNCH("k3_cartesian");
     return FRENET_OK;
 }
@@ -2073,7 +2142,9 @@ int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const Fre
     if (B->n_obs > 0 && !B->obs_xy) return fail(FRENET_ERR_BAD_ARG, "k4: obstacle table missing");
     const size_t smem = (size_t)3 * B->n_obs * sizeof(double);
     if (int rc = set_smem(k4_collision, smem, "k4: too many obstacles for shared memory")) return rc;
-    k4_collision<<<n_rows(L), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B);
+    int parts = 1;
+    while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * (kRowThreads / kWarp) < L->n_d) parts *= 2;
+    k4_collision<<<n_rows(L) * parts, kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B, parts);
     FRENET_CHECK_LAUNCH("k4_collision");
     return FRENET_OK;
 }
@@ -2091,18 +2162,7 @@ int frenet_k3_offroad(const FrenetLattice* L, const FrenetRoad* road, const Fren
 }
 
 int frenet_k5_argmin(const FrenetLattice* L, const FrenetBuffers* B, int32_t use_mask, frenet_stream_t stream) {
-    if (int rc = check_lattice(L)) return rc;
-    if (!B || !B->cost || !B->cand_flags || !B->result) return fail(FRENET_ERR_BAD_ARG, "k5: NULL buffer");
-    if ((use_mask & 2) && !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "k5: curvature mask requested but curv_ok is NULL");
-    if ((use_mask & 4) && !B->coll_free) return fail(FRENET_ERR_BAD_ARG, "k5: collision mask requested but coll_free is NULL");
-    if ((use_mask & 8) && !B->road_ok) return fail(FRENET_ERR_BAD_ARG, "k5: road mask requested but road_ok is NULL");
-    // small lattices (the reference's default has 320-384 candidates) leave most of a 512-thread CTA idle: a narrower CTA lets
-    // more scenarios be resident per SM (the lexicographic minimum does not depend on the block size)
-    const int64_t C = (int64_t)L->n_v_cap * L->n_t * L->n_d;
-    const int threads = C <= 1024 ? 128 : kArgminThreads;
-    k5_argmin<<<L->n_scen, threads, 0, (cudaStream_t)stream>>>(*L, *B, use_mask);
-    FRENET_CHECK_LAUNCH("k5_argmin");
-    return FRENET_OK;
+    return launch_k5(L, nullptr, B, use_mask, -1, 0, (cudaStream_t)stream);
 }
 
 int frenet_gather_winner(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, int32_t sel, int32_t has_xy,
@@ -2134,10 +2194,12 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     if ((stages & FRENET_STAGE_CURVATURE) && !fuse_curv && (rc = frenet_k3_curvature(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_K4) && !fuse_k4 && (rc = frenet_k4_collision(L, P, B, stream))) return rc;
     if ((stages & FRENET_STAGE_OFFROAD) && (rc = frenet_k3_offroad(L, nullptr, B, stream))) return rc;
-    if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
     // the winner block carries x, y when they exist: K3 / K4 ran in this call, or a mask computed from them is in use
     const int winner_xy = ((stages & (FRENET_STAGE_K3 | FRENET_STAGE_K4)) ||
                            (use_mask & (FRENET_MASK_CURVATURE | FRENET_MASK_COLLISION | FRENET_MASK_ROAD))) ? 1 : 0;
+    if ((stages & FRENET_STAGE_K5) && (stages & FRENET_STAGE_GATHER) && !(stages & FRENET_STAGE_NO_FUSE))
+        return launch_k5(L, P, B, use_mask, gather_sel, winner_xy, (cudaStream_t)stream);   // argmin and winner gather in one launch
+    if ((stages & FRENET_STAGE_K5) && (rc = frenet_k5_argmin(L, B, use_mask, stream))) return rc;
     if ((stages & FRENET_STAGE_GATHER) && (rc = frenet_gather_winner(L, P, B, gather_sel, winner_xy, stream)))
         return rc;
     return rc;
