@@ -23,20 +23,21 @@ def short(n):
 
 
 seq = [(short(r[idx["Kernel Name"]]), float(r[idx["Metric Value"]]), r[idx["Grid Size"]]) for r in rows[1:]]
-# one pipeline step = points_to_cartesian, k1, fused k2, k5, gather (5 launches); the bench does 3 warm-up steps first
-step_names = ["points_to_cartesian", "k1_coefficients", "k2_evaluate<1, 1,", "k5_argmin", "gather_winner"]
-starts = [i for i in range(len(seq) - 4) if all(seq[i + j][0].startswith(step_names[j]) for j in range(5))]
+# one pipeline step = points_to_cartesian, k1, fused k2, k5 (which also gathers the winner): 4 launches; the bench does 3 warm-up steps first
+step_names = ["points_to_cartesian", "k1_coefficients", "k2_evaluate<1, 1,", "k5_argmin"]
+n_step = len(step_names)
+starts = [i for i in range(len(seq) - n_step + 1) if all(seq[i + j][0].startswith(step_names[j]) for j in range(n_step))]
 lines = [f"# ncu launch list summary ({tag})", "",
          f"Source: `{os.path.basename(launches)}` (`ncu --metrics gpu__time_duration.sum --clock-control none`, same command as the",
          "bench line: `python bench.py --steps 5 --warmup 3 --no-cpu`).  Per-launch times are cold-cache and serialised:",
          "compare SHARES with the CUDA-event numbers of bench.py, not absolutes.", "",
-         f"Pipeline steps found: {len(starts)} (5 launches each).  Mean over steps {min(3, len(starts))}..{len(starts) - 1}:", "",
+         f"Pipeline steps found: {len(starts)} ({n_step} launches each).  Mean over steps {min(3, len(starts))}..{len(starts) - 1}:", "",
          "| kernel | grid | mean us | share of step |", "|---|---|---|---|"]
 use = starts[3:] if len(starts) > 3 else starts
 tot = collections.OrderedDict((n, 0.0) for n in step_names)
 grid = {}
 for i in use:
-    for n0, (n, t, g) in zip(step_names, seq[i:i + 5]):
+    for n0, (n, t, g) in zip(step_names, seq[i:i + n_step]):
         tot[n0] += t
         grid[n0] = g
 step_total = sum(tot.values())
