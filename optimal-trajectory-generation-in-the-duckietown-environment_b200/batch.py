@@ -240,10 +240,12 @@ class BatchPlanner:
             self._n_v_sum = int(e.result["n_valid"].sum()) // max(self.geom.n_t * self.geom.n_d, 1)
         return e.result
 
-    def gather_records(self, n_total: int, group=None) -> np.ndarray:
+    def gather_records(self, n_total: int, group=None, sync: bool = True):
         """All ranks' result records of the last launch, in scenario order: ONE NCCL all-gather straight from the device
         block K5 wrote (no host staging), then one copy to the host.  Must follow a launch on this stream; shard sizes
-        follow `shard_range`.  Without a process group it returns this planner's own records."""
+        follow `shard_range`.  Without a process group it returns this planner's own records.
+        sync=False only enqueues the collective and the copy (equal shards) and returns None: the records are in the array a later
+        synchronising call returns, once the stream has been synchronised."""
         import torch.distributed as dist
         e = self.engine
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -261,6 +263,8 @@ class BatchPlanner:
             self._gather_host = torch.empty(world * local.numel(), dtype=torch.uint8, pin_memory=True)
         dist.all_gather_into_tensor(self._gather_buf, local, group=group)
         self._gather_host.copy_(self._gather_buf, non_blocking=True)
+        if not sync:
+            return None
         torch.cuda.current_stream(e.device).synchronize()
         return self._gather_host.numpy().view(np.dtype(nat.RESULT_DTYPE))
 
