@@ -702,7 +702,10 @@ def test_randomised_shapes_and_parameters_against_oracle():
     # horizons down to 0.05 s put coefficients of 1e5 x the values into play: the contract tolerance (1e-5 relative) applies,
     # tightened tenfold; the fixtures above hold the well-conditioned cases to 1e-9
     FUZZ_RTOL = 1e-6
-    rng = np.random.default_rng(2026)
+    import os
+    # OTG_FUZZ_SEED / OTG_FUZZ_MAX_B: soak runs with other seeds and larger batches (several rows per CTA in the short-horizon kernel)
+    rng = np.random.default_rng(int(os.environ.get("OTG_FUZZ_SEED", "2026")))
+    max_b = int(os.environ.get("OTG_FUZZ_MAX_B", "4"))
     circ, circ_o = Circle(8, 5, 2), fo.CirclePath(8, 5, 2)
     spl, spl_o = Spline(workloads.SPLINE_WX, workloads.SPLINE_WY), fo.SplinePath(workloads.SPLINE_WX, workloads.SPLINE_WY)
     n_cases = 0
@@ -728,7 +731,7 @@ def test_randomised_shapes_and_parameters_against_oracle():
             kw["delta_t"] = period
             kw["dt"] = float(rng.choice([0.25, 0.5, 0.8]))
         prm = base.with_(**kw)
-        B = int(rng.integers(1, 5))
+        B = int(rng.integers(1, max_b + 1))
         p0 = np.stack([rng.uniform(-0.5, 0.5, B) * width, rng.uniform(-.5, .5, B), rng.uniform(-.5, .5, B)], 1)
         s0 = np.stack([rng.uniform(0, 30, B), rng.uniform(0, 4, B), rng.uniform(-.5, .5, B)], 1)
         dd = rng.uniform(-1, 1, B) * width
