@@ -159,7 +159,8 @@ typedef struct FrenetBuffers {
     int32_t n_obs_steps;       /* EXTENSION: 0 = snapshot table `obs_xy` (the reference: every step is tested against the obstacles'
                                   CURRENT positions, lib/tests/test_moving_obstacle_planner.py:89-91); K > 0 = predicted table below */
     const double* obs_xy_t;    /* [n_scen][n_obs][n_obs_steps][2] predicted positions: step k is tested against entry min(k, K-1) */
-    float* obs_bounds;         /* scratch [n_scen][ceil(n_pad_max/32)][n_obs][4] (per 32-step chunk bounding circles, K4 fills it) */
+    float* obs_bounds;         /* scratch of n_scen * ceil(n_pad_max/32) * n_obs * 4 floats: per chunk of 32 (or 64) steps and obstacle the
+                                  bounding circle (cx, cy, r, padded r) of its predicted positions; the collision stage fills it */
     /* K1 outputs */
     double* coef_lon;          /* [n_scen][R][6] a0..a5 (a5 = 0 for the velocity-keeping quartic) */
     double* coef_lat;          /* [n_scen][C][6] */
