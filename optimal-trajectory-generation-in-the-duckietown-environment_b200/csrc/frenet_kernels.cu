@@ -748,7 +748,7 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // table (kXY).
 // Every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead): the mapping for long
 // horizons.  Lattices of at most 32 padded samples go through k2_short below instead.
-template <bool kXY, int kColl, bool kLimits>
+template <bool kXY, int kColl, bool kLimits, bool kSplit>
 __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts) {
     extern __shared__ __align__(16) double sm[];
     const int npm = L.n_pad_max;
@@ -772,10 +772,12 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
 
-    // opts bits 8..: a row is split over `parts` CTAs (small batches, where one CTA per row would leave most of the GPU idle): every
-    // part repeats the row's longitudinal phase and takes every parts-th round of candidates
-    const int parts = max(1, opts >> 8), part = blockIdx.x % parts;
-    const int64_t br = blockIdx.x / parts;
+    // gridDim.y > 1: a row is split over several CTAs (small batches, where one CTA per row would leave most of the GPU idle): every
+    // part repeats the row's longitudinal phase and takes every parts-th round of candidates.  kSplit = false compiles the split away
+    // (this kernel has no register to spare in the batched case).
+#define parts (kSplit ? (int)gridDim.y : 1)
+#define part (kSplit ? (int)blockIdx.y : 0)
+    const int64_t br = blockIdx.x;
     const RowAddr A = row_addr(L, br);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int flags = B.row_flags[br];
@@ -1006,6 +1008,9 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         }
     }
 }
+
+#undef parts
+#undef part
 
 // ------------------------------------------------------------------------------------------------
 // K2 (+K3 +K4 fused) for SHORT horizons: at most 32 padded samples per candidate (the reference's default lattice has 11..26)
@@ -1275,8 +1280,8 @@ __global__ void __launch_bounds__(kRowThreads) k3_cartesian(FrenetLattice L, Fre
     double* fny = fnx + npm;
     double* tab = fny + npm;           // [n_knots][9] spline table staged in shared memory
 
-    const int part = blockIdx.x % parts;   // small batches: a row's candidates are split over `parts` CTAs
-    const int64_t br = blockIdx.x / parts;
+    const int part = blockIdx.y;   // small batches: a row's candidates are split over `parts` = gridDim.y CTAs
+    const int64_t br = blockIdx.x;
     const int flags = B.row_flags[br];
     if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) return;
     const RowAddr A = row_addr(L, br);
@@ -1422,8 +1427,8 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
     double2* obs = reinterpret_cast<double2*>(sm);
     float2* obsf = reinterpret_cast<float2*>(sm + 2 * O);
 
-    const int part = blockIdx.x % parts;   // small batches: a row's candidates are split over `parts` CTAs
-    const int64_t br = blockIdx.x / parts;
+    const int part = blockIdx.y;   // small batches: a row's candidates are split over `parts` = gridDim.y CTAs
+    const int64_t br = blockIdx.x;
     const RowAddr A = row_addr(L, br);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int flags = B.row_flags[br];
@@ -2011,15 +2016,16 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     // a single planner (or a handful) has too few rows to fill the GPU with one CTA each: split the rows' candidates over several CTAs
     int parts = 1;
     while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * (kRowThreads / kWarp) < L->n_d) parts *= 2;
-    opts |= parts << 8;
-    const unsigned grid = n_rows(L) * parts;
-#define FRENET_LAUNCH_K2(LIM)                                                                                           \
-    do {                                                                                                                \
-        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM>, smem, "k2: row does not fit shared memory")) return rc;     \
-        k2_evaluate<kXY, kColl, LIM><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B, opts);                              \
+    const dim3 grid(n_rows(L), parts);
+#define FRENET_LAUNCH_K2(LIM, SPLIT)                                                                                           \
+    do {                                                                                                                       \
+        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, SPLIT>, smem, "k2: row does not fit shared memory")) return rc;     \
+        k2_evaluate<kXY, kColl, LIM, SPLIT><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B, opts);                        \
     } while (0)
-    if (limits) FRENET_LAUNCH_K2(true);
-    else FRENET_LAUNCH_K2(false);
+    if (limits && parts > 1) FRENET_LAUNCH_K2(true, true);
+    else if (limits) FRENET_LAUNCH_K2(true, false);
+    else if (parts > 1) FRENET_LAUNCH_K2(false, true);
+    else FRENET_LAUNCH_K2(false, false);
 #undef FRENET_LAUNCH_K2
     FRENET_CHECK_LAUNCH("k2_evaluate");
     return FRENET_OK;
@@ -2113,7 +2119,7 @@ int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const Fre
     if (int rc = set_smem(k3_cartesian, smem, "k3: horizon / spline table too large for shared memory")) return rc;
     int parts = 1;
     while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * 2 * (kRowThreads / kWarp) < L->n_d) parts *= 2;
-    k3_cartesian<<<n_rows(L) * parts, kRowThreads, smem, (cudaStream_t)stream>>>(*L, *path, *B, parts);
+    k3_cartesian<<<dim3(n_rows(L), parts), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *path, *B, parts);
     FRENET_CHECK_LAUNCH("k3_cartesian");
     return FRENET_OK;
 }
@@ -2144,7 +2150,7 @@ int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const Fre
     if (int rc = set_smem(k4_collision, smem, "k4: too many obstacles for shared memory")) return rc;
     int parts = 1;
     while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * (kRowThreads / kWarp) < L->n_d) parts *= 2;
-    k4_collision<<<n_rows(L) * parts, kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B, parts);
+    k4_collision<<<dim3(n_rows(L), parts), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B, parts);
     FRENET_CHECK_LAUNCH("k4_collision");
     return FRENET_OK;
 }
