@@ -102,7 +102,15 @@ for row in r[2:]:
     key = "k2k3k4_fused" if "<1, 1," in name or "(bool)1, (bool)1" in name else ("k2k3_fused" if "<1, 0," in name else "k2_evaluate")
     traffic[key] = rd + wr
     md.append(f"DRAM traffic per launch: {rd / 1e9:.3f} GB read + {wr / 1e9:.3f} GB written = **{(rd + wr) / 1e9:.3f} GB**.")
-open(os.path.join(out_dir, out_name), "w").write("\n".join(md) + "\n")
+# a hand-written "Executed SASS by region" section (from the source page of the same capture) survives a regeneration
+out_path = os.path.join(out_dir, out_name)
+keep = ""
+if os.path.exists(out_path):
+    old_text = open(out_path).read()
+    at = old_text.find("## Executed SASS by region")
+    if at >= 0:
+        keep = "\n" + old_text[at:]
+open(out_path, "w").write("\n".join(md) + "\n" + keep)
 if len(sys.argv) <= 4:      # only the full-size capture feeds traffic.json (bytes per launch of the bench's own launch)
     tpath = os.path.join(out_dir, "traffic.json")
     old = json.load(open(tpath)) if os.path.exists(tpath) else {}
