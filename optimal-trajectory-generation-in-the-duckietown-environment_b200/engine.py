@@ -123,6 +123,7 @@ class FrenetEngine:
         if self.device.type != "cuda":
             raise RuntimeError("FrenetEngine needs a CUDA device")
         self.n_scen = int(n_scen)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.geom: LatticeGeometry | None = None
         self.n_v_cap = 0
         self.n_obs = 0
@@ -465,7 +466,7 @@ class FrenetEngine:
             self._graphs[key] = g
             return                      # the warm-up run already produced this call's results
         g.replay()
-        torch.cuda.current_stream(self.device).synchronize()
+        torch.cuda.current_stream(self._dev_index).synchronize()
         if stages & nat.STAGE_K2:
             self.generation += 1
             self.has_xy = bool(stages & nat.STAGE_K3)

@@ -259,8 +259,13 @@ class _LatticePlanner(Planner):
         eng.n_v[0] = len(V)
         if follow:
             eng.target[0] = self._target_triples(geom.T)
-        P = make_params(self, self._rule, period, follow)
-        self.__dict__["_params"] = P
+        # the parameter block is rebuilt only when one of the attributes it is made from changed (callers may mutate them)
+        pkey = (self.kj, self.kt, self.kd, self.ks, self.kdots, self.klat, self.klong, self.low_speed_threshold, period, follow,
+                self.__dict__.get("S_thresh"), self.__dict__.get("v_max"), self.__dict__.get("a_max"), self.__dict__.get("kappa_max"))
+        if self.__dict__.get("_params_key") != pkey:
+            self.__dict__["_params"] = make_params(self, self._rule, period, follow)
+            self.__dict__["_params_key"] = pkey
+        P = self._params
         eng.run_graph(P, None, nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER, 0, nat.SEL_CTOT)
         self.__dict__["_winner_cache"] = {"ctot": self._frenet_from_winner("argmin_ctot")}
         paths = LatticePaths(self, len(V), follow)
@@ -273,15 +278,13 @@ class _LatticePlanner(Planner):
         n = int(eng.winner_steps[0])
         if n == 0:
             return None
-        w = eng.winner[0]
+        rows = eng.winner[0, :, :n].tolist()      # one conversion for the whole block: t, 8 state rows, x, y, costs
         f = Frenet()
-        c = int(eng.result[0][result_field])
-        f.index = c
-        for row, name in enumerate(_WINNER_ROWS[:9]):
-            setattr(f, name, w[row, :n].tolist())
+        f.index = int(eng.result[0][result_field])
+        f.t, f.d, f.dot_d, f.ddot_d, f.dddot_d, f.s, f.dot_s, f.ddot_s, f.dddot_s = rows[:9]
         if eng.has_xy:
-            f.x, f.y = w[9, :n].tolist(), w[10, :n].tolist()
-        f.cd, f.cv, f.ct, f.ctot = (float(v) for v in w[11, :4])
+            f.x, f.y = rows[9], rows[10]
+        f.cd, f.cv, f.ct, f.ctot = eng.winner[0, 11, :4].tolist()
         return f
 
     def _winner(self, key: str):
