@@ -276,6 +276,38 @@ def test_config5_sample_matches_reference():
         assert res["status"][i] == (nat.STATUS_OK if z["argmin_masked"][i] >= 0 else nat.STATUS_NO_FEASIBLE)
 
 
+def test_config5_on_the_circle_path_against_oracle():
+    """the config-5 sweep also runs on the circle path.  Four full-size scenarios (dense lattice, 128 obstacles
+    placed through the circle's own frame) against the oracle: costs, Cartesian samples, collision masks, first blockers, picks."""
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200 import workloads
+    sc = workloads.config5_scenarios()
+    idx = np.array([3, 700, 2100, 4000])
+    tr, op = Circle(*workloads.CIRCLE_LHR), fo.CirclePath(*workloads.CIRCLE_LHR)
+    prm = _dense_prm()
+    ox, oy = fo.frenet_to_cartesian(op, sc["obs_s"][idx], sc["obs_d"][idx])
+    obs = np.stack([ox, oy], 2)
+    eng = _gpu.run_batch(prm, sc["p0"][idx], sc["s0"][idx], sc["t0"][idx], dd=sc["dd"][idx], trajectory=tr, obstacles=obs)
+    n_blocked = 0
+    for i, b in enumerate(idx):
+        L = fo.generate(prm, sc["p0"][b], sc["s0"][b], float(sc["t0"][b]), dd=float(sc["dd"][b]))
+        f = eng.padded_fields(eng.fetch_scenario(i))
+        compare_packed(f, pack_lattice(L, t_field=False), GPU_RTOL, f"circle5[{i}]")
+        x, y = fo.lattice_to_cartesian(op, L)
+        nmax = f["x"].shape[1]
+        valid = np.arange(nmax)[None, :] < L.nsteps[:, None]
+        assert_close(f["x"], np.where(valid, x[:, :nmax], np.nan), GPU_RTOL, f"circle5[{i}].x", per_row=True)
+        assert_close(f["y"], np.where(valid, y[:, :nmax], np.nan), GPU_RTOL, f"circle5[{i}].y", per_row=True)
+        ok, first = fo.check_collisions(x, y, L.nsteps, obs[i])
+        assert np.array_equal(f["coll_free"], ok) or _margin_ok(x, y, L.nsteps, obs[i], f["coll_free"], ok)
+        same = f["coll_free"] == ok
+        assert np.array_equal(f["first_blocker"][same], first[same])
+        n_blocked += int((~ok).sum())
+        _check_argmin(int(eng.result[i]["argmin_ctot"]), fo.first_argmin(L.ctot, L.keep), L.ctot, f"circle5[{i}]")
+        _check_argmin(int(eng.result[i]["argmin_masked"]), fo.first_argmin(L.ctot, ok & L.keep), L.ctot, f"circle5[{i}] masked")
+    assert n_blocked > 0
+
+
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("lattice,no_fuse", [("default", False), ("default", True), ("long", False), ("long", True)])
 def test_batch_against_oracle_with_limits_and_curvature(lattice, no_fuse):
