@@ -326,7 +326,7 @@ class FrenetEngine:
         return h[1]
 
     # -- launches ------------------------------------------------------------------------------
-    def upload(self, stream=None, record_event: bool = True):
+    def upload(self, record_event: bool = True):
         """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles).  An event marks the
         end of the copy so that the host may refill the pinned block for the NEXT call while this call's kernels run
         (`wait_staging_free`)."""
