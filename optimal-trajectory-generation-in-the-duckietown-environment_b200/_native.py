@@ -24,6 +24,7 @@ PATH_CIRCLE, PATH_SPLINE, PATH_PARABOLA = 0, 1, 2
 SEL_CTOT, SEL_CD, SEL_CV, SEL_CT, SEL_MASKED = 0, 1, 2, 3, 4
 STAGE_K1, STAGE_K2, STAGE_K3, STAGE_K4, STAGE_K5, STAGE_GATHER, STAGE_CURVATURE, STAGE_NO_FUSE = 1, 2, 4, 8, 16, 32, 64, 128
 STAGE_OFFROAD = 256
+FUSE_COLLISION, FUSE_CURVATURE = 1, 2
 MASK_KINEMATIC, MASK_CURVATURE, MASK_COLLISION, MASK_ROAD = 1, 2, 4, 8
 
 c_double_p = C.c_void_p   # device pointers are passed as integers (tensor.data_ptr())

@@ -443,6 +443,18 @@ def test_error_codes_and_edge_cases():
     assert eng.result[0]["n_valid"] == int(L.keep.sum())
     if not L.keep.any():
         assert eng.result[0]["status"] == nat.STATUS_EMPTY and eng.result[0]["argmin_ctot"] == -1
+    # stages that need a buffer the caller did not provide are refused, not launched
+    P = nat.FrenetParams()
+    rc = nat.lib.frenet_plan(C.byref(eng.L), C.byref(P), None, C.byref(eng.B), nat.STAGE_OFFROAD, 0, 0, None)
+    assert rc == nat.ERR_BAD_ARG                                  # no per-scenario road_params and no FrenetRoad
+    rc = nat.lib.frenet_plan(C.byref(eng.L), C.byref(P), None, C.byref(eng.B), nat.STAGE_K5, nat.MASK_ROAD, 0, None)
+    saved_road = eng.B.road_ok
+    eng.B.road_ok = None
+    rc = nat.lib.frenet_plan(C.byref(eng.L), C.byref(P), None, C.byref(eng.B), nat.STAGE_K5, nat.MASK_ROAD, 0, None)
+    assert rc == nat.ERR_BAD_ARG and b"road" in nat.lib.frenet_last_error()
+    eng.B.road_ok = saved_road
+    rc = nat.lib.frenet_k2_fused(C.byref(eng.L), C.byref(P), None, C.byref(eng.B), nat.FUSE_COLLISION, None)
+    assert rc == nat.ERR_BAD_ARG                                  # fused needs a path
 
 
 def test_fused_kernel_equals_separate_launches():
