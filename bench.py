@@ -15,8 +15,11 @@ every one of them sampled, costed, feasibility-checked, transformed to Cartesian
           states + obstacle parameters from pinned memory and D2H of result records + winner trajectories
           inside the timed region.
   roofline / kernels : each kernel timed alone with CUDA events over the same buffers.
-  cpu_baseline : the NumPy oracle (oracle/frenet_oracle.py - a vectorised port of the reference; the reference
-          itself is pure Python and cannot travel to the GPU box) on the host cores, bounded sample.
+  cpu_baseline : the reference's CPU path on the host cores, bounded samples of the same workload:
+          (i) the UNMODIFIED reference (oracle/_ref, a build-time copy of its pure-Python `lib/` package, see
+          oracle/build_ref.py) single-threaded and in one process per core, (ii) the NumPy oracle (oracle/frenet_oracle.py,
+          a vectorised port) in one process per core.  The scenarios computed on the CPU are compared with the GPU's
+          records of the same scenarios after the timed region (`parity_spot_check`).
 """
 from __future__ import annotations
 
@@ -38,10 +41,18 @@ N_OBS = 128
 METRIC = "candidate-timesteps/sec (feasibility+collision-checked)"
 
 
-def workload(lo, hi):
+FIELD_NOTE = {"spread": "obstacles uniform over a 25 m x 16 m field starting 3 m ahead of each robot (round-1 parity fixtures)",
+              "literal": "SURVEY 8(d) verbatim: s_o ~ U(s0, s0 + 15), d_o ~ N(0, 2), no clearance"}
+# Bounded sample of the dense lattice for the unmodified reference (pure Python, ~2e4 candidate-timesteps/s per core): the rows of
+# the scenario's centre target speed (num_sample = 0) and every fourth horizon (dt = 0.4): 400 of its ~1e4 candidates, same D axis,
+# same sampling period, same 128 obstacles.  Candidate-timesteps/s is per unit of work, so the figure extrapolates to the full lattice.
+REF_SLICE = dict(num_sample=0, dt=0.4)
+
+
+def workload(lo, hi, field="spread"):
     import otg_b200  # noqa: F401
     from otg_b200 import workloads as w
-    sc = w.config5_scenarios()
+    sc = w.config5_scenarios(field=field)
     t0 = sc["t0"][lo:hi]
     fs, fd = w.moving_obstacle_frenet(sc["obs_s"][lo:hi], sc["obs_d"][lo:hi], sc["obs_speed"][lo:hi], sc["obs_offset"][lo:hi], t0[:, None])
     return dict(p0=sc["p0"][lo:hi], s0=sc["s0"][lo:hi], dd=sc["dd"][lo:hi], t0=t0, obs_s=fs, obs_d=fd)
@@ -58,17 +69,33 @@ def dense_params():
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
 def _cpu_one(args):
-    p0, s0, t0, dd, fs, fd = args
+    """One scenario of the step through the NumPy port; returns the work done and what the GPU record must agree with."""
+    p0, s0, t0, dd, fs, fd, slice_kw = args
     from otg_b200 import workloads as w
     from oracle import frenet_oracle as fo
-    prm = fo.OracleParams.defaults("v1").with_(**w.DENSE_PARAMS)
+    prm = fo.OracleParams.defaults("v1").with_(**w.DENSE_PARAMS).with_(**slice_kw)
     sp = fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY)
     ox, oy = fo.frenet_to_cartesian(sp, fs, fd)
     L = fo.generate(prm, p0, s0, t0, dd=dd)
     x, y = fo.lattice_to_cartesian(sp, L)
     ok, _ = fo.check_collisions(x, y, L.nsteps, np.stack([ox, oy], 1))
-    fo.first_argmin(L.ctot, ok)
-    return int(L.nsteps.sum())
+    w_ = fo.first_argmin(L.ctot, ok)
+    return dict(cand_ts=int(L.nsteps.sum()), argmin_masked=int(w_), n_survivors=int(ok.sum()),
+                min_masked_ctot=float(L.ctot[w_]) if w_ >= 0 else float("inf"))
+
+
+def _ref_one(args):
+    """The same scenario (its REF_SLICE rows) through the UNMODIFIED reference (oracle/_ref)."""
+    p0, s0, t0, dd, fs, fd, slice_kw = args
+    from otg_b200 import workloads as w
+    from oracle import ref_runner as rr
+    return rr.replan_pipeline({**w.DENSE_PARAMS, **slice_kw}, (w.SPLINE_WX, w.SPLINE_WY), p0, s0, t0, dd, (fs, fd))
+
+
+def _ref_latency(_):
+    from oracle import ref_runner as rr
+    a, b = rr.default_lattice_replan(3)
+    return a, b
 
 
 def cpu_replan_latency(n_calls=30):
@@ -97,45 +124,66 @@ def cpu_replan_latency(n_calls=30):
             "calls": n_calls}
 
 
-def cpu_pass(pool, wl, n):
-    jobs = [(wl["p0"][i], wl["s0"][i], float(wl["t0"][i]), float(wl["dd"][i]), wl["obs_s"][i], wl["obs_d"][i]) for i in range(n)]
+def _jobs(wl, n, slice_kw):
+    return [(wl["p0"][i], wl["s0"][i], float(wl["t0"][i]), float(wl["dd"][i]), wl["obs_s"][i], wl["obs_d"][i], slice_kw) for i in range(n)]
+
+
+def cpu_pass(pool, wl, n, fn=_cpu_one, slice_kw=None):
+    """n scenarios through `fn` in the pool; returns (per-scenario results, candidate-timesteps, seconds)."""
+    jobs = _jobs(wl, n, slice_kw or {})
     t = time.perf_counter()
-    cts = sum(pool.map(_cpu_one, jobs, chunksize=1))
-    return cts, time.perf_counter() - t
+    res = pool.map(fn, jobs, chunksize=1) if pool is not None else [fn(j) for j in jobs]
+    dt = time.perf_counter() - t
+    return res, sum(r["cand_ts"] for r in res), dt
+
+
+def have_ref():
+    from oracle import ref_runner as rr
+    return rr.available()
 
 
 def run_reference(args):
-    """`--impl reference`: the CPU implementation of the path (oracle port) with all host cores, same config."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores, same config and metric.
+    With oracle/_ref present this is the UNMODIFIED reference (kind "reference"), each step one REF_SLICE sample of one scenario
+    per core; otherwise the NumPy port on one whole scenario per core (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = cores   # scenarios per step: a bounded sample of the 512-scenario shard (one scenario, about 1 s, per core)
+    n = cores
     wl = workload(0, n)
+    ref = have_ref()
+    fn, slice_kw = (_ref_one, REF_SLICE) if ref else (_cpu_one, {})
     with mp.get_context("spawn").Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_pass(pool, wl, min(n, cores))
+            cpu_pass(pool, wl, n, fn, slice_kw)
         tot_c, tot_t = 0, 0.0
         for _ in range(args.steps):
-            c, t = cpu_pass(pool, wl, n)
+            _, c, t = cpu_pass(pool, wl, n, fn, slice_kw)
             tot_c += c
             tot_t += t
     v = tot_c / tot_t
-    sample = f"{n} of the {SCEN_PER_GPU} scenarios of one GPU shard per step, {cores} worker processes"
+    if ref:
+        sample = (f"per step: {n} scenarios of the shard, one per worker process ({cores} processes), each the rows of its centre target "
+                  f"speed and every 4th horizon (num_sample=0, dt=0.4: 400 of ~1e4 candidates) through the unmodified reference "
+                  f"(initialize + frenet_to_glob + check_paths + min); {tot_c // args.steps} candidate-timesteps per step")
+    else:
+        sample = f"{n} of the {SCEN_PER_GPU} scenarios of one GPU shard per step, {cores} worker processes, NumPy port (oracle/_ref missing)"
     line = {"metric": METRIC, "value": v, "unit": "candidate-timesteps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": config_dict(args.gpus),
-            "cpu_baseline": {"value": v, "unit": "candidate-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "candidate-timesteps/s", "cores": cores, "kind": "reference" if ref else "port", "sample": sample},
             "e2e": {"value": v, "unit": "candidate-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, field="spread"):
     return {"workload": "BASELINE config 5: batched moving-obstacle sweep, dense V1 lattice (d_road_width=0.1, dt=0.1, "
                         "num_sample=3, delta_t=0.02; 9600-11200 candidates x 51..147 steps), spline path, 128 moving "
-                        "obstacles per scenario, R=0.7",
+                        f"obstacles per scenario, R=0.7; obstacle field '{field}': {FIELD_NOTE[field]}",
+            "obstacle_field": field,
             "scenarios_per_gpu": SCEN_PER_GPU, "scenarios_per_step": SCEN_PER_GPU * n_gpus, "n_obstacles": N_OBS,
             "parallelism": f"scenario-sharded x{n_gpus}, one gather of result records",
             "l2": "each step writes ~28 GB of lattice state per GPU (>> 126 MB L2): no L2 flush needed"}
@@ -304,6 +352,74 @@ def all_checks_mode(wl, steps, dev):
     return out
 
 
+def _event_ms(fn, reps):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def literal_field_legs(dev, lo, hi, steps):
+    """SURVEY 8(d)'s obstacle fields taken literally, next to the headline's: config 5 with s_o ~ U(s0, s0 + 15), d_o ~ N(0, 2)
+    (same scenarios, same lattice) and config 4 with default_rng(64), s_o ~ U(5, 30), d_o ~ N(0, 2) on one planner."""
+    import ctypes as C
+    import torch
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat, workloads as w
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.trajectory import SplineTrajectory2D
+    spl = SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY)
+    out = {}
+    wl = workload(lo, hi, field="literal")
+    bp = BatchPlanner(dense_params(), spl, hi - lo, N_OBS, "v1", dev)
+    bp.stage_inputs(**wl)
+    bp.engine.upload()
+    for _ in range(3):
+        bp.launch_resident()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        bp.launch_resident()
+        bp.engine.download(sync=False)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    e = bp.engine
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    fused = _event_ms(lambda: nat.check(nat.lib.frenet_k2_fused(C.byref(e.L), C.byref(bp.params), C.byref(bp.path.desc), C.byref(e.B), 1, stream)), 5)
+    bp.launch_resident()
+    e.download(sync=True)
+    nvalid = float(e.result["n_valid"].sum())
+    out["config5_literal"] = {"value": bp.cand_timesteps() / (ms * 1e-3), "unit": "candidate-timesteps/s", "ms_per_step": ms,
+                              "k2k3k4_fused_ms": fused, "survivor_fraction": float(e.result["n_survivors"].sum()) / max(nvalid, 1.0),
+                              "scenarios_with_feasible": int((e.result["status"] == 0).sum()), "scenarios": hi - lo,
+                              "field": FIELD_NOTE["literal"]}
+    del bp
+    torch.cuda.empty_cache()
+    # config 4, both fields: one planner, 64 obstacles, all sensed
+    for field in ("literal", "spread"):
+        sc = w.config4_scenario(field=field)
+        bp = BatchPlanner(dense_params(), spl, 1, 64, "v1", dev)
+        kw = dict(p0=np.array([sc["p0"]]), s0=np.array([sc["s0"]]), t0=np.array([sc["t0"]]), dd=np.array([sc["dd"]]),
+                  obs_s=sc["obs_s"][None], obs_d=sc["obs_d"][None])
+        r = bp.plan(**kw)
+        ms4 = _event_ms(bp.launch_resident, 20)
+        out[f"config4_{field}"] = {"ms_per_replan_device": ms4, "candidate_timesteps": r.cand_timesteps,
+                                   "value": r.cand_timesteps / (ms4 * 1e-3), "n_candidates": int(r.records["n_valid"][0]),
+                                   "n_survivors": int(r.records["n_survivors"][0]), "argmin": int(r.records["argmin_ctot"][0]),
+                                   "argmin_masked": int(r.records["argmin_masked"][0]), "field": FIELD_NOTE[field]}
+        del bp
+    torch.cuda.empty_cache()
+    return out
+
+
 def default_lattice_batch(dev, n_scen=32768, steps=10):
     """The reference's OWN lattice (configs 1-3: 320-384 candidates x 11..26 steps, circle path, 10 obstacles) as a batch of
     independent planners - the short-horizon form of the pipeline kernel."""
@@ -452,6 +568,25 @@ def replan_latency(n_calls=200):
     return out
 
 
+def spot_check(cpu_results, records):
+    """CPU results (list of dicts from _cpu_one / _ref_one) against the GPU's FrenetResult records of the same scenarios:
+    survivor counts exact, masked pick exact (a different index with a cost within 1e-6 relative counts as a tie, the north
+    star's exception), minimum masked cost to 1e-9 relative."""
+    n = len(cpu_results)
+    mism, ties, worst = 0, 0, 0.0
+    for r, g in zip(cpu_results, records):
+        a, b = r["min_masked_ctot"], float(g["min_masked_ctot"])
+        same_cost = (a == b) or (np.isfinite(a) and np.isfinite(b) and abs(a - b) <= 1e-9 * max(abs(a), abs(b)))
+        if np.isfinite(a) and np.isfinite(b):
+            worst = max(worst, abs(a - b) / max(abs(a), abs(b), 1e-300))
+        if r["n_survivors"] != int(g["n_survivors"]) or not same_cost:
+            mism += 1
+        elif r["argmin_masked"] != int(g["argmin_masked"]):
+            ties += 1       # equal minimum cost, different index: only possible for an exact / near tie
+    return {"n": n, "mismatches": mism, "near_ties": ties, "max_rel_cost_diff": worst,
+            "fields": ["n_survivors (exact)", "argmin_masked (exact, ties reported)", "min_masked_ctot (1e-9 rel)"]}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -487,21 +622,22 @@ def run_gpu(args):
     bp.stage_inputs(**wl)
     bp.engine.upload()
     for _ in range(args.warmup):
-        bp.launch_resident()
-        bp.engine.download(sync=world == 1)
-        gather()
+        bp.launch_pipelined(n_total)
+    bp.pipeline_wait()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    # Every step's kernels, the D2H copy of its records + winners and (N > 1) the all-gather of the records are enqueued on one
-    # stream; the host does not wait per step (the e2e arm below is the one that hands every step's results to the host).
+    # Every step: the kernels on the compute stream; the D2H copy of its records + winners and (N > 1) the one collective of the
+    # path - the all-gather of the records - on a side stream, under the next step's kernels (two output blocks alternate).  The
+    # host does not wait per step (the e2e arm below is the one that hands every step's results to the host); the timed region
+    # ends when the last step's results have arrived too.
     for _ in range(args.steps):
-        bp.launch_resident()
-        bp.engine.download(sync=False)         # records + winners leave the device every step
-        gather(sync=False)                     # the one collective of the path
+        bp.launch_pipelined(n_total)
+    bp.pipeline_join()
     ev1.record()
     barrier()
+    bp.pipeline_wait()
     ms_dev = ev0.elapsed_time(ev1)
     clk = clocks.stop() if clocks else None
     cts_step_local = bp.cand_timesteps()
@@ -574,24 +710,62 @@ def run_gpu(args):
         in_pipeline = ("k1_coefficients", "k2k3k4_fused", "k5_argmin_plus_gather")   # what frenet_plan launches
         dom = max((k for k in algo if k in in_pipeline), key=lambda k: kern[k])
         pipeline_ms = sum(kern[k] for k in in_pipeline)
+        # Bytes.  `frac` uses the bytes this design must move: the s-fields are stored once per ROW (the n_d = 80 candidates of a row
+        # share them; the parity tests read all ten fields of every candidate through that view), i.e. 48 B per candidate-timestep
+        # (d and its three derivatives, x, y) + 32 B per row-timestep.  SURVEY 8(d) counts the s-fields per candidate: 80 B per candidate-timestep
+        # for the fused pipeline.  `frac_survey_bytes` is the same time against that figure; it can exceed 1 because those bytes
+        # are never written.
+        survey = {"k2k3k4_fused": 80 * cts, "k2k3_fused": 80 * cts, "k2_evaluate": 64 * cts + 40 * ncand}
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
-                    "share_of_step": kern[dom] / pipeline_ms}
-        tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+                    "share_of_step": kern[dom] / pipeline_ms, "ms": kern[dom], "algorithmic_bytes": algo[dom],
+                    "bytes_per_candidate_timestep": 48, "bytes_per_row_timestep": 32,
+                    "frac_survey_bytes": survey[dom] / (kern[dom] * 1e-3) / 1e9 / peak, "survey_bytes_per_candidate_timestep": 80,
+                    "bytes_note": "longitudinal samples stored once per row, not per candidate (row de-duplication): 48 B/cand-ts + 32 B/row-ts instead of SURVEY 8(d)'s 80 B/cand-ts"}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
         if os.path.exists(tr):
-            roofline["traffic"] = json.load(open(tr)).get(dom)
+            tj = json.load(open(tr))
+            roofline["traffic"] = tj.get(dom)
+            roofline["traffic_source"] = tj.get("source", "committed ncu capture (profiles/), not measured in this run")
 
-        # CPU baseline on rank 0, N = 1 only: bounded sample of the same workload
-        cpu = None
+        # CPU baseline on rank 0, N = 1 only: bounded samples of the same workload, and a spot check of the GPU's records
+        cpu, spot = None, None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             n = min(2 * cores, SCEN_PER_GPU)
+            spot = {}
             with mp.get_context("spawn").Pool(cores) as pool:
                 cpu_pass(pool, wl, min(cores, n))   # warm the workers
-                c, tcpu = cpu_pass(pool, wl, n)
-            cpu = {"value": c / tcpu, "unit": "candidate-timesteps/s", "cores": cores, "kind": "port",
-                   "sample": f"first {n} of the {SCEN_PER_GPU} scenarios of the step, oracle (NumPy port) in {cores} processes, {tcpu:.1f} s",
-                   "replan_latency": cpu_replan_latency()}
+                res_port, c, tcpu = cpu_pass(pool, wl, n)
+                port = {"value": c / tcpu, "unit": "candidate-timesteps/s", "cores": cores, "kind": "port",
+                        "sample": f"first {n} of the {SCEN_PER_GPU} scenarios of the step, NumPy port in {cores} processes, {tcpu:.1f} s"}
+                spot["port"] = spot_check(res_port, allrec[:n])
+                cpu = dict(port)
+                cpu["port_all_cores"] = port
+                cpu["replan_latency"] = cpu_replan_latency()
+                if have_ref():
+                    nref = min(cores, SCEN_PER_GPU)
+                    res_ref, c, tref = cpu_pass(pool, wl, nref, _ref_one, REF_SLICE)
+                    what = ("rows of the centre target speed and every 4th horizon (num_sample=0, dt=0.4: 400 of ~1e4 candidates, same D axis, "
+                            "sampling period and 128 obstacles) of one scenario, unmodified reference (initialize + frenet_to_glob + check_paths + min); "
+                            "candidate-timesteps/s is per unit of work, so it extrapolates to the full lattice")
+                    allc = {"value": c / tref, "unit": "candidate-timesteps/s", "cores": cores, "kind": "reference", "seconds": tref,
+                            "sample": f"first {nref} scenarios of the step, one per process, each: {what}"}
+                    _, c1, t1 = cpu_pass(None, wl, 1, _ref_one, REF_SLICE)
+                    one = {"value": c1 / t1, "unit": "candidate-timesteps/s", "cores": 1, "kind": "reference", "seconds": t1,
+                           "sample": f"first scenario of the step: {what}"}
+                    lat_ref = pool.map(_ref_latency, [0])[0]
+                    cpu.update(value=allc["value"], kind="reference", sample=allc["sample"], reference_all_cores=allc,
+                               reference_single_thread=one)
+                    cpu["replan_latency"]["reference_config1_replanner_p50_us"] = lat_ref[0] * 1e6
+                    cpu["replan_latency"]["reference_config3_replan_transform_collide_pick_p50_us"] = lat_ref[1] * 1e6
+                    # the GPU on the very same slice of the same scenarios
+                    from otg_b200.planner import TrajectoryPlannerParams
+                    bq = BatchPlanner(TrajectoryPlannerParams(**{**w.DENSE_PARAMS, **REF_SLICE}), SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY),
+                                      nref, N_OBS, "v1", dev)
+                    rq = bq.plan(**{k: v[:nref] for k, v in wl.items()})
+                    spot["reference"] = spot_check(res_ref, rq.records)
+                    del bq
 
         line = {"metric": METRIC, "value": cts_step * args.steps / (ms_dev * 1e-3), "unit": "candidate-timesteps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -601,14 +775,16 @@ def run_gpu(args):
                         "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": bp.h2d_bytes * world,
                         "d2h_bytes_per_step": bp.d2h_bytes * world},
                 "gpu_launches": bp.launches_per_plan * args.steps,
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity_spot_check": spot, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
-                "replan_latency": replan_latency() if world == 1 else None,
+                "replan_latency": replan_latency() if (world == 1 and not args.kernels_only) else None,
+                "literal_obstacle_fields": None,
                 "predicted_obstacles": None, "all_feasibility_checks": None, "default_lattice_batch": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
-        if world == 1:
+        if world == 1 and not args.kernels_only:
             del bp
             torch.cuda.empty_cache()
+            line["literal_obstacle_fields"] = literal_field_legs(dev, lo, hi, max(3, args.steps // 3))
             line["predicted_obstacles"] = predicted_mode(wl, max(3, args.steps // 3), dev)
             line["all_feasibility_checks"] = all_checks_mode(wl, max(3, args.steps // 3), dev)
             line["default_lattice_batch"] = default_lattice_batch(dev)
@@ -626,6 +802,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernels-only", action="store_true", help="headline step + per-kernel timings only (A/B runs of kernel builds)")
     ap.add_argument("--scenarios", type=int, default=512, help="scenarios per GPU and step (512 = the benchmark; "
                     "smaller only for profiler captures)")
     args = ap.parse_args()

@@ -315,6 +315,32 @@ int frenet_sensor_gate(const double* robot_pose, const double* obs_xy, int32_t n
 int frenet_polyline_collision(const double* x, const double* y, const int64_t* offsets, int32_t n_paths, const double* obs_xy,
                               int32_t n_obs, double radius_sq, uint8_t* coll_free, int32_t* first_blocker, frenet_stream_t stream);
 
+/* Buffer sizing for hosts that do not use the Python engine (SURVEY section 8b "frenet_plan_workspace_bytes"): the byte size of
+ * every array FrenetLattice / FrenetBuffers point to, for a lattice shape and obstacle capacity.  Only the size fields of `lat`
+ * are read (n_scen, n_v_cap, n_t, n_d, n_pad_max, row_elems, cand_elems); its pointers may be NULL.  The layout inside each
+ * array is documented at the top of this header.  `total` = the sum with every array rounded up to 256 bytes, i.e. the size of
+ * ONE allocation that holds them all back to back in the order of the fields below. */
+typedef struct FrenetSizes {
+    int64_t rows, candidates;     /* n_scen * n_v_cap * n_t, times n_d */
+    /* inputs */
+    int64_t state, scal, target, axis_v, n_v, axis_d, axis_t, n_steps, t_offset, t_pow;
+    int64_t obs_xy, obs_active, obs_xy_t, obs_bounds;
+    /* outputs */
+    int64_t coef_lon, coef_lat, row_S, row_flags, lon, lat, cost, cand_flags, curv_ok, coll_free, first_blocker, road_ok;
+    int64_t result, winner, winner_steps;
+    /* optional per-scenario lane inputs */
+    int64_t path_origin, lane_params, road_params;
+    int64_t total;
+} FrenetSizes;
+int frenet_workspace_bytes(const FrenetLattice* lat, int32_t n_obs, int32_t n_obs_steps, FrenetSizes* out);
+
+/* How frenet_k2_evaluate / frenet_k2_fused will launch for a shape: rows of a scenario per CTA (short-horizon kernel, > 1 only for
+ * lattices of at most 32 padded samples), CTAs per row (long-horizon kernel on small batches), grid size and dynamic shared
+ * memory per CTA.  path NULL = K2 alone.  Returns FRENET_ERR_CAPACITY if the shape does not fit 227 KB of shared memory.
+ * Any output pointer may be NULL. */
+int frenet_k2_launch_shape(const FrenetLattice* lat, const FrenetPath* path, int32_t n_obs, int32_t n_obs_steps, int32_t with_collision,
+                           int32_t* rows_per_cta, int32_t* ctas_per_row, int64_t* grid, int64_t* shared_bytes);
+
 #ifdef __cplusplus
 }
 #endif

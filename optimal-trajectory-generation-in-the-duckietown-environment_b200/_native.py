@@ -74,6 +74,16 @@ class FrenetBuffers(C.Structure):
                 ("lane_params", C.c_void_p), ("road_params", C.c_void_p)]
 
 
+class FrenetSizes(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "rows", "candidates",
+        "state", "scal", "target", "axis_v", "n_v", "axis_d", "axis_t", "n_steps", "t_offset", "t_pow",
+        "obs_xy", "obs_active", "obs_xy_t", "obs_bounds",
+        "coef_lon", "coef_lat", "row_S", "row_flags", "lon", "lat", "cost", "cand_flags", "curv_ok", "coll_free", "first_blocker", "road_ok",
+        "result", "winner", "winner_steps",
+        "path_origin", "lane_params", "road_params", "total")]
+
+
 class FrenetRoad(C.Structure):
     _fields_ = [("right", C.c_double * 3), ("left", C.c_double * 3), ("has_right", C.c_int32), ("has_left", C.c_int32)]
 
@@ -122,6 +132,9 @@ def _load():
                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
         "frenet_points_to_cartesian": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                                  C.c_int64, C.c_void_p]),
+        "frenet_workspace_bytes": (C.c_int, [P(FrenetLattice), C.c_int32, C.c_int32, P(FrenetSizes)]),
+        "frenet_k2_launch_shape": (C.c_int, [P(FrenetLattice), P(FrenetPath), C.c_int32, C.c_int32, C.c_int32, P(C.c_int32), P(C.c_int32),
+                                             P(C.c_int64), P(C.c_int64)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)    # AttributeError here = header and library out of sync

@@ -215,6 +215,61 @@ class BatchPlanner:
         self._place()
         e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
 
+    def launch_pipelined(self, n_total: int | None = None, group=None):
+        """One resident step whose results leave the device on a SIDE stream: the D2H copy of records + winners and - with a
+        process group - the one collective of the path (all-gather of the 64-byte records over NCCL) run under the next step's
+        kernels instead of in front of them.  Two output blocks alternate, so a rank may run one step ahead of the slowest one;
+        `pipeline_wait()` returns the records of the last step enqueued."""
+        import torch.distributed as dist
+        e = self.engine
+        if not hasattr(self, "_pipe"):
+            e.enable_out_slots(2)
+            self._pipe = dict(side=torch.cuda.Stream(device=e.device), done=[None, None], gbuf=[None, None], ghost=[None, None], last=1)
+        P = self._pipe
+        slot = P["last"] ^ 1
+        compute = torch.cuda.current_stream(e.device)
+        if P["done"][slot] is not None:
+            compute.wait_event(P["done"][slot])       # the side-stream work of the step that used this block two steps ago
+        e.select_out_slot(slot)
+        self.launch_resident()
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        side = P["side"]
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            e._out_host.copy_(e._out_dev, non_blocking=True)
+            if world > 1:
+                if n_total is None or n_total != world * self.n_scen:
+                    raise ValueError("launch_pipelined needs equal shards: n_total = world size x scenarios of this planner")
+                o = e._out_offs["result"]
+                local = e._out_dev[o:o + self.n_scen * nat.RESULT_BYTES]
+                if P["gbuf"][slot] is None:
+                    P["gbuf"][slot] = torch.empty(world * local.numel(), dtype=torch.uint8, device=e.device)
+                    P["ghost"][slot] = torch.empty(world * local.numel(), dtype=torch.uint8, pin_memory=True)
+                dist.all_gather_into_tensor(P["gbuf"][slot], local, group=group)
+                P["ghost"][slot].copy_(P["gbuf"][slot], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        P["done"][slot] = done
+        P["last"] = slot
+
+    def pipeline_join(self):
+        """Make the current stream wait for all side-stream work enqueued so far (for timing the whole pipeline with events)."""
+        P = getattr(self, "_pipe", None)
+        if P:
+            for ev in P["done"]:
+                if ev is not None:
+                    torch.cuda.current_stream(self.engine.device).wait_event(ev)
+
+    def pipeline_wait(self):
+        """Records of the last pipelined step: all ranks' (scenario order) with a process group, else this planner's."""
+        P = self._pipe
+        P["done"][P["last"]].synchronize()
+        if P["ghost"][P["last"]] is not None:
+            return P["ghost"][P["last"]].numpy().view(np.dtype(nat.RESULT_DTYPE))
+        return self.engine.result
+
     def replanner(self, time, robot_pose=None, sensor=None, obs_xy=None, sync: bool = True):
         """One `planner.replanner(time)` for every scenario WITHOUT a host round trip for the planner state
         (trajectory_planner.py:206-212, 223-234): the new initial state is the previous (masked) winner sampled at `time`,
@@ -249,13 +304,14 @@ class BatchPlanner:
         import torch.distributed as dist
         e = self.engine
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            torch.cuda.current_stream(e.device).synchronize()
-            return e.result
+            return self._local_records()
         world = dist.get_world_size(group)
-        cap = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
-        if cap != self.n_scen:      # ragged shards: go through the padded host path
-            torch.cuda.current_stream(e.device).synchronize()
-            return gather_results(e.result, n_total, group, e.device)
+        if n_total % world != 0:    # ragged shards (decided from n_total alone, so EVERY rank takes this branch): padded host path
+            if not sync:
+                raise ValueError("gather_records(sync=False) needs equal shards (n_total divisible by the world size)")
+            return gather_results(self._local_records(), n_total, group, self._collective_device(group))
+        if n_total // world != self.n_scen:
+            raise ValueError(f"this planner holds {self.n_scen} scenarios, its shard of {n_total} over {world} ranks has {n_total // world}")
         o = e._out_offs["result"]
         local = e._out_dev[o:o + self.n_scen * nat.RESULT_BYTES]
         if getattr(self, "_gather_buf", None) is None or self._gather_buf.numel() != world * local.numel():
@@ -267,6 +323,15 @@ class BatchPlanner:
             return None
         torch.cuda.current_stream(e.device).synchronize()
         return self._gather_host.numpy().view(np.dtype(nat.RESULT_DTYPE))
+
+    def _local_records(self):
+        """This planner's records of the last launch, once the stream has drained."""
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        return self.engine.result
+
+    def _collective_device(self, group=None):
+        import torch.distributed as dist
+        return self.engine.device if dist.get_backend(group) == "nccl" else None
 
     @property
     def launches_per_plan(self) -> int:

@@ -52,10 +52,33 @@ constexpr int kMaxSmem = 227 * 1024;
 #ifndef FRENET_K2_MIN_CTAS_COLL
 #define FRENET_K2_MIN_CTAS_COLL 4
 #endif
+// the row-table collision variant keeps the collision work out of the sampling loop: same register budget as the collision-free kernels
+#ifndef FRENET_K2_MIN_CTAS_TABLE
+#define FRENET_K2_MIN_CTAS_TABLE 3
+#endif
+// warps that share one 32-step chunk of the row table (the listed obstacles are dealt round-robin to them); 0 = as many as it takes
+// to give every warp of the CTA one item
+#ifndef FRENET_TABLE_SPLIT
+#define FRENET_TABLE_SPLIT 0
+#endif
 // 1: the collision variants of the long-horizon kernel reload the candidate's coefficients from shared memory in every iteration instead of
 // keeping them in twelve registers across the collision test: no spills at the 64-register cap, fused kernel 6.2 -> 5.8 ms on B200
 #ifndef FRENET_K2_RELOAD_COEF
 #define FRENET_K2_RELOAD_COEF 1
+#endif
+// 1 (default): the snapshot collision stage of the long-horizon pipeline kernel works on ROW level: the n_d candidates of a row share the
+// path frame and their lateral polynomials are affine in the lateral target, so every (step, obstacle) pair blocks a contiguous range
+// of candidate indices.  The ranges are found once per row (fp32 with explicit error margins), certain hits become bit masks, and only
+// candidates in the thin uncertain band are re-tested with the reference's fp64 expression.  0: the round-1 form (bounding-circle cull
+// + fp32 pre-test + fp64 test per candidate inside the sampling loop); kept for same-box A/B runs.
+#ifndef FRENET_ROW_TABLE
+#define FRENET_ROW_TABLE 1
+#endif
+// EXPERIMENT (profiles/r2_sass_store_path.md): 1 = a candidate's [6][npad] block is staged in shared memory by the warp that owns it and
+// leaves the SM as ONE bulk asynchronous copy (cp.async.bulk.global.shared::cta, SASS UBLKCP) issued by one lane, instead of six
+// 16-byte STG per lane and iteration.  Needs 6 * n_pad_max doubles of staging per warp, which costs a resident CTA per SM.
+#ifndef FRENET_BULK_STORE
+#define FRENET_BULK_STORE 0
 #endif
 // 1: unit normal of the path as the normalised, rotated tangent; 0: through atan2 + sincos like the reference's code.
 #ifndef FRENET_FRAME_NORMALISE
@@ -511,7 +534,7 @@ __device__ __forceinline__ int collide_pair(double xa, double ya, double xb, dou
 // span: steps per chunk (32 for one step per lane, 64 where a lane carries two).
 __global__ void __launch_bounds__(128) obstacle_chunk_bounds(const double* __restrict__ obs_t, const uint8_t* __restrict__ active, int O,
                                                              int K, int n_chunks, int span, float4* __restrict__ bounds) {
-    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int b = blockIdx.x / n_chunks, chunk = blockIdx.x % n_chunks;   // (scenario on grid.x: grid.y is limited to 65535)
     for (int o = threadIdx.x; o < O; o += blockDim.x) {
         float4 out = make_float4(CUDART_INF_F, CUDART_INF_F, 0.0f, 0.0f);
         if (active == nullptr || active[(int64_t)b * O + o] != 0) {
@@ -721,6 +744,215 @@ __device__ __forceinline__ int collide_groups_predicted(double xa, double ya, do
     return mine;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-level collision table (snapshot obstacles, long-horizon pipeline kernel)
+// ------------------------------------------------------------------------------------------------
+// The n_d candidates of a row share the path frame (p_k, n_k), and K1's lateral quintic is affine in the lateral target D_i:
+//     d_i(k) = A_k + B_k D_i           (B_k = 10 u^3 - 15 u^4 + 6 u^5 >= 0 with u = argument / horizon).
+// With b = t_k . (q - p_k) and a = n_k . (q - p_k) (t_k = (n_y, -n_x), |n_k| = 1) the reference's test of candidate i against obstacle q
+// at step k (lib/tests/test_obstacle_planner.py:48) reads  b^2 + (a - A_k - B_k D_i)^2 <= R^2 :  for a uniform lateral axis each
+// (step, obstacle) pair blocks a contiguous RANGE of candidate indices.  A warp takes 32 consecutive steps (lane = step), lists the
+// obstacles inside the oriented bounding box of the chunk's band of candidates, and for every listed obstacle each lane computes two
+// index ranges in fp32: OUTER (nothing outside it can hit at this step) and INNER (everything inside it hits), separated by explicit
+// error margins (below).  Per (chunk, obstacle) the warp keeps ONE outer interval - the hull of the lanes' outer ranges, conservative -
+// and ONE inner interval: the union of the lanes' inner ranges when they form a connected run (consecutive steps whose ranges
+// overlap or touch; then the union IS the hull), else none.  Per candidate the lowest obstacle whose inner interval contains it is
+// the first blocker, unless a lower obstacle contains it only in its outer interval: those few (candidate, obstacle) pairs - about
+// 1 % of the candidates on the config-5 scenes - are re-tested with the reference's fp64 expression on the stored samples.
+// Masks and first blockers are therefore bit-identical to a brute-force fp64 sweep (scripts/row_collision_model.py replays the
+// classification on the CPU and checks both inclusions; tests/test_gpu_parity.py compares with the standalone K4 and the oracle).
+//
+// Error budget of one pair (fp32 unit roundoff u = 2^-24): the inputs of b, a and d_i - a carry
+//     delta = 8 u (|dx| + |dy| + |A_k| + |B_k| max|D|)  +  2e-12 M + 1e-9      (M = max_k sum_j |a_j| |u_k|^j of the row's polynomials:
+// the fp64 affine model itself; rows with non-finite frames, |A| + |B| max|D| > 1e12 or M > 1e15 take the per-candidate sweep), hence
+//     | b^2 + (d_i - a)^2 - R^2 |_error <= tau = 4.5 (R + delta) delta + 16 u R^2   near the boundary,
+// and the candidate index of a range end carries eps = 16 u ((r + |c|) / B + max|D|) / dD + 1e-4 (approximate sqrt / reciprocal
+// are covered by a relative 1e-6 on r and by eps).  Large |B_k| (low-speed rows sampled beyond their horizon, |d| up to 1e12) only
+// widen the band in metres, not in candidate indices: the index error scales with delta / (B dD).
+constexpr int kTableMaxD = 128;    // candidates per row the packed intervals can index; wider rows take the per-candidate sweep
+constexpr int kMaybeCap = 4;       // uncertain obstacles remembered per candidate; more -> per-candidate sweep for that candidate
+constexpr float kU32 = 5.9604645e-8f;
+constexpr unsigned kIvlEmpty = 0x00ff00ffu;   // lo = 255, hi = 0 for both intervals
+
+__device__ __forceinline__ int float_order(float f) {   // monotone float -> int map (for redux.sync min / max)
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_min_f(float v) { return order_float(__reduce_min_sync(kFull, float_order(v))); }
+__device__ __forceinline__ float warp_max_f(float v) { return order_float(__reduce_max_sync(kFull, float_order(v))); }
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct RowTable {
+    float* mA;                  // [n_pad_max] A_k (fp32)
+    float* mB;                  // [n_pad_max] B_k
+    unsigned* ivl;              // [chunks][n_obs] per listed obstacle: outer lo | hi << 8 | inner lo << 16 | hi << 24
+    unsigned short* id;         // [chunks][n_obs] the listed obstacles of each chunk, ascending
+    int* cnt;                   // [chunks]
+    int* first;                 // [n_d] lowest certain blocker per candidate (kNoBlocker if none)
+    int* n_maybe;               // [n_d] uncertain obstacles below it (> kMaybeCap: overflow)
+    unsigned short* maybe_id;   // [n_d][kMaybeCap]
+    unsigned short* scratch;    // [warps][n_obs] a warp's private obstacle list
+};
+
+// One warp, steps [32 ch, 32 ch + 32) of the row: list the obstacles near the chunk's band, classify every (step, listed obstacle)
+// pair, keep the intervals.  `sub` / `nsub`: the listed obstacles are dealt round-robin to the nsub warps working on the same chunk.
+__device__ __forceinline__ void row_table_chunk(const RowTable& T, int ch, int sub, int nsub, int N, const double* fpx, const double* fpy,
+                                                const double* fnx, const double* fny, const double2* __restrict__ obs, int O, double D0,
+                                                double D1, int n_d, float R, float R2f, float cM, unsigned short* list, int lane) {
+    const int k = ch * kWarp + lane;
+    const bool valid = k < N;
+    const int kk = valid ? k : N - 1;
+    const double px = fpx[kk], py = fpy[kk];
+    const float nxf = __double2float_rn(fnx[kk]), nyf = __double2float_rn(fny[kk]);
+    const float A = T.mA[kk], Bk = T.mB[kk];
+    const float D0f = __double2float_rn(D0), D1f = __double2float_rn(D1);
+    const float Dmaxf = fmaxf(fabsf(D0f), fabsf(D1f)) * 1.000001f;
+    const float invd = (float)max(n_d - 1, 1) / (D1f - D0f);
+    // oriented bounding box of the band {p_k + n_k d : d between d_first(k) and d_last(k)} in the frame of the chunk's middle step
+    const int midl = min(kWarp / 2, N - 1 - ch * kWarp);
+    const double cx = __shfl_sync(kFull, px, midl), cy = __shfl_sync(kFull, py, midl);
+    const float nmx = __shfl_sync(kFull, nxf, midl), nmy = __shfl_sync(kFull, nyf, midl);
+    const float rx = __double2float_rn(px - cx), ry = __double2float_rn(py - cy);
+    const float da = fmaf(Bk, D0f, A), db = fmaf(Bk, D1f, A);
+    const float e1x = fmaf(nxf, da, rx), e1y = fmaf(nyf, da, ry), e2x = fmaf(nxf, db, rx), e2y = fmaf(nyf, db, ry);
+    const float u1 = fmaf(e1x, nmy, -e1y * nmx), v1 = fmaf(e1x, nmx, e1y * nmy);   // tangent (n_y, -n_x) and normal coordinates
+    const float u2 = fmaf(e2x, nmy, -e2y * nmx), v2 = fmaf(e2x, nmx, e2y * nmy);
+    float umin = warp_min_f(fminf(u1, u2)), umax = warp_max_f(fmaxf(u1, u2));
+    float vmin = warp_min_f(fminf(v1, v2)), vmax = warp_max_f(fmaxf(v1, v2));
+    const float ext = fmaxf(fmaxf(fabsf(umin), fabsf(umax)), fmaxf(fabsf(vmin), fabsf(vmax)));
+    const float m = R * 1.0001f + ext * 1e-5f + 1e-4f;   // robot radius + far more than the fp32 error of the box and of the obstacle's offset
+    umin -= m; umax += m; vmin -= m; vmax += m;
+    int cnt = 0;
+    for (int ob = 0; ob < O; ob += kWarp) {
+        const int o = ob + lane;
+        bool in = false;
+        if (o < O) {
+            const double2 q = obs[o];   // obstacles the sensor did not report sit at +inf: every comparison below is false for them
+            const float qx = __double2float_rn(q.x - cx), qy = __double2float_rn(q.y - cy);
+            const float u = fmaf(qx, nmy, -qy * nmx), v = fmaf(qx, nmx, qy * nmy);
+            in = (u >= umin) && (u <= umax) && (v >= vmin) && (v <= vmax);
+        }
+        const unsigned bal = __ballot_sync(kFull, in);
+        if (in) list[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)o;
+        cnt += __popc(bal);
+    }
+    if (sub == 0 && lane == 0) T.cnt[ch] = cnt;
+    __syncwarp();
+    const float SAB = fabsf(A) + fabsf(Bk) * Dmaxf;
+    const bool flat = n_d == 1 || !(Bk >= 1e-6f);      // all candidates (almost) share one point at this step
+    const float inv = flat ? 0.0f : rcp_approx(Bk);
+    const float nd1 = (float)(n_d - 1);
+    unsigned* ivl = T.ivl + ch * O;
+    unsigned short* ids = T.id + ch * O;
+    for (int j = sub; j < cnt; j += nsub) {
+        const int o = list[j];
+        const double2 q = obs[o];
+        const float dxf = __double2float_rn(q.x - px), dyf = __double2float_rn(q.y - py);
+        const float b = fmaf(dxf, nyf, -dyf * nxf);
+        const float a = fmaf(dxf, nxf, dyf * nyf);
+        const float delta = fmaf(8.0f * kU32, fabsf(dxf) + fabsf(dyf) + SAB, cM);
+        const float tau = fmaf(4.5f * (R + delta), delta, 16.0f * kU32 * R2f);
+        const float bb = b * b;
+        const float gout = (R2f + tau) - bb;
+        const bool rel = valid && (gout >= 0.0f);
+        unsigned packed = kIvlEmpty;
+        if (__any_sync(kFull, rel)) {
+            int lo_m = 255, hi_m = -1, lo_c = 255, hi_c = -1;   // empty ranges
+            if (rel) {
+                const float gin = (R2f - tau) - bb;
+                const float rout = sqrt_approx(gout) * 1.000001f;
+                const float rin = gin > 0.0f ? sqrt_approx(gin) * 0.999999f : -1.0f;
+                const float c = A - a;   // d_i - a = c + B_k D_i
+                if (flat) {
+                    const float spread = fabsf(Bk) * Dmaxf;   // |B_k D_i| <= spread
+                    if (fmaxf(fabsf(c) - spread, 0.0f) <= rout) { lo_m = 0; hi_m = n_d - 1; }
+                    if (fabsf(c) + spread <= rin) { lo_c = 0; hi_c = n_d - 1; }
+                } else {
+                    const float eps = fmaf(16.0f * kU32 * invd, fmaf(rout + fabsf(c), inv, Dmaxf), 1e-4f);
+                    const float x_lo = fmaf((-rout - c), inv, -D0f) * invd, x_hi = fmaf((rout - c), inv, -D0f) * invd;
+                    lo_m = (int)ceilf(fminf(fmaxf(x_lo - eps, 0.0f), nd1 + 1.0f));
+                    hi_m = (int)floorf(fmaxf(fminf(x_hi + eps, nd1), -1.0f));
+                    if (rin >= 0.0f) {
+                        const float y_lo = fmaf((-rin - c), inv, -D0f) * invd, y_hi = fmaf((rin - c), inv, -D0f) * invd;
+                        lo_c = (int)ceilf(fminf(fmaxf(y_lo + eps, 0.0f), nd1 + 1.0f));
+                        hi_c = (int)floorf(fmaxf(fminf(y_hi - eps, nd1), -1.0f));
+                    }
+                }
+                if (lo_m > hi_m) { lo_m = 255; hi_m = -1; }
+                if (lo_c > hi_c) { lo_c = 255; hi_c = -1; }
+            }
+            // outer interval: hull of the lanes' outer ranges
+            const int LO = __reduce_min_sync(kFull, lo_m), HI = __reduce_max_sync(kFull, hi_m);
+            // inner interval: the union of the lanes' inner ranges if they form a connected run of steps
+            const bool ne = lo_c <= hi_c;
+            const unsigned bal = __ballot_sync(kFull, ne);
+            int LOc = 255, HIc = 0;
+            if (bal) {
+                const unsigned run = bal >> (__ffs(bal) - 1);
+                const int nlo = __shfl_down_sync(kFull, lo_c, 1), nhi = __shfl_down_sync(kFull, hi_c, 1);
+                const bool gap = ne && lane < kWarp - 1 && ((bal >> (lane + 1)) & 1u) && (nlo > hi_c + 1 || lo_c > nhi + 1);
+                const bool connected = ((run + 1u) & run) == 0u && !__any_sync(kFull, gap);
+                const int a0 = __reduce_min_sync(kFull, lo_c), a1 = __reduce_max_sync(kFull, hi_c);
+                if (connected) { LOc = a0; HIc = a1; }
+            }
+            if (LO <= HI) packed = (unsigned)LO | ((unsigned)HI << 8) | ((unsigned)LOc << 16) | ((unsigned)HIc << 24);
+        }
+        if (lane == 0) {
+            ivl[j] = packed;
+            ids[j] = (unsigned short)o;
+        }
+    }
+    __syncwarp();   // the scratch list is reused by this warp's next chunk
+}
+
+// Per candidate: lowest certain blocker, and the obstacles below it that only `maybe` block.
+__device__ __forceinline__ void row_table_resolve(const RowTable& T, int n_d, int O, int nch) {
+    for (int id = threadIdx.x; id < n_d; id += blockDim.x) {
+        int first = kNoBlocker, nm = 0;
+        for (int ch = 0; ch < nch; ++ch) {
+            const unsigned* ivl = T.ivl + ch * O;
+            const unsigned short* ids = T.id + ch * O;
+            const int cnt = T.cnt[ch];
+            for (int j = 0; j < cnt; ++j) {
+                const int o = ids[j];
+                if (o >= first) break;          // ascending within a chunk
+                const unsigned e = ivl[j];
+                if (id >= (int)((e >> 16) & 255u) && id <= (int)(e >> 24)) { first = o; break; }
+            }
+        }
+        for (int ch = 0; ch < nch; ++ch) {
+            const unsigned* ivl = T.ivl + ch * O;
+            const unsigned short* ids = T.id + ch * O;
+            const int cnt = T.cnt[ch];
+            for (int j = 0; j < cnt; ++j) {
+                const int o = ids[j];
+                if (o >= first) break;
+                const unsigned e = ivl[j];
+                if (id >= (int)(e & 255u) && id <= (int)((e >> 8) & 255u)) {      // (not certain: a certain one below `first` cannot exist)
+                    bool dup = false;
+                    for (int q = 0; q < min(nm, kMaybeCap); ++q) dup |= T.maybe_id[id * kMaybeCap + q] == (unsigned short)o;
+                    if (!dup) {
+                        if (nm < kMaybeCap) T.maybe_id[id * kMaybeCap + nm] = (unsigned short)o;
+                        ++nm;
+                    }
+                }
+            }
+        }
+        T.first[id] = first;
+        T.n_maybe[id] = nm;
+    }
+}
+
 // Stage a scenario's obstacle snapshot in shared memory.
 __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, double2* obs, float2* obsf) {
     const int O = B.n_obs;
@@ -748,9 +980,23 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // table (kXY).
 // Every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead): the mapping for long
 // horizons.  Lattices of at most 32 padded samples go through k2_short below instead.
+constexpr bool kRowTable = FRENET_ROW_TABLE != 0;
+constexpr int k2_min_ctas(int coll) {
+    if (FRENET_BULK_STORE) return 2;
+    return coll == 0 ? FRENET_K2_MIN_CTAS : (coll == 1 && kRowTable) ? FRENET_K2_MIN_CTAS_TABLE : FRENET_K2_MIN_CTAS_COLL;
+}
+// shared memory of the row table, in doubles (after the spline table)
+__host__ __device__ inline size_t row_table_doubles(int npm, int n_d, int n_obs) {
+    const int chunks = (npm + kWarp - 1) / kWarp;
+    const size_t bytes = (size_t)npm * 8 + (size_t)chunks * n_obs * 6 + 8 + (size_t)chunks * 4 + (size_t)n_d * (8 + 2 * kMaybeCap) + 8 +
+                         (size_t)(kRowThreads / kWarp) * n_obs * 2;
+    return (bytes + 15) / 8;
+}
+
 template <bool kXY, int kColl, bool kLimits, bool kSplit>
-__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts) {
+__global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts, float radius_up) {
     extern __shared__ __align__(16) double sm[];
+    constexpr bool kTable = kColl == 1 && kRowTable;   // snapshot collisions through the row-level table
     const int npm = L.n_pad_max;
     double2* obs = reinterpret_cast<double2*>(sm);
     float2* obsf = reinterpret_cast<float2*>(sm + 2 * B.n_obs);
@@ -767,7 +1013,27 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     int* resi = reinterpret_cast<int*>(resc + L.n_d * 4);          // [n_d][2] flags, first blocker
     double* axd = resc + L.n_d * 5;                                // [n_d] lateral target axis
     double* tab = axd + L.n_d;                                     // [n_knots][9] spline table (kXY, spline path)
-    __shared__ double red[3][kRowThreads / 32];
+    RowTable RT;
+    if (kTable) {
+        RT.mA = reinterpret_cast<float*>(tab + ((kXY && path.kind == FRENET_PATH_SPLINE) ? 9 * path.n_knots : 0));
+        RT.mB = RT.mA + npm;
+        const int chunks = (npm + kWarp - 1) / kWarp;
+        RT.ivl = reinterpret_cast<unsigned*>(RT.mB + npm);
+        RT.cnt = reinterpret_cast<int*>(RT.ivl + chunks * B.n_obs);
+        RT.first = RT.cnt + chunks;
+        RT.n_maybe = RT.first + L.n_d;
+        RT.maybe_id = reinterpret_cast<unsigned short*>(RT.n_maybe + L.n_d);
+        RT.id = RT.maybe_id + kMaybeCap * L.n_d;
+        RT.scratch = RT.id + chunks * B.n_obs + ((chunks * B.n_obs) & 1);
+    }
+#if FRENET_BULK_STORE
+    // per-warp staging block [6][n_pad_max] behind everything else (16-byte aligned: every block before it is a whole number of doubles pairs)
+    double* bulk_stage = tab + ((kXY && path.kind == FRENET_PATH_SPLINE) ? 9 * path.n_knots : 0) + (kTable ? row_table_doubles(npm, L.n_d, B.n_obs) : 0);
+    bulk_stage = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(bulk_stage) + 15) & ~uintptr_t(15));
+#endif
+    __shared__ double red[4][kRowThreads / 32];
+    __shared__ float sh_model[2];   // row table: usable (1 / 0), M
+    __shared__ int sh_next;         // next candidate to hand out (dynamic distribution over the warps)
     __shared__ double sh_carry[kLimits ? kRowThreads / 32 : 1][4];   // curvature: the last pair of a warp's previous iteration
     __shared__ double sh_clong;
     __shared__ int sh_rowfeas;
@@ -814,7 +1080,33 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         }
         if (kXY && path.kind == FRENET_PATH_SPLINE) {
             for (int i = tid; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
-            __syncthreads();   // phase A reads the table
+            if (!kTable) __syncthreads();   // phase A reads the table
+        }
+        if (kTable) {
+            if (tid == 0) sh_next = 0;
+            __syncthreads();   // phase A reads the spline table and the first / last candidate's coefficients
+        }
+    }
+    // Row table: usable only if the lateral axis is a uniform ascending grid and the staged coefficients are affine in the target
+    // (what K1 produces; anything else - a caller's own coefficients - takes the per-candidate sweep).
+    bool table_bad = false;
+    double D0 = 0.0, D1 = 0.0;
+    if (kTable) {
+        const int nd = L.n_d;
+        D0 = axd[0];
+        D1 = axd[nd - 1];
+        table_bad = nd > kTableMaxD || B.n_obs > 65535 || (nd > 1 && !(D1 > D0));
+        if (nd > 1 && tid < nd) {     // (n_d <= 128 < blockDim.x whenever the table is used)
+            const int i = tid;
+            const double span = D1 - D0, inv_n = 1.0 / (double)(nd - 1), inv_s = 1.0 / span;
+            const double Di = axd[i];
+            table_bad |= !(fabs(Di - fma((double)i * inv_n, span, D0)) <= 1e-9 * (fabs(D0) + fabs(D1)));
+            const double wi = (Di - D0) * inv_s;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double lo = coef[j], hi = coef[(nd - 1) * 6 + j];
+                table_bad |= !(fabs(coef[i * 6 + j] - fma(wi, hi - lo, lo)) <= 1e-12 * fmax(fabs(lo), fabs(hi)) + 1e-300);
+            }
         }
     }
 
@@ -825,6 +1117,9 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
         pl.load(B.coef_lon + br * 6);
         double* lon = B.lon + A.lon_off;
         double acc = 0.0, vmax = 0.0, amax = 0.0;
+        double model_m = table_bad ? CUDART_INF : 0.0;   // row table: magnitude of the lateral polynomials' terms; +inf = not usable
+        const double inv_span = (kTable && L.n_d > 1) ? 1.0 / (D1 - D0) : 0.0;
+        const double dmax_abs = fmax(fabs(D0), fabs(D1));
         // Samples k in [N, npad) are padding: they are evaluated and stored like real samples so that every 32-byte
         // sector of the output is written in full (a partially written sector costs a DRAM read-modify-write, which
         // halves the achieved store bandwidth), but they take no part in costs, limits or collisions.
@@ -851,6 +1146,21 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                 const double sp = B.path_origin ? B.path_origin[2 * A.b] + (s - B.path_origin[2 * A.b + 1]) : s;   // frenet_to_glob_planner
                 path_frame(path.kind, path.circle, tab, path.n_knots, sp, px, py, nx, ny, lane_q);
                 fpx[k] = px; fpy[k] = py; fnx[k] = nx; fny[k] = ny;
+                if (kTable && k < A.N) {
+                    // affine model of the row's lateral offsets at this step, from its first and last candidate (Horner like Poly::eval)
+                    const double u = low ? fabs(s - s0) : t, ua = fabs(u);
+                    const double* c0 = coef;
+                    const double* c1 = coef + (L.n_d - 1) * 6;
+                    const double d0 = fma(fma(fma(fma(fma(c0[5], u, c0[4]), u, c0[3]), u, c0[2]), u, c0[1]), u, c0[0]);
+                    const double d1 = fma(fma(fma(fma(fma(c1[5], u, c1[4]), u, c1[3]), u, c1[2]), u, c1[1]), u, c1[0]);
+                    const double m0 = fma(fma(fma(fma(fma(fabs(c0[5]), ua, fabs(c0[4])), ua, fabs(c0[3])), ua, fabs(c0[2])), ua, fabs(c0[1])), ua, fabs(c0[0]));
+                    const double m1 = fma(fma(fma(fma(fma(fabs(c1[5]), ua, fabs(c1[4])), ua, fabs(c1[3])), ua, fabs(c1[2])), ua, fabs(c1[1])), ua, fabs(c1[0]));
+                    const double Bk = (d1 - d0) * inv_span, Ak = d0 - Bk * D0;
+                    RT.mA[k] = __double2float_rn(Ak);
+                    RT.mB[k] = __double2float_rn(Bk);
+                    const bool fine = (fabs(Ak) + fabs(Bk) * dmax_abs <= 1e12) && (fabs(px) + fabs(py) + fabs(nx) + fabs(ny) < 1e30);   // false for NaN
+                    model_m = fine ? fmax(model_m, fmax(m0, m1)) : CUDART_INF;
+                }
             }
         }
         // longitudinal jerk sum and limits: per-warp partials combined in a fixed order (deterministic)
@@ -859,18 +1169,25 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             vmax = warp_max(vmax);
             amax = warp_max(amax);
         }
+        if (kTable) model_m = warp_max(model_m);   // (fmax drops a NaN operand: m0 / m1 NaN would vanish, but then Ak / Bk are NaN too and `fine` is false)
         if (lane == 0) {
             red[0][warp] = acc;
             red[1][warp] = vmax;
             red[2][warp] = amax;
+            red[3][warp] = model_m;
         }
         __syncthreads();
         if (tid == 0) {   // trajectory_planner.py:143-144, 153-154
-            double jsum = 0.0, vm = 0.0, am = 0.0;
+            double jsum = 0.0, vm = 0.0, am = 0.0, mm = 0.0;
             for (int w = 0; w < nwarps; ++w) {
                 jsum += red[0][w];
                 vm = fmax(vm, red[1][w]);
                 am = fmax(am, red[2][w]);
+                mm = fmax(mm, red[3][w]);
+            }
+            if (kTable) {
+                sh_model[0] = (mm <= 1e15) ? 1.0f : 0.0f;
+                sh_model[1] = __double2float_ru(fmin(mm, 1e15));
             }
             const double T = L.axis_t[A.iT];
             double s_last, v_last, a_last, j_last;
@@ -890,10 +1207,24 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     }
     const double clong = sh_clong;
     const bool rowfeas = sh_rowfeas;
+    // Row table (see row_table_chunk): built by all warps once per row, then resolved per candidate.
+    const bool table_ok = kTable && sh_model[0] != 0.0f;
+    const float Rf = radius_up;   // robot radius, rounded up on the host
+    const int nch = (A.N + kWarp - 1) / kWarp;
+    if (kTable && table_ok) {
+        // The chunks' obstacle lists are dealt to the warps so that (almost) every warp gets one item; nobody waits for the table:
+        // it is consulted only after the sampling loops below (the candidates are handed out dynamically, which evens out the warps
+        // that built more of it).
+        const float R2f = __double2float_rn(P.radius_sq);
+        const float cM = fmaf(2e-12f, sh_model[1], 1e-9f);
+        const int nsub = FRENET_TABLE_SPLIT > 0 ? FRENET_TABLE_SPLIT : max(1, (nwarps + nch - 1) / nch);
+        for (int item = warp; item < nch * nsub; item += nwarps)
+            row_table_chunk(RT, item / nsub, item % nsub, nsub, A.N, fpx, fpy, fnx, fny, obs, B.n_obs, D0, D1, L.n_d, Rf, R2f, cM,
+                            RT.scratch + warp * B.n_obs, lane);
+    }
     // row constants of the lateral cost, fetched once (not per candidate, where a global load would stall the warp's epilogue)
     const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
     const double dd_target = B.scal[(int64_t)A.b * 3];
-    const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
     // predicted mode: the scenario's table [n_obs][n_obs_steps] stays in global memory (L2 resident: every row of a scenario reads it)
     const double2* tblp = kColl == 2 ? reinterpret_cast<const double2*>(B.obs_xy_t) + (int64_t)A.b * B.n_obs * B.n_obs_steps : nullptr;
     const int npad = A.npad, N = A.N;
@@ -904,13 +1235,36 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 
     // Phase B: a warp per candidate; every lane owns TWO consecutive time steps per iteration (64 steps per warp
     // iteration, 16-byte loads from shared memory and 16-byte stores to HBM); no global loads in this loop.
-    // Candidates are dealt round-robin to the warps; their results are staged in shared memory and published after a barrier.
-    for (int id = warp + nwarps * part; id < L.n_d; id += nwarps * parts) {
+    // Candidates are dealt round-robin to the warps (handed out dynamically in the row-table variant, where some warps
+    // arrive late from building the table); their results are staged in shared memory and published after a barrier.
+    // Candidate of hand-out slot q: id = q * parts + part.
+    int slot = warp;
+    for (;;) {
+        if (kTable) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&sh_next, 1);
+            slot = __shfl_sync(kFull, t, 0);
+        }
+        const int id = slot * parts + part;
+        if (id >= L.n_d) break;
         Poly pq;
         pq.load(coef + id * 6);
         // [6][npad] block of this candidate; `out` walks along k, the fields sit `fs` bytes apart
+#if FRENET_BULK_STORE
+        double* stg = bulk_stage + warp * (kCandFields * npm);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous candidate's block has left the staging buffer
+        __syncwarp();
+        unsigned out = (unsigned)__cvta_generic_to_shared(stg + 2 * lane);      // shared-window address: the stores below are STS.128
+#define FRENET_PUT(addr, v0, v1) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory")
+#else
+#define FRENET_PUT(addr, v0, v1) (*reinterpret_cast<double2*>(addr) = make_double2(v0, v1))
         char* out = reinterpret_cast<char*>(B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + 2 * lane);
+#endif
+#if FRENET_BULK_STORE
+        const unsigned fs = (unsigned)(npad * sizeof(double));
+#else
         const int64_t fs = (int64_t)npad * sizeof(double);
+#endif
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
         bool curv_bad = false;
@@ -923,16 +1277,16 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             const double2 u = *reinterpret_cast<const double2*>(su + kk);
             double da, va, aa, ja, db, vb, ab, jb;
 #if FRENET_K2_RELOAD_COEF
-            if (kColl) pq.load_shared_here(coef + id * 6);
+            if (kColl && !kTable) pq.load_shared_here(coef + id * 6);
 #endif
             pq.eval(u.x, da, va, aa, ja);
             pq.eval(u.y, db, vb, ab, jb);
-            char* o = out;
+            auto o = out;
             if (store) {
-                *reinterpret_cast<double2*>(o) = make_double2(da, db);
-                *reinterpret_cast<double2*>(o += fs) = make_double2(va, vb);
-                *reinterpret_cast<double2*>(o += fs) = make_double2(aa, ab);
-                *reinterpret_cast<double2*>(o += fs) = make_double2(ja, jb);
+                FRENET_PUT(o, da, db);
+                FRENET_PUT(o += fs, va, vb);
+                FRENET_PUT(o += fs, aa, ab);
+                FRENET_PUT(o += fs, ja, jb);
             }
             if (valid_a) {
                 acc = fma(ja, ja, acc);
@@ -948,8 +1302,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                 const double xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)), xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));   // pt + n * d,
                 const double ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)), yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));   // unfused like the reference
                 if (store) {
-                    *reinterpret_cast<double2*>(o += fs) = make_double2(xa, xb);
-                    *reinterpret_cast<double2*>(o += fs) = make_double2(ya, yb);
+                    FRENET_PUT(o += fs, xa, xb);
+                    FRENET_PUT(o += fs, ya, yb);
                 }
                 if (kLimits) {
                     if (do_curv) {
@@ -967,7 +1321,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
                     }
                 }
                 // (padding lanes carry the trajectory's continuation: they can only widen the cull circle, never hit)
-                if (kColl == 1)
+                if (kColl == 1 && !kTable)
                     best = collide_pair(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq,
                                         best, lane);
                 if (kColl == 2)
@@ -976,6 +1330,17 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             }
             out += 2 * kWarp * sizeof(double);
         }
+#if FRENET_BULK_STORE
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' generic-proxy stores become visible to the copy engine
+        __syncwarp();
+        if (lane == 0) {
+            double* gdst = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad);
+            const unsigned ssrc = (unsigned)__cvta_generic_to_shared(stg);
+            const unsigned bytes = (unsigned)((kXY ? kCandFields : 4) * npad * sizeof(double));
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#endif
         acc = warp_sum(acc);
         if (kLimits) {
             amax = warp_max(amax);
@@ -992,10 +1357,63 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             resi[id * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0) | (curv_bad ? 0 : kCurvOkBit);
             resi[id * 2 + 1] = best;
         }
+        if (!kTable) slot += nwarps;
+    }
+#if FRENET_BULK_STORE
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the copies that read it; the
+                                                                              // collision post-pass below re-reads the blocks from global memory
+#endif
+    if (kTable) {
+        // Collision results from the row table, once every candidate has been sampled (nobody waited for the table above).
+        __syncthreads();
+        if (table_ok) {
+            row_table_resolve(RT, L.n_d, B.n_obs, nch);
+            __syncthreads();
+        }
+        // The few candidates with an uncertain obstacle below their first certain blocker - and every candidate of a row the table
+        // does not cover - re-read their samples (written by this CTA, visible after the barrier) and run the reference's fp64 test.
+        for (int q = warp; q * parts + part < L.n_d; q += nwarps) {
+            const int id = q * parts + part;
+            int best = kNoBlocker, nm = kMaybeCap + 1;
+            if (table_ok) {
+                best = RT.first[id];
+                nm = RT.n_maybe[id];
+            }
+            if (nm > 0) {
+                const double* xs = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + 4 * npad;
+                const double* ys = xs + npad;
+                if (nm > kMaybeCap) {   // per-candidate sweep over the obstacles below `best`
+                    for (int kb = 0; kb < N; kb += 2 * kWarp) {
+                        const int k0 = kb + 2 * lane;
+                        const int kk = k0 < npad ? k0 : kb;
+                        const double2 xv = *reinterpret_cast<const double2*>(xs + kk), yv = *reinterpret_cast<const double2*>(ys + kk);
+                        best = collide_pair(xv.x, yv.x, xv.y, yv.y, k0 < N, k0 + 1 < N, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf,
+                                            P.radius_sq, best, lane);
+                    }
+                } else {
+                    for (int j = 0; j < nm; ++j) {
+                        const int o = RT.maybe_id[id * kMaybeCap + j];
+                        if (o >= best) continue;        // (a lower one has been confirmed already)
+                        const double2 ob = obs[o];
+                        bool hit = false;
+                        for (int kb = 0; kb < N; kb += 2 * kWarp) {
+                            const int k0 = kb + 2 * lane;
+                            const int kk = k0 < npad ? k0 : kb;
+                            const double2 xv = *reinterpret_cast<const double2*>(xs + kk), yv = *reinterpret_cast<const double2*>(ys + kk);
+                            const double dxa = xv.x - ob.x, dya = yv.x - ob.y, dxb = xv.y - ob.x, dyb = yv.y - ob.y;
+                            hit |= (k0 < N && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= P.radius_sq)) ||
+                                   (k0 + 1 < N && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= P.radius_sq));
+                        }
+                        if (__any_sync(kFull, hit)) best = o;
+                    }
+                }
+            }
+            if (lane == 0) resi[id * 2 + 1] = best;
+        }
     }
     __syncthreads();
     for (int id = tid; id < L.n_d; id += blockDim.x) {
-        if ((id / nwarps) % parts != part) continue;   // another part's candidate
+        if (id % parts != part) continue;   // another part's candidate
         const int64_t c = A.cand0 + id;
 #pragma unroll
         for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = resc[id * 4 + f];
@@ -1011,6 +1429,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
 
 #undef parts
 #undef part
+#undef FRENET_PUT
 
 // ------------------------------------------------------------------------------------------------
 // K2 (+K3 +K4 fused) for SHORT horizons: at most 32 padded samples per candidate (the reference's default lattice has 11..26)
@@ -1531,7 +1950,9 @@ __global__ void __launch_bounds__(256) predict_obstacles(FrenetPath path, const 
         const int64_t bo = i / K;
         const int b = (int)(bo / O);
         const double t = t0[(int64_t)b * t0_stride] + (double)k * period;
-        const double tau = obs_s[bo] + fmod(t * obs_speed[bo], 50.0);   // time_offset + t * speed % 50
+        double wrapped = fmod(t * obs_speed[bo], 50.0);                  // time_offset + t * speed % 50 with Python's `%`:
+        if (wrapped < 0.0) wrapped += 50.0;                              // the result takes the sign of the divisor
+        const double tau = obs_s[bo] + wrapped;
         double px, py, nx, ny;
         path_frame(path.kind, path.circle, tab, path.n_knots, tau, px, py, nx, ny);
         const double d = obs_d[bo];
@@ -1571,12 +1992,13 @@ __global__ void __launch_bounds__(128) advance_state(FrenetLattice L, FrenetBuff
     // np.arange(round(ds0 - q n), round(ds0 + q n + q), q): length ceil((stop - start) / step), values start + i * ((start + step) - start)
     const double lo = rint(ds0 - q * num_sample), hi = rint(ds0 + q * num_sample + q);
     int nv = (int)ceil((hi - lo) / q);
+    const bool axis_overflow = nv > L.n_v_cap;      // the host path raises here; reported as status 2 (the axis is truncated)
     nv = min(max(nv, 0), L.n_v_cap);
     const double delta = (lo + q) - lo;
     double* av = const_cast<double*>(L.axis_v) + (int64_t)b * L.n_v_cap;
     for (int i = 0; i < L.n_v_cap; ++i) av[i] = lo + (double)i * delta;
     const_cast<int32_t*>(L.n_v)[b] = nv;
-    if (status) status[b] = 0;
+    if (status) status[b] = axis_overflow ? 2 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1973,10 +2395,50 @@ int launch_obstacle_bounds(const FrenetLattice* L, const FrenetBuffers* B, int s
     if (!B->obs_xy_t || !B->obs_bounds) return fail(FRENET_ERR_BAD_ARG, "predicted obstacle table or bounds scratch missing");
     const int n_chunks = (L->n_pad_max + span - 1) / span;
     if (n_chunks == 0 || L->n_scen == 0 || B->n_obs == 0) return FRENET_OK;
-    obstacle_chunk_bounds<<<dim3(n_chunks, L->n_scen), 128, 0, stream>>>(B->obs_xy_t, B->obs_active, B->n_obs, B->n_obs_steps, n_chunks, span,
+    if ((int64_t)n_chunks * L->n_scen > 0x7fffffffLL) return fail(FRENET_ERR_BAD_ARG, "obstacle bounds: too many scenarios for one launch");
+    obstacle_chunk_bounds<<<(unsigned)(n_chunks * L->n_scen), 128, 0, stream>>>(B->obs_xy_t, B->obs_active, B->n_obs, B->n_obs_steps, n_chunks, span,
                                                                          reinterpret_cast<float4*>(B->obs_bounds));
     FRENET_CHECK_LAUNCH("obstacle_chunk_bounds");
     return FRENET_OK;
+}
+
+// How the evaluate kernel is launched for a shape (shared by launch_k2 and frenet_k2_launch_shape).
+struct K2Shape {
+    bool pair;        // long horizons: k2_evaluate, one CTA per row (split over `parts` CTAs for small batches); else k2_short
+    int rows_per_cta; // k2_short: consecutive rows of a scenario per CTA
+    int parts;
+    size_t smem;
+    unsigned grid;
+};
+
+K2Shape k2_shape(const FrenetLattice* L, bool xy, int coll, int n_knots_spline, int n_obs) {
+    K2Shape S;
+    const size_t spline = (size_t)9 * n_knots_spline;
+    S.pair = L->n_pad_max > kWarp;   // long horizons: two steps per lane
+    if (!S.pair) {
+        // short horizons: G consecutive rows of a scenario per CTA - as many as fit 48 KB of shared memory while the grid still
+        // fills the GPU a few times over (a single planner keeps one row per CTA: its latency is what matters)
+        const int R = L->n_v_cap * L->n_t;
+        const size_t fixed = (size_t)L->n_d + spline + (coll == 1 ? (size_t)4 * ((3 * n_obs + 3) / 4) : 0) + (coll == 2 ? (size_t)2 * n_obs : 0);
+        auto bytes = [&](int g) { return (fixed + (size_t)g * ((size_t)L->n_pad_max * (xy ? 5 : 1) + (size_t)L->n_d * 11 + 5)) * sizeof(double); };
+        int G = R < kWarp ? R : kWarp;   // (phase B keeps one row per lane)
+        while (G > 1 && (bytes(G) > 48 * 1024 || (int64_t)L->n_scen * ((R + G - 1) / G) < 8 * 148)) G = (G + 1) / 2;
+        S.rows_per_cta = G;
+        S.parts = 1;
+        S.smem = bytes(G);
+        S.grid = (unsigned)((int64_t)L->n_scen * ((R + G - 1) / G));
+        return S;
+    }
+    S.rows_per_cta = 1;
+    S.smem = ((size_t)L->n_pad_max * (xy ? 5 : 1) + (size_t)L->n_d * 12 + spline + (coll == 1 ? (size_t)4 * ((3 * n_obs + 3) / 4) : 0) +
+              (coll == 1 && kRowTable ? row_table_doubles(L->n_pad_max, L->n_d, n_obs) : 0) +
+              (FRENET_BULK_STORE ? (size_t)(kRowThreads / kWarp) * kCandFields * L->n_pad_max + 2 : 0) +
+              (coll == 2 ? (size_t)2 * predicted_chunks(L) * n_obs : 0)) * sizeof(double);
+    // a single planner (or a handful) has too few rows to fill the GPU with one CTA each: split the rows' candidates over several CTAs
+    S.parts = 1;
+    while (S.parts < 8 && (int64_t)n_rows(L) * S.parts < 4 * 148 && S.parts * (kRowThreads / kWarp) < L->n_d) S.parts *= 2;
+    S.grid = n_rows(L);
+    return S;
 }
 
 template <bool kXY, int kColl>
@@ -1984,28 +2446,19 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     // opts bit 0: also test the curvature limit in the kernel (needs kXY; selects the limits variant)
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0) || (kXY && (opts & 1));
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
-    const size_t smem = ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 12 + (spline ? (size_t)9 * path->n_knots : 0) +
-                         (kColl == 1 ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0) +
-                         (kColl == 2 ? (size_t)2 * predicted_chunks(L) * B->n_obs : 0)) * sizeof(double);
+    const K2Shape S = k2_shape(L, kXY, kColl, spline ? path->n_knots : 0, B->n_obs);
     static const FrenetPath no_path = {};
     const FrenetPath& pd = kXY ? *path : no_path;
-    const bool pair = L->n_pad_max > kWarp;   // long horizons: two steps per lane
-    if (!pair) {
-        // short horizons: G consecutive rows of a scenario per CTA - as many as fit 48 KB of shared memory while the grid still
-        // fills the GPU a few times over (a single planner keeps one row per CTA: its latency is what matters)
-        const int R = L->n_v_cap * L->n_t;
-        const size_t fixed = (size_t)L->n_d + (spline ? (size_t)9 * path->n_knots : 0) +
-                             (kColl == 1 ? (size_t)4 * ((3 * B->n_obs + 3) / 4) : 0) + (kColl == 2 ? (size_t)2 * B->n_obs : 0);
-        auto bytes = [&](int g) { return (fixed + (size_t)g * ((size_t)L->n_pad_max * (kXY ? 5 : 1) + (size_t)L->n_d * 11 + 5)) * sizeof(double); };
-        int G = R < kWarp ? R : kWarp;   // (phase B keeps one row per lane)
-        while (G > 1 && (bytes(G) > 48 * 1024 || (int64_t)L->n_scen * ((R + G - 1) / G) < 8 * 148)) G = (G + 1) / 2;
-        const size_t sm_short = bytes(G);
-        const unsigned grid_short = (unsigned)((int64_t)L->n_scen * ((R + G - 1) / G));
-        if (grid_short == 0) return FRENET_OK;
+    if (S.grid == 0) return FRENET_OK;
+    // robot radius in fp32, rounded up (the culls and the row table only need a conservative value)
+    float radius_up = (float)sqrt(P->radius_sq);
+    while ((double)radius_up * (double)radius_up < P->radius_sq) radius_up = nextafterf(radius_up, INFINITY);
+    radius_up = nextafterf(radius_up, INFINITY);
+    if (!S.pair) {
 #define FRENET_LAUNCH_SHORT(LIM)                                                                                             \
     do {                                                                                                                     \
-        if (int rc = set_smem(k2_short<kXY, kColl, LIM>, sm_short, "k2: row group does not fit shared memory")) return rc;   \
-        k2_short<kXY, kColl, LIM><<<grid_short, kRowThreads, sm_short, stream>>>(*L, *P, pd, *B, G, opts);                         \
+        if (int rc = set_smem(k2_short<kXY, kColl, LIM>, S.smem, "k2: row group does not fit shared memory")) return rc;     \
+        k2_short<kXY, kColl, LIM><<<S.grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, S.rows_per_cta, opts);            \
     } while (0)
         if (limits) FRENET_LAUNCH_SHORT(true);
         else FRENET_LAUNCH_SHORT(false);
@@ -2013,18 +2466,15 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
         FRENET_CHECK_LAUNCH("k2_short");
         return FRENET_OK;
     }
-    // a single planner (or a handful) has too few rows to fill the GPU with one CTA each: split the rows' candidates over several CTAs
-    int parts = 1;
-    while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * (kRowThreads / kWarp) < L->n_d) parts *= 2;
-    const dim3 grid(n_rows(L), parts);
+    const dim3 grid(S.grid, S.parts);
 #define FRENET_LAUNCH_K2(LIM, SPLIT)                                                                                           \
     do {                                                                                                                       \
-        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, SPLIT>, smem, "k2: row does not fit shared memory")) return rc;     \
-        k2_evaluate<kXY, kColl, LIM, SPLIT><<<grid, kRowThreads, smem, stream>>>(*L, *P, pd, *B, opts);                        \
+        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, SPLIT>, S.smem, "k2: row does not fit shared memory")) return rc;   \
+        k2_evaluate<kXY, kColl, LIM, SPLIT><<<grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up);           \
     } while (0)
-    if (limits && parts > 1) FRENET_LAUNCH_K2(true, true);
+    if (limits && S.parts > 1) FRENET_LAUNCH_K2(true, true);
     else if (limits) FRENET_LAUNCH_K2(true, false);
-    else if (parts > 1) FRENET_LAUNCH_K2(false, true);
+    else if (S.parts > 1) FRENET_LAUNCH_K2(false, true);
     else FRENET_LAUNCH_K2(false, false);
 #undef FRENET_LAUNCH_K2
     FRENET_CHECK_LAUNCH("k2_evaluate");
@@ -2301,6 +2751,68 @@ int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const do
     points_to_cartesian<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*path, s, d, n, x, y, out_stride);
     FRENET_CHECK_LAUNCH("points_to_cartesian");
     return FRENET_OK;
+}
+
+int frenet_workspace_bytes(const FrenetLattice* L, int32_t n_obs, int32_t n_obs_steps, FrenetSizes* out) {
+    if (!out) return fail(FRENET_ERR_BAD_ARG, "workspace: output is NULL");
+    if (!L || L->n_scen <= 0 || L->n_v_cap <= 0 || L->n_t <= 0 || L->n_d <= 0 || L->n_pad_max <= 0 || L->row_elems <= 0 ||
+        L->cand_elems != L->row_elems * L->n_d || (L->row_elems & 3) || n_obs < 0 || n_obs_steps < 0)
+        return fail(FRENET_ERR_BAD_ARG, "workspace: inconsistent lattice sizes");
+    memset(out, 0, sizeof(*out));
+    const int64_t Bn = L->n_scen, R = (int64_t)L->n_v_cap * L->n_t, C = R * L->n_d;
+    out->rows = Bn * R;
+    out->candidates = Bn * C;
+    out->state = Bn * 6 * 8;
+    out->scal = Bn * 3 * 8;
+    out->target = Bn * L->n_t * 3 * 8;
+    out->axis_v = Bn * L->n_v_cap * 8;
+    out->n_v = Bn * 4;
+    out->axis_d = (int64_t)L->n_d * 8;
+    out->axis_t = (int64_t)L->n_t * 8;
+    out->n_steps = (int64_t)L->n_t * 4;
+    out->t_offset = (int64_t)(L->n_t + 1) * 4;
+    out->t_pow = (int64_t)L->n_pad_max * 4 * 8;
+    out->obs_xy = Bn * n_obs * 2 * 8;
+    out->obs_active = Bn * n_obs;
+    out->obs_xy_t = Bn * n_obs * (int64_t)n_obs_steps * 2 * 8;
+    out->obs_bounds = n_obs_steps > 0 ? Bn * ((L->n_pad_max + kWarp - 1) / kWarp) * n_obs * 4 * 4 : 0;
+    out->coef_lon = Bn * R * 6 * 8;
+    out->coef_lat = Bn * C * 6 * 8;
+    out->row_S = Bn * R * 8;
+    out->row_flags = Bn * R * 4;
+    out->lon = Bn * L->row_elems * kLonFields * 8;
+    out->lat = Bn * L->cand_elems * kCandFields * 8;
+    out->cost = 4 * Bn * C * 8;
+    out->cand_flags = Bn * C;
+    out->curv_ok = Bn * C;
+    out->coll_free = Bn * C;
+    out->first_blocker = Bn * C * 4;
+    out->road_ok = Bn * C;
+    out->result = Bn * (int64_t)sizeof(FrenetResult);
+    out->winner = Bn * FRENET_WINNER_ROWS * L->n_pad_max * 8;
+    out->winner_steps = Bn * 4;
+    out->path_origin = Bn * 2 * 8;
+    out->lane_params = Bn * 4 * 8;
+    out->road_params = Bn * 8 * 8;
+    const int64_t* f = &out->state;
+    int64_t tot = 0;
+    for (; f <= &out->road_params; ++f) tot += (*f + 255) / 256 * 256;   // every buffer on its own 256-byte boundary
+    out->total = tot;
+    return FRENET_OK;
+}
+
+int frenet_k2_launch_shape(const FrenetLattice* L, const FrenetPath* path, int32_t n_obs, int32_t n_obs_steps, int32_t with_collision,
+                           int32_t* rows_per_cta, int32_t* ctas_per_row, int64_t* grid, int64_t* shared_bytes) {
+    if (!L || L->n_scen <= 0 || L->n_v_cap <= 0 || L->n_t <= 0 || L->n_d <= 0 || L->n_pad_max <= 0 || n_obs < 0)
+        return fail(FRENET_ERR_BAD_ARG, "launch shape: inconsistent lattice sizes");
+    const bool xy = path != nullptr;
+    const int coll = (xy && with_collision) ? (n_obs_steps > 0 && n_obs > 0 ? 2 : 1) : 0;
+    const K2Shape S = k2_shape(L, xy, coll, (xy && path->kind == FRENET_PATH_SPLINE) ? path->n_knots : 0, n_obs);
+    if (rows_per_cta) *rows_per_cta = S.rows_per_cta;
+    if (ctas_per_row) *ctas_per_row = S.parts;
+    if (grid) *grid = (int64_t)S.grid * S.parts;
+    if (shared_bytes) *shared_bytes = (int64_t)S.smem;
+    return S.smem > (size_t)kMaxSmem ? fail(FRENET_ERR_CAPACITY, "launch shape: the row does not fit shared memory") : FRENET_OK;
 }
 
 }  // extern "C"

@@ -115,6 +115,20 @@ def _align(n, a=256):
     return (n + a - 1) // a * a
 
 
+def _on_device(fn):
+    """Run an engine method with the engine's GPU as the current CUDA device: the kernels are `<<<>>>` launches on the CURRENT
+    device, and attribute setting, pinned allocation and graph capture follow it too.  One integer compare when it already is."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == self._dev_index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self._dev_index):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class FrenetEngine:
     """HBM buffers + launch logic for `n_scen` independent planner instances sharing one lattice geometry."""
 
@@ -139,6 +153,7 @@ class FrenetEngine:
         self.per_scenario_lanes = False   # every scenario has its own lane-centre parabola and lane boundaries (lane_params, road_params)
 
     # -- allocation ---------------------------------------------------------------------------
+    @_on_device
     def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0, n_obs_steps: int = 0):
         """(Re)allocate for a geometry / capacities; cheap when nothing changed.
         n_obs_steps > 0 additionally allocates a predicted obstacle table [B][n_obs][n_obs_steps][2] (extension)."""
@@ -210,13 +225,10 @@ class FrenetEngine:
             ooffs[name] = otot
             otot += _align(sz)
         self._out_offs = ooffs
-        self._out_host = torch.empty(otot, dtype=torch.uint8, pin_memory=True)
-        self._out_dev = torch.zeros(otot, dtype=torch.uint8, device=dev)
-        ov = self._out_host.numpy()
-        ov[:] = 0
-        self.winner = ov[:Bn * 12 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 12, geom.n_pad_max)
-        self.result = ov[ooffs["result"]:ooffs["result"] + Bn * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE))
-        self.winner_steps = ov[ooffs["winner_steps"]:ooffs["winner_steps"] + Bn * 4].view(np.int32)
+        self._out_bytes = otot
+        self._out_blocks = []          # (pinned host block, device block); a second one is added by enable_out_slots(2)
+        self._add_out_block()
+        self._bind_out_block(0)
         op = self._out_dev.data_ptr()
 
         # large state
@@ -263,6 +275,53 @@ class FrenetEngine:
         Bf.road_params = ip + offs["road_params"] if self.per_scenario_lanes else None
         self._cap_key = key
 
+    def _add_out_block(self):
+        host = torch.empty(self._out_bytes, dtype=torch.uint8, pin_memory=True)
+        host.numpy()[:] = 0
+        self._out_blocks.append((host, torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device)))
+
+    def _bind_out_block(self, slot: int):
+        """Make output block `slot` the one the next launch writes and `result` / `winner` / `winner_steps` view."""
+        Bn, geom, ooffs = self.n_scen, self.geom, self._out_offs
+        self._out_host, self._out_dev = self._out_blocks[slot]
+        self.out_slot = slot
+        ov = self._out_host.numpy()
+        self.winner = ov[:Bn * 12 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 12, geom.n_pad_max)
+        self.result = ov[ooffs["result"]:ooffs["result"] + Bn * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE))
+        self.winner_steps = ov[ooffs["winner_steps"]:ooffs["winner_steps"] + Bn * 4].view(np.int32)
+        op = self._out_dev.data_ptr()
+        self.B.result = op + ooffs["result"]
+        self.B.winner, self.B.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
+
+    def enable_out_slots(self, n: int = 2):
+        """A second output block (result records + winner trajectories), so that step i's results can leave the device on a
+        side stream while step i + 1 already writes the other block (BatchPlanner.launch_pipelined)."""
+        while len(self._out_blocks) < n:
+            self._add_out_block()
+        self._graphs.clear()
+
+    def select_out_slot(self, slot: int):
+        if slot != self.out_slot:
+            self._bind_out_block(slot)
+
+    def workspace_sizes(self) -> nat.FrenetSizes:
+        """Byte sizes of every buffer of this shape as the C ABI reports them (frenet_workspace_bytes)."""
+        out = nat.FrenetSizes()
+        nat.check(nat.lib.frenet_workspace_bytes(C.byref(self.L), int(self.n_obs), int(self.n_obs_steps), C.byref(out)))
+        return out
+
+    def launch_shape(self, path: "PathHandle | None" = None, collision: int = 0) -> dict:
+        """How the evaluate kernel launches for the configured shape (frenet_k2_launch_shape)."""
+        rows, parts, grid, smem = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        nat.check(nat.lib.frenet_k2_launch_shape(C.byref(self.L), C.byref(path.desc) if path is not None else None, int(self.B.n_obs),
+                                                 int(self.B.n_obs_steps), int(collision), C.byref(rows), C.byref(parts), C.byref(grid),
+                                                 C.byref(smem)))
+        return {"rows_per_cta": rows.value, "ctas_per_row": parts.value, "grid": grid.value, "shared_bytes": smem.value}
+
+    def rows_per_cta(self, with_xy: bool = True, collision: int = 0) -> int:
+        path = next(iter(self._paths.values()))[1] if (with_xy and self._paths) else None
+        return self.launch_shape(path, collision)["rows_per_cta"]
+
     def hbm_bytes(self) -> int:
         ts = [self.coef_lon, self.coef_lat, self.row_S, self.row_flags, self.lon, self.lat, self.cost, self.cand_flags,
               self.curv_ok, self.coll_free, self.first_blocker, self.road_ok, self._in_dev, self._out_dev, self._geom_dev] + [
@@ -298,6 +357,7 @@ class FrenetEngine:
                 self.B.lane_params = ip + self._in_offs["lane_params"] if on else None
                 self.B.road_params = ip + self._in_offs["road_params"] if on else None
 
+    @_on_device
     def offroad(self, right_fit=None, left_fit=None):
         """road_ok for every candidate against the lane boundary fits (a, b, c) of y = a x^2 + b x + c; None = that boundary
         was not detected (check_paths + check_offroad, lib/tests/test_mapper_planner_obstacles.py:62-70, 112-124)."""
@@ -326,6 +386,7 @@ class FrenetEngine:
         return h[1]
 
     # -- launches ------------------------------------------------------------------------------
+    @_on_device
     def upload(self, record_event: bool = True):
         """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles).  An event marks the
         end of the copy so that the host may refill the pinned block for the NEXT call while this call's kernels run
@@ -342,6 +403,7 @@ class FrenetEngine:
         if ev is not None:
             ev.synchronize()
 
+    @_on_device
     def upload_region(self, *names):
         """H2D of individual input arrays of the packed block (e.g. "robot_pose", "obs_xy") without touching the rest -
         used when the planner state itself lives on the device between replans."""
@@ -354,6 +416,7 @@ class FrenetEngine:
             o = self._in_offs[name]
             self._in_dev[o:o + sizes[name]].copy_(self._in_host[o:o + sizes[name]], non_blocking=True)
 
+    @_on_device
     def advance_state(self, time, lookup_period: float, d_d_s: float, num_sample: int):
         """Device-side replan bookkeeping (frenet_advance_state): next state = gathered winner at `time`, new V axes."""
         if not hasattr(self, "_time_dev") or self._time_dev.numel() != self.n_scen:
@@ -375,6 +438,7 @@ class FrenetEngine:
         nv = self._in_dev[o["n_v"]:o["n_v"] + B * 4].cpu().numpy().view(np.int32)
         return st, sc, nv
 
+    @_on_device
     def launch(self, params: nat.FrenetParams, path: PathHandle | None, stages: int, use_mask: int = 0,
                gather_sel: int = nat.SEL_CTOT, n_obs: int | None = None):
         """Enqueue the selected pipeline stages on torch's current stream (asynchronous)."""
@@ -395,6 +459,7 @@ class FrenetEngine:
         if stages & nat.STAGE_K4:
             self.has_collision = True
 
+    @_on_device
     def place_obstacles(self, path: PathHandle):
         """Frenet -> Cartesian of the uploaded obstacle table `obs_sd` ([2][B][O]: arc lengths, lateral offsets)
         straight into the device `obs_xy` table ([B][O][2]) that K4 reads - the device side of
@@ -407,6 +472,7 @@ class FrenetEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(nat.lib.frenet_points_to_cartesian(C.byref(path.desc), sd, sd + n * 8, n, xy, xy + 8, 2, C.c_void_p(stream)))
 
+    @_on_device
     def sensor_gate(self, rng: float, aperture: float):
         """Device-side `ProximitySensor.sense` for the whole batch: fills the device `obs_active` mask from the uploaded
         `robot_pose` and the device `obs_xy` table (lib/sensor/proximity_sensor.py:41-75)."""
@@ -419,6 +485,7 @@ class FrenetEngine:
         o = self._in_offs["obs_active"]
         return self._in_dev[o:o + self.n_scen * max(self.n_obs, 1)].cpu().numpy().reshape(self.n_scen, max(self.n_obs, 1))
 
+    @_on_device
     def predict_obstacles(self, path: PathHandle, period: float):
         """EXTENSION: fill the predicted table from the uploaded `obs_sd` / `obs_speed` and each scenario's t_initial with the
         reference's moving-obstacle time law (lib/sensor/dynamic_obstacle.py:43-56), one entry per sample period."""
@@ -432,6 +499,7 @@ class FrenetEngine:
                                                    ip + self._in_offs["scal"] + 16, 3, self.n_scen, self.n_obs, self.n_obs_steps,
                                                    float(period), self.obs_xy_t.data_ptr(), C.c_void_p(stream)))
 
+    @_on_device
     def download(self, sync: bool = True):
         """One D2H copy of the packed per-call outputs (result records, winner trajectories)."""
         self._out_host.copy_(self._out_dev, non_blocking=True)
@@ -444,13 +512,14 @@ class FrenetEngine:
         self.launch(params, path, stages, use_mask, gather_sel, n_obs)
         self.download(sync=True)
 
+    @_on_device
     def run_graph(self, params, path, stages, use_mask=0, gather_sel=nat.SEL_CTOT, n_obs=None):
         """`run` replayed from a CUDA graph (H2D copy, kernels, D2H copy as one launch): the launch-bound single-replan
         path.  The graph bakes in the kernel arguments (parameters, sizes, pointers), so it is keyed by them and
         re-captured when any of them changes; the per-replan inputs travel through the pinned block, which the graph's
         copy node reads at replay time."""
         key = (bytes(params), id(path), int(stages), int(use_mask), int(gather_sel), self.B.n_obs if n_obs is None else int(n_obs),
-               self._cap_key)
+               self._cap_key, self.out_slot)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) > 16:
@@ -526,6 +595,7 @@ class FrenetEngine:
             res["first_blocker"] = sc["first_blocker"][:C_]
         return res
 
+    @_on_device
     def points_to_cartesian(self, path: PathHandle, s, d):
         """Point-wise Frenet -> Cartesian on the device; s, d array-likes of equal length; returns (x, y) NumPy."""
         s = torch.as_tensor(np.ascontiguousarray(s, dtype=np.float64)).to(self.device)
@@ -537,6 +607,7 @@ class FrenetEngine:
                                                      y.data_ptr(), 1, C.c_void_p(stream)))
         return x.cpu().numpy(), y.cpu().numpy()
 
+    @_on_device
     def polyline_collision(self, xs, ys, obstacles_xy, radius_sq: float):
         """Generic K4: `xs`, `ys` are lists of per-path coordinate sequences; returns (coll_free bool[n], first_blocker int[n])."""
         n = len(xs)

@@ -291,6 +291,8 @@ class _LatticePlanner(Planner):
         """`min(self.paths, key=attrgetter(key))` of the CURRENT lattice (first minimal element wins)."""
         cache = self.__dict__.setdefault("_winner_cache", {})
         if key in cache:
+            if cache[key] is None:      # empty lattice (every row dropped / empty axis): the reference's min([]) raises
+                raise ValueError("min() arg is an empty sequence")
             return cache[key]
         eng = self._engine
         eng.launch(self._params, None, nat.STAGE_GATHER, 0, _SEL_OF_KEY[key])

@@ -30,27 +30,43 @@ OBSTACLE_HALF_WIDTH = 8.0
 DENSE_PARAMS = dict(d_road_width=0.1, dt=0.1, num_sample=3, delta_t=0.02)
 
 
-def config4_scenario():
-    """Single planner on the spline path, dense lattice, 64 static obstacles (all active)."""
-    # seed 66: the first seed >= 64 whose field leaves part of the lattice collision free
-    # (2313 of 9600 candidates survive and the masked argmin differs from the unmasked one)
-    rng = np.random.default_rng(66)
-    s_o = rng.uniform(5 + OBSTACLE_CLEARANCE, 5 + OBSTACLE_CLEARANCE + OBSTACLE_SPAN, 64)
-    d_o = rng.uniform(-OBSTACLE_HALF_WIDTH, OBSTACLE_HALF_WIDTH, 64)
+def config4_scenario(field: str = "spread"):
+    """Single planner on the spline path, dense lattice, 64 static obstacles (all active).
+
+    field="spread" (the parity fixtures of round 1): seed 66, uniform 25 m x 16 m field with a 3 m clearance.
+    field="literal": SURVEY section 8d verbatim - `default_rng(64)`, `s_o ~ U(5, 30)`, `d_o ~ N(0, 2)` (the reference's own
+    scenes draw the lateral offset from N(0, 2) too, lib/tests/test_obstacle_planner.py:142-157)."""
+    if field == "literal":
+        rng = np.random.default_rng(64)
+        s_o = rng.uniform(5, 30, 64)
+        d_o = rng.normal(0, 2, 64)
+    else:
+        # seed 66: the first seed >= 64 whose field leaves part of the lattice collision free
+        # (2313 of 9600 candidates survive and the masked argmin differs from the unmasked one)
+        rng = np.random.default_rng(66)
+        s_o = rng.uniform(5 + OBSTACLE_CLEARANCE, 5 + OBSTACLE_CLEARANCE + OBSTACLE_SPAN, 64)
+        d_o = rng.uniform(-OBSTACLE_HALF_WIDTH, OBSTACLE_HALF_WIDTH, 64)
     return dict(p0=(0.3, 0.1, 0.0), s0=(5.0, 2.5, 0.1), t0=0.1, dd=0.0,
                 obs_s=s_o, obs_d=d_o)
 
 
-def config5_scenarios(n_scenarios: int = 4096, n_obstacles: int = 128, seed: int = 4096):
-    """Batched sweep: independent planner states around the low-speed threshold, 128 moving
-    obstacles per scenario spread over the 25 m x 16 m field ahead of each robot."""
+def config5_scenarios(n_scenarios: int = 4096, n_obstacles: int = 128, seed: int = 4096, field: str = "spread"):
+    """Batched sweep: independent planner states around the low-speed threshold, 128 moving obstacles per scenario.
+
+    field="spread" (round-1 fixtures and headline): obstacles uniform over the 25 m x 16 m field ahead of each robot, 3 m clearance.
+    field="literal": SURVEY section 8d verbatim - `s_o ~ U(s0, s0 + 15)`, `d_o ~ N(0, 2)`: about 3x denser and without a
+    clearance, so most scenes have an obstacle on the robot's own start point (every candidate blocked at step 0)."""
     rng = np.random.default_rng(seed)
     B, O = n_scenarios, n_obstacles
     p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.5, .5, B), rng.uniform(-.5, .5, B)], axis=1)
     s0 = np.stack([rng.uniform(0, 25, B), rng.uniform(0, 4, B), rng.uniform(-.5, .5, B)], axis=1)
     dd = rng.uniform(-1, 1, B)
-    obs_s = s0[:, 0:1] + rng.uniform(OBSTACLE_CLEARANCE, OBSTACLE_CLEARANCE + OBSTACLE_SPAN, (B, O))
-    obs_d = rng.uniform(-OBSTACLE_HALF_WIDTH, OBSTACLE_HALF_WIDTH, (B, O))
+    if field == "literal":
+        obs_s = s0[:, 0:1] + rng.uniform(0, 15, (B, O))
+        obs_d = rng.normal(0, 2, (B, O))
+    else:
+        obs_s = s0[:, 0:1] + rng.uniform(OBSTACLE_CLEARANCE, OBSTACLE_CLEARANCE + OBSTACLE_SPAN, (B, O))
+        obs_d = rng.uniform(-OBSTACLE_HALF_WIDTH, OBSTACLE_HALF_WIDTH, (B, O))
     obs_speed = rng.uniform(0, 1, (B, O))
     obs_offset = rng.integers(-1, 1, (B, O)).astype(np.float64)
     return dict(p0=p0, s0=s0, dd=dd, t0=np.full(B, 0.1), obs_s=obs_s, obs_d=obs_d,

@@ -46,10 +46,12 @@ def pack_lattice(L, t_field=True):
     return out
 
 
-def assert_close(a, b, rtol, what="", atol_scale=None, per_row=False):
+def assert_close(a, b, rtol, what="", atol_scale=None, per_row=False, extra_atol=None):
     """Relative comparison scaled by the magnitude of the reference array (NaN padding must match).
     per_row: the absolute floor scales with each row's own magnitude (ill-conditioned low-speed candidates
-    reach |d| ~ 1e15 next to ordinary ones in the same array)."""
+    reach |d| ~ 1e15 next to ordinary ones in the same array).
+    extra_atol: array (broadcastable) added to the tolerance - the rounding floor of the sample itself, e.g.
+    64 eps x the magnitude of the terms a polynomial derivative sums up (see poly_term_bound)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
@@ -65,8 +67,25 @@ def assert_close(a, b, rtol, what="", atol_scale=None, per_row=False):
         scale = atol_scale if atol_scale is not None else max(1.0, float(np.nanmax(np.abs(b))) if (~nb).any() else 1.0)
     err = np.abs(np.where(na, 0.0, a - b))
     tol = rtol * np.maximum(np.abs(np.where(nb, 0.0, b)), scale * 1e-3) if atol_scale is None else rtol * scale
+    if extra_atol is not None:
+        tol = tol + np.nan_to_num(np.asarray(extra_atol, dtype=np.float64), nan=0.0, posinf=np.inf)
     bad = err > tol
     assert not bad.any(), f"{what}: max err {err.max():.3e} at {np.argwhere(bad)[:3].tolist()} (rtol {rtol})"
+
+
+_DERIV_FACTORS = ((1, 1, 1, 1, 1, 1), (0, 1, 2, 3, 4, 5), (0, 0, 2, 6, 12, 20), (0, 0, 0, 6, 24, 60))
+
+
+def poly_term_bound(coef, arg, order):
+    """sum_j f_j |a_j| |u|^(j - order): the magnitude of the terms the `order`-th derivative of a polynomial adds up at u.
+    Any two evaluation orders (the reference's power form, Horner, synthetic division) and any two routes to the
+    coefficients (np.linalg.solve, closed form) agree only to a few eps of THIS, not of the value - which matters where the
+    value is a cancellation (e.g. the end acceleration 0 of a low-speed quintic with a horizon of millimetres, whose 3x3
+    system has a condition number of 1e11).  coef [..., 6], arg [..., N] -> [..., N]."""
+    f = _DERIV_FACTORS[order]
+    with np.errstate(all="ignore"):
+        u = np.abs(np.asarray(arg, dtype=np.float64))
+        return sum(f[j] * np.abs(coef[..., j, None]) * u ** max(j - order, 0) for j in range(6))
 
 
 def compare_packed(got, ref, rtol, what="", fields=None):

@@ -46,6 +46,46 @@ def test_gather_results_world2_gloo(n_total):
         assert dict(out) == {0: True, 1: True}
 
 
+def _records_worker(rank, world, n_total, port, out):
+    """BatchPlanner.gather_records with RAGGED shards: every rank must take the padded path (round-1 advisor finding: the long
+    ranks used to take the device path and return world * cap records).  The planner is a stub without an engine - only the
+    branch selection and the collective are under test."""
+    sys.path.insert(0, ROOT)
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat
+    from otg_b200.batch import BatchPlanner, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(n_total, rank, world)
+    rec = np.zeros(hi - lo, dtype=np.dtype(nat.RESULT_DTYPE))
+    rec["argmin_masked"] = np.arange(lo, hi)
+    rec["n_valid"] = rank + 1
+    bp = object.__new__(BatchPlanner)
+    bp.n_scen, bp.engine = hi - lo, None
+    bp._local_records = lambda: rec
+    bp._collective_device = lambda group=None: None
+    allrec = bp.gather_records(n_total)
+    ok = len(allrec) == n_total and np.array_equal(allrec["argmin_masked"], np.arange(n_total)) and \
+        all(np.all(allrec["n_valid"][slice(*shard_range(n_total, r, world))] == r + 1) for r in range(world))
+    try:
+        bp.gather_records(n_total, sync=False)
+        ok = False
+    except ValueError:
+        pass
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(2, 7), (3, 7)])
+def test_gather_records_ragged_shards_gloo(world, n_total):
+    port = 31500 + (os.getpid() + 7 * world + n_total) % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_records_worker, args=(world, n_total, port, out), nprocs=world, join=True)
+        assert dict(out) == {r: True for r in range(world)}
+
+
 def test_gather_without_process_group_is_identity():
     sys.path.insert(0, ROOT)
     import otg_b200  # noqa: F401

@@ -8,7 +8,7 @@ fact held to GPU_RTOL below, far tighter than the contract.
 import numpy as np
 import pytest
 
-from _golden import golden, prefixed, compare_packed, assert_close, near_tie, pack_lattice, RTOL
+from _golden import golden, prefixed, compare_packed, assert_close, near_tie, pack_lattice, poly_term_bound, RTOL
 from oracle import frenet_oracle as fo
 
 pytestmark = pytest.mark.gpu
@@ -823,8 +823,16 @@ def test_randomised_shapes_and_parameters_against_oracle():
                 mag_lon = np.maximum(np.nanmax(np.abs(L.lon[:, 0, :]), axis=1), 1e-2)
             ill = (bound_lat > 1e4 * mag_lat) | (bound_lon > 1e4 * mag_lon)[L.row_of] | ~np.isfinite(bound_lat)
             well = ~ill[keep]
-            for name in ("d", "dot_d", "ddot_d", "dddot_d", "s", "dot_s", "ddot_s", "dddot_s"):
-                assert_close(got[name][:, :nmax][well], ref[name][well], FUZZ_RTOL, f"fuzz[{case},{b}].{name}", per_row=True)
+            # Derivatives of a well-conditioned VALUE can still be cancellations (the end acceleration 0 of a low-speed quintic
+            # whose horizon S is millimetres: 3x3 system with condition number 1e11, terms of 1e7 summing to 0): the floor of
+            # each sample is a few eps of the terms its own derivative adds up (scripts/fuzz_triage.py, profiles/r2_history.md).
+            tl_c = np.abs(L.t - t0[b])[L.row_of]
+            for j, name in enumerate(("d", "dot_d", "ddot_d", "dddot_d")):
+                floor = 256 * np.finfo(float).eps * poly_term_bound(L.clat, arg, j)[keep][well]
+                assert_close(got[name][:, :nmax][well], ref[name][well], FUZZ_RTOL, f"fuzz[{case},{b}].{name}", per_row=True, extra_atol=floor)
+            for j, name in enumerate(("s", "dot_s", "ddot_s", "dddot_s")):
+                floor = 256 * np.finfo(float).eps * poly_term_bound(L.clon[L.row_of], tl_c, j)[keep][well]
+                assert_close(got[name][:, :nmax][well], ref[name][well], FUZZ_RTOL, f"fuzz[{case},{b}].{name}", per_row=True, extra_atol=floor)
             for k in ("cd", "cv", "ct", "ctot"):
                 assert_close(got[k][well], ref[k][well], FUZZ_RTOL, f"fuzz[{case},{b}].{k}")
             x, y = fo.lattice_to_cartesian(op, L)
@@ -1025,3 +1033,144 @@ def test_batched_lane_runs_with_per_scenario_fits():
         _check_argmin(int(res.records["argmin_masked"][b]), fo.first_argmin(L.ctot, mask), L.ctot, f"lanes[{b}] masked")
         assert res.records["n_survivors"][b] == int(mask.sum())
     assert n_off > 0 and n_hit > 0 and n_keep > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# Round 2: row-level collision table of the pipeline kernel, row groups of the short-horizon kernel
+# ------------------------------------------------------------------------------------------------
+def _run_custom_axis(D, prm, p0, s0, t0, dd, obs, trajectory, no_fuse, active=None):
+    """Like _gpu.run_batch, but with an explicit lateral axis (non-uniform grids, more than 128 targets)."""
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat, lattice as lat
+    from otg_b200.engine import FrenetEngine, LatticeGeometry, make_params
+    import _gpu
+    a = _gpu.planner_attrs(prm)
+    B = len(t0)
+    geom = LatticeGeometry(np.asarray(D, dtype=np.float64), np.arange(*lat.t_interval(a, prm.variant)), lat.sample_period(a, prm.variant))
+    axes = [lat.long_axis(a, s0[b, 1], False) for b in range(B)]
+    eng = FrenetEngine(B)
+    eng.configure(geom, max(len(x) for x in axes), obs.shape[1])
+    eng.state[:, :3], eng.state[:, 3:] = p0, s0
+    eng.scal[:, 0], eng.scal[:, 1], eng.scal[:, 2] = dd, prm.desired_speed, t0
+    eng.axis_v[:] = 0
+    for b, x in enumerate(axes):
+        eng.axis_v[b, :len(x)] = x
+        eng.n_v[b] = len(x)
+    eng.obs_xy[:] = obs
+    eng.obs_active[:] = 1 if active is None else active
+    stages = nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K3 | nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER | (nat.STAGE_NO_FUSE if no_fuse else 0)
+    P = make_params(a, lat.VARIANTS[prm.variant]["rule"], lat.sample_period(a, prm.variant), False)
+    eng.run(P, eng.path_handle(trajectory), stages, nat.MASK_COLLISION, nat.SEL_MASKED)
+    return eng
+
+
+@pytest.mark.parametrize("field", ["spread", "literal"])
+def test_row_collision_table_equals_per_candidate_sweep(field):
+    """The fused pipeline kernel derives collision masks from a row-level table (candidate index ranges per (step, obstacle) pair,
+    exact fp64 re-test in the uncertain band); the standalone K4 sweeps every candidate against the obstacles.  Masks, first
+    blockers, survivor counts and the masked pick must be bit-identical - on both obstacle fields of config 5, including low-speed
+    rows whose lateral polynomial leaves the table's range (per-candidate fallback) and scenes where everything is blocked."""
+    _gpu, nat, Circle, Spline = _imports()
+    from otg_b200 import workloads as w
+    sc = w.config5_scenarios(field=field)
+    idx = np.r_[0:20, 1000:1012, 4090:4096]
+    fs, fd = w.moving_obstacle_frenet(sc["obs_s"][idx], sc["obs_d"][idx], sc["obs_speed"][idx], sc["obs_offset"][idx], sc["t0"][idx, None])
+    sp_o = fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY)
+    ox, oy = fo.frenet_to_cartesian(sp_o, fs, fd)
+    obs = np.stack([ox, oy], 2)
+    active = np.ones(obs.shape[:2], dtype=np.uint8)
+    active[::3, ::5] = 0                        # some obstacles not sensed
+    kw = dict(p0=sc["p0"][idx], s0=sc["s0"][idx], t0=sc["t0"][idx], dd=sc["dd"][idx], trajectory=Spline(w.SPLINE_WX, w.SPLINE_WY),
+              obstacles=obs, active=active, gather_sel=nat.SEL_MASKED)
+    a = _gpu.run_batch(_dense_prm(), **kw)
+    ra, fa, ba = a.result.copy(), a.coll_free.cpu().numpy().copy(), a.first_blocker.cpu().numpy().copy()
+    valid = (a.cand_flags.cpu().numpy() & nat.CAND_VALID) != 0
+    b = _gpu.run_batch(_dense_prm(), no_fuse=True, **kw)
+    assert np.array_equal(b.result, ra)
+    assert np.array_equal(b.coll_free.cpu().numpy()[valid], fa[valid])
+    assert np.array_equal(b.first_blocker.cpu().numpy()[valid], ba[valid])
+    blocked = int((fa[valid] == 0).sum())
+    assert blocked > 0 and (field == "literal" or blocked < valid.sum())
+    # and against the oracle's brute-force sweep for three scenes
+    for i in (0, 7, len(idx) - 1):
+        L = fo.generate(_dense_prm(), kw["p0"][i], kw["s0"][i], kw["t0"][i], dd=kw["dd"][i])
+        x, y = fo.lattice_to_cartesian(sp_o, L)
+        act = active[i] != 0
+        ok, first = fo.check_collisions(x, y, L.nsteps, obs[i][act])
+        C_ = L.n_candidates
+        assert np.array_equal(fa[i, :C_] != 0, ok) or _margin_ok(x, y, L.nsteps, obs[i][act], fa[i, :C_] != 0, ok)
+        same = (fa[i, :C_] != 0) == ok
+        want = np.where(first >= 0, np.nonzero(act)[0][np.maximum(first, 0)], -1)
+        assert np.array_equal(ba[i, :C_][same], want[same])
+
+
+@pytest.mark.parametrize("axis", ["non_uniform", "wide", "single", "descending_pair"])
+def test_row_collision_table_falls_back_on_axes_it_does_not_cover(axis):
+    """The table needs a uniform ascending lateral axis of at most 128 targets; anything else must silently take the
+    per-candidate sweep and still equal the separate launches and the oracle."""
+    _gpu, nat, Circle, Spline = _imports()
+    from otg_b200 import workloads as w
+    rng = np.random.default_rng(11)
+    D = {"non_uniform": np.sort(rng.uniform(-3, 3, 37)), "wide": np.arange(-6.5, 6.5, 0.1), "single": np.array([0.4]),
+         "descending_pair": np.array([1.0, -1.0])}[axis]
+    prm = fo.OracleParams.defaults("v1").with_(delta_t=0.02, dt=0.5)
+    B, O = 6, 40
+    p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.5, .5, B), rng.uniform(-.5, .5, B)], 1)
+    s0 = np.stack([rng.uniform(0, 25, B), rng.uniform(0, 4, B), rng.uniform(-.5, .5, B)], 1)
+    t0, dd = np.full(B, 0.1), rng.uniform(-1, 1, B)
+    sp_o = fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY)
+    ox, oy = fo.frenet_to_cartesian(sp_o, s0[:, 0:1] + rng.uniform(0.5, 9, (B, O)), rng.uniform(-4, 4, (B, O)))
+    obs = np.stack([ox, oy], 2)
+    sp = Spline(w.SPLINE_WX, w.SPLINE_WY)
+    a = _run_custom_axis(D, prm, p0, s0, t0, dd, obs, sp, no_fuse=False)
+    b = _run_custom_axis(D, prm, p0, s0, t0, dd, obs, sp, no_fuse=True)
+    valid = (a.cand_flags.cpu().numpy() & nat.CAND_VALID) != 0
+    assert valid.any()
+    assert np.array_equal(a.result, b.result)
+    assert np.array_equal(a.coll_free.cpu().numpy()[valid], b.coll_free.cpu().numpy()[valid])
+    assert np.array_equal(a.first_blocker.cpu().numpy()[valid], b.first_blocker.cpu().numpy()[valid])
+    free = a.coll_free.cpu().numpy()[valid]
+    assert 0 < free.sum() < free.size or axis in ("single", "descending_pair")
+
+
+def test_short_horizon_kernel_with_several_rows_per_cta():
+    """The reference's default lattice in a batch large enough that the short-horizon kernel takes G = 12 rows of a scenario per
+    CTA (600 planners x 24 rows): every field of a sample of scenarios and every scenario's record against the oracle."""
+    _gpu, nat, Circle, _ = _imports()
+    rng = np.random.default_rng(77)
+    B, O = 600, 10
+    prm = fo.OracleParams.defaults("v1")
+    p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.3, .3, B), rng.uniform(-.3, .3, B)], 1)
+    s0 = np.stack([rng.uniform(0, 30, B), rng.uniform(0, 4, B), rng.uniform(-.3, .3, B)], 1)
+    t0, dd = rng.uniform(0, 2, B), rng.uniform(-1, 1, B)
+    circ_o = fo.CirclePath(8, 5, 2)
+    ox, oy = fo.frenet_to_cartesian(circ_o, s0[:, 0:1] + rng.uniform(1, 8, (B, O)), rng.uniform(-3, 3, (B, O)))
+    obs = np.stack([ox, oy], 2)
+    eng = _gpu.run_batch(prm, p0, s0, t0, dd=dd, trajectory=Circle(8, 5, 2), obstacles=obs, gather_sel=nat.SEL_MASKED)
+    assert eng.rows_per_cta(with_xy=True, collision=1) >= 2
+    cost = eng.cost.cpu().numpy()
+    free = eng.coll_free.cpu().numpy()
+    n_ties = 0
+    for b in range(B):
+        L = fo.generate(prm, p0[b], s0[b], t0[b], dd=dd[b])
+        C_ = L.n_candidates
+        x, y = fo.lattice_to_cartesian(circ_o, L)
+        ok, first = fo.check_collisions(x, y, L.nsteps, obs[b])
+        assert eng.result[b]["n_valid"] == C_
+        assert_close(cost[3, b, :C_], L.ctot, GPU_RTOL, f"rows/cta[{b}].ctot")
+        assert_close(cost[0, b, :C_], L.cd, GPU_RTOL, f"rows/cta[{b}].cd")
+        assert np.array_equal(free[b, :C_] != 0, ok) or _margin_ok(x, y, L.nsteps, obs[b], free[b, :C_] != 0, ok), b
+        if np.array_equal(free[b, :C_] != 0, ok):
+            got, want = int(eng.result[b]["argmin_masked"]), fo.first_argmin(L.ctot, ok)
+            n_ties += got != want
+            _check_argmin(got, want, L.ctot, f"rows/cta[{b}] masked")
+        if b % 37 == 0:
+            f = eng.padded_fields(eng.fetch_scenario(b))
+            ref = pack_lattice(L, t_field=False)
+            nmax = ref["d"].shape[1]
+            for name in ("d", "dot_d", "ddot_d", "dddot_d", "s", "dot_s", "ddot_s", "dddot_s"):
+                assert_close(f[name][:, :nmax], ref[name], GPU_RTOL, f"rows/cta[{b}].{name}", per_row=True)
+            valid = np.arange(nmax)[None, :] < L.nsteps[:, None]
+            assert_close(f["x"][:, :nmax], np.where(valid, x[:, :nmax], np.nan), GPU_RTOL, f"rows/cta[{b}].x", per_row=True)
+            assert np.array_equal(f["first_blocker"], first)
+    assert n_ties <= 2
