@@ -420,6 +420,54 @@ def literal_field_legs(dev, lo, hi, steps):
     return out
 
 
+def fp32_fast_path(wl, steps, dev, peak, records_f64):
+    """Separate `dtype: "f32"` leg (never the headline): the candidate blocks are STORED as floats (24 B instead of 48 B per
+    candidate-timestep, north star tolerance 1e-3); arithmetic, costs, collision masks and argmin stay fp64, so the records must
+    equal the fp64 path's."""
+    import ctypes as C
+    import torch
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat, workloads as w
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.trajectory import SplineTrajectory2D
+    n = len(wl["t0"])
+    bp = BatchPlanner(dense_params(), SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY), n, N_OBS, "v1", dev, lat_f32=True)
+    bp.stage_inputs(**wl)
+    bp.engine.upload()
+    for _ in range(3):
+        bp.launch_resident()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        bp.launch_resident()
+        bp.engine.download(sync=False)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    e = bp.engine
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L, P, Bf, path = C.byref(e.L), C.byref(bp.params), C.byref(e.B), C.byref(bp.path.desc)
+    fused = _event_ms(lambda: nat.check(nat.lib.frenet_k2_fused(L, P, path, Bf, 1, stream)), 10)
+    k2k3 = _event_ms(lambda: nat.check(nat.lib.frenet_k2_fused(L, P, path, Bf, 0, stream)), 10)
+    bp.launch_resident()
+    e.download(sync=True)
+    g = bp.geom
+    cts = bp.cand_timesteps()
+    nrow_ts, ncand = int(g.n_steps.astype(np.int64).sum()) * bp._n_v_sum, g.n_t * g.n_d * bp._n_v_sum
+    by = 24 * cts + 32 * nrow_ts + ncand * (48 + 33)
+    same = bool(records_f64 is not None and np.array_equal(np.asarray(e.result), np.asarray(records_f64)))
+    out = {"dtype": "f32 storage of the candidate blocks (d and its three derivatives, x, y); fp64 arithmetic, costs, collision test, winner",
+           "value": cts / (ms * 1e-3), "unit": "candidate-timesteps/s", "ms_per_step": ms,
+           "k2k3k4_fused": {"ms": fused, "algorithmic_gb": (by + 5 * ncand) / 1e9, "gbs": (by + 5 * ncand) / (fused * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": (by + 5 * ncand) / (fused * 1e-3) / 1e9 / peak},
+           "k2k3_fused": {"ms": k2k3, "algorithmic_gb": by / 1e9, "gbs": by / (k2k3 * 1e-3) / 1e9, "frac_of_hbm_peak": by / (k2k3 * 1e-3) / 1e9 / peak},
+           "bytes_per_candidate_timestep": 24, "records_equal_fp64_path": same, "tolerance": "1e-3 relative on the stored samples (tests/test_gpu_parity.py)"}
+    del bp
+    torch.cuda.empty_cache()
+    return out
+
+
 def default_lattice_batch(dev, n_scen=32768, steps=10):
     """The reference's OWN lattice (configs 1-3: 320-384 candidates x 11..26 steps, circle path, 10 obstacles) as a batch of
     independent planners - the short-horizon form of the pipeline kernel."""
@@ -745,6 +793,7 @@ def run_gpu(args):
                 cpu["replan_latency"] = cpu_replan_latency()
                 if have_ref():
                     nref = min(cores, SCEN_PER_GPU)
+                    pool.map(_ref_latency, [0] * cores, chunksize=1)      # warm the workers: import of the reference package
                     res_ref, c, tref = cpu_pass(pool, wl, nref, _ref_one, REF_SLICE)
                     what = ("rows of the centre target speed and every 4th horizon (num_sample=0, dt=0.4: 400 of ~1e4 candidates, same D axis, "
                             "sampling period and 128 obstacles) of one scenario, unmodified reference (initialize + frenet_to_glob + check_paths + min); "
@@ -778,13 +827,15 @@ def run_gpu(args):
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity_spot_check": spot, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
                 "replan_latency": replan_latency() if (world == 1 and not args.kernels_only) else None,
-                "literal_obstacle_fields": None,
+                "literal_obstacle_fields": None, "fp32_fast_path": None,
                 "predicted_obstacles": None, "all_feasibility_checks": None, "default_lattice_batch": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
+        rec_f64 = np.array(allrec[:hi - lo], copy=True) if world == 1 else None
         if world == 1 and not args.kernels_only:
             del bp
             torch.cuda.empty_cache()
             line["literal_obstacle_fields"] = literal_field_legs(dev, lo, hi, max(3, args.steps // 3))
+            line["fp32_fast_path"] = fp32_fast_path(wl, max(3, args.steps // 3), dev, peak, rec_f64)
             line["predicted_obstacles"] = predicted_mode(wl, max(3, args.steps // 3), dev)
             line["all_feasibility_checks"] = all_checks_mode(wl, max(3, args.steps // 3), dev)
             line["default_lattice_batch"] = default_lattice_batch(dev)

@@ -24,7 +24,7 @@
  * owns one longitudinal polynomial, candidate c = r * n_d + i_d one lateral polynomial - the
  * order in which `generate_range_polynomials` appends (lib/planner/trajectory_planner.py:128-180).
  * Horizon i_T has n_steps[i_T] samples t_k = k * sample_period (np.arange(0, T + dt, dt)), stored
- * padded to npad(i_T) = n_steps rounded up to a multiple of 4 doubles; t_offset[i_T] is the prefix sum
+ * padded to npad(i_T) = n_steps rounded up to a multiple of 4 (8 with lat_f32) elements; t_offset[i_T] is the prefix sum
  * of the padded counts.  With  within(r) = i_v * t_offset[n_t] + t_offset[i_T] :
  *
  *   longitudinal block of row r   (4 fields s, ds, dds, ddds, each npad long, back to back):
@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define FRENET_B200_ABI_VERSION 1
+#define FRENET_B200_ABI_VERSION 2
 
 typedef void* frenet_stream_t; /* cudaStream_t */
 
@@ -104,7 +104,12 @@ typedef struct FrenetLattice {
     int32_t n_t;
     int32_t n_d;
     int32_t n_pad_max;       /* max_i (t_offset[i+1] - t_offset[i]) */
-    int32_t reserved;
+    int32_t lat_f32;         /* fp32 FAST PATH (0 = off): 1 = `lat` holds FLOATS - the candidate blocks d, dd, ddd, dddd, x, y are stored in
+                                fp32 (24 instead of 48 bytes per candidate-timestep), same element offsets, and the padded step counts
+                                are multiples of 8 (whole 32-byte sectors).  Only the fused pipeline kernel of long horizons supports it
+                                (frenet_k2_fused / frenet_plan with K2 + K3 fused); all arithmetic, the longitudinal samples `lon`, the
+                                costs, the collision test and the gathered winner stay fp64, so masks and argmin are those of the fp64
+                                path and only the stored lateral / Cartesian samples carry fp32 rounding (north star: 1e-3 relative) */
     int64_t row_elems;       /* n_v_cap * t_offset[n_t] */
     int64_t cand_elems;      /* row_elems * n_d */
     const double* axis_d;    /* [n_d]   np.arange(*di_interval) */
@@ -190,6 +195,11 @@ typedef struct FrenetBuffers {
     /* batched lane runs: every scenario has its own lane fit (both optional, NULL = the shared FrenetPath / FrenetRoad) */
     const double* lane_params; /* [n_scen][4] a, b, c, ds of the scenario's lane-centre parabola (path kind FRENET_PATH_PARABOLA) */
     const double* road_params; /* [n_scen][8] right boundary (h, k, a, given != 0), left boundary (h, k, a, given != 0) */
+    /* per-scenario switches of a batch (ABI 2; both optional, NULL = off) */
+    const uint8_t* follow;     /* [n_scen] 1 = this scenario plans in follow mode (overrides FrenetParams.follow scenario by scenario):
+                                  agents that fell back to following their leading obstacle next to agents that keep their speed */
+    const uint8_t* scen_mask;  /* [n_scen] 1 = process this scenario, 0 = leave its outputs untouched (K1, K2 / fused, K5, gather,
+                                  frenet_advance_state): the follow re-plan of the blocked scenarios only */
 } FrenetBuffers;
 
 /* Lane boundaries for frenet_k3_offroad: each a parabola in vertex form (h, k, a) =
@@ -286,7 +296,34 @@ int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const 
  * Scenarios without a winner keep their state and get status[b] = 1 (the reference raises there); status may be NULL.
  * The buffers written are the `state`, `scal`, `axis_v`, `n_v` inputs themselves (cast away const: they are device memory). */
 int frenet_advance_state(const FrenetLattice* lat, const FrenetBuffers* buf, const double* time, int64_t time_stride,
-                         double lookup_period, double d_d_s, int32_t num_sample, int32_t* status, frenet_stream_t stream);
+                         double lookup_period, double d_d_s, int32_t num_sample, int32_t follow, int32_t* status, frenet_stream_t stream);
+/* (follow != 0, or buf->follow[b] != 0 where that array is given: the scenario's axis is si_interval - target offsets centred on 0,
+ * trajectory_planner.py:119 - instead of the target speeds around its new speed; status[b] = 2: the axis did not fit n_v_cap) */
+
+/* Follow-mode target triples on the device, V1 semantics (lib/planner/trajectory_planner.py:131-136) with an
+ * ObstacleTrajectory target (lib/sensor/dynamic_obstacle.py:43-77): for every scenario b with buf->follow[b] != 0 (and only[b] != 0
+ * when `only` is given) and every horizon T, buf->target[b][iT] = (st, dst, ddst) computed from the scenario's state, t_initial and
+ * its leading obstacle lead[b] (index into obs_s / obs_d / obs_speed [n_scen][n_obs]: time offset, lateral offset, speed of the
+ * obstacle's time law).  `estimate` [n_scen]: arc length of the robot's projection onto the path (frenet_sim_project) - it defines the
+ * live transformer frame compute_s / compute_ds / compute_dds project into. */
+int frenet_follow_targets(const FrenetPath* path, const FrenetLattice* lat, const FrenetBuffers* buf, const int32_t* lead, const double* obs_s,
+                          const double* obs_d, const double* obs_speed, int32_t n_obs, const double* estimate, double delta_t, double d_target,
+                          const uint8_t* only, frenet_stream_t stream);
+
+/* The all-blocked branch of the moving-obstacle driver for a batch (lib/tests/test_moving_obstacle_planner.py:92-97): scenarios whose
+ * result record shows candidates but no survivor get redo[b] = 1, follow[b] = 1, lead[b] = first blocker of their first candidate
+ * (`leading_obstacles[0]`) and the follow-mode axis si_interval in lat->axis_v / lat->n_v; all others redo[b] = 0.  The caller then
+ * runs frenet_follow_targets(only = redo) and frenet_plan with buf->scen_mask = redo, without the collision stage and with use_mask 0
+ * (the reference takes the minimum over the UNFILTERED follow lattice).  lead / follow / redo: device arrays [n_scen]. */
+int frenet_follow_select(const FrenetLattice* lat, const FrenetBuffers* buf, double d_d_s, int32_t num_sample, int32_t* lead, uint8_t* follow,
+                         uint8_t* redo, frenet_stream_t stream);
+
+/* Target triples of the Optimal variant on the device (lib/optimal_frenet_frame/target.py:17-52, trajectory_planner_optimal.py:130-133):
+ * spec [n_scen][16] = leading quintic s0[3], s1[3], Ts, DTs, mode (0 plain, 1 follow, 2 merge, 3 stop), D0, second target s0[3], s1[3];
+ * buf->target[b][iT] = the sampled target at index round((t_initial + T) / delta_t).  status [n_scen] (may be NULL): 0 ok, 1 index
+ * outside the sampled target (the reference raises IndexError), 2 stop target does not end at rest (the reference asserts). */
+int frenet_optimal_targets(const FrenetLattice* lat, const FrenetBuffers* buf, const double* spec, double delta_t, int32_t* status,
+                           frenet_stream_t stream);
 
 /* Robot side of the closed loop for a batch of agents; per-agent scalar work kept on the device so
  * that a simulation step needs no host round trip.

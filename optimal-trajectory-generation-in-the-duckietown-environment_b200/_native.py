@@ -13,7 +13,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # OTG_B200_LIB selects another build of the same library (A/B experiments with compile-time tuning knobs)
 LIB_PATH = os.environ.get("OTG_B200_LIB") or os.path.join(_PKG_DIR, "libfrenet_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY = 0, -1, -2, -3
 STATUS_OK, STATUS_NO_FEASIBLE, STATUS_EMPTY = 0, 1, 2
@@ -38,7 +38,7 @@ class FrenetParams(C.Structure):
 
 class FrenetLattice(C.Structure):
     _fields_ = [("n_scen", C.c_int32), ("n_v_cap", C.c_int32), ("n_t", C.c_int32), ("n_d", C.c_int32),
-                ("n_pad_max", C.c_int32), ("reserved", C.c_int32), ("row_elems", C.c_int64), ("cand_elems", C.c_int64),
+                ("n_pad_max", C.c_int32), ("lat_f32", C.c_int32), ("row_elems", C.c_int64), ("cand_elems", C.c_int64),
                 ("axis_d", C.c_void_p), ("axis_t", C.c_void_p), ("n_steps", C.c_void_p), ("t_offset", C.c_void_p),
                 ("t_pow", C.c_void_p), ("axis_v", C.c_void_p), ("n_v", C.c_void_p)]
 
@@ -71,7 +71,8 @@ class FrenetBuffers(C.Structure):
                 ("result", C.c_void_p),
                 ("winner", C.c_void_p), ("winner_steps", C.c_void_p),
                 ("path_origin", C.c_void_p), ("road_ok", C.c_void_p),
-                ("lane_params", C.c_void_p), ("road_params", C.c_void_p)]
+                ("lane_params", C.c_void_p), ("road_params", C.c_void_p),
+                ("follow", C.c_void_p), ("scen_mask", C.c_void_p)]
 
 
 class FrenetSizes(C.Structure):
@@ -122,7 +123,12 @@ def _load():
         "frenet_predict_obstacles": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                                C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
         "frenet_advance_state": (C.c_int, [P(FrenetLattice), P(FrenetBuffers), C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32,
-                                           C.c_void_p, C.c_void_p]),
+                                           C.c_int32, C.c_void_p, C.c_void_p]),
+        "frenet_follow_targets": (C.c_int, [P(FrenetPath), P(FrenetLattice), P(FrenetBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+        "frenet_follow_select": (C.c_int, [P(FrenetLattice), P(FrenetBuffers), C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
+        "frenet_optimal_targets": (C.c_int, [P(FrenetLattice), P(FrenetBuffers), C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
         "frenet_sim_project": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_void_p]),
         "frenet_sim_control_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,

@@ -84,19 +84,23 @@ class BatchPlanner:
     """
 
     def __init__(self, params, trajectory, n_scen: int, n_obs: int = 0, variant: str = "v1", device=None,
-                 robot_radius: float = 0.7, predict_steps: int = 0):
+                 robot_radius: float = 0.7, predict_steps: int = 0, lat_f32: bool = False):
         self.p = params
         self.variant = variant
         self.n_scen = int(n_scen)
         self.n_obs = int(n_obs)
         self.engine = FrenetEngine(self.n_scen, device)
         self.period = lat.sample_period(params, variant)
-        self.geom = LatticeGeometry.from_intervals(lat.di_interval(params, variant), lat.t_interval(params, variant), self.period)
+        # lat_f32: fp32 FAST PATH (north star: 1e-3) - the sampled lateral / Cartesian state is STORED as floats (half the HBM bytes);
+        # arithmetic, costs, collision masks, argmin and the gathered winner stay fp64.  Dense (long-horizon) lattices only.
+        self.lat_f32 = bool(lat_f32)
+        self.geom = LatticeGeometry.from_intervals(lat.di_interval(params, variant), lat.t_interval(params, variant), self.period,
+                                                   8 if self.lat_f32 else 4)
         # predict_steps > 0 (EXTENSION): obstacles are propagated over the horizon on the device and step k of every
         # candidate is tested against the obstacles' predicted positions at t_initial + k * period; 0 = the reference's
         # snapshot semantics (every step against the positions at t_initial).
         self.predict_steps = int(predict_steps)
-        self.engine.configure(self.geom, lat.max_long_axis_len(params), self.n_obs, self.predict_steps)
+        self.engine.configure(self.geom, lat.max_long_axis_len(params), self.n_obs, self.predict_steps, self.lat_f32)
         self.path = self.engine.path_handle(trajectory)
         self.radius_sq = robot_radius ** 2
         self.params = make_params(params, lat.VARIANTS[variant]["rule"], self.period, False, self.radius_sq)
@@ -270,11 +274,45 @@ class BatchPlanner:
             return P["ghost"][P["last"]].numpy().view(np.dtype(nat.RESULT_DTYPE))
         return self.engine.result
 
-    def replanner(self, time, robot_pose=None, sensor=None, obs_xy=None, sync: bool = True):
+    def enable_follow_fallback(self, obs_time_offset, obs_offset, obs_speed, d_target: float = 2.0):
+        """Batched form of the moving-obstacle driver's all-blocked branch (lib/tests/test_moving_obstacle_planner.py:92-97), on the
+        device: a scenario whose candidates all collide re-plans in follow mode behind `leading_obstacles[0]` - the first blocker of
+        its first candidate - and, like the reference planner whose `s_target` stays set, keeps planning in follow mode afterwards.
+        obs_time_offset / obs_offset / obs_speed [B][O]: the obstacles' ObstacleTrajectory parameters (time law
+        `time_offset + (t * speed) % 50`, lateral offset; lib/sensor/dynamic_obstacle.py:36-56) that `compute_s / ds / dds` need;
+        d_target: the planner's `d_target` (2.0 in `initialize`, trajectory_planner.py:91)."""
+        e = self.engine
+        e.enable_follow()
+        e.follow_dev.zero_()
+        e.lead_dev.fill_(-1)
+        e.obs_sd[0], e.obs_sd[1] = obs_time_offset, obs_offset
+        e.obs_speed[:] = obs_speed
+        e.upload_region("obs_sd", "obs_speed")
+        self._follow = dict(d_target=float(d_target))
+
+    def pipeline_with_follow(self, estimate):
+        """The pipeline on the state resident in HBM, then - with `enable_follow_fallback` - the follow re-plan of the scenarios
+        that came out without a survivor, all on the device.  estimate: device tensor [B], arc length of every robot's projection
+        (what `transformer.estimatePosition` returned this step): it anchors the frame the follow targets are measured in."""
+        e = self.engine
+        fb = getattr(self, "_follow", None)
+        if fb is not None:
+            e.follow_targets(self.path, estimate, self.p.delta_t, fb["d_target"])          # scenarios that already follow
+        e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
+        if fb is not None and (self.stages & nat.STAGE_K4):
+            e.follow_select(self.p.d_d_s, self.p.num_sample)
+            e.follow_targets(self.path, estimate, self.p.delta_t, fb["d_target"], only=e.redo_dev)
+            e.set_scenario_mask(e.redo_dev)
+            # the reference takes min(paths, key=ctot) over the UNFILTERED follow lattice (it still runs frenet_to_glob on it)
+            e.launch(self.params, self.path, self.stages & ~nat.STAGE_K4, 0, nat.SEL_MASKED)
+            e.set_scenario_mask(None)
+
+    def replanner(self, time, robot_pose=None, sensor=None, obs_xy=None, sync: bool = True, estimate=None):
         """One `planner.replanner(time)` for every scenario WITHOUT a host round trip for the planner state
         (trajectory_planner.py:206-212, 223-234): the new initial state is the previous (masked) winner sampled at `time`,
         taken on the device; then the pipeline runs again.  Call `plan(...)` once first (it plays the role of
-        `initialize`).  robot_pose + sensor=(range, aperture) re-evaluate the cone gate; obs_xy moves the obstacles."""
+        `initialize`).  robot_pose + sensor=(range, aperture) re-evaluate the cone gate; obs_xy moves the obstacles.
+        estimate [B] (with `enable_follow_fallback`): arc length of the robots' projections, see `pipeline_with_follow`."""
         e = self.engine
         regions = []
         if robot_pose is not None:
@@ -286,10 +324,17 @@ class BatchPlanner:
         if regions:
             e.upload_region(*regions)
         lookup = getattr(self.p, "sampling_t", None) if self.variant == "dt_obstacles" else self.p.delta_t
-        e.advance_state(time, lookup, self.p.d_d_s, self.p.num_sample)
+        e.advance_state(time, lookup, self.p.d_d_s, self.p.num_sample, follow=bool(self.params.follow))
         if self.n_obs and sensor is not None:
             e.sensor_gate(float(sensor[0]), float(sensor[1]))
-        e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
+        if getattr(self, "_follow", None) is not None:
+            if estimate is None:
+                raise ValueError("the follow fallback needs the robots' projections (estimate=)")
+            if not isinstance(estimate, torch.Tensor):
+                estimate = torch.as_tensor(np.ascontiguousarray(estimate, dtype=np.float64)).to(e.device)
+            self.pipeline_with_follow(estimate)
+        else:
+            e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
         e.download(sync=sync)
         if sync:
             self._n_v_sum = int(e.result["n_valid"].sum()) // max(self.geom.n_t * self.geom.n_d, 1)

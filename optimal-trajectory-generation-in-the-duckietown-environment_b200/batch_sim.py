@@ -50,9 +50,13 @@ class BatchSimulator:
         nat.check(nat.lib.frenet_sim_project(C.byref(self.bp.path.desc), self._ptr("robot_pose"), self.estimate.data_ptr(), self.gn_iter,
                                              self.gn_damping, self.fpose.data_ptr(), self.curvature.data_ptr(), self.n, self._stream()))
 
-    def reset(self, robot_pose, t0: float, obs_xy=None):
+    def enable_follow_fallback(self, obs_time_offset, obs_offset, obs_speed, d_target: float = 2.0):
+        """All-blocked agents re-plan in follow mode behind their first blocker, on the device (BatchPlanner.enable_follow_fallback)."""
+        self.bp.enable_follow_fallback(obs_time_offset, obs_offset, obs_speed, d_target)
+
+    def reset(self, robot_pose, t0: float, obs_xy=None, s0=None):
         """Place the agents and initialise their planners like the experiments do (test_planner.py:31-38): project the robot,
-        start the lattice from (s, 0, 0), (d, 0, 0) of its Frenet pose."""
+        start the lattice from (s, 0, 0), (d, 0, 0) of its Frenet pose (s0 [B]: start arc lengths given explicitly instead)."""
         e = self.bp.engine
         self.estimate.fill_(self.gn_guess)
         e.robot_pose[:] = np.asarray(robot_pose, dtype=np.float64).reshape(self.n, 3)
@@ -65,7 +69,8 @@ class BatchSimulator:
             kw = dict(obs_xy=np.zeros((self.n, self.bp.n_obs, 2)) if obs_xy is None else obs_xy,
                       obs_active=np.zeros((self.n, self.bp.n_obs), dtype=np.uint8))     # initialize() does not look at obstacles
         e.robot_pose[:] = np.asarray(robot_pose, dtype=np.float64).reshape(self.n, 3)   # plan() re-uploads the whole block
-        return self.bp.plan(np.stack([f[:, 1], z, z], 1), np.stack([f[:, 0], z, z], 1), np.full(self.n, float(t0)), **kw)
+        s_start = f[:, 0] if s0 is None else np.broadcast_to(np.asarray(s0, dtype=np.float64), (self.n,))
+        return self.bp.plan(np.stack([f[:, 1], z, z], 1), np.stack([s_start, z, z], 1), np.full(self.n, float(t0)), **kw)
 
     def step(self, time: float, obs_xy=None, sync: bool = False):
         """One closed-loop step for every agent; returns the (pinned) result records if `sync`."""
@@ -78,7 +83,7 @@ class BatchSimulator:
         e.advance_state(time, lookup, bp.p.d_d_s, bp.p.num_sample)
         if bp.n_obs and self.sensor is not None:
             e.sensor_gate(float(self.sensor[0]), float(self.sensor[1]))
-        e.launch(bp.params, bp.path, bp.stages, bp.use_mask, nat.SEL_MASKED)
+        bp.pipeline_with_follow(self.estimate)
         nat.check(nat.lib.frenet_sim_control_step(self.fpose.data_ptr(), self._ptr("state"), self.curvature.data_ptr(), self.ctrl_b,
                                                   self.kp_s, self.kp_d, self.dt, self._ptr("robot_pose"), self.control.data_ptr(),
                                                   self.n, self._stream()))

@@ -54,12 +54,13 @@ constexpr int kMaxSmem = 227 * 1024;
 #endif
 // the row-table collision variant keeps the collision work out of the sampling loop: same register budget as the collision-free kernels
 #ifndef FRENET_K2_MIN_CTAS_TABLE
-#define FRENET_K2_MIN_CTAS_TABLE 3
+#define FRENET_K2_MIN_CTAS_TABLE 4
 #endif
 // warps that share one 32-step chunk of the row table (the listed obstacles are dealt round-robin to them); 0 = as many as it takes
-// to give every warp of the CTA one item
+// to give every warp of the CTA one item.  Measured on B200 (profiles/r2_history.md): 1 is fastest - the per-item set-up (bounding box,
+// obstacle listing) is not worth duplicating
 #ifndef FRENET_TABLE_SPLIT
-#define FRENET_TABLE_SPLIT 0
+#define FRENET_TABLE_SPLIT 1
 #endif
 // 1: the collision variants of the long-horizon kernel reload the candidate's coefficients from shared memory in every iteration instead of
 // keeping them in twelve registers across the collision test: no spills at the 64-register cap, fused kernel 6.2 -> 5.8 ms on B200
@@ -153,6 +154,10 @@ struct Poly {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(a2), "=d"(a3) : "r"(sa));
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(a4), "=d"(a5) : "r"(sa));
     }
+    // p(t) alone, the same FMA sequence as eval's v0 (bit-identical)
+    __device__ __forceinline__ double value(double t) const {
+        return fma(fma(fma(fma(fma(a5, t, a4), t, a3), t, a2), t, a1), t, a0);
+    }
     // v0 = p(t), v1 = p'(t), v2 = p''(t), v3 = p'''(t)
     __device__ __forceinline__ void eval(double t, double& v0, double& v1, double& v2, double& v3) const {
         const double b4 = fma(a5, t, a4);
@@ -244,6 +249,12 @@ __device__ __forceinline__ RowAddr row_addr(const FrenetLattice& L, int64_t br) 
     return A;
 }
 
+// Per-scenario switches of a batch (both optional): `follow` overrides FrenetParams.follow scenario by scenario (agents that fell
+// back to following their leading obstacle next to agents that keep their speed), `scen_mask` restricts a launch to a subset of
+// the scenarios (the follow re-plan of the blocked ones); the others' outputs stay untouched.
+__device__ __forceinline__ bool follow_of(const FrenetParams& P, const FrenetBuffers& B, int b) { return B.follow ? B.follow[b] != 0 : P.follow != 0; }
+__device__ __forceinline__ bool skipped(const FrenetBuffers& B, int b) { return B.scen_mask != nullptr && B.scen_mask[b] == 0; }
+
 // ------------------------------------------------------------------------------------------------
 // K1: candidate generation, one thread per lattice cell (scenario, v, T, d)
 // ------------------------------------------------------------------------------------------------
@@ -258,6 +269,7 @@ __global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetPa
     const int64_t br = (int64_t)b * L.n_v_cap * L.n_t + r;
     double* cl = B.coef_lon + br * 6;
     double* cq = B.coef_lat + gid * 6;
+    if (skipped(B, b)) return;
 
     if (iv >= L.n_v[b]) {   // row beyond this scenario's longitudinal axis
         if (id == 0) {
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetPa
     const double v = L.axis_v[(int64_t)b * L.n_v_cap + iv];
 
     double a[6];
-    if (P.follow) {   // trajectory_planner.py:132-138: quintic to (st + offset, dst, ddst)
+    if (follow_of(P, B, b)) {   // trajectory_planner.py:132-138: quintic to (st + offset, dst, ddst)
         const double* tg = B.target + ((int64_t)b * L.n_t + iT) * 3;
         quintic_bvp(s0, ds0, dds0, tg[0] + v, tg[1], tg[2], T, a);
     } else {          // :147 velocity keeping
@@ -770,7 +782,7 @@ __device__ __forceinline__ int collide_groups_predicted(double xa, double ya, do
 // are covered by a relative 1e-6 on r and by eps).  Large |B_k| (low-speed rows sampled beyond their horizon, |d| up to 1e12) only
 // widen the band in metres, not in candidate indices: the index error scales with delta / (B dD).
 constexpr int kTableMaxD = 128;    // candidates per row the packed intervals can index; wider rows take the per-candidate sweep
-constexpr int kMaybeCap = 4;       // uncertain obstacles remembered per candidate; more -> per-candidate sweep for that candidate
+constexpr int kMaybeCap = 8;       // uncertain obstacles remembered per candidate; more -> per-candidate sweep for that candidate
 constexpr float kU32 = 5.9604645e-8f;
 constexpr unsigned kIvlEmpty = 0x00ff00ffu;   // lo = 255, hi = 0 for both intervals
 
@@ -915,41 +927,42 @@ __device__ __forceinline__ void row_table_chunk(const RowTable& T, int ch, int s
     __syncwarp();   // the scratch list is reused by this warp's next chunk
 }
 
-// Per candidate: lowest certain blocker, and the obstacles below it that only `maybe` block.
-__device__ __forceinline__ void row_table_resolve(const RowTable& T, int n_d, int O, int nch) {
-    for (int id = threadIdx.x; id < n_d; id += blockDim.x) {
-        int first = kNoBlocker, nm = 0;
-        for (int ch = 0; ch < nch; ++ch) {
-            const unsigned* ivl = T.ivl + ch * O;
-            const unsigned short* ids = T.id + ch * O;
-            const int cnt = T.cnt[ch];
-            for (int j = 0; j < cnt; ++j) {
-                const int o = ids[j];
-                if (o >= first) break;          // ascending within a chunk
-                const unsigned e = ivl[j];
-                if (id >= (int)((e >> 16) & 255u) && id <= (int)(e >> 24)) { first = o; break; }
+// Per candidate: lowest certain blocker, and the obstacles below it that only `maybe` block.  All threads of the CTA take part:
+// work item (chunk, candidate) scans that chunk's list; the candidates' results are combined with shared-memory atomics.
+// Pass 1 (T.first preset to kNoBlocker): lowest obstacle whose inner interval contains the candidate.
+__device__ __forceinline__ void row_table_resolve_first(const RowTable& T, int n_d, int O, int nch) {
+    for (int w = threadIdx.x; w < n_d * nch; w += blockDim.x) {
+        const int ch = w / n_d, id = w - ch * n_d;
+        const unsigned* ivl = T.ivl + ch * O;
+        const unsigned short* ids = T.id + ch * O;
+        const int cnt = T.cnt[ch];
+        for (int j = 0; j < cnt; ++j) {
+            const unsigned e = ivl[j];
+            if (id >= (int)((e >> 16) & 255u) && id <= (int)(e >> 24)) {
+                atomicMin(T.first + id, (int)ids[j]);   // ascending within a chunk: the first match is the chunk's lowest
+                break;
             }
         }
-        for (int ch = 0; ch < nch; ++ch) {
-            const unsigned* ivl = T.ivl + ch * O;
-            const unsigned short* ids = T.id + ch * O;
-            const int cnt = T.cnt[ch];
-            for (int j = 0; j < cnt; ++j) {
-                const int o = ids[j];
-                if (o >= first) break;
-                const unsigned e = ivl[j];
-                if (id >= (int)(e & 255u) && id <= (int)((e >> 8) & 255u)) {      // (not certain: a certain one below `first` cannot exist)
-                    bool dup = false;
-                    for (int q = 0; q < min(nm, kMaybeCap); ++q) dup |= T.maybe_id[id * kMaybeCap + q] == (unsigned short)o;
-                    if (!dup) {
-                        if (nm < kMaybeCap) T.maybe_id[id * kMaybeCap + nm] = (unsigned short)o;
-                        ++nm;
-                    }
-                }
+    }
+}
+// Pass 2 (T.n_maybe preset to 0): obstacles below it that contain the candidate only in their outer interval.  The same obstacle can
+// be listed by several chunks; it is then re-tested more than once, which is harmless.
+__device__ __forceinline__ void row_table_resolve_maybe(const RowTable& T, int n_d, int O, int nch) {
+    for (int w = threadIdx.x; w < n_d * nch; w += blockDim.x) {
+        const int ch = w / n_d, id = w - ch * n_d;
+        const unsigned* ivl = T.ivl + ch * O;
+        const unsigned short* ids = T.id + ch * O;
+        const int cnt = T.cnt[ch];
+        const int first = T.first[id];
+        for (int j = 0; j < cnt; ++j) {
+            const int o = ids[j];
+            if (o >= first) break;          // ascending within a chunk
+            const unsigned e = ivl[j];
+            if (id >= (int)(e & 255u) && id <= (int)((e >> 8) & 255u)) {      // (an inner interval below `first` cannot contain it)
+                const int slot = atomicAdd(T.n_maybe + id, 1);
+                if (slot < kMaybeCap) T.maybe_id[id * kMaybeCap + slot] = (unsigned short)o;
             }
         }
-        T.first[id] = first;
-        T.n_maybe[id] = nm;
     }
 }
 
@@ -993,7 +1006,11 @@ __host__ __device__ inline size_t row_table_doubles(int npm, int n_d, int n_obs)
     return (bytes + 15) / 8;
 }
 
-template <bool kXY, int kColl, bool kLimits, bool kSplit>
+// kF32 (fp32 FAST PATH, BASELINE north star "1e-3 if an fp32 fast path is offered"): the candidate blocks (d and its three derivatives, x, y) are
+//          STORED as floats (24 instead of 48 bytes per candidate-timestep; FrenetLattice.lat_f32).  Everything is still computed in
+//          fp64 - costs, feasibility, the collision table and its exact re-tests work on the fp64 values, so masks, argmin and costs
+//          are those of the fp64 path - and the longitudinal samples, which feed the next replan, stay fp64.
+template <bool kXY, int kColl, bool kLimits, bool kSplit, bool kF32 = false>
 __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts, float radius_up) {
     extern __shared__ __align__(16) double sm[];
     constexpr bool kTable = kColl == 1 && kRowTable;   // snapshot collisions through the row-level table
@@ -1046,6 +1063,8 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
     const int64_t br = blockIdx.x;
     const RowAddr A = row_addr(L, br);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (skipped(B, A.b)) return;
+    const bool follow = follow_of(P, B, A.b);
     const int flags = B.row_flags[br];
 
     if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
@@ -1193,7 +1212,7 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
             double s_last, v_last, a_last, j_last;
             eval_power_form(pl, (double)(A.N - 1) * dt, L.t_pow + 4 * (A.N - 1), s_last, v_last, a_last, j_last);
             double term;
-            if (P.follow) {
+            if (follow) {
                 const double e = s_last - B.target[((int64_t)A.b * L.n_t + A.iT) * 3];
                 term = __dmul_rn(P.ks, __dmul_rn(e, e));
             } else {
@@ -1239,10 +1258,11 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
     // arrive late from building the table); their results are staged in shared memory and published after a barrier.
     // Candidate of hand-out slot q: id = q * parts + part.
     int slot = warp;
+    const unsigned next_addr = (unsigned)__cvta_generic_to_shared(&sh_next);
     for (;;) {
         if (kTable) {
             int t = 0;
-            if (lane == 0) t = atomicAdd(&sh_next, 1);
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(next_addr) : "memory");
             slot = __shfl_sync(kFull, t, 0);
         }
         const int id = slot * parts + part;
@@ -1257,13 +1277,18 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
         unsigned out = (unsigned)__cvta_generic_to_shared(stg + 2 * lane);      // shared-window address: the stores below are STS.128
 #define FRENET_PUT(addr, v0, v1) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory")
 #else
-#define FRENET_PUT(addr, v0, v1) (*reinterpret_cast<double2*>(addr) = make_double2(v0, v1))
-        char* out = reinterpret_cast<char*>(B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + 2 * lane);
+#define FRENET_PUT(addr, v0, v1)                                                                                             \
+    do {                                                                                                                     \
+        if (kF32) *reinterpret_cast<float2*>(addr) = make_float2(__double2float_rn(v0), __double2float_rn(v1));              \
+        else *reinterpret_cast<double2*>(addr) = make_double2(v0, v1);                                                       \
+    } while (0)
+        const int64_t cand_elem = A.cand_off + (int64_t)id * (kCandFields * npad) + 2 * lane;
+        char* out = kF32 ? reinterpret_cast<char*>(reinterpret_cast<float*>(B.lat) + cand_elem) : reinterpret_cast<char*>(B.lat + cand_elem);
 #endif
 #if FRENET_BULK_STORE
         const unsigned fs = (unsigned)(npad * sizeof(double));
 #else
-        const int64_t fs = (int64_t)npad * sizeof(double);
+        const int64_t fs = (int64_t)npad * (kF32 ? sizeof(float) : sizeof(double));
 #endif
         double acc = 0.0, amax = 0.0;
         int best = kNoBlocker;
@@ -1328,7 +1353,7 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
                     best = collide_pair_predicted(xa, ya, xb, yb, valid_a, valid_b, min(2 * kWarp, N - kb), kk, tblp, B.n_obs_steps,
                                                   cbs + (kb / (2 * kWarp)) * B.n_obs, B.n_obs, Rf, P.radius_sq, best, lane);
             }
-            out += 2 * kWarp * sizeof(double);
+            out += 2 * kWarp * (kF32 ? sizeof(float) : sizeof(double));
         }
 #if FRENET_BULK_STORE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' generic-proxy stores become visible to the copy engine
@@ -1350,8 +1375,8 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
             const double e = axd[id] - dd_target;
             const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
             resc[id * 4] = clat;
-            resc[id * 4 + 1] = P.follow ? 0.0 : clong;
-            resc[id * 4 + 2] = P.follow ? clong : 0.0;
+            resc[id * 4 + 1] = follow ? 0.0 : clong;
+            resc[id * 4 + 2] = follow ? clong : 0.0;
             resc[id * 4 + 3] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
             const bool kin = kLimits ? (rowfeas && amax <= P.a_max) : true;
             resi[id * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0) | (curv_bad ? 0 : kCurvOkBit);
@@ -1365,13 +1390,21 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
 #endif
     if (kTable) {
         // Collision results from the row table, once every candidate has been sampled (nobody waited for the table above).
+        if (table_ok && tid < L.n_d) {      // (n_d <= 128 <= blockDim.x whenever the table is used)
+            RT.first[tid] = kNoBlocker;
+            RT.n_maybe[tid] = 0;
+        }
         __syncthreads();
         if (table_ok) {
-            row_table_resolve(RT, L.n_d, B.n_obs, nch);
+            row_table_resolve_first(RT, L.n_d, B.n_obs, nch);
+            __syncthreads();
+            row_table_resolve_maybe(RT, L.n_d, B.n_obs, nch);
             __syncthreads();
         }
         // The few candidates with an uncertain obstacle below their first certain blocker - and every candidate of a row the table
-        // does not cover - re-read their samples (written by this CTA, visible after the barrier) and run the reference's fp64 test.
+        // does not cover - get the reference's fp64 test on their samples, recomputed from shared memory exactly as the sampling loop
+        // formed them (same FMA sequence, same unfused pt + n * d), so that nothing is read back from HBM (and the fp32 fast path,
+        // whose stored samples are rounded, tests the same fp64 points).
         for (int q = warp; q * parts + part < L.n_d; q += nwarps) {
             const int id = q * parts + part;
             int best = kNoBlocker, nm = kMaybeCap + 1;
@@ -1380,15 +1413,25 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
                 nm = RT.n_maybe[id];
             }
             if (nm > 0) {
-                const double* xs = B.lat + A.cand_off + (int64_t)id * (kCandFields * npad) + 4 * npad;
-                const double* ys = xs + npad;
+                Poly pq;
+                pq.load(coef + id * 6);
+                auto pair_at = [&](int kb, double& xa, double& ya, double& xb, double& yb) {
+                    const int k0 = kb + 2 * lane;
+                    const int kk = k0 < npad ? k0 : kb;     // lanes beyond the padding shadow the chunk's first pair (never valid)
+                    const double2 u = *reinterpret_cast<const double2*>(su + kk);
+                    const double da = pq.value(u.x), db = pq.value(u.y);
+                    const double2 px = *reinterpret_cast<const double2*>(fpx + kk), py = *reinterpret_cast<const double2*>(fpy + kk);
+                    const double2 nx = *reinterpret_cast<const double2*>(fnx + kk), ny = *reinterpret_cast<const double2*>(fny + kk);
+                    xa = __dadd_rn(px.x, __dmul_rn(nx.x, da)); xb = __dadd_rn(px.y, __dmul_rn(nx.y, db));
+                    ya = __dadd_rn(py.x, __dmul_rn(ny.x, da)); yb = __dadd_rn(py.y, __dmul_rn(ny.y, db));
+                };
                 if (nm > kMaybeCap) {   // per-candidate sweep over the obstacles below `best`
                     for (int kb = 0; kb < N; kb += 2 * kWarp) {
                         const int k0 = kb + 2 * lane;
-                        const int kk = k0 < npad ? k0 : kb;
-                        const double2 xv = *reinterpret_cast<const double2*>(xs + kk), yv = *reinterpret_cast<const double2*>(ys + kk);
-                        best = collide_pair(xv.x, yv.x, xv.y, yv.y, k0 < N, k0 + 1 < N, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf,
-                                            P.radius_sq, best, lane);
+                        double xa, ya, xb, yb;
+                        pair_at(kb, xa, ya, xb, yb);
+                        best = collide_pair(xa, ya, xb, yb, k0 < N, k0 + 1 < N, min(2 * kWarp, N - kb), obs, obsf, B.n_obs, Rf, P.radius_sq, best,
+                                            lane);
                     }
                 } else {
                     for (int j = 0; j < nm; ++j) {
@@ -1398,9 +1441,9 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
                         bool hit = false;
                         for (int kb = 0; kb < N; kb += 2 * kWarp) {
                             const int k0 = kb + 2 * lane;
-                            const int kk = k0 < npad ? k0 : kb;
-                            const double2 xv = *reinterpret_cast<const double2*>(xs + kk), yv = *reinterpret_cast<const double2*>(ys + kk);
-                            const double dxa = xv.x - ob.x, dya = yv.x - ob.y, dxb = xv.y - ob.x, dyb = yv.y - ob.y;
+                            double xa, ya, xb, yb;
+                            pair_at(kb, xa, ya, xb, yb);
+                            const double dxa = xa - ob.x, dya = ya - ob.y, dxb = xb - ob.x, dyb = yb - ob.y;
                             hit |= (k0 < N && (__dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya)) <= P.radius_sq)) ||
                                    (k0 + 1 < N && (__dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb)) <= P.radius_sq));
                         }
@@ -1475,6 +1518,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
     const double dt = P.sample_period;
     const double s0 = B.state[(int64_t)b * 6 + 3];
     const double* lane_q = (kXY && B.lane_params) ? B.lane_params + 4 * (int64_t)b : nullptr;
+    if (skipped(B, b)) return;
+    const bool follow = follow_of(P, B, b);
 
     // Phase 0: lateral coefficients of the whole group, lateral axis, obstacles, spline table.
     {
@@ -1546,7 +1591,7 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             double s_last, v_last, a_last, j_last;
             eval_power_form(pl, (double)(A.N - 1) * dt, L.t_pow + 4 * (A.N - 1), s_last, v_last, a_last, j_last);
             double term;
-            if (P.follow) {
+            if (follow) {
                 const double e = s_last - B.target[((int64_t)b * L.n_t + A.iT) * 3];
                 term = __dmul_rn(P.ks, __dmul_rn(e, e));
             } else {
@@ -1661,8 +1706,8 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             const double e = axd[id] - dd_target;
             const double clat = __dadd_rn(__dadd_rn(__dmul_rn(P.kj, acc), __dmul_rn(P.kt, horizon)), __dmul_rn(P.kd, __dmul_rn(e, e)));
             resc[c * 4] = clat;
-            resc[c * 4 + 1] = P.follow ? 0.0 : clong;
-            resc[c * 4 + 2] = P.follow ? clong : 0.0;
+            resc[c * 4 + 1] = follow ? 0.0 : clong;
+            resc[c * 4 + 2] = follow ? clong : 0.0;
             resc[c * 4 + 3] = __dadd_rn(__dmul_rn(P.klat, clat), __dmul_rn(P.klong, clong));
             const bool kin = kLimits ? (rowi[4 * g + 3] && amax <= P.a_max) : true;
             resi[c * 2] = FRENET_CAND_VALID | (kin ? FRENET_CAND_KINEMATIC_OK : 0) | (curv_bad ? 0 : kCurvOkBit);
@@ -1963,9 +2008,10 @@ __global__ void __launch_bounds__(256) predict_obstacles(FrenetPath path, const 
 
 // replan_ctot's bookkeeping on the device (trajectory_planner.py:183-195, 206-212, 120), one thread per scenario.
 __global__ void __launch_bounds__(128) advance_state(FrenetLattice L, FrenetBuffers B, const double* __restrict__ time, int64_t time_stride,
-                                                     double lookup_period, double q, int num_sample, int32_t* __restrict__ status) {
+                                                     double lookup_period, double q, int num_sample, int follow_all, int32_t* __restrict__ status) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= L.n_scen) return;
+    if (skipped(B, b)) return;
     const int n = B.winner_steps[b];
     if (n <= 0) {
         if (status) status[b] = 1;
@@ -1990,7 +2036,9 @@ __global__ void __launch_bounds__(128) advance_state(FrenetLattice L, FrenetBuff
     st[5] = w[7 * npm + k];                                                       // s, ds, dds
     const_cast<double*>(B.scal)[(int64_t)b * 3 + 2] = t;
     // np.arange(round(ds0 - q n), round(ds0 + q n + q), q): length ceil((stop - start) / step), values start + i * ((start + step) - start)
-    const double lo = rint(ds0 - q * num_sample), hi = rint(ds0 + q * num_sample + q);
+    // follow mode: the axis holds the target OFFSETS of si_interval, centred on 0 (trajectory_planner.py:119)
+    const double centre = (B.follow ? B.follow[b] != 0 : follow_all != 0) ? 0.0 : ds0;
+    const double lo = rint(centre - q * num_sample), hi = rint(centre + q * num_sample + q);
     int nv = (int)ceil((hi - lo) / q);
     const bool axis_overflow = nv > L.n_v_cap;      // the host path raises here; reported as status 2 (the axis is truncated)
     nv = min(max(nv, 0), L.n_v_cap);
@@ -2135,6 +2183,177 @@ __global__ void __launch_bounds__(128) sim_control_step(const double* __restrict
     p[2] += dt * vt;
 }
 
+// trajectory.compute_second_derivative as the host classes give it: the circle's is the DIFFERENCE of two forward-chord first
+// derivatives h = 1e-5 apart, not divided by h (circle_trajectory.py:74-78); the spline's is calcdd per coordinate, which like
+// calc / calcd returns the knot abscissa outside the knot range (spline_trajectory.py:75-88, 161-164).
+__device__ __forceinline__ void path_second_derivative(int kind, const double* __restrict__ c, const double* __restrict__ tab, int n, double t,
+                                                       double& ax, double& ay) {
+    if (kind == FRENET_PATH_CIRCLE) {
+        const double h = 1e-5;
+        double px, py, g1x, g1y, g0x, g0y;
+        path_pt_grad(kind, c, tab, n, t + h / 2, px, py, g1x, g1y);
+        path_pt_grad(kind, c, tab, n, t - h / 2, px, py, g0x, g0y);
+        ax = g1x - g0x;
+        ay = g1y - g0y;
+        return;
+    }
+    if (kind == FRENET_PATH_PARABOLA) {   // d2/dx2 (x, a x^2 + b x + c)
+        ax = 0.0;
+        ay = 2.0 * c[0];
+        return;
+    }
+    const double first = tab[0], last = tab[(n - 1) * 9];
+    if (t < first) { ax = ay = first; return; }
+    if (t >= last) { ax = ay = last; return; }
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid * 9] <= t) lo = mid; else hi = mid;
+    }
+    const double* q = tab + lo * 9;
+    const double u = t - q[0];
+    ax = 2.0 * q[3] + 6.0 * q[4] * u;
+    ay = 2.0 * q[7] + 6.0 * q[8] * u;
+}
+
+// Follow-mode target triples of V1 (trajectory_planner.py:131-136) for every (scenario in follow mode, horizon), on the device:
+//   time = t_initial + T;   st = s0 + tgt.compute_s(time) - d_target + delta_t * tgt.compute_ds(time)
+//   dst = ds0 + tgt.compute_ds(time) - delta_t * tgt.compute_dds(time);   ddst = dds0 + tgt.compute_dds(time)
+// with tgt = ObstacleTrajectory of the scenario's leading obstacle (lib/sensor/dynamic_obstacle.py:43-77): compute_s is the first
+// component of the live transformer's `transform` of the obstacle's point at the time law, compute_ds / compute_dds the same of the
+// PATH's first / second derivative at parameter `time` (sic).  The transformer is the robot's projection frame
+// (FrenetGNTransformOld.estimatePosition, gn_transform_old.py:18-56), rebuilt here from the projection's arc length `estimate`.
+__global__ void __launch_bounds__(128) follow_targets(FrenetPath path, FrenetLattice L, FrenetBuffers B, const int32_t* __restrict__ lead,
+                                                      const double* __restrict__ obs_s, const double* __restrict__ obs_d,
+                                                      const double* __restrict__ obs_speed, int O, const double* __restrict__ estimate,
+                                                      double delta_t, double d_target, const uint8_t* __restrict__ only, double* __restrict__ target) {
+    extern __shared__ __align__(16) double tab[];
+    if (path.kind == FRENET_PATH_SPLINE) {
+        for (int i = threadIdx.x; i < path.n_knots * 9; i += blockDim.x) tab[i] = path.spline_table[i];
+        __syncthreads();
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n_scen * L.n_t) return;
+    const int b = i / L.n_t, iT = i % L.n_t;
+    if ((only && !only[b]) || !(B.follow && B.follow[b])) return;
+    const int o = lead[b];
+    if (o < 0 || o >= O) return;
+    const int64_t bo = (int64_t)b * O + o;
+    const double time = __dadd_rn(B.scal[(int64_t)b * 3 + 2], L.axis_t[iT]);
+    double wrapped = fmod(__dmul_rn(time, obs_speed[bo]), 50.0);
+    if (wrapped < 0.0) wrapped += 50.0;
+    const double tau = __dadd_rn(obs_s[bo], wrapped);
+    double px, py, nx, ny;
+    path_frame(path.kind, path.circle, tab, path.n_knots, tau, px, py, nx, ny);
+    const double ox = __dadd_rn(px, __dmul_rn(nx, obs_d[bo])), oy = __dadd_rn(py, __dmul_rn(ny, obs_d[bo]));
+    // the transformer's frame: point and heading of the path at the robot's projection
+    double tx, ty, gx, gy;
+    path_pt_grad(path.kind, path.circle, tab, path.n_knots, estimate[b], tx, ty, gx, gy);
+    double sn, cs;
+    sincos(atan2(gy, gx), &sn, &cs);
+    const double anchor = __dadd_rn(__dmul_rn(cs, tx), __dmul_rn(sn, ty));           // (R^T t)[0]
+    auto along = [&](double x, double y) { return __dadd_rn(__dadd_rn(__dmul_rn(cs, x), __dmul_rn(sn, y)), -anchor); };   // (R^T p - R^T t)[0]
+    const double c_s = along(ox, oy);
+    double qx, qy, d1x, d1y, d2x, d2y;
+    path_pt_grad(path.kind, path.circle, tab, path.n_knots, time, qx, qy, d1x, d1y);
+    path_second_derivative(path.kind, path.circle, tab, path.n_knots, time, d2x, d2y);
+    const double c_ds = along(d1x, d1y), c_dds = along(d2x, d2y);
+    const double* st = B.state + (int64_t)b * 6;
+    double* out = target + ((int64_t)b * L.n_t + iT) * 3;
+    out[0] = __dadd_rn(__dadd_rn(__dadd_rn(st[3], c_s), -d_target), __dmul_rn(delta_t, c_ds));
+    out[1] = __dadd_rn(__dadd_rn(st[4], c_ds), -__dmul_rn(delta_t, c_dds));
+    out[2] = __dadd_rn(st[5], c_dds);
+}
+
+// The all-blocked branch of the moving-obstacle driver (lib/tests/test_moving_obstacle_planner.py:92-97) for a batch: a scenario
+// whose candidates ALL collide switches to follow mode behind leading_obstacles[0] - the first blocker of its first candidate -
+// and is marked for the re-plan (`redo`); its longitudinal axis becomes si_interval.  Scenarios with survivors get redo = 0.
+__global__ void __launch_bounds__(128) follow_select(FrenetLattice L, FrenetBuffers B, double q, int num_sample, int32_t* __restrict__ lead,
+                                                     uint8_t* __restrict__ follow, uint8_t* __restrict__ redo) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.n_scen) return;
+    const FrenetResult r = B.result[b];
+    const bool blocked = r.n_valid > 0 && r.n_survivors == 0;
+    redo[b] = blocked ? 1 : 0;
+    if (!blocked) return;
+    const int64_t C = (int64_t)L.n_v_cap * L.n_t * L.n_d;
+    int first = -1;
+    for (int64_t c = 0; c < C && first < 0; ++c)
+        if (B.cand_flags[b * C + c] & FRENET_CAND_VALID) first = B.first_blocker[b * C + c];
+    if (first < 0) {   // blocked by another filter than the obstacles: nobody to follow
+        redo[b] = 0;
+        return;
+    }
+    lead[b] = first;
+    follow[b] = 1;
+    const double lo = rint(-q * num_sample), hi = rint(q * num_sample + q);
+    int nv = (int)ceil((hi - lo) / q);
+    nv = min(max(nv, 0), L.n_v_cap);
+    const double delta = (lo + q) - lo;
+    double* av = const_cast<double*>(L.axis_v) + (int64_t)b * L.n_v_cap;
+    for (int i = 0; i < L.n_v_cap; ++i) av[i] = lo + (double)i * delta;
+    const_cast<int32_t*>(L.n_v)[b] = nv;
+}
+
+// Sampled targets of the Optimal variant (lib/optimal_frenet_frame/target.py:17-52) for a batch: the leading vehicle's quintic
+// through (s0_t, s1_t) over Ts, sampled every DTs, turned into a follow / merge / stop target, then indexed at
+// round((t_initial + T - 0) / delta_t) like trajectory_planner_optimal.py:130-133.  spec [n_scen][16]:
+// s0[3], s1[3], Ts, DTs, mode (0 plain, 1 follow, 2 merge, 3 stop), D0, second target s0[3], s1[3] (merge).
+// status[b]: 0 ok, 1 index outside the sampled target (the reference raises IndexError), 2 stop target not at rest (it asserts).
+__device__ __forceinline__ void quintic_at(const double a[6], double t, double v[4]) {
+    Poly p;
+    p.load(a);
+    const double tp[4] = {pow(t, 2.0), pow(t, 3.0), pow(t, 4.0), pow(t, 5.0)};
+    eval_power_form(p, t, tp, v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(128) optimal_targets(FrenetLattice L, FrenetBuffers B, const double* __restrict__ spec, double delta_t,
+                                                       double* __restrict__ target, int32_t* __restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n_scen * L.n_t) return;
+    const int b = i / L.n_t, iT = i % L.n_t;
+    if (skipped(B, b)) return;
+    const double* q = spec + 16 * (int64_t)b;
+    const double Ts = q[6], DTs = q[7];
+    const int mode = (int)q[8];
+    double a[6], a2[6];
+    quintic_bvp(q[0], q[1], q[2], q[3], q[4], q[5], Ts, a);
+    const int n = (int)ceil((Ts + DTs) / DTs);        // len(np.arange(0, Ts + DTs, DTs))
+    const int k = (int)rint((B.scal[(int64_t)b * 3 + 2] + L.axis_t[iT]) / delta_t);
+    int st = 0;
+    int kk = k < 0 ? k + n : k;                       // a negative index wraps like a Python list
+    if (kk < 0 || kk >= n) { st = 1; kk = min(max(kk, 0), n - 1); }
+    double v[4];
+    quintic_at(a, (double)kk * DTs, v);
+    double s = v[0], ds = v[1], dds = v[2];
+    if (mode == 1) {          // get_frenet_follow_target
+        bool constant_acc = true;
+        double v0[4], vj[4];
+        quintic_at(a, 0.0, v0);
+        for (int j = 1; j < n && constant_acc; ++j) {
+            quintic_at(a, (double)j * DTs, vj);
+            constant_acc = vj[2] == v0[2];
+        }
+        s = __dadd_rn(__dadd_rn(v[0], -q[9]), __dmul_rn(DTs, v[1]));
+        ds = __dadd_rn(v[1], -__dmul_rn(DTs, v[2]));
+        if (!constant_acc) dds = __dadd_rn(v[2], -__dmul_rn(DTs, v[3]));
+    } else if (mode == 2) {   // get_frenet_merge_target
+        quintic_bvp(q[10], q[11], q[12], q[13], q[14], q[15], Ts, a2);
+        double w[4];
+        quintic_at(a2, (double)kk * DTs, w);
+        s = __dmul_rn(0.5, __dadd_rn(v[0], w[0]));
+    } else if (mode == 3) {   // get_frenet_stop_target asserts the target ends at rest
+        double e[4];
+        quintic_at(a, (double)(n - 1) * DTs, e);
+        if (!(e[1] == 0.0 && e[2] == 0.0)) st = 2;
+    }
+    double* out = target + ((int64_t)b * L.n_t + iT) * 3;
+    out[0] = s;
+    out[1] = ds;
+    out[2] = dds;
+    if (status && st != 0) atomicMax(status + b, st);   // (the caller clears status first)
+}
+
 // Cone gate of the proximity sensor (lib/sensor/proximity_sensor.py:41-75), one thread per (scenario, obstacle).
 __global__ void __launch_bounds__(256) sensor_gate(const double* __restrict__ pose, const double* __restrict__ obs_xy, int n_scen, int O,
                                                    double range, double aperture, uint8_t* __restrict__ active) {
@@ -2219,6 +2438,28 @@ __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetP
     const double t0 = B.scal[(int64_t)b * 3 + 2];
     const double* cand = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad);
     const double* lon = B.lon + A.lon_off;
+    if (L.lat_f32) {
+        // fp32 fast path: the winner's lateral samples become the next replan's initial state, so they are re-evaluated in fp64 from
+        // the candidate's coefficients (same synthetic division, same argument as the evaluate kernel); x, y come from the floats
+        const float* candf = reinterpret_cast<const float*>(B.lat) + A.cand_off + (int64_t)id * (kCandFields * A.npad);
+        Poly pq;
+        pq.load(B.coef_lat + ((int64_t)b * L.n_v_cap * L.n_t * L.n_d + c) * 6);
+        const bool low = B.row_flags[(int64_t)b * L.n_v_cap * L.n_t + r] & FRENET_ROW_LOWSPEED;
+        const double s0 = B.state[(int64_t)b * 6 + 3];
+        for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
+            w[k] = (double)k * P.sample_period + t0;
+            const double u = low ? fabs(lon[k] - s0) : (double)k * P.sample_period;
+            double v0, v1, v2, v3;
+            pq.eval(u, v0, v1, v2, v3);
+            w[1 * L.n_pad_max + k] = v0; w[2 * L.n_pad_max + k] = v1; w[3 * L.n_pad_max + k] = v2; w[4 * L.n_pad_max + k] = v3;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) w[(5 + f) * L.n_pad_max + k] = lon[f * A.npad + k];
+            if (has_xy) {
+                w[9 * L.n_pad_max + k] = (double)candf[4 * A.npad + k];
+                w[10 * L.n_pad_max + k] = (double)candf[5 * A.npad + k];
+            }
+        }
+    } else
     for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
         w[k] = (double)k * P.sample_period + t0;   // f.t[i] += t_initial (:178-179)
 #pragma unroll
@@ -2251,6 +2492,7 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
     const int64_t base = (int64_t)b * C;
     const int64_t candF = (int64_t)L.n_scen * C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (skipped(B, b)) return;
 
     Best best[kKeys];
 #pragma unroll
@@ -2346,6 +2588,7 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
 // Winner gather: the sampled state optimal_at_time indexes (trajectory_planner.py:183-195), 11 rows + a cost row.
 __global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetParams P, FrenetBuffers B, int sel, int has_xy) {
     const int b = blockIdx.x;
+    if (skipped(B, b)) return;
     gather_one(L, P, B, b, winner_index(B.result[b], sel), has_xy);
 }
 
@@ -2358,8 +2601,9 @@ int check_lattice(const FrenetLattice* L) {
         return fail(FRENET_ERR_BAD_ARG, "lattice sizes must be positive");
     if (!L->axis_d || !L->axis_t || !L->n_steps || !L->t_offset || !L->t_pow || !L->axis_v || !L->n_v)
         return fail(FRENET_ERR_BAD_ARG, "lattice axis pointer is NULL");
-    if (L->row_elems <= 0 || L->cand_elems != L->row_elems * L->n_d || (L->row_elems & 3))
+    if (L->row_elems <= 0 || L->cand_elems != L->row_elems * L->n_d || (L->row_elems & (L->lat_f32 ? 7 : 3)))
         return fail(FRENET_ERR_BAD_ARG, "inconsistent lattice strides");
+    if (L->lat_f32 != 0 && L->lat_f32 != 1) return fail(FRENET_ERR_BAD_ARG, "lat_f32 must be 0 or 1");
     if ((int64_t)L->n_scen * L->n_v_cap * L->n_t > 0x7fffffffLL)
         return fail(FRENET_ERR_BAD_ARG, "too many rows for one launch");
     return FRENET_OK;
@@ -2454,6 +2698,7 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     float radius_up = (float)sqrt(P->radius_sq);
     while ((double)radius_up * (double)radius_up < P->radius_sq) radius_up = nextafterf(radius_up, INFINITY);
     radius_up = nextafterf(radius_up, INFINITY);
+    if (!S.pair && L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "fp32 fast path: lattices of at most 32 padded samples are not supported");
     if (!S.pair) {
 #define FRENET_LAUNCH_SHORT(LIM)                                                                                             \
     do {                                                                                                                     \
@@ -2464,6 +2709,22 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
         else FRENET_LAUNCH_SHORT(false);
 #undef FRENET_LAUNCH_SHORT
         FRENET_CHECK_LAUNCH("k2_short");
+        return FRENET_OK;
+    }
+    if (L->lat_f32) {
+        // fp32 fast path: the fused long-horizon kernel only (the batched dense-lattice workload it is meant for)
+        if (!kXY || kColl == 2) return fail(FRENET_ERR_BAD_ARG, "fp32 fast path: only the fused K2+K3(+K4 snapshot) kernel stores floats");
+        if constexpr (kXY && kColl != 2) {
+            const dim3 grid1(S.grid, 1);
+            if (limits) {
+                if (int rc = set_smem(k2_evaluate<true, kColl, true, false, true>, S.smem, "k2: row does not fit shared memory")) return rc;
+                k2_evaluate<true, kColl, true, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up);
+            } else {
+                if (int rc = set_smem(k2_evaluate<true, kColl, false, false, true>, S.smem, "k2: row does not fit shared memory")) return rc;
+                k2_evaluate<true, kColl, false, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up);
+            }
+            FRENET_CHECK_LAUNCH("k2_evaluate (fp32 fast path)");
+        }
         return FRENET_OK;
     }
     const dim3 grid(S.grid, S.parts);
@@ -2486,7 +2747,7 @@ int check_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers*
     if (!P || !B || !B->state || !B->scal || !B->coef_lon || !B->coef_lat || !B->row_S || !B->row_flags || !B->lon || !B->lat ||
         !B->cost || !B->cand_flags)
         return fail(FRENET_ERR_BAD_ARG, "k2: NULL buffer");
-    if (P->follow && !B->target) return fail(FRENET_ERR_BAD_ARG, "k2: follow mode needs target triples");
+    if ((P->follow || B->follow) && !B->target) return fail(FRENET_ERR_BAD_ARG, "k2: follow mode needs target triples");
     return FRENET_OK;
 }
 
@@ -2529,7 +2790,7 @@ int frenet_k1_coefficients(const FrenetLattice* L, const FrenetParams* P, const 
     if (int rc = check_lattice(L)) return rc;
     if (!P || !B || !B->state || !B->coef_lon || !B->coef_lat || !B->row_S || !B->row_flags)
         return fail(FRENET_ERR_BAD_ARG, "k1: NULL buffer");
-    if (P->follow && !B->target) return fail(FRENET_ERR_BAD_ARG, "k1: follow mode needs target triples");
+    if ((P->follow || B->follow) && !B->target) return fail(FRENET_ERR_BAD_ARG, "k1: follow mode needs target triples");
     const int64_t total = (int64_t)L->n_scen * L->n_v_cap * L->n_t * L->n_d;
     const int64_t blocks = (total + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(FRENET_ERR_BAD_ARG, "k1: too many candidates for one launch");
@@ -2565,6 +2826,7 @@ int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const Fre
     if (int rc = check_lattice(L)) return rc;
     if (int rc = check_path(path)) return rc;
     if (!B || !B->row_flags || !B->lon || !B->lat) return fail(FRENET_ERR_BAD_ARG, "k3: NULL buffer");
+    if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "k3: the standalone kernels read fp64 candidate blocks (fp32 fast path: use frenet_plan / frenet_k2_fused)");
     const size_t smem = ((size_t)4 * L->n_pad_max + (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0)) * sizeof(double);
     if (int rc = set_smem(k3_cartesian, smem, "k3: horizon / spline table too large for shared memory")) return rc;
     int parts = 1;
@@ -2577,6 +2839,7 @@ int frenet_k3_cartesian(const FrenetLattice* L, const FrenetParams* P, const Fre
 int frenet_k3_curvature(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
     if (!P || !B || !B->row_flags || !B->lat || !B->curv_ok) return fail(FRENET_ERR_BAD_ARG, "curvature: NULL buffer");
+    if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "curvature: the standalone kernels read fp64 candidate blocks (fp32 fast path: use frenet_plan / frenet_k2_fused)");
     k3_curvature<<<n_rows(L), kRowThreads, 0, (cudaStream_t)stream>>>(*L, *P, *B);
     FRENET_CHECK_LAUNCH("k3_curvature");
     return FRENET_OK;
@@ -2585,6 +2848,7 @@ int frenet_k3_curvature(const FrenetLattice* L, const FrenetParams* P, const Fre
 int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
     if (!P || !B || !B->row_flags || !B->lat || !B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "k4: NULL buffer");
+    if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "k4: the standalone kernels read fp64 candidate blocks (fp32 fast path: use frenet_plan / frenet_k2_fused)");
     if (B->n_obs < 0 || B->n_obs_steps < 0) return fail(FRENET_ERR_BAD_ARG, "k4: negative obstacle count");
     if (B->n_obs_steps > 0 && B->n_obs > 0) {   // predicted table
         const int n_chunks = (L->n_pad_max + kWarp - 1) / kWarp;
@@ -2611,6 +2875,7 @@ int frenet_k3_offroad(const FrenetLattice* L, const FrenetRoad* road, const Fren
     static const FrenetRoad no_road = {};
     if (!road) road = &no_road;        // per-scenario boundaries come from buf->road_params
     if (!B->lat || !B->road_ok || !B->row_flags) return fail(FRENET_ERR_BAD_ARG, "k3_offroad: lat, road_ok and row_flags are required");
+    if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "k3_offroad: the standalone kernels read fp64 candidate blocks (fp32 fast path: use frenet_plan / frenet_k2_fused)");
     if (n_rows(L) == 0) return FRENET_OK;
     k3_offroad<<<n_rows(L), kRowThreads, 0, (cudaStream_t)stream>>>(*L, *road, *B);
     FRENET_CHECK_LAUNCH("k3_offroad");
@@ -2680,13 +2945,51 @@ int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const 
 }
 
 int frenet_advance_state(const FrenetLattice* L, const FrenetBuffers* B, const double* time, int64_t time_stride, double lookup_period,
-                         double d_d_s, int32_t num_sample, int32_t* status, frenet_stream_t stream) {
+                         double d_d_s, int32_t num_sample, int32_t follow, int32_t* status, frenet_stream_t stream) {
     if (int rc = check_lattice(L)) return rc;
     if (!B || !B->winner || !B->winner_steps || !B->state || !B->scal || !time) return fail(FRENET_ERR_BAD_ARG, "advance: NULL buffer");
     if (!(lookup_period > 0.0) || !(d_d_s > 0.0) || num_sample < 0) return fail(FRENET_ERR_BAD_ARG, "advance: bad interval parameters");
     advance_state<<<(L->n_scen + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*L, *B, time, time_stride, lookup_period, d_d_s, num_sample,
-                                                                             status);
+                                                                             follow, status);
     FRENET_CHECK_LAUNCH("advance_state");
+    return FRENET_OK;
+}
+
+int frenet_follow_targets(const FrenetPath* path, const FrenetLattice* L, const FrenetBuffers* B, const int32_t* lead, const double* obs_s,
+                          const double* obs_d, const double* obs_speed, int32_t n_obs, const double* estimate, double delta_t, double d_target,
+                          const uint8_t* only, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (int rc = check_path(path)) return rc;
+    if (!B || !B->state || !B->scal || !B->target || !B->follow || !lead || !obs_s || !obs_d || !obs_speed || !estimate || n_obs <= 0)
+        return fail(FRENET_ERR_BAD_ARG, "follow targets: NULL buffer");
+    const size_t smem = (path->kind == FRENET_PATH_SPLINE ? (size_t)9 * path->n_knots : 0) * sizeof(double);
+    if (int rc = set_smem(follow_targets, smem, "follow targets: spline table too large for shared memory")) return rc;
+    const int64_t n = (int64_t)L->n_scen * L->n_t;
+    follow_targets<<<(unsigned)((n + 127) / 128), 128, smem, (cudaStream_t)stream>>>(*path, *L, *B, lead, obs_s, obs_d, obs_speed, n_obs, estimate,
+                                                                                    delta_t, d_target, only, const_cast<double*>(B->target));
+    FRENET_CHECK_LAUNCH("follow_targets");
+    return FRENET_OK;
+}
+
+int frenet_follow_select(const FrenetLattice* L, const FrenetBuffers* B, double d_d_s, int32_t num_sample, int32_t* lead, uint8_t* follow,
+                         uint8_t* redo, frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!B || !B->result || !B->cand_flags || !B->first_blocker || !lead || !follow || !redo)
+        return fail(FRENET_ERR_BAD_ARG, "follow select: NULL buffer");
+    if (!(d_d_s > 0.0) || num_sample < 0) return fail(FRENET_ERR_BAD_ARG, "follow select: bad interval parameters");
+    follow_select<<<(L->n_scen + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*L, *B, d_d_s, num_sample, lead, follow, redo);
+    FRENET_CHECK_LAUNCH("follow_select");
+    return FRENET_OK;
+}
+
+int frenet_optimal_targets(const FrenetLattice* L, const FrenetBuffers* B, const double* spec, double delta_t, int32_t* status,
+                           frenet_stream_t stream) {
+    if (int rc = check_lattice(L)) return rc;
+    if (!B || !B->scal || !B->target || !spec) return fail(FRENET_ERR_BAD_ARG, "optimal targets: NULL buffer");
+    if (!(delta_t > 0.0)) return fail(FRENET_ERR_BAD_ARG, "optimal targets: delta_t must be positive");
+    const int64_t n = (int64_t)L->n_scen * L->n_t;
+    optimal_targets<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*L, *B, spec, delta_t, const_cast<double*>(B->target), status);
+    FRENET_CHECK_LAUNCH("optimal_targets");
     return FRENET_OK;
 }
 
@@ -2756,7 +3059,7 @@ int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const do
 int frenet_workspace_bytes(const FrenetLattice* L, int32_t n_obs, int32_t n_obs_steps, FrenetSizes* out) {
     if (!out) return fail(FRENET_ERR_BAD_ARG, "workspace: output is NULL");
     if (!L || L->n_scen <= 0 || L->n_v_cap <= 0 || L->n_t <= 0 || L->n_d <= 0 || L->n_pad_max <= 0 || L->row_elems <= 0 ||
-        L->cand_elems != L->row_elems * L->n_d || (L->row_elems & 3) || n_obs < 0 || n_obs_steps < 0)
+        L->cand_elems != L->row_elems * L->n_d || (L->row_elems & (L->lat_f32 ? 7 : 3)) || n_obs < 0 || n_obs_steps < 0)
         return fail(FRENET_ERR_BAD_ARG, "workspace: inconsistent lattice sizes");
     memset(out, 0, sizeof(*out));
     const int64_t Bn = L->n_scen, R = (int64_t)L->n_v_cap * L->n_t, C = R * L->n_d;
@@ -2781,7 +3084,7 @@ int frenet_workspace_bytes(const FrenetLattice* L, int32_t n_obs, int32_t n_obs_
     out->row_S = Bn * R * 8;
     out->row_flags = Bn * R * 4;
     out->lon = Bn * L->row_elems * kLonFields * 8;
-    out->lat = Bn * L->cand_elems * kCandFields * 8;
+    out->lat = Bn * L->cand_elems * kCandFields * (L->lat_f32 ? 4 : 8);
     out->cost = 4 * Bn * C * 8;
     out->cand_flags = Bn * C;
     out->curv_ok = Bn * C;

@@ -46,12 +46,13 @@ class LatticeGeometry:
     sample k of that array is exactly `k * period`.
     """
 
-    def __init__(self, D, T, period: float):
+    def __init__(self, D, T, period: float, pad: int = PAD_STEPS):
         self.D = np.ascontiguousarray(D, dtype=np.float64)
         self.T = np.ascontiguousarray(T, dtype=np.float64)
         self.period = float(period)
+        self.pad = int(pad)          # 4 doubles = one 32-byte sector; 8 for the fp32 fast path (8 floats)
         self.n_steps = np.array([len(np.arange(0, Tj + period, period)) for Tj in self.T], dtype=np.int32)
-        npad = (self.n_steps + PAD_STEPS - 1) // PAD_STEPS * PAD_STEPS
+        npad = (self.n_steps + self.pad - 1) // self.pad * self.pad
         self.n_pad = npad.astype(np.int32)
         self.t_offset = np.concatenate([[0], np.cumsum(npad)]).astype(np.int32)
         self.n_t, self.n_d = len(self.T), len(self.D)
@@ -60,11 +61,11 @@ class LatticeGeometry:
         # t_k ** n exactly as the reference forms them (Python float pow), k = 0 .. n_pad_max - 1
         self.t_pow = np.array([[float(np.float64(k) * np.float64(self.period)) ** n for n in (2, 3, 4, 5)]
                                for k in range(self.n_pad_max)], dtype=np.float64).reshape(self.n_pad_max, 4)
-        self.key = (self.D.tobytes(), self.T.tobytes(), self.period)
+        self.key = (self.D.tobytes(), self.T.tobytes(), self.period, self.pad)
 
     @staticmethod
-    def from_intervals(di_interval, t_interval, period):
-        return LatticeGeometry(np.arange(*di_interval), np.arange(*t_interval), period)
+    def from_intervals(di_interval, t_interval, period, pad: int = PAD_STEPS):
+        return LatticeGeometry(np.arange(*di_interval), np.arange(*t_interval), period, pad)
 
     def steps_of_candidates(self, n_v: int) -> np.ndarray:
         """Step count of every candidate in list order for an axis of n_v longitudinal targets."""
@@ -154,11 +155,16 @@ class FrenetEngine:
 
     # -- allocation ---------------------------------------------------------------------------
     @_on_device
-    def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0, n_obs_steps: int = 0):
+    def configure(self, geom: LatticeGeometry, n_v_cap: int, n_obs: int = 0, n_obs_steps: int = 0, lat_f32: bool = False):
         """(Re)allocate for a geometry / capacities; cheap when nothing changed.
-        n_obs_steps > 0 additionally allocates a predicted obstacle table [B][n_obs][n_obs_steps][2] (extension)."""
+        n_obs_steps > 0 additionally allocates a predicted obstacle table [B][n_obs][n_obs_steps][2] (extension).
+        lat_f32: fp32 FAST PATH - the candidate blocks (d and its derivatives, x, y) are stored as floats (FrenetLattice.lat_f32);
+        the geometry must then be padded to 8 samples."""
         n_obs, n_obs_steps = int(n_obs), int(n_obs_steps)
-        key = (geom.key, int(n_v_cap), n_obs, n_obs_steps)
+        lat_f32 = bool(lat_f32)
+        if lat_f32 and geom.pad % 8:
+            raise ValueError("the fp32 fast path needs a geometry padded to 8 samples (LatticeGeometry(..., pad=8))")
+        key = (geom.key, int(n_v_cap), n_obs, n_obs_steps, lat_f32)
         if key == self._cap_key:
             return
         dev, Bn = self.device, self.n_scen
@@ -238,7 +244,8 @@ class FrenetEngine:
         self.row_S = torch.empty((Bn, R), **f64)
         self.row_flags = torch.empty((Bn, R), dtype=torch.int32, device=dev)
         self.lon = torch.empty((Bn, row_elems * 4), **f64)     # per row:       [4][npad]  s, ds, dds, ddds
-        self.lat = torch.empty((Bn, cand_elems * 6), **f64)    # per candidate: [6][npad]  d, dd, ddd, dddd, x, y
+        self.lat_f32 = lat_f32
+        self.lat = torch.empty((Bn, cand_elems * 6), dtype=torch.float32 if lat_f32 else torch.float64, device=dev)   # per candidate: [6][npad]  d, dd, ddd, dddd, x, y
         self.cost = torch.empty((4, Bn, Cc), **f64)
         self.cand_flags = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.curv_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
@@ -253,6 +260,7 @@ class FrenetEngine:
 
         L = self.L
         L.n_scen, L.n_v_cap, L.n_t, L.n_d, L.n_pad_max = Bn, self.n_v_cap, nT, nD, geom.n_pad_max
+        L.lat_f32 = 1 if lat_f32 else 0
         L.row_elems, L.cand_elems = row_elems, cand_elems
         L.axis_d, L.axis_t, L.n_steps, L.t_offset, L.t_pow = gp + o_d, gp + o_t, gp + o_n, gp + o_o, gp + o_p
         L.axis_v, L.n_v = ip + offs["axis_v"], ip + offs["n_v"]
@@ -416,9 +424,56 @@ class FrenetEngine:
             o = self._in_offs[name]
             self._in_dev[o:o + sizes[name]].copy_(self._in_host[o:o + sizes[name]], non_blocking=True)
 
+    # -- per-scenario follow mode on the device --------------------------------
+    def enable_follow(self):
+        """Device arrays of the batched follow fallback: per-scenario follow flag (wired into FrenetBuffers.follow), leading
+        obstacle and re-plan mask."""
+        if getattr(self, "follow_dev", None) is None or self.follow_dev.numel() != self.n_scen:
+            self.follow_dev = torch.zeros(self.n_scen, dtype=torch.uint8, device=self.device)
+            self.lead_dev = torch.full((self.n_scen,), -1, dtype=torch.int32, device=self.device)
+            self.redo_dev = torch.zeros(self.n_scen, dtype=torch.uint8, device=self.device)
+        self.B.follow = self.follow_dev.data_ptr()
+        self._graphs.clear()
+
+    def set_scenario_mask(self, mask: "torch.Tensor | None"):
+        """Restrict the next launches to the scenarios with mask[b] != 0 (device uint8 [n_scen]); None = all."""
+        self.B.scen_mask = mask.data_ptr() if mask is not None else None
+
     @_on_device
-    def advance_state(self, time, lookup_period: float, d_d_s: float, num_sample: int):
-        """Device-side replan bookkeeping (frenet_advance_state): next state = gathered winner at `time`, new V axes."""
+    def follow_targets(self, path: "PathHandle", estimate: torch.Tensor, delta_t: float, d_target: float, only: "torch.Tensor | None" = None):
+        """frenet_follow_targets: target triples of the scenarios in follow mode from their leading obstacle's time law (the uploaded
+        `obs_sd` / `obs_speed`), the robot's projection `estimate` (device [n_scen]) and the staged state."""
+        ip = self._in_dev.data_ptr()
+        n = self.n_scen * max(self.n_obs, 1)
+        sd = ip + self._in_offs["obs_sd"]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_follow_targets(C.byref(path.desc), C.byref(self.L), C.byref(self.B), self.lead_dev.data_ptr(), sd, sd + n * 8,
+                                                ip + self._in_offs["obs_speed"], int(self.n_obs), estimate.data_ptr(), float(delta_t),
+                                                float(d_target), only.data_ptr() if only is not None else None, C.c_void_p(stream)))
+
+    @_on_device
+    def follow_select(self, d_d_s: float, num_sample: int):
+        """frenet_follow_select: scenarios without a survivor switch to follow mode behind their first blocker and get redo = 1."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_follow_select(C.byref(self.L), C.byref(self.B), float(d_d_s), int(num_sample), self.lead_dev.data_ptr(),
+                                               self.follow_dev.data_ptr(), self.redo_dev.data_ptr(), C.c_void_p(stream)))
+
+    @_on_device
+    def optimal_targets(self, spec, delta_t: float) -> torch.Tensor:
+        """frenet_optimal_targets: the Optimal variant's sampled follow / merge / stop targets evaluated on the device into the
+        target triples; spec [n_scen][16] (see the header).  Returns the device status array."""
+        sp = torch.as_tensor(np.ascontiguousarray(spec, dtype=np.float64).reshape(self.n_scen, 16)).to(self.device)
+        status = torch.zeros(self.n_scen, dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(nat.lib.frenet_optimal_targets(C.byref(self.L), C.byref(self.B), sp.data_ptr(), float(delta_t), status.data_ptr(),
+                                                 C.c_void_p(stream)))
+        self._opt_spec = sp
+        return status
+
+    @_on_device
+    def advance_state(self, time, lookup_period: float, d_d_s: float, num_sample: int, follow: bool = False):
+        """Device-side replan bookkeeping (frenet_advance_state): next state = gathered winner at `time`, new V axes (the target
+        offsets of si_interval for scenarios in follow mode: `follow`, or per scenario through FrenetBuffers.follow)."""
         if not hasattr(self, "_time_dev") or self._time_dev.numel() != self.n_scen:
             self._time_dev = torch.empty(self.n_scen, dtype=torch.float64, device=self.device)
             self._adv_status = torch.zeros(self.n_scen, dtype=torch.int32, device=self.device)
@@ -428,7 +483,8 @@ class FrenetEngine:
             self._time_dev.copy_(torch.as_tensor(np.ascontiguousarray(time, dtype=np.float64)), non_blocking=True)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(nat.lib.frenet_advance_state(C.byref(self.L), C.byref(self.B), self._time_dev.data_ptr(), 1, float(lookup_period),
-                                               float(d_d_s), int(num_sample), self._adv_status.data_ptr(), C.c_void_p(stream)))
+                                               float(d_d_s), int(num_sample), 1 if follow else 0, self._adv_status.data_ptr(),
+                                               C.c_void_p(stream)))
 
     def device_state(self):
         """(state [B][6], scal [B][3], n_v [B]) as they currently are ON THE DEVICE."""

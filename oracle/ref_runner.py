@@ -58,7 +58,9 @@ def load():
     if REF_DIR not in sys.path:
         sys.path.insert(0, REF_DIR)
     import logging
+    import warnings
     logging.disable(logging.CRITICAL)      # the reference logs every planner step at INFO
+    warnings.filterwarnings("ignore", category=SyntaxWarning)   # its plotting modules carry '\o' / '\d' in ordinary string literals
     from lib.planner import TrajectoryPlannerV1, TrajectoryPlannerParams
     from lib.trajectory import CircleTrajectory2D, SplineTrajectory2D
     from lib.sensor import StaticObstacle

@@ -1174,3 +1174,156 @@ def test_short_horizon_kernel_with_several_rows_per_cta():
             assert_close(f["x"][:, :nmax], np.where(valid, x[:, :nmax], np.nan), GPU_RTOL, f"rows/cta[{b}].x", per_row=True)
             assert np.array_equal(f["first_blocker"], first)
     assert n_ties <= 2
+
+
+def test_batched_follow_fallback_on_the_device_matches_the_reference_driver():
+    """SURVEY section 8f row 4: the all-blocked branch of the moving-obstacle driver (test_moving_obstacle_planner.py:92-97) for a
+    BATCH of agents with no host round trip - follow_select picks `leading_obstacles[0]`, follow_targets evaluates the
+    ObstacleTrajectory's compute_s / compute_ds / compute_dds in the live transformer frame, the blocked agents re-plan in follow
+    mode and stay in it.  Three identical agents must reproduce the recorded reference run (tests/golden/follow_fallback.npz);
+    a fourth one whose obstacle is far away runs in the same batch and must keep its velocity-keeping lattice."""
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200.batch_sim import BatchSimulator
+    from otg_b200.planner import TrajectoryPlannerParams
+    z = golden("follow_fallback")
+    B = 4
+    sim = BatchSimulator(TrajectoryPlannerParams(), Circle(8, 5, 2), B, 1)
+    sim.enable_follow_fallback(np.full((B, 1), 1.0), np.zeros((B, 1)), np.full((B, 1), 0.3))     # time_offset, lateral offset, speed
+    far = np.array([[-40.0, 30.0]])
+
+    def obstacles(i):
+        o = np.repeat(z["obs_xy"][i][None, None, :], B, axis=0)
+        o[3] = far
+        return o
+
+    sim.reset(np.zeros((B, 3)), float(z["time"][0]), obs_xy=obstacles(0), s0=0.5)
+    fired = []
+    for i in range(len(z["time"])):
+        rec = sim.step(float(z["time"][i]), obs_xy=obstacles(i), sync=True)
+        redo = sim.bp.engine.redo_dev.cpu().numpy()
+        follow = sim.bp.engine.follow_dev.cpu().numpy()
+        assert (redo[:3] == z["fired"][i]).all() and redo[3] == 0, i
+        if redo[0]:
+            fired.append(i)
+        # the reference records len(planner.paths): the survivors of check_paths, or - when it fired - the unfiltered follow lattice
+        assert (rec["n_survivors"][:3] == z["ncand"][i]).all(), (i, rec["n_survivors"], z["ncand"][i])
+        assert (rec["argmin_masked"][:3] == z["argmin"][i]).all(), (i, rec["argmin_masked"], z["argmin"][i])
+        assert_close(rec["min_masked_ctot"][:3], np.full(3, z["ctot_min"][i]), GPU_RTOL, f"follow fallback ctot @ {i}")
+        st, _, _ = sim.bp.engine.device_state()
+        assert_close(st[:3, 3:], np.repeat(z["ret_s"][i][None], 3, 0), GPU_RTOL, f"ret_s @ {i}", atol_scale=1.0)
+        assert_close(st[:3, :3], np.repeat(z["ret_p"][i][None], 3, 0), GPU_RTOL, f"ret_p @ {i}", atol_scale=1.0)
+        assert_close(sim.robot_pose()[:3], np.repeat(z["robot_pose"][i][None], 3, 0), 1e-8, f"pose @ {i}", atol_scale=10.0)
+        assert follow[3] == 0 and rec["n_valid"][3] in (320, 384) and rec["status"][3] == nat.STATUS_OK
+        if fired:
+            assert (follow[:3] == 1).all()          # like the reference planner, whose s_target stays set
+    assert fired == np.nonzero(z["fired"])[0].tolist() and len(fired) == 5
+
+
+def test_fp32_fast_path_keeps_the_decisions_and_rounds_only_the_stored_samples():
+    """BASELINE north star: "within 1e-5 relative in fp64, or 1e-3 if an fp32 fast path is offered".  With `lat_f32` the candidate
+    blocks (d, d', d'', d''', x, y) are stored as floats; arithmetic, costs, the collision table and the gathered winner stay
+    fp64.  So: records (argmin, survivors, costs) and the winner's state rows equal the fp64 path's bit for bit, masks and first
+    blockers are identical, and the stored samples agree with the oracle to 1e-3 relative (in fact to fp32 rounding)."""
+    _gpu, nat, _, Spline = _imports()
+    import ctypes as C
+    from otg_b200 import workloads as w
+    from otg_b200.batch import BatchPlanner
+    from otg_b200.planner import TrajectoryPlannerParams
+    sc = w.config5_scenarios()
+    idx = np.r_[0:6, 2000:2004]
+    fs, fd = w.moving_obstacle_frenet(sc["obs_s"][idx], sc["obs_d"][idx], sc["obs_speed"][idx], sc["obs_offset"][idx], sc["t0"][idx, None])
+    spl = Spline(w.SPLINE_WX, w.SPLINE_WY)
+    kw = dict(p0=sc["p0"][idx], s0=sc["s0"][idx], t0=sc["t0"][idx], dd=sc["dd"][idx], obs_s=fs, obs_d=fd)
+    prm = TrajectoryPlannerParams(**w.DENSE_PARAMS)
+    a = BatchPlanner(prm, spl, len(idx), fs.shape[1], "v1")
+    ra = a.plan(**kw)
+    b = BatchPlanner(prm, spl, len(idx), fs.shape[1], "v1", lat_f32=True)
+    rb = b.plan(**kw)
+    assert b.engine.lat.dtype.itemsize == 4 and a.engine.lat.dtype.itemsize == 8
+    assert np.array_equal(ra.records, rb.records)
+    assert np.array_equal(ra.winner_steps, rb.winner_steps)
+    for i in range(len(idx)):
+        n = int(ra.winner_steps[i])
+        assert np.array_equal(ra.winner[i, :9, :n], rb.winner[i, :9, :n])            # t, d.., s..: re-evaluated in fp64 for the winner
+        assert np.array_equal(ra.winner[i, 11, :4], rb.winner[i, 11, :4])
+        assert_close(rb.winner[i, 9:11, :n], ra.winner[i, 9:11, :n], 1e-6, f"f32 winner xy [{i}]", atol_scale=60.0)
+    valid = (a.engine.cand_flags.cpu().numpy() & nat.CAND_VALID) != 0
+    assert np.array_equal(a.engine.cand_flags.cpu().numpy(), b.engine.cand_flags.cpu().numpy())
+    assert np.array_equal(a.engine.coll_free.cpu().numpy()[valid], b.engine.coll_free.cpu().numpy()[valid])
+    assert np.array_equal(a.engine.first_blocker.cpu().numpy()[valid], b.engine.first_blocker.cpu().numpy()[valid])
+    assert np.array_equal(a.engine.cost.cpu().numpy(), b.engine.cost.cpu().numpy(), equal_nan=True)
+    sp_o = fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY)
+    for i in (0, 7):
+        L = fo.generate(_dense_prm(), kw["p0"][i], kw["s0"][i], kw["t0"][i], dd=kw["dd"][i])
+        f = b.engine.padded_fields(b.engine.fetch_scenario(i, with_xy=True, with_collision=False))
+        ref = pack_lattice(L, t_field=False)
+        nmax = ref["d"].shape[1]
+        x, y = fo.lattice_to_cartesian(sp_o, L)
+        valid_k = np.arange(nmax)[None, :] < L.nsteps[:, None]
+        with np.errstate(all="ignore"):
+            arg = np.where(L.low_speed[:, None], np.abs(L.lon[:, 0, :] - kw["s0"][i, 0]), L.t - kw["t0"][i])[L.row_of]
+        for j, name in enumerate(("d", "dot_d", "ddot_d", "dddot_d")):
+            # a float carries 2^-24 of the VALUE; samples that are cancellations additionally the terms' rounding (see the fuzz test)
+            assert_close(f[name][:, :nmax], ref[name], 1e-3, f"f32[{i}].{name}", per_row=True,
+                         extra_atol=256 * np.finfo(float).eps * poly_term_bound(L.clat, arg, j))
+        for name in ("s", "dot_s", "ddot_s", "dddot_s"):
+            assert_close(f[name][:, :nmax], ref[name], GPU_RTOL, f"f32[{i}].{name}", per_row=True)      # longitudinal state stays fp64
+        assert_close(f["x"][:, :nmax], np.where(valid_k, x[:, :nmax], np.nan), 1e-3, f"f32[{i}].x", per_row=True)
+        assert_close(f["y"][:, :nmax], np.where(valid_k, y[:, :nmax], np.nan), 1e-3, f"f32[{i}].y", per_row=True)
+        err = np.nanmax(np.abs(f["x"][:, :nmax] - np.where(valid_k, x[:, :nmax], np.nan)))
+        assert err < 1e-5, err          # metres: fp32 rounding of coordinates below 60 m
+    # what the fast path does not cover fails loudly instead of reading floats as doubles
+    e = b.engine
+    stream = C.c_void_p(0)
+    assert nat.lib.frenet_k3_cartesian(C.byref(e.L), C.byref(b.params), C.byref(b.path.desc), C.byref(e.B), stream) == nat.ERR_BAD_ARG
+    assert nat.lib.frenet_k4_collision(C.byref(e.L), C.byref(b.params), C.byref(e.B), stream) == nat.ERR_BAD_ARG
+    assert nat.lib.frenet_k2_evaluate(C.byref(e.L), C.byref(b.params), C.byref(e.B), stream) == nat.ERR_BAD_ARG
+    with pytest.raises(nat.FrenetError):
+        from otg_b200.trajectory import CircleTrajectory2D
+        BatchPlanner(TrajectoryPlannerParams(), CircleTrajectory2D(8, 5, 2), 4, 0, "v1", lat_f32=True).plan(
+            np.zeros((4, 3)), np.tile([1.0, 2.5, 0.0], (4, 1)), np.full(4, 0.1))
+
+
+def test_optimal_targets_on_the_device():
+    """SURVEY section 8f row 4, Optimal variant: Target.update + get_frenet_follow_target / merge / stop
+    (lib/optimal_frenet_frame/target.py:17-52) and the index look-up of trajectory_planner_optimal.py:130-133 evaluated by
+    frenet_optimal_targets for a batch, against the oracle's restatement (itself pinned to the reference's recorded targets)."""
+    _gpu, nat, *_ = _imports()
+    from otg_b200.engine import FrenetEngine, LatticeGeometry
+    from otg_b200 import lattice as lat
+    prm = fo.OracleParams.defaults("optimal")
+    a = _gpu.planner_attrs(prm)
+    geom = LatticeGeometry.from_intervals(lat.di_interval(a, "optimal"), lat.t_interval(a, "optimal"), prm.delta_t)
+    T = geom.T
+    cases = [  # s0, s1, Ts, mode, D0, second target
+        ((0.0, 2.0, 0.0), (30.0, 2.5, 0.0), 10.0, 0, 0.0, None),
+        ((2.0, 3.0, 0.0), (40.0, 3.0, 0.0), 10.0, 1, 1.0, None),          # follow, constant acceleration 0 ... (checked sample by sample)
+        ((2.0, 3.0, 0.5), (45.0, 1.0, -0.2), 10.0, 1, 1.5, None),         # follow, acceleration not constant: the formal rule
+        ((0.0, 2.0, 0.0), (30.0, 2.0, 0.0), 10.0, 2, 0.0, ((5.0, 2.0, 0.0), (36.0, 2.0, 0.0))),   # merge
+        ((0.0, 3.0, 0.0), (12.0, 0.0, 0.0), 8.0, 3, 0.0, None),           # stop (ends at rest)
+        ((0.0, 3.0, 0.0), (12.0, 0.5, 0.0), 8.0, 3, 0.0, None),           # stop target that does NOT end at rest -> status 2
+    ]
+    B = len(cases)
+    t_init = np.array([0.0, 0.0, 2.5, 5.0, 0.0, 0.0])
+    eng = FrenetEngine(B)
+    eng.configure(geom, 4, 0)
+    eng.scal[:, 2] = t_init
+    eng.upload()
+    spec = np.zeros((B, 16))
+    want = np.zeros((B, geom.n_t, 3))
+    for b, (s0, s1, Ts, mode, D0, second) in enumerate(cases):
+        spec[b, :3], spec[b, 3:6], spec[b, 6], spec[b, 7], spec[b, 8], spec[b, 9] = s0, s1, Ts, 0.1, mode, D0
+        tg = fo.target_frenet(s0, s1, Ts)
+        if mode == 1:
+            tg = fo.follow_target(tg, D0)
+        if mode == 2:
+            spec[b, 10:13], spec[b, 13:16] = second
+            tg = fo.merge_target(tg, fo.target_frenet(second[0], second[1], Ts))
+        want[b] = fo.optimal_target_triples(tg, T, t_init[b], prm.delta_t)
+    status = eng.optimal_targets(spec, prm.delta_t).cpu().numpy()
+    got = eng._in_dev[eng._in_offs["target"]:eng._in_offs["target"] + B * geom.n_t * 24].cpu().numpy().view(np.float64).reshape(B, geom.n_t, 3)
+    assert status.tolist() == [0, 0, 0, 0, 0, 2]
+    assert_close(got, want, GPU_RTOL, "device optimal targets", atol_scale=50.0)
+    eng.scal[:, 2] = 1e6          # far beyond the sampled target: the reference raises IndexError -> status 1
+    eng.upload()
+    assert (eng.optimal_targets(spec, prm.delta_t).cpu().numpy()[:5] == 1).all()

@@ -38,7 +38,8 @@ def test_struct_layouts_match_the_header():
     """Field order of the ctypes mirrors == field order in the header (a silent mismatch would corrupt launches)."""
     text = open(HEADER).read()
     for cname, ctype in (("FrenetParams", nat.FrenetParams), ("FrenetLattice", nat.FrenetLattice), ("FrenetPath", nat.FrenetPath),
-                         ("FrenetResult", nat.FrenetResult), ("FrenetBuffers", nat.FrenetBuffers), ("FrenetRoad", nat.FrenetRoad)):
+                         ("FrenetResult", nat.FrenetResult), ("FrenetBuffers", nat.FrenetBuffers), ("FrenetRoad", nat.FrenetRoad),
+                         ("FrenetSizes", nat.FrenetSizes)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -51,6 +52,42 @@ def test_struct_layouts_match_the_header():
         assert names == [f[0] for f in ctype._fields_], cname
     assert ctypes.sizeof(nat.FrenetResult) == 64
     assert np.dtype(nat.RESULT_DTYPE).itemsize == 64
+
+
+def test_workspace_sizes_and_launch_shape_from_the_abi_alone():
+    """frenet_workspace_bytes / frenet_k2_launch_shape are host-only: a C host sizes every buffer without the Python engine
+    (SURVEY section 8b `frenet_plan_workspace_bytes`).  Checked against the layout rules of the header for BASELINE config 5."""
+    from otg_b200 import lattice as lat, workloads as w
+    from otg_b200.engine import LatticeGeometry
+    from otg_b200.planner import TrajectoryPlannerParams
+    p = TrajectoryPlannerParams(**w.DENSE_PARAMS)
+    for pad, f32 in ((4, 0), (8, 1)):
+        g = LatticeGeometry.from_intervals(lat.di_interval(p, "v1"), lat.t_interval(p, "v1"), p.delta_t, pad)
+        L = nat.FrenetLattice()
+        L.n_scen, L.n_v_cap, L.n_t, L.n_d, L.n_pad_max, L.lat_f32 = 512, 7, g.n_t, g.n_d, g.n_pad_max, f32
+        L.row_elems = 7 * g.sum_pad
+        L.cand_elems = L.row_elems * g.n_d
+        sz = nat.FrenetSizes()
+        assert nat.lib.frenet_workspace_bytes(ctypes.byref(L), 128, 0, ctypes.byref(sz)) == nat.OK
+        R, Cc = 7 * g.n_t, 7 * g.n_t * g.n_d
+        assert (sz.rows, sz.candidates) == (512 * R, 512 * Cc)
+        assert sz.lat == 512 * L.cand_elems * 6 * (4 if f32 else 8) and sz.lon == 512 * L.row_elems * 4 * 8
+        assert sz.cost == 4 * 512 * Cc * 8 and sz.result == 512 * 64 and sz.winner == 512 * 12 * g.n_pad_max * 8
+        assert sz.obs_xy == 512 * 128 * 16 and sz.obs_xy_t == 0 and sz.coef_lat == 512 * Cc * 48
+        fields = [f[0] for f in nat.FrenetSizes._fields_][2:-1]
+        assert sz.total == sum((getattr(sz, k) + 255) // 256 * 256 for k in fields)
+        assert sz.total < 180e9
+    rows, parts, grid, smem = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
+    path = nat.FrenetPath()
+    path.kind, path.n_knots = nat.PATH_SPLINE, 6
+    assert nat.lib.frenet_k2_launch_shape(ctypes.byref(L), ctypes.byref(path), 128, 0, 1, ctypes.byref(rows), ctypes.byref(parts),
+                                          ctypes.byref(grid), ctypes.byref(smem)) == nat.OK
+    assert rows.value == 1 and parts.value == 1 and grid.value == 512 * 7 * g.n_t and 16 * 1024 < smem.value < 56 * 1024
+    L.n_scen = 1                       # one planner: the rows' candidates are split over several CTAs
+    assert nat.lib.frenet_k2_launch_shape(ctypes.byref(L), ctypes.byref(path), 64, 0, 1, None, ctypes.byref(parts), ctypes.byref(grid), None) == nat.OK
+    assert parts.value > 1 and grid.value == parts.value * 7 * g.n_t
+    L.row_elems += 1
+    assert nat.lib.frenet_workspace_bytes(ctypes.byref(L), 128, 0, ctypes.byref(sz)) == nat.ERR_BAD_ARG
 
 
 def test_calls_fail_cleanly_without_a_device_or_buffers():
