@@ -2447,7 +2447,7 @@ __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetP
         const bool low = B.row_flags[(int64_t)b * L.n_v_cap * L.n_t + r] & FRENET_ROW_LOWSPEED;
         const double s0 = B.state[(int64_t)b * 6 + 3];
         for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
-            w[k] = (double)k * P.sample_period + t0;
+            w[k] = __dadd_rn(__dmul_rn((double)k, P.sample_period), t0);   // two roundings, like the reference's arange()[k] + t_initial
             const double u = low ? fabs(lon[k] - s0) : (double)k * P.sample_period;
             double v0, v1, v2, v3;
             pq.eval(u, v0, v1, v2, v3);
@@ -2461,7 +2461,7 @@ __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetP
         }
     } else
     for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
-        w[k] = (double)k * P.sample_period + t0;   // f.t[i] += t_initial (:178-179)
+        w[k] = __dadd_rn(__dmul_rn((double)k, P.sample_period), t0);   // f.t[i] += t_initial (:178-179): product and sum rounded separately
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
             w[(1 + f) * L.n_pad_max + k] = cand[f * A.npad + k];

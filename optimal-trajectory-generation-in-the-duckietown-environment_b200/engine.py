@@ -121,9 +121,11 @@ def _on_device(fn):
     device, and attribute setting, pinned allocation and graph capture follow it too.  One integer compare when it already is."""
     import functools
 
+    get_device = torch._C._cuda_getDevice      # the bare runtime call: torch.cuda.current_device() adds ~3 us of lazy-init checks per call
+
     @functools.wraps(fn)
     def wrapper(self, *a, **k):
-        if torch.cuda.current_device() == self._dev_index:
+        if get_device() == self._dev_index:
             return fn(self, *a, **k)
         with torch.cuda.device(self._dev_index):
             return fn(self, *a, **k)
