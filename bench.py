@@ -559,7 +559,7 @@ def closed_loop(dev, n_agents=8192, steps=30):
     return out
 
 
-def replan_latency(n_calls=200):
+def replan_latency(n_calls=200, **planner_kw):
     """Metric 2: wall time of ONE replan through the drop-in planner API, host perf_counter around
     the Python calls (H2D of inputs, kernels, D2H of the result record + winner trajectory, Python return).
     Reference figures measured in the survey container (1 CPU thread): 70.6 ms (config 1), ~122 ms (config 2), 14.3 s (dense)."""
@@ -577,7 +577,7 @@ def replan_latency(n_calls=200):
 
     out = {}
     # config 1: default lattice (320 candidates, 5920 cand-ts), planner.replanner only
-    pl = TrajectoryPlannerV1(TrajectoryPlannerParams())
+    pl = TrajectoryPlannerV1(TrajectoryPlannerParams(), **planner_kw)
     pl.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(0.0, 0.0, 0.0))
     ts = []
     for i in range(n_calls + 20):
@@ -592,7 +592,7 @@ def replan_latency(n_calls=200):
     sensor = ProximitySensor(3.5, np.pi / 6)
     sensor.attach(robot)
     sensor.set_obstacle([StaticObstacle(np.array(p)) for p in ([5.0, 0.3], [6.0, -1.0], [4.5, 2.5])])
-    pl = TrajectoryPlannerV1(TrajectoryPlannerParams())
+    pl = TrajectoryPlannerV1(TrajectoryPlannerParams(), **planner_kw)
     pl.initialize(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(3.0, 2.0, 0.0))
     ts = []
     for i in range(n_calls + 20):
@@ -606,7 +606,7 @@ def replan_latency(n_calls=200):
     # config 4: dense lattice (9600 candidates, 954720 cand-ts), spline path, 64 obstacles, one planner
     sc = w.config4_scenario()
     spl = SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY)
-    pl = TrajectoryPlannerV1(TrajectoryPlannerParams(**w.DENSE_PARAMS), _n_obs_cap=64)
+    pl = TrajectoryPlannerV1(TrajectoryPlannerParams(**w.DENSE_PARAMS), _n_obs_cap=64, **planner_kw)
     pl.initialize(t0=sc["t0"], p0=sc["p0"], s0=sc["s0"], dd=sc["dd"])
     eng = pl._engine
     ox, oy = eng.points_to_cartesian(eng.path_handle(spl), sc["obs_s"], sc["obs_d"])
@@ -701,6 +701,19 @@ def run_gpu(args):
     bp.pipeline_wait()
     ms_dev = ev0.elapsed_time(ev1)
     clk = clocks.stop() if clocks else None
+    # N > 1: the same loop WITHOUT the collective, so the line can say how much of the loss against N = 1 is the all-gather and
+    # how much is the spread between the ranks' own GPUs (the job's time is the slowest rank's)
+    ms_own = ms_dev
+    if world > 1:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            bp.launch_pipelined(n_total, gather=False)
+        bp.pipeline_join()
+        ev1.record()
+        barrier()
+        bp.pipeline_wait()
+        ms_own = ev0.elapsed_time(ev1)
     cts_step_local = bp.cand_timesteps()
 
     # ---- end-to-end arm: host buffers through the public API ----
@@ -722,7 +735,14 @@ def run_gpu(args):
     ms_e2e = 1e3 * (time.perf_counter() - t0)
 
     t = torch.tensor([ms_dev, ms_e2e, float(cts_step_local)], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([ms_dev / args.steps, ms_own / args.steps], dtype=torch.float64, device=dev)
+        allr = torch.empty(world * 2, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.cpu().numpy().reshape(world, 2)
+        per_rank = {"ms_per_step_with_gather": [float(v) for v in allr[:, 0]], "ms_per_step_without_gather": [float(v) for v in allr[:, 1]],
+                    "note": "device time of each rank's own timed loop; the job's ms_per_step is the maximum of the first list"}
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone()
@@ -842,7 +862,8 @@ def run_gpu(args):
                 "replan_latency": replan_latency() if (world == 1 and not args.kernels_only) else None,
                 "literal_obstacle_fields": None, "fp32_fast_path": None,
                 "predicted_obstacles": None, "all_feasibility_checks": None, "default_lattice_batch": None, "closed_loop": None,
-                "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))}}
+                "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))},
+                "per_rank": per_rank}
         rec_f64 = np.array(allrec[:hi - lo], copy=True) if world == 1 else None
         if world == 1 and not args.kernels_only:
             del bp

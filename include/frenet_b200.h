@@ -48,7 +48,9 @@
 extern "C" {
 #endif
 
-#define FRENET_B200_ABI_VERSION 2
+#define FRENET_B200_ABI_VERSION 3
+#define FRENET_PARTIAL_BYTES 72   /* one partial argmin record of the one-launch replan (buf->partials) */
+#define FRENET_MAX_ROW_PARTS 8    /* a row is split over at most this many CTAs */
 
 typedef void* frenet_stream_t; /* cudaStream_t */
 
@@ -200,6 +202,14 @@ typedef struct FrenetBuffers {
                                   agents that fell back to following their leading obstacle next to agents that keep their speed */
     const uint8_t* scen_mask;  /* [n_scen] 1 = process this scenario, 0 = leave its outputs untouched (K1, K2 / fused, K5, gather,
                                   frenet_advance_state): the follow re-plan of the blocked scenarios only */
+    /* one-launch replan (ABI 3; optional, NULL = FRENET_STAGE_ONE_LAUNCH unavailable) */
+    int32_t* tickets;          /* [n_scen] scratch, zero before the first launch (the kernel leaves it zero): completion tickets of a
+                                  scenario's CTAs - the CTA that takes the last one finishes the argmin and gathers the winner */
+    double* winner_masked;     /* optional [n_scen][12][n_pad_max]: FRENET_STAGE_ONE_LAUNCH also gathers the MASKED pick here (next to
+                                  the selection `gather_sel` in `winner`), so one launch answers the planner and check_paths */
+    int32_t* winner_masked_steps; /* [n_scen], with winner_masked */
+    void* partials;            /* scratch of n_scen * R * FRENET_MAX_ROW_PARTS * FRENET_PARTIAL_BYTES bytes: every CTA's own partial
+                                  argmin record (frenet_workspace_bytes reports the size as `partials`) */
 } FrenetBuffers;
 
 /* Lane boundaries for frenet_k3_offroad: each a parabola in vertex form (h, k, a) =
@@ -215,7 +225,15 @@ enum {
     FRENET_STAGE_K1 = 1, FRENET_STAGE_K2 = 2, FRENET_STAGE_K3 = 4, FRENET_STAGE_K4 = 8,
     FRENET_STAGE_K5 = 16, FRENET_STAGE_GATHER = 32, FRENET_STAGE_CURVATURE = 64,
     FRENET_STAGE_NO_FUSE = 128, /* launch K2, K3, K4 separately even when frenet_plan could fuse them */
-    FRENET_STAGE_OFFROAD = 256  /* lane-boundary filter from buf->road_params (per scenario), between K4 and K5 */
+    FRENET_STAGE_OFFROAD = 256, /* lane-boundary filter from buf->road_params (per scenario), between K4 and K5 */
+    FRENET_STAGE_ONE_LAUNCH = 512 /* K1 | K2 (| K3 (| K4)) | K5 | GATHER as ONE kernel launch: every CTA of the evaluate kernel solves
+                                     its own rows' boundary-value systems first, and the scenario's last CTA to finish runs the argmin
+                                     and the winner gather (needs buf->tickets).  Same results as the separate launches; meant for a
+                                     single planner, whose replan is a chain of launch latencies.  Not combined with the curvature /
+                                     off-road stages, predicted obstacles, FRENET_STAGE_NO_FUSE or the fp32 fast path.
+                                     Second form: K4 | K5 | GATHER | ONE_LAUNCH (long-horizon lattices, path required) - the collision
+                                     stage alone on a lattice that is already sampled, from the row-level table (no stored sample is
+                                     read back), plus the argmin / gather tail: check_paths on obstacles that arrive after the replan. */
 };
 
 int frenet_abi_version(void);
@@ -367,6 +385,8 @@ typedef struct FrenetSizes {
     int64_t result, winner, winner_steps;
     /* optional per-scenario lane inputs */
     int64_t path_origin, lane_params, road_params;
+    /* optional scratch of FRENET_STAGE_ONE_LAUNCH */
+    int64_t tickets, partials;
     int64_t total;
 } FrenetSizes;
 int frenet_workspace_bytes(const FrenetLattice* lat, int32_t n_obs, int32_t n_obs_steps, FrenetSizes* out);

@@ -13,7 +13,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # OTG_B200_LIB selects another build of the same library (A/B experiments with compile-time tuning knobs)
 LIB_PATH = os.environ.get("OTG_B200_LIB") or os.path.join(_PKG_DIR, "libfrenet_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY = 0, -1, -2, -3
 STATUS_OK, STATUS_NO_FEASIBLE, STATUS_EMPTY = 0, 1, 2
@@ -24,6 +24,8 @@ PATH_CIRCLE, PATH_SPLINE, PATH_PARABOLA = 0, 1, 2
 SEL_CTOT, SEL_CD, SEL_CV, SEL_CT, SEL_MASKED = 0, 1, 2, 3, 4
 STAGE_K1, STAGE_K2, STAGE_K3, STAGE_K4, STAGE_K5, STAGE_GATHER, STAGE_CURVATURE, STAGE_NO_FUSE = 1, 2, 4, 8, 16, 32, 64, 128
 STAGE_OFFROAD = 256
+STAGE_ONE_LAUNCH = 512
+PARTIAL_BYTES, MAX_ROW_PARTS = 72, 8
 FUSE_COLLISION, FUSE_CURVATURE = 1, 2
 MASK_KINEMATIC, MASK_CURVATURE, MASK_COLLISION, MASK_ROAD = 1, 2, 4, 8
 
@@ -72,7 +74,8 @@ class FrenetBuffers(C.Structure):
                 ("winner", C.c_void_p), ("winner_steps", C.c_void_p),
                 ("path_origin", C.c_void_p), ("road_ok", C.c_void_p),
                 ("lane_params", C.c_void_p), ("road_params", C.c_void_p),
-                ("follow", C.c_void_p), ("scen_mask", C.c_void_p)]
+                ("follow", C.c_void_p), ("scen_mask", C.c_void_p), ("tickets", C.c_void_p), ("winner_masked", C.c_void_p),
+                ("winner_masked_steps", C.c_void_p), ("partials", C.c_void_p)]
 
 
 class FrenetSizes(C.Structure):
@@ -82,7 +85,7 @@ class FrenetSizes(C.Structure):
         "obs_xy", "obs_active", "obs_xy_t", "obs_bounds",
         "coef_lon", "coef_lat", "row_S", "row_flags", "lon", "lat", "cost", "cand_flags", "curv_ok", "coll_free", "first_blocker", "road_ok",
         "result", "winner", "winner_steps",
-        "path_origin", "lane_params", "road_params", "total")]
+        "path_origin", "lane_params", "road_params", "tickets", "partials", "total")]
 
 
 class FrenetRoad(C.Structure):

@@ -219,11 +219,12 @@ class BatchPlanner:
         self._place()
         e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
 
-    def launch_pipelined(self, n_total: int | None = None, group=None):
+    def launch_pipelined(self, n_total: int | None = None, group=None, gather: bool = True):
         """One resident step whose results leave the device on a SIDE stream: the D2H copy of records + winners and - with a
         process group - the one collective of the path (all-gather of the 64-byte records over NCCL) run under the next step's
         kernels instead of in front of them.  Two output blocks alternate, so a rank may run one step ahead of the slowest one;
-        `pipeline_wait()` returns the records of the last step enqueued."""
+        `pipeline_wait()` returns the records of the last step enqueued.  gather=False leaves the collective out (this rank's
+        records only) - bench.py uses it to separate the collective's cost from the ranks' own spread."""
         import torch.distributed as dist
         e = self.engine
         if not hasattr(self, "_pipe"):
@@ -238,7 +239,7 @@ class BatchPlanner:
         self.launch_resident()
         ready = torch.cuda.Event()
         ready.record(compute)
-        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        world = dist.get_world_size(group) if (gather and dist.is_available() and dist.is_initialized()) else 1
         side = P["side"]
         side.wait_event(ready)
         with torch.cuda.stream(side):
@@ -257,6 +258,7 @@ class BatchPlanner:
             done.record(side)
         P["done"][slot] = done
         P["last"] = slot
+        P["gathered"] = world > 1
 
     def pipeline_join(self):
         """Make the current stream wait for all side-stream work enqueued so far (for timing the whole pipeline with events)."""
@@ -270,7 +272,7 @@ class BatchPlanner:
         """Records of the last pipelined step: all ranks' (scenario order) with a process group, else this planner's."""
         P = self._pipe
         P["done"][P["last"]].synchronize()
-        if P["ghost"][P["last"]] is not None:
+        if P.get("gathered"):
             return P["ghost"][P["last"]].numpy().view(np.dtype(nat.RESULT_DTYPE))
         return self.engine.result
 

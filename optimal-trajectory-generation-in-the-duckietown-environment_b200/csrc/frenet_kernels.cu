@@ -258,10 +258,9 @@ __device__ __forceinline__ bool skipped(const FrenetBuffers& B, int b) { return 
 // ------------------------------------------------------------------------------------------------
 // K1: candidate generation, one thread per lattice cell (scenario, v, T, d)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+// One lattice cell: the row's longitudinal polynomial (written by the row's first cell) and the cell's lateral quintic.
+__device__ __forceinline__ void k1_cell(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int64_t gid) {
     const int64_t C = (int64_t)L.n_v_cap * L.n_t * L.n_d;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= C * L.n_scen) return;
     const int b = (int)(gid / C);
     const int c = (int)(gid % C);
     const int r = c / L.n_d, id = c % L.n_d;
@@ -318,6 +317,165 @@ __global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetPa
     if (!dropped) quintic_bvp(p0, dp0, ddp0, L.axis_d[id], 0.0, 0.0, low ? S : T, q);   // :160 / :169
 #pragma unroll
     for (int j = 0; j < 6; ++j) cq[j] = q[j];
+}
+
+__global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetParams P, FrenetBuffers B) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)L.n_v_cap * L.n_t * L.n_d * L.n_scen) return;
+    k1_cell(L, P, B, gid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ONE-LAUNCH replan (FRENET_STAGE_ONE_LAUNCH): a single planner's replan is a chain of launch latencies, not of work - K1, the
+// evaluate kernel and K5 + the winner gather each run a few microseconds.  With kMono the evaluate kernels do all of it: every CTA
+// first solves the boundary-value systems of its own rows (the K1 cells it is about to sample), and the CTA that finishes LAST
+// (a ticket per scenario, taken after a device-wide fence) runs the argmin and the winner gather for the scenario.
+// ------------------------------------------------------------------------------------------------
+// Partial argmin records: each CTA reduces the candidates it produced itself (they are still in its L1 / L2), so the scenario's
+// last CTA combines a few hundred records instead of sweeping every candidate (a single K5 CTA over the 9600 candidates of a dense
+// lattice takes longer than the evaluate kernel).  The lexicographic (cost, index) minimum is associative: same result as K5.
+constexpr int kKeys = 5;   // ctot, cd, cv, ct, masked ctot
+struct Best {
+    double v;
+    int i;
+    __device__ __forceinline__ void init() { v = CUDART_INF; i = 0x7fffffff; }
+    __device__ __forceinline__ void take(double nv, int ni) {   // lexicographic (cost, index); NaN never wins
+        if (nv < v || (nv == v && ni < i)) { v = nv; i = ni; }
+    }
+};
+struct Partial {
+    double v[kKeys];
+    int i[kKeys];
+    int nvalid, nsurv, pad;
+};
+static_assert(sizeof(Partial) == FRENET_PARTIAL_BYTES, "Partial record size is part of the ABI (buf->partials)");
+
+// Block-wide combination; the result is valid in thread 0.  (Called by every thread of the CTA.)
+__device__ __forceinline__ void block_best(Best (&best)[kKeys], int& nvalid, int& nsurv) {
+    __shared__ double sv[kKeys][kRowThreads / 32];
+    __shared__ int si[kKeys][kRowThreads / 32];
+    __shared__ int sc[2][kRowThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();          // (the arrays may still be read from a previous call)
+#pragma unroll
+    for (int q = 0; q < kKeys; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(kFull, best[q].v, o);
+            const int oi = __shfl_xor_sync(kFull, best[q].i, o);
+            best[q].take(ov, oi);
+        }
+        if (lane == 0) { sv[q][warp] = best[q].v; si[q][warp] = best[q].i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nvalid += __shfl_xor_sync(kFull, nvalid, o);
+        nsurv += __shfl_xor_sync(kFull, nsurv, o);
+    }
+    if (lane == 0) { sc[0][warp] = nvalid; sc[1][warp] = nsurv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; ++w) {
+#pragma unroll
+            for (int q = 0; q < kKeys; ++q) best[q].take(sv[q][w], si[q][w]);
+            nvalid += sc[0][w];
+            nsurv += sc[1][w];
+        }
+    }
+}
+
+template <bool kCg>
+__device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int c, int has_xy,
+                                           double* winner_out = nullptr, int32_t* steps_out = nullptr);
+__device__ __forceinline__ int winner_index(const FrenetResult& res, int sel);
+
+// The CTA's own candidates: `count` of them, the i-th at scenario-relative index first + i * stride.  Then the ticket; the holder of
+// the scenario's last one combines the partial records, writes the result record and gathers the winner.
+__device__ __forceinline__ void mono_tail(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int cta, int ctas_per_scen,
+                                          int first, int count, int stride, int use_mask, int gather_sel, int has_xy) {
+    __shared__ int sh_last, sh_winner, sh_winner2;
+    const int C = L.n_v_cap * L.n_t * L.n_d;
+    const int64_t base = (int64_t)b * C, candF = (int64_t)L.n_scen * C;
+    Best best[kKeys];
+#pragma unroll
+    for (int q = 0; q < kKeys; ++q) best[q].init();
+    int nvalid = 0, nsurv = 0;
+    __syncthreads();          // the CTA's per-candidate results are in global memory (written by other threads of this CTA)
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const int c = first + i * stride;
+        const int64_t g = base + c;
+        const int fl = B.cand_flags[g];
+        if (!(fl & FRENET_CAND_VALID)) continue;
+        const double cd = B.cost[g], cv = B.cost[candF + g], ct = B.cost[2 * candF + g], ctot = B.cost[3 * candF + g];
+        ++nvalid;
+        best[0].take(ctot, c);
+        best[1].take(cd, c);
+        best[2].take(cv, c);
+        best[3].take(ct, c);
+        bool pass = true;
+        if (use_mask & 1) pass = pass && (fl & FRENET_CAND_KINEMATIC_OK);
+        if (use_mask & 4) pass = pass && B.coll_free[g];
+        if (pass) {
+            ++nsurv;
+            best[4].take(ctot, c);
+        }
+    }
+    block_best(best, nvalid, nsurv);
+    Partial* part_rec = reinterpret_cast<Partial*>(B.partials) + (int64_t)b * ctas_per_scen;
+    if (threadIdx.x == 0) {
+        Partial pr;
+#pragma unroll
+        for (int q = 0; q < kKeys; ++q) { pr.v[q] = best[q].v; pr.i[q] = best[q].i; }
+        pr.nvalid = nvalid; pr.nsurv = nsurv; pr.pad = 0;
+        part_rec[cta] = pr;
+    }
+    __threadfence();          // this thread's stores (samples, costs, the record) are visible device-wide before the ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(B.tickets + b, 1);
+        sh_last = t == ctas_per_scen - 1;
+        if (sh_last) B.tickets[b] = 0;      // ready for the next launch (stream order)
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < kKeys; ++q) best[q].init();
+    nvalid = nsurv = 0;
+    for (int i = threadIdx.x; i < ctas_per_scen; i += blockDim.x) {
+        const Partial* pr = part_rec + i;
+#pragma unroll
+        for (int q = 0; q < kKeys; ++q) best[q].take(__ldcg(&pr->v[q]), __ldcg(&pr->i[q]));
+        nvalid += __ldcg(&pr->nvalid);
+        nsurv += __ldcg(&pr->nsurv);
+    }
+    block_best(best, nvalid, nsurv);
+    if (threadIdx.x == 0) {
+        FrenetResult res;
+        auto idx = [](const Best& x) { return x.i == 0x7fffffff ? -1 : x.i; };
+        res.argmin_ctot = idx(best[0]);
+        res.argmin_cd = idx(best[1]);
+        res.argmin_cv = idx(best[2]);
+        res.argmin_ct = idx(best[3]);
+        res.argmin_masked = idx(best[4]);
+        res.n_valid = nvalid;
+        res.n_survivors = nsurv;
+        res.status = nvalid == 0 ? FRENET_STATUS_EMPTY : (res.argmin_masked < 0 ? FRENET_STATUS_NO_FEASIBLE : FRENET_STATUS_OK);
+        res.min_ctot = best[0].v;
+        res.min_masked_ctot = best[4].v;
+        res.reserved[0] = res.reserved[1] = 0.0;
+        B.result[b] = res;
+        sh_winner = gather_sel >= 0 ? winner_index(res, gather_sel) : -1;
+        sh_winner2 = res.argmin_masked;
+    }
+    if (gather_sel >= 0) {
+        __syncthreads();
+        gather_one<true>(L, P, B, b, sh_winner, has_xy);
+        // the masked pick as well, in its own block: a replan launched with the obstacles the driver will most likely present to
+        // check_paths next leaves BOTH answers behind (the planner's unmasked winner and the driver's masked one)
+        if (B.winner_masked && B.winner_masked_steps) gather_one<true>(L, P, B, b, sh_winner2, has_xy, B.winner_masked, B.winner_masked_steps);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1010,8 +1168,11 @@ __host__ __device__ inline size_t row_table_doubles(int npm, int n_d, int n_obs)
 //          STORED as floats (24 instead of 48 bytes per candidate-timestep; FrenetLattice.lat_f32).  Everything is still computed in
 //          fp64 - costs, feasibility, the collision table and its exact re-tests work on the fp64 values, so masks, argmin and costs
 //          are those of the fp64 path - and the longitudinal samples, which feed the next replan, stay fp64.
-template <bool kXY, int kColl, bool kLimits, bool kSplit, bool kF32 = false>
-__global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts, float radius_up) {
+// kCollOnly: the collision stage ALONE for a lattice that has been sampled already (check_paths on new obstacles): phase A and the
+//          row table as usual, no sampling loop, no stores except coll_free / first_blocker - the standalone K4 result without
+//          reading a single stored sample back (the exact re-tests recompute their points from the coefficients).
+template <bool kXY, int kColl, bool kLimits, bool kSplit, bool kF32, bool kCollOnly = false>
+__device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const FrenetParams& P, const FrenetPath& path, const FrenetBuffers& B, int opts, float radius_up) {
     extern __shared__ __align__(16) double sm[];
     constexpr bool kTable = kColl == 1 && kRowTable;   // snapshot collisions through the row-level table
     const int npm = L.n_pad_max;
@@ -1070,9 +1231,11 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
     if (!(flags & FRENET_ROW_EXISTS) || (flags & FRENET_ROW_DROPPED)) {
         for (int id = tid; id < L.n_d; id += blockDim.x) {
             const int64_t c = A.cand0 + id;
-            B.cand_flags[c] = 0;
+            if (!kCollOnly) {
+                B.cand_flags[c] = 0;
 #pragma unroll
-            for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = 0.0;
+                for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = 0.0;
+            }
             if (kColl) {
                 B.coll_free[c] = 0;
                 B.first_blocker[c] = -1;
@@ -1146,7 +1309,7 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
             const double t = (double)k * dt;   // == np.arange(0, T + dt, dt)[k]
             double s, v, a, j;
             eval_power_form(pl, t, L.t_pow + 4 * k, s, v, a, j);
-            if (part == 0) {
+            if (part == 0 && !kCollOnly) {
                 lon[k] = s;
                 lon[A.npad + k] = v;
                 lon[2 * A.npad + k] = a;
@@ -1260,6 +1423,7 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
     int slot = warp;
     const unsigned next_addr = (unsigned)__cvta_generic_to_shared(&sh_next);
     for (;;) {
+        if (kCollOnly) break;
         if (kTable) {
             int t = 0;
             if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(next_addr) : "memory");
@@ -1458,15 +1622,37 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
     for (int id = tid; id < L.n_d; id += blockDim.x) {
         if (id % parts != part) continue;   // another part's candidate
         const int64_t c = A.cand0 + id;
+        if (!kCollOnly) {
 #pragma unroll
-        for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = resc[id * 4 + f];
-        B.cand_flags[c] = (uint8_t)resi[id * 2];
-        if (do_curv) B.curv_ok[c] = (resi[id * 2] & kCurvOkBit) ? 1 : 0;
+            for (int f = 0; f < 4; ++f) B.cost[f * A.candF + c] = resc[id * 4 + f];
+            B.cand_flags[c] = (uint8_t)resi[id * 2];
+            if (do_curv) B.curv_ok[c] = (resi[id * 2] & kCurvOkBit) ? 1 : 0;
+        }
         if (kColl) {
             const int best = resi[id * 2 + 1];
             B.coll_free[c] = best == kNoBlocker ? 1 : 0;
             B.first_blocker[c] = best == kNoBlocker ? -1 : best;
         }
+    }
+}
+
+// kMono: the one-launch replan (see mono_tail) - K1 of the row in front, K5 + gather by the scenario's last CTA behind.
+template <bool kXY, int kColl, bool kLimits, bool kSplit, bool kF32 = false, bool kMono = false, bool kCollOnly = false>
+__global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl))      // (kMono too: a dense single planner is hundreds of CTAs, occupancy matters)
+k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts, float radius_up, int use_mask, int gather_sel, int has_xy) {
+    if (kMono && !kCollOnly) {
+        // every part of a split row solves the row's n_d cells itself (identical values: the duplicate stores are harmless)
+        const int64_t cand0 = (int64_t)blockIdx.x * L.n_d;
+        for (int id = threadIdx.x; id < L.n_d; id += blockDim.x) k1_cell(L, P, B, cand0 + id);
+        __syncthreads();
+    }
+    k2_evaluate_body<kXY, kColl, kLimits, kSplit, kF32, kCollOnly>(L, P, path, B, opts, radius_up);
+    if (kMono) {
+        const int R = L.n_v_cap * L.n_t;
+        const int b = (int)(blockIdx.x / R), r = (int)(blockIdx.x % R);
+        if (skipped(B, b)) return;
+        // this CTA produced the candidates part, part + parts, ... of row r
+        mono_tail(L, P, B, b, r * parts + part, R * parts, r * L.n_d + part, (L.n_d - part + parts - 1) / parts, parts, use_mask, gather_sel, has_xy);
     }
 }
 
@@ -1485,7 +1671,7 @@ __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl)) k2_evaluate(F
 // [G n_d][6] lateral coefficients | [G n_d][5] per-candidate results | [n_d] lateral axis | [G][2] row cost and horizon |
 // [G] candidate block offsets | [G][4] ints: N, npad, usable, feasible | spline table (kXY).
 template <bool kXY, int kColl, bool kLimits>
-__global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS) k2_short(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int G, int opts) {
+__device__ __forceinline__ void k2_short_body(const FrenetLattice& L, const FrenetParams& P, const FrenetPath& path, const FrenetBuffers& B, int G, int opts) {
     extern __shared__ __align__(16) double sm[];
     const int npm = L.n_pad_max, nd = L.n_d;
     const int R = L.n_v_cap * L.n_t;
@@ -1728,6 +1914,26 @@ __global__ void __launch_bounds__(kRowThreads, kColl ? FRENET_K2_MIN_CTAS_COLL :
             B.coll_free[gc] = (usable && best == kNoBlocker) ? 1 : 0;
             B.first_blocker[gc] = (!usable || best == kNoBlocker) ? -1 : best;
         }
+    }
+}
+
+template <bool kXY, int kColl, bool kLimits, bool kMono = false>
+__global__ void __launch_bounds__(kRowThreads, kMono ? 1 : (kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS))
+k2_short(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int G, int opts, int use_mask, int gather_sel, int has_xy) {
+    const int R = L.n_v_cap * L.n_t;
+    const int groups = (R + G - 1) / G;
+    if (kMono) {
+        const int b = blockIdx.x / groups, row0 = (blockIdx.x % groups) * G;
+        const int cells = min(G, R - row0) * L.n_d;
+        const int64_t cand0 = ((int64_t)b * R + row0) * L.n_d;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) k1_cell(L, P, B, cand0 + i);
+        __syncthreads();
+    }
+    k2_short_body<kXY, kColl, kLimits>(L, P, path, B, G, opts);
+    if (kMono) {
+        const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+        if (skipped(B, b)) return;
+        mono_tail(L, P, B, b, g, groups, g * G * L.n_d, min(G, R - g * G) * L.n_d, 1, use_mask, gather_sel, has_xy);
     }
 }
 
@@ -2409,15 +2615,6 @@ __global__ void __launch_bounds__(256) polyline_collision(const double* __restri
 // ------------------------------------------------------------------------------------------------
 // K5: first-wins argmin, one CTA per scenario
 // ------------------------------------------------------------------------------------------------
-struct Best {
-    double v;
-    int i;
-    __device__ __forceinline__ void init() { v = CUDART_INF; i = 0x7fffffff; }
-    __device__ __forceinline__ void take(double nv, int ni) {   // lexicographic (cost, index); NaN never wins
-        if (nv < v || (nv == v && ni < i)) { v = nv; i = ni; }
-    }
-};
-
 // The winner block of one scenario (the arrays `optimal_at_time` indexes, trajectory_planner.py:183-195), copied by all threads of the CTA.
 __device__ __forceinline__ int winner_index(const FrenetResult& res, int sel) {
     return sel == FRENET_SEL_CTOT ? res.argmin_ctot
@@ -2427,14 +2624,26 @@ __device__ __forceinline__ int winner_index(const FrenetResult& res, int sel) {
                                   : res.argmin_masked;
 }
 
-__device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int c, int has_xy) {
+// kCg: loads bypass L1 (the one-launch replan reads what other CTAs of the SAME kernel wrote)
+template <bool kCg, typename T>
+__device__ __forceinline__ T ld_res(const T* p) {
+    if (kCg) return __ldcg(p);
+    return *p;
+}
+
+template <bool kCg>
+__device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int c, int has_xy,
+                                           double* winner_out, int32_t* steps_out) {
+    // (default: the buffers' winner block; the one-launch replan also fills buf->winner_masked through the explicit form)
+    double* const wbase = winner_out ? winner_out : B.winner;
+    int32_t* const steps = steps_out ? steps_out : B.winner_steps;
     if (c < 0) {
-        if (threadIdx.x == 0) B.winner_steps[b] = 0;
+        if (threadIdx.x == 0) steps[b] = 0;
         return;
     }
     const int r = c / L.n_d, id = c % L.n_d;
     const RowAddr A = row_addr(L, (int64_t)b * L.n_v_cap * L.n_t + r);
-    double* w = B.winner + (int64_t)b * FRENET_WINNER_ROWS * L.n_pad_max;
+    double* w = wbase + (int64_t)b * FRENET_WINNER_ROWS * L.n_pad_max;
     const double t0 = B.scal[(int64_t)b * 3 + 2];
     const double* cand = B.lat + A.cand_off + (int64_t)id * (kCandFields * A.npad);
     const double* lon = B.lon + A.lon_off;
@@ -2464,30 +2673,28 @@ __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetP
         w[k] = __dadd_rn(__dmul_rn((double)k, P.sample_period), t0);   // f.t[i] += t_initial (:178-179): product and sum rounded separately
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-            w[(1 + f) * L.n_pad_max + k] = cand[f * A.npad + k];
-            w[(5 + f) * L.n_pad_max + k] = lon[f * A.npad + k];
+            w[(1 + f) * L.n_pad_max + k] = ld_res<kCg>(cand + f * A.npad + k);
+            w[(5 + f) * L.n_pad_max + k] = ld_res<kCg>(lon + f * A.npad + k);
         }
         if (has_xy) {
-            w[9 * L.n_pad_max + k] = cand[4 * A.npad + k];
-            w[10 * L.n_pad_max + k] = cand[5 * A.npad + k];
+            w[9 * L.n_pad_max + k] = ld_res<kCg>(cand + 4 * A.npad + k);
+            w[10 * L.n_pad_max + k] = ld_res<kCg>(cand + 5 * A.npad + k);
         }
     }
-    if (threadIdx.x < 4) w[11 * L.n_pad_max + threadIdx.x] = B.cost[threadIdx.x * A.candF + A.cand0 + id];
-    if (threadIdx.x == 0) B.winner_steps[b] = A.N;
+    if (threadIdx.x < 4) w[11 * L.n_pad_max + threadIdx.x] = ld_res<kCg>(B.cost + threadIdx.x * A.candF + A.cand0 + id);
+    if (threadIdx.x == 0) steps[b] = A.N;
 }
 
-constexpr int kKeys = 5;   // ctot, cd, cv, ct, masked ctot
 constexpr int kArgminThreads = 512;
 
 // gather_sel >= 0: the CTA also copies that selection's winner block (gather_winner) once the record is known - one launch less
 // in every pipeline that wants both.
-__global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, FrenetParams P, FrenetBuffers B, int use_mask, int gather_sel,
-                                                            int has_xy) {
+template <bool kCg>
+__device__ void k5_scenario(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int use_mask, int gather_sel, int has_xy, int b) {
     __shared__ int sh_winner;
     __shared__ double sv[kKeys][kArgminThreads / 32];
     __shared__ int si[kKeys][kArgminThreads / 32];
     __shared__ int scount[2][kArgminThreads / 32];
-    const int b = blockIdx.x;
     const int C = L.n_v_cap * L.n_t * L.n_d;
     const int64_t base = (int64_t)b * C;
     const int64_t candF = (int64_t)L.n_scen * C;
@@ -2510,14 +2717,14 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
             const int c = c0 + u * blockDim.x;
             const bool in = c < C;
             const int64_t g = base + (in ? c : c0);
-            fl[u] = in ? B.cand_flags[g] : 0;
-            cd[u] = B.cost[g];
-            cv[u] = B.cost[candF + g];
-            ct[u] = B.cost[2 * candF + g];
-            ctot[u] = B.cost[3 * candF + g];
-            m_curv[u] = (use_mask & 2) ? B.curv_ok[g] : 1;
-            m_coll[u] = (use_mask & 4) ? B.coll_free[g] : 1;
-            m_road[u] = (use_mask & 8) ? B.road_ok[g] : 1;
+            fl[u] = in ? ld_res<kCg>(B.cand_flags + g) : 0;
+            cd[u] = ld_res<kCg>(B.cost + g);
+            cv[u] = ld_res<kCg>(B.cost + candF + g);
+            ct[u] = ld_res<kCg>(B.cost + 2 * candF + g);
+            ctot[u] = ld_res<kCg>(B.cost + 3 * candF + g);
+            m_curv[u] = (use_mask & 2) ? ld_res<kCg>(B.curv_ok + g) : 1;
+            m_coll[u] = (use_mask & 4) ? ld_res<kCg>(B.coll_free + g) : 1;
+            m_road[u] = (use_mask & 8) ? ld_res<kCg>(B.road_ok + g) : 1;
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -2581,15 +2788,20 @@ __global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, Fre
     }
     if (gather_sel >= 0) {
         __syncthreads();
-        gather_one(L, P, B, b, sh_winner, has_xy);
+        gather_one<kCg>(L, P, B, b, sh_winner, has_xy);
     }
+}
+
+__global__ void __launch_bounds__(kArgminThreads) k5_argmin(FrenetLattice L, FrenetParams P, FrenetBuffers B, int use_mask, int gather_sel,
+                                                            int has_xy) {
+    k5_scenario<false>(L, P, B, use_mask, gather_sel, has_xy, blockIdx.x);
 }
 
 // Winner gather: the sampled state optimal_at_time indexes (trajectory_planner.py:183-195), 11 rows + a cost row.
 __global__ void __launch_bounds__(128) gather_winner(FrenetLattice L, FrenetParams P, FrenetBuffers B, int sel, int has_xy) {
     const int b = blockIdx.x;
     if (skipped(B, b)) return;
-    gather_one(L, P, B, b, winner_index(B.result[b], sel), has_xy);
+    gather_one<false>(L, P, B, b, winner_index(B.result[b], sel), has_xy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2679,14 +2891,19 @@ K2Shape k2_shape(const FrenetLattice* L, bool xy, int coll, int n_knots_spline, 
               (FRENET_BULK_STORE ? (size_t)(kRowThreads / kWarp) * kCandFields * L->n_pad_max + 2 : 0) +
               (coll == 2 ? (size_t)2 * predicted_chunks(L) * n_obs : 0)) * sizeof(double);
     // a single planner (or a handful) has too few rows to fill the GPU with one CTA each: split the rows' candidates over several CTAs
+    // - but only as far as all CTAs are resident at once (one wave): a CTA's life is mostly the latency of its row set-up, which a
+    // second wave would pay again (config 4: 120 rows x 8 parts = 960 CTAs in two waves took 34 us, x 4 in one wave less)
     S.parts = 1;
-    while (S.parts < 8 && (int64_t)n_rows(L) * S.parts < 4 * 148 && S.parts * (kRowThreads / kWarp) < L->n_d) S.parts *= 2;
+    const int64_t slots = (int64_t)k2_min_ctas(coll) * 148;
+    while (S.parts < FRENET_MAX_ROW_PARTS && (int64_t)n_rows(L) * S.parts * 2 <= slots && S.parts * (kRowThreads / kWarp) < L->n_d) S.parts *= 2;
     S.grid = n_rows(L);
     return S;
 }
 
+// mono != nullptr: the one-launch replan - {use_mask, gather_sel, has_xy} of the K5 + gather tail (see mono_tail)
 template <bool kXY, int kColl>
-int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int opts, cudaStream_t stream) {
+int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int opts, cudaStream_t stream,
+              const int* mono = nullptr) {
     // opts bit 0: also test the curvature limit in the kernel (needs kXY; selects the limits variant)
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0) || (kXY && (opts & 1));
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
@@ -2700,13 +2917,23 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     radius_up = nextafterf(radius_up, INFINITY);
     if (!S.pair && L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "fp32 fast path: lattices of at most 32 padded samples are not supported");
     if (!S.pair) {
-#define FRENET_LAUNCH_SHORT(LIM)                                                                                             \
-    do {                                                                                                                     \
-        if (int rc = set_smem(k2_short<kXY, kColl, LIM>, S.smem, "k2: row group does not fit shared memory")) return rc;     \
-        k2_short<kXY, kColl, LIM><<<S.grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, S.rows_per_cta, opts);            \
+#define FRENET_LAUNCH_SHORT(LIM, MONO)                                                                                              \
+    do {                                                                                                                            \
+        if (int rc = set_smem(k2_short<kXY, kColl, LIM, MONO>, S.smem, "k2: row group does not fit shared memory")) return rc;      \
+        k2_short<kXY, kColl, LIM, MONO><<<S.grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, S.rows_per_cta, opts,              \
+                                                                                 mono ? mono[0] : 0, mono ? mono[1] : -1, mono ? mono[2] : 0); \
     } while (0)
-        if (limits) FRENET_LAUNCH_SHORT(true);
-        else FRENET_LAUNCH_SHORT(false);
+        if constexpr (kColl != 2) {
+            if (mono && mono[3]) return fail(FRENET_ERR_BAD_ARG, "one launch: the collision-only form needs a long-horizon lattice (more than 32 padded samples)");
+            if (mono) {
+                if (limits) FRENET_LAUNCH_SHORT(true, true);
+                else FRENET_LAUNCH_SHORT(false, true);
+                FRENET_CHECK_LAUNCH("k2_short (one launch)");
+                return FRENET_OK;
+            }
+        }
+        if (limits) FRENET_LAUNCH_SHORT(true, false);
+        else FRENET_LAUNCH_SHORT(false, false);
 #undef FRENET_LAUNCH_SHORT
         FRENET_CHECK_LAUNCH("k2_short");
         return FRENET_OK;
@@ -2718,25 +2945,43 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
             const dim3 grid1(S.grid, 1);
             if (limits) {
                 if (int rc = set_smem(k2_evaluate<true, kColl, true, false, true>, S.smem, "k2: row does not fit shared memory")) return rc;
-                k2_evaluate<true, kColl, true, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up);
+                k2_evaluate<true, kColl, true, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, 0, -1, 0);
             } else {
                 if (int rc = set_smem(k2_evaluate<true, kColl, false, false, true>, S.smem, "k2: row does not fit shared memory")) return rc;
-                k2_evaluate<true, kColl, false, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up);
+                k2_evaluate<true, kColl, false, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, 0, -1, 0);
             }
             FRENET_CHECK_LAUNCH("k2_evaluate (fp32 fast path)");
         }
         return FRENET_OK;
     }
     const dim3 grid(S.grid, S.parts);
-#define FRENET_LAUNCH_K2(LIM, SPLIT)                                                                                           \
-    do {                                                                                                                       \
-        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, SPLIT>, S.smem, "k2: row does not fit shared memory")) return rc;   \
-        k2_evaluate<kXY, kColl, LIM, SPLIT><<<grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up);           \
+#define FRENET_LAUNCH_K2(LIM, SPLIT, MONO)                                                                                                  \
+    do {                                                                                                                                    \
+        if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, SPLIT, false, MONO>, S.smem, "k2: row does not fit shared memory")) return rc;   \
+        k2_evaluate<kXY, kColl, LIM, SPLIT, false, MONO><<<grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up,            \
+                                                                                                mono ? mono[0] : 0, mono ? mono[1] : -1, mono ? mono[2] : 0); \
     } while (0)
-    if (limits && S.parts > 1) FRENET_LAUNCH_K2(true, true);
-    else if (limits) FRENET_LAUNCH_K2(true, false);
-    else if (S.parts > 1) FRENET_LAUNCH_K2(false, true);
-    else FRENET_LAUNCH_K2(false, false);
+    if constexpr (kColl != 2) {
+        if constexpr (kXY && kColl == 1 && kRowTable) {
+            if (mono && mono[3]) {   // collision stage alone on an existing lattice + the K5 / gather tail
+                if (int rc = set_smem(k2_evaluate<true, 1, false, true, false, true, true>, S.smem, "k2: row does not fit shared memory")) return rc;
+                k2_evaluate<true, 1, false, true, false, true, true><<<grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, mono[0], mono[1], mono[2]);
+                FRENET_CHECK_LAUNCH("k2_evaluate (collision only, one launch)");
+                return FRENET_OK;
+            }
+        }
+        if (mono && mono[3]) return fail(FRENET_ERR_BAD_ARG, "one launch: the collision-only form is not available in this build / mode");
+        if (mono) {     // (always the split form: gridDim.y may be 1)
+            if (limits) FRENET_LAUNCH_K2(true, true, true);
+            else FRENET_LAUNCH_K2(false, true, true);
+            FRENET_CHECK_LAUNCH("k2_evaluate (one launch)");
+            return FRENET_OK;
+        }
+    }
+    if (limits && S.parts > 1) FRENET_LAUNCH_K2(true, true, false);
+    else if (limits) FRENET_LAUNCH_K2(true, false, false);
+    else if (S.parts > 1) FRENET_LAUNCH_K2(false, true, false);
+    else FRENET_LAUNCH_K2(false, false, false);
 #undef FRENET_LAUNCH_K2
     FRENET_CHECK_LAUNCH("k2_evaluate");
     return FRENET_OK;
@@ -2900,6 +3145,41 @@ int frenet_gather_winner(const FrenetLattice* L, const FrenetParams* P, const Fr
 int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int32_t stages,
                 int32_t use_mask, int32_t gather_sel, frenet_stream_t stream) {
     int rc = FRENET_OK;
+    if (stages & FRENET_STAGE_ONE_LAUNCH) {
+        const int need = FRENET_STAGE_K1 | FRENET_STAGE_K2 | FRENET_STAGE_K5 | FRENET_STAGE_GATHER;
+        if ((stages & ~FRENET_STAGE_ONE_LAUNCH) == (FRENET_STAGE_K4 | FRENET_STAGE_K5 | FRENET_STAGE_GATHER)) {
+            // the collision stage alone on a lattice that is already sampled, through the row table (no stored sample is read back),
+            // with the argmin + gather tail: what check_paths needs when the obstacles arrive after the replan
+            if ((rc = check_k2(L, P, B))) return rc;
+            if ((rc = check_path(path))) return rc;
+            if (!B->tickets || !B->partials) return fail(FRENET_ERR_BAD_ARG, "one launch: buf->tickets / buf->partials is NULL");
+            if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "one launch: not available on the fp32 fast path");
+            if (!B->result || !B->winner || !B->winner_steps || !B->coll_free || !B->first_blocker)
+                return fail(FRENET_ERR_BAD_ARG, "one launch: NULL result / winner / collision buffer");
+            if ((use_mask & 2) || (use_mask & 8)) return fail(FRENET_ERR_BAD_ARG, "one launch: curvature / road masks are not produced by this launch");
+            if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "one launch: obstacle table missing");
+            if (B->n_obs_steps > 0 && B->n_obs > 0) return fail(FRENET_ERR_BAD_ARG, "one launch: predicted obstacles are not supported");
+            const int mono[4] = {use_mask, gather_sel, 1, 1};
+            return launch_k2<true, 1>(L, P, path, B, 0, (cudaStream_t)stream, mono);
+        }
+        if ((stages & need) != need || (stages & (FRENET_STAGE_CURVATURE | FRENET_STAGE_NO_FUSE | FRENET_STAGE_OFFROAD)) ||
+            ((stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_K3)))
+            return fail(FRENET_ERR_BAD_ARG, "one launch: needs K1 | K2 | K5 | GATHER (K3, K3 | K4 optional) and none of CURVATURE / NO_FUSE / OFFROAD");
+        if ((rc = check_k2(L, P, B))) return rc;
+        if (!B->tickets || !B->partials) return fail(FRENET_ERR_BAD_ARG, "one launch: buf->tickets / buf->partials is NULL");
+        if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "one launch: not available on the fp32 fast path");
+        if (!B->result || !B->winner || !B->winner_steps) return fail(FRENET_ERR_BAD_ARG, "one launch: NULL result / winner buffer");
+        if ((use_mask & 2) || (use_mask & 8)) return fail(FRENET_ERR_BAD_ARG, "one launch: curvature / road masks are not produced by this launch");
+        if ((use_mask & 4) && !(stages & FRENET_STAGE_K4)) return fail(FRENET_ERR_BAD_ARG, "one launch: collision mask without K4");
+        const int mono[4] = {use_mask, gather_sel, (stages & FRENET_STAGE_K3) ? 1 : 0, 0};
+        if (!(stages & FRENET_STAGE_K3)) return launch_k2<false, 0>(L, P, nullptr, B, 0, (cudaStream_t)stream, mono);
+        if ((rc = check_path(path))) return rc;
+        if (!(stages & FRENET_STAGE_K4)) return launch_k2<true, 0>(L, P, path, B, 0, (cudaStream_t)stream, mono);
+        if (!B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "one launch: collision output is NULL");
+        if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "one launch: obstacle table missing");
+        if (B->n_obs_steps > 0 && B->n_obs > 0) return fail(FRENET_ERR_BAD_ARG, "one launch: predicted obstacles are not supported");
+        return launch_k2<true, 1>(L, P, path, B, 0, (cudaStream_t)stream, mono);
+    }
     if ((stages & FRENET_STAGE_K1) && (rc = frenet_k1_coefficients(L, P, B, stream))) return rc;
     // K2 and K3 (and K4 when nothing sits between them) run as ONE kernel unless the caller asks for separate launches:
     // same arithmetic, same outputs, but every sample is written once instead of being re-read by K3 and K4.
@@ -3097,9 +3377,11 @@ int frenet_workspace_bytes(const FrenetLattice* L, int32_t n_obs, int32_t n_obs_
     out->path_origin = Bn * 2 * 8;
     out->lane_params = Bn * 4 * 8;
     out->road_params = Bn * 8 * 8;
+    out->tickets = Bn * 4;
+    out->partials = Bn * R * FRENET_MAX_ROW_PARTS * FRENET_PARTIAL_BYTES;
     const int64_t* f = &out->state;
     int64_t tot = 0;
-    for (; f <= &out->road_params; ++f) tot += (*f + 255) / 256 * 256;   // every buffer on its own 256-byte boundary
+    for (; f <= &out->partials; ++f) tot += (*f + 255) / 256 * 256;   // every buffer on its own 256-byte boundary
     out->total = tot;
     return FRENET_OK;
 }

@@ -38,12 +38,42 @@ def _is_live(paths) -> bool:
     return isinstance(paths, LatticePaths) and paths._engine.generation == paths._generation
 
 
+def _attach_xy_source(eng, frenet_paths, planner):
+    """Picks that were gathered before K3 ran have no x, y; the reference's frenet_to_glob appends them to the same objects
+    (`opt_path_tot` IS an element of `paths`).  They get a fetcher that reads the candidate's x / y block from the lattice the
+    first time somebody looks (nothing on the replan path pays for it)."""
+    from ..planner.frenet import WinnerFrenet
+    gen = eng.generation
+    n_v = int(eng.n_v[0])
+
+    def source_for(w):
+        def fetch(name):
+            if eng.generation != gen or not eng.has_xy:
+                return []
+            lat_off, _, npad, nsteps = eng.cand_offsets(n_v)
+            c = w.index
+            j = 4 if name == "x" else 5
+            at = int(lat_off[c]) + j * int(npad[c])
+            return eng.lat[0, at:at + int(nsteps[c])].cpu().numpy().tolist()
+        return fetch
+
+    for cache in (frenet_paths._best, planner.__dict__.get("_winner_cache", {})):
+        for w in cache.values():
+            if isinstance(w, WinnerFrenet) and w._n_valid == 9 and "_xy_source" not in w.__dict__:
+                w._xy_source = source_for(w)
+
+
 def frenet_to_glob(planner, trajectory, frenet_paths):
     """Adds Cartesian x, y to every path (test_obstacle_planner.py:18-25): K3."""
     if _is_live(frenet_paths):
         eng = frenet_paths._engine
-        if not eng.has_xy:
+        eng.set_relative_s(False)
+        if not eng.has_xy or getattr(eng, "xy_path", None) is not trajectory:
             eng.launch(planner._params, eng.path_handle(trajectory), nat.STAGE_K3)
+            eng.xy_path = trajectory
+            _attach_xy_source(eng, frenet_paths, planner)
+        if hasattr(planner, "generate_range_polynomials") and planner.__dict__.get("_speculate", True):
+            planner.__dict__["_spec_path"] = trajectory      # the next replan transforms against this path right away
         return frenet_paths
     eng = _engine_for_lists()
     paths = list(frenet_paths)
@@ -107,6 +137,8 @@ def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
     attached robot's pose (proximity_sensor.py:53-57)."""
     sensed = sensor.sense(rpose)
     if not sensed:
+        if _is_live(frenet_paths):
+            frenet_paths._planner.__dict__["_spec_obs"] = frenet_paths._planner.__dict__["_last_obs"] = None
         return frenet_paths, sensed, np.zeros(0, dtype=np.int64)
     if _is_live(frenet_paths):
         eng = frenet_paths._engine
@@ -122,14 +154,37 @@ def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
             free, first = eng.polyline_collision([f["x"][c, :nst[c]] for c in pos], [f["y"][c, :nst[c]] for c in pos],
                                                  np.array([ob.position for ob in sensed], dtype=np.float64), robot_radius ** 2)
             return frenet_paths.filtered(free), sensed, first[~free]
-        eng.obs_xy[0, :n] = np.array([ob.position for ob in sensed], dtype=np.float64)
-        eng.obs_active[0, :n] = 1
+        pos = np.array([ob.position for ob in sensed], dtype=np.float64)
+        # The replan speculates on the obstacle set when it repeated (a static scene): if it already tested exactly these positions,
+        # masks, first blockers, the record and the masked pick are on hand and nothing is launched.
+        last = planner.__dict__.get("_last_obs")
+        planner.__dict__["_spec_obs"] = pos if (last is not None and last.shape == pos.shape and np.array_equal(last, pos)
+                                                and planner.__dict__.get("_speculate", True)) else None
+        planner.__dict__["_last_obs"] = pos
+        tested = getattr(eng, "spec_pos", None)
+        hit = tested is not None and eng.has_collision and tested.shape == pos.shape and np.array_equal(tested, pos)
+        # (zero-copy engines: a K3 launch of frenet_to_glob may still be running - it never reads the obstacle arrays)
+        if not hit:
+            eng.spec_pos = None
+            eng.obs_xy[0, :n] = pos
+            eng.obs_active[0, :n] = 1
         # K4, then K5 with the collision mask and a gather of the masked winner: one graph replay (H2D of the obstacle
         # table, three kernels, D2H of the record + winner)
-        eng.run_graph(planner._params, None, nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER, nat.MASK_COLLISION,
-                      nat.SEL_MASKED, n_obs=n)
+        xy_path = getattr(eng, "xy_path", None)
+        if hit:
+            pass
+        elif (xy_path is not None and eng.geom.n_pad_max > 32 and not eng.relative_s and eng.partials is not None
+                and planner.__dict__.get("_one_launch", True)):
+            # long horizons: the collision stage from the row-level table (nothing is read back from the lattice) with the masked
+            # argmin + gather in its tail - ONE kernel instead of K4 sweeping every stored sample, then K5
+            eng.run_graph(planner._params, eng.path_handle(xy_path), nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER | nat.STAGE_ONE_LAUNCH,
+                          nat.MASK_COLLISION, nat.SEL_MASKED, n_obs=n)
+        else:
+            eng.run_graph(planner._params, None, nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER, nat.MASK_COLLISION,
+                          nat.SEL_MASKED, n_obs=n)
         C_ = frenet_paths._n_all
-        winner = planner._frenet_from_winner("argmin_masked")
+        winner = planner._frenet_from_winner("argmin_masked", masked_block=hit)
+
         def fetch_mask():
             frenet_paths._check_live()
             return eng.coll_free[0, :C_].cpu().numpy() != 0

@@ -60,6 +60,7 @@ def frenet_to_glob_planner(planner, trajectory, frenet_paths, projection):
         eng.path_origin[0] = (float(projection), float(planner.s0[0]))
         eng.upload_region("path_origin")
         eng.launch(planner._params, _lane_handle(eng, trajectory), nat.STAGE_K3)
+        eng.xy_path = None          # (a lane transform: drivers.frenet_to_glob must not take these x, y for a path's)
         return frenet_paths
     paths = list(frenet_paths)
     if paths:

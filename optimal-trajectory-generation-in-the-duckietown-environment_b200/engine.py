@@ -135,7 +135,21 @@ def _on_device(fn):
 class FrenetEngine:
     """HBM buffers + launch logic for `n_scen` independent planner instances sharing one lattice geometry."""
 
-    def __init__(self, n_scen: int = 1, device=None):
+    def __init__(self, n_scen: int = 1, device=None, zero_copy: bool = False, masked_winner: bool = False):
+        """zero_copy: the packed per-call inputs and outputs are NOT mirrored in HBM - the kernels read the pinned host block and
+        write the result record + winner trajectory straight into pinned host memory over PCIe (under unified addressing a pinned
+        allocation has the same address on the device).  For ONE planner these are a few hundred bytes in and a few KB out, and a
+        replan is launch-bound.  "out" maps only the outputs (posted writes, nothing waits for them); True maps the inputs too
+        (every CTA then pays a PCIe round trip for its first loads - measured in profiles/r2_history.md, latency section).
+        Batches keep device blocks (their state stays resident)."""
+        if zero_copy not in (False, True, "out"):
+            raise ValueError('zero_copy must be False, True or "out"')
+        self.zero_copy = zero_copy        # "out": only the result record + winner block are written straight to pinned host memory
+        self._zc_in = zero_copy is True
+        self._zc_out = bool(zero_copy)
+        # masked_winner: a second winner block that the one-launch replan fills with the MASKED pick (FrenetBuffers.winner_masked)
+        self.masked_winner = bool(masked_winner)
+        self._pending = False         # zero_copy: a launch was enqueued and not waited for yet (it may still read the pinned inputs)
         self.device = require_cuda() if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("FrenetEngine needs a CUDA device")
@@ -205,7 +219,7 @@ class FrenetEngine:
             offs[name] = tot
             tot += _align(sz)
         self._in_host = torch.empty(tot, dtype=torch.uint8, pin_memory=True)
-        self._in_dev = torch.empty(tot, dtype=torch.uint8, device=dev)
+        self._in_dev = self._in_host if self._zc_in else torch.empty(tot, dtype=torch.uint8, device=dev)
         hv = self._in_host.numpy()
         self.state = hv[offs["state"]:offs["state"] + Bn * 48].view(np.float64).reshape(Bn, 6)
         self.scal = hv[offs["scal"]:offs["scal"] + Bn * 24].view(np.float64).reshape(Bn, 3)
@@ -228,6 +242,8 @@ class FrenetEngine:
 
         # packed small outputs
         osz = [("winner", Bn * 12 * geom.n_pad_max * 8), ("result", Bn * nat.RESULT_BYTES), ("winner_steps", Bn * 4)]
+        if self.masked_winner:
+            osz += [("winner_masked", Bn * 12 * geom.n_pad_max * 8), ("winner_masked_steps", Bn * 4)]
         ooffs, otot = {}, 0
         for name, sz in osz:
             ooffs[name] = otot
@@ -254,6 +270,10 @@ class FrenetEngine:
         self.coll_free = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.first_blocker = torch.empty((Bn, Cc), dtype=torch.int32, device=dev)
         self.road_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
+        # FRENET_STAGE_ONE_LAUNCH scratch: completion tickets per scenario, a partial argmin record per CTA (small batches only -
+        # the mode exists for launch-bound replans)
+        self.tickets = torch.zeros(Bn, dtype=torch.int32, device=dev)
+        self.partials = torch.empty(Bn * R * nat.MAX_ROW_PARTS * nat.PARTIAL_BYTES, dtype=torch.uint8, device=dev) if Bn * R <= 65536 else None
         self.n_obs_steps = n_obs_steps
         self.obs_xy_t = self.obs_bounds = None
         if n_obs_steps > 0 and n_obs > 0:
@@ -280,6 +300,8 @@ class FrenetEngine:
         Bf.result = op + ooffs["result"]
         Bf.winner, Bf.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
         Bf.road_ok = self.road_ok.data_ptr()
+        Bf.tickets = self.tickets.data_ptr()
+        Bf.partials = self.partials.data_ptr() if self.partials is not None else None
         Bf.path_origin = ip + offs["path_origin"] if self.relative_s else None
         Bf.lane_params = ip + offs["lane_params"] if self.per_scenario_lanes else None
         Bf.road_params = ip + offs["road_params"] if self.per_scenario_lanes else None
@@ -288,7 +310,7 @@ class FrenetEngine:
     def _add_out_block(self):
         host = torch.empty(self._out_bytes, dtype=torch.uint8, pin_memory=True)
         host.numpy()[:] = 0
-        self._out_blocks.append((host, torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device)))
+        self._out_blocks.append((host, host if self._zc_out else torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device)))
 
     def _bind_out_block(self, slot: int):
         """Make output block `slot` the one the next launch writes and `result` / `winner` / `winner_steps` view."""
@@ -302,6 +324,12 @@ class FrenetEngine:
         op = self._out_dev.data_ptr()
         self.B.result = op + ooffs["result"]
         self.B.winner, self.B.winner_steps = op + ooffs["winner"], op + ooffs["winner_steps"]
+        if self.masked_winner:
+            o = ooffs["winner_masked"]
+            self.winner_masked = ov[o:o + Bn * 12 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 12, geom.n_pad_max)
+            o = ooffs["winner_masked_steps"]
+            self.winner_masked_steps = ov[o:o + Bn * 4].view(np.int32)
+            self.B.winner_masked, self.B.winner_masked_steps = op + ooffs["winner_masked"], op + ooffs["winner_masked_steps"]
 
     def enable_out_slots(self, n: int = 2):
         """A second output block (result records + winner trajectories), so that step i's results can leave the device on a
@@ -401,7 +429,8 @@ class FrenetEngine:
         """One H2D copy of the packed per-call inputs (state, scalars, V axes, targets, obstacles).  An event marks the
         end of the copy so that the host may refill the pinned block for the NEXT call while this call's kernels run
         (`wait_staging_free`)."""
-        self._in_dev.copy_(self._in_host, non_blocking=True)
+        if not self._zc_in:
+            self._in_dev.copy_(self._in_host, non_blocking=True)
         if record_event:
             if not hasattr(self, "_h2d_done"):
                 self._h2d_done = torch.cuda.Event()
@@ -422,7 +451,7 @@ class FrenetEngine:
                  "obs_sd": self.n_scen * max(self.n_obs, 1) * 16, "obs_speed": self.n_scen * max(self.n_obs, 1) * 8,
                  "robot_pose": self.n_scen * 24, "path_origin": self.n_scen * 16, "lane_params": self.n_scen * 32,
                  "road_params": self.n_scen * 64, "n_v": self.n_scen * 4, "obs_active": self.n_scen * max(self.n_obs, 1)}
-        for name in names:
+        for name in (() if self._zc_in else names):
             o = self._in_offs[name]
             self._in_dev[o:o + sizes[name]].copy_(self._in_host[o:o + sizes[name]], non_blocking=True)
 
@@ -508,6 +537,7 @@ class FrenetEngine:
         pp = C.byref(path.desc) if path is not None else None
         nat.check(nat.lib.frenet_plan(C.byref(self.L), C.byref(params), pp, C.byref(self.B), int(stages), int(use_mask),
                                       int(gather_sel), C.c_void_p(stream)))
+        self._pending = True
         if stages & nat.STAGE_K2:
             self.generation += 1
             self.has_xy = False
@@ -560,9 +590,18 @@ class FrenetEngine:
     @_on_device
     def download(self, sync: bool = True):
         """One D2H copy of the packed per-call outputs (result records, winner trajectories)."""
-        self._out_host.copy_(self._out_dev, non_blocking=True)
+        if not self._zc_out:
+            self._out_host.copy_(self._out_dev, non_blocking=True)
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
+            self._pending = False
+
+    def host_block_free(self):
+        """zero_copy engines: before the host rewrites the pinned input block, wait for launches that may still be reading it
+        (only a launch that nobody waited for leaves the flag set - the graph paths end with a synchronize)."""
+        if self._zc_in and self._pending:
+            torch.cuda.current_stream(self.device).synchronize()
+            self._pending = False
 
     def run(self, params, path, stages, use_mask=0, gather_sel=nat.SEL_CTOT, n_obs=None):
         """upload -> pipeline -> download, synchronous."""
@@ -591,9 +630,11 @@ class FrenetEngine:
                 self.download(sync=False)
             self.generation, self.has_xy, self.has_collision = gen, has_xy, has_coll
             self._graphs[key] = g
+            self._pending = False
             return                      # the warm-up run already produced this call's results
         g.replay()
         torch.cuda.current_stream(self._dev_index).synchronize()
+        self._pending = False
         if stages & nat.STAGE_K2:
             self.generation += 1
             self.has_xy = bool(stages & nat.STAGE_K3)

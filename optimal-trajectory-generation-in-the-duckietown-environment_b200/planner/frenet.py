@@ -22,3 +22,49 @@ class Frenet:
 
     def __repr__(self):
         return f"Frenet(index={self.index}, steps={len(self.t)}, ctot={self.ctot:.6g})"
+
+
+_ROW_OF = {name: i for i, name in enumerate(LIST_FIELDS)}
+
+
+class WinnerFrenet(Frenet):
+    """A Frenet whose list fields are made on first use from a private copy of the device's winner block.
+
+    A replan hands back ONE such object (the pick); the next replan needs six numbers of it (`optimal_at_time`), which `_value`
+    reads straight from the block.  Turning all eleven rows of a dense-lattice winner into Python lists costs ~10 us - a third of a
+    single replan's host time - so that is left to whoever actually looks at a field; from then on the field IS a plain list
+    (append / extend / index like the reference's), and a list that exists always wins over the block."""
+
+    def __init__(self, rows, n_rows_valid, costs, index):
+        # (no Frenet.__init__: the list slots stay unset until they are asked for)
+        self._rows = rows
+        self._n_valid = n_rows_valid          # 9 without Cartesian samples, 11 with
+        self.cd, self.cv, self.ct, self.ctot = costs
+        self.index = index
+
+    def __getattr__(self, name):              # only reached when normal lookup fails, i.e. for a list slot that is still unset
+        i = _ROW_OF.get(name)
+        if i is None:
+            raise AttributeError(name)
+        rows = self.__dict__.get("_rows")
+        if rows is None:
+            raise AttributeError(name)
+        if i < self._n_valid:
+            val = rows[i].tolist()
+        else:
+            # x, y of a pick that was gathered BEFORE the transform ran: frenet_to_glob leaves a fetcher behind (the reference
+            # appends x, y to the very objects the planner's opt_path_* attributes point at)
+            src = self.__dict__.get("_xy_source")
+            val = src(name) if src is not None else []
+        setattr(self, name, val)
+        return val
+
+    def _value(self, name, index):
+        """field[index] as a Python float without materialising the list (a list that already exists is used instead)."""
+        try:
+            return object.__getattribute__(self, name)[index]
+        except AttributeError:
+            return float(self._rows[_ROW_OF[name]][index])
+
+    def __repr__(self):
+        return f"Frenet(index={self.index}, steps={self._rows.shape[1]}, ctot={self.ctot:.6g})"

@@ -19,7 +19,7 @@ import numpy as np
 from .. import _native as nat
 from .. import lattice as lat
 from ..engine import FrenetEngine, LatticeGeometry, make_params
-from .frenet import Frenet
+from .frenet import Frenet, WinnerFrenet
 from .params import (TrajectoryPlannerParams, TrajectoryPlannerParamsDT, TrajectoryPlannerParamsDTObstacles,
                      TrajectoryPlannerParamsOptimal)
 from .base import Planner
@@ -184,7 +184,7 @@ class _LatticePlanner(Planner):
     def _engine(self) -> FrenetEngine:
         e = self.__dict__.get("_engine_obj")
         if e is None:
-            e = FrenetEngine(1, self.__dict__.get("device"))
+            e = FrenetEngine(1, self.__dict__.get("device"), zero_copy=self.__dict__.get("_zero_copy", "out"), masked_winner=True)
             self.__dict__["_engine_obj"] = e
             self.__dict__["_geom_cache"] = {}
             self.__dict__["_n_v_cap"] = 0
@@ -252,6 +252,7 @@ class _LatticePlanner(Planner):
         if len(V) > self._n_v_cap or self._n_v_cap == 0:      # an empty axis (no candidates at all) still needs a valid layout
             self.__dict__["_n_v_cap"] = max(1, len(V), lat.max_long_axis_len(self))
         eng.configure(geom, self._n_v_cap, self._n_obs_cap)
+        eng.host_block_free()
         eng.state[0, :3] = self.p0
         eng.state[0, 3:] = self.s0
         eng.scal[0] = (self.dd, self.desired_speed, self.t_initial)
@@ -266,26 +267,47 @@ class _LatticePlanner(Planner):
             self.__dict__["_params"] = make_params(self, self._rule, period, follow)
             self.__dict__["_params_key"] = pkey
         P = self._params
-        eng.run_graph(P, None, nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER, 0, nat.SEL_CTOT)
+        stages = nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER
+        if self.__dict__.get("_one_launch", True):
+            stages |= nat.STAGE_ONE_LAUNCH     # K1, the evaluate kernel and K5 + gather as ONE kernel (a replan is launch-bound)
+        # the driver's next call is frenet_to_glob on the path it used last time (drivers.frenet_to_glob remembers it here): the
+        # transform is fused into this launch and that call finds x, y already there
+        spec = self.__dict__.get("_spec_path")
+        handle = None
+        if spec is not None and not eng.relative_s:
+            stages |= nat.STAGE_K3
+            handle = eng.path_handle(spec)
+        # ... and if the driver presented the SAME obstacles to check_paths twice in a row (a static scene), it will most likely do
+        # so again: the collision stage (nearly free inside the fused kernel) and the masked pick ride along, and check_paths only
+        # has to compare its obstacle list with the one that was tested (drivers.collision_filter)
+        spec_obs = self.__dict__.get("_spec_obs")
+        use_mask, n_obs, eng.spec_pos = 0, None, None
+        if (handle is not None and spec_obs is not None and (stages & nat.STAGE_ONE_LAUNCH) and eng.masked_winner
+                and eng.partials is not None and 0 < len(spec_obs) <= eng.n_obs):
+            n_obs = len(spec_obs)
+            eng.obs_xy[0, :n_obs] = spec_obs
+            eng.obs_active[0, :n_obs] = 1
+            stages |= nat.STAGE_K4
+            use_mask = nat.MASK_COLLISION
+            eng.spec_pos = spec_obs
+        eng.run_graph(P, handle, stages, use_mask, nat.SEL_CTOT, n_obs=n_obs)
+        eng.xy_path = spec if handle is not None else None
         self.__dict__["_winner_cache"] = {"ctot": self._frenet_from_winner("argmin_ctot")}
         paths = LatticePaths(self, len(V), follow)
         paths._best["ctot"] = self._winner_cache["ctot"]     # None when the lattice is empty
         return paths
 
-    def _frenet_from_winner(self, result_field: str):
-        """Frenet object from the engine's winner block (None if the selection is empty)."""
+    def _frenet_from_winner(self, result_field: str, masked_block: bool = False):
+        """Frenet object from the engine's winner block (None if the selection is empty); masked_block: from the second block,
+        which a replan launched with obstacles fills with the masked pick."""
         eng = self._engine
-        n = int(eng.winner_steps[0])
+        block, steps = (eng.winner_masked, eng.winner_masked_steps) if masked_block else (eng.winner, eng.winner_steps)
+        n = int(steps[0])
         if n == 0:
             return None
-        rows = eng.winner[0, :, :n].tolist()      # one conversion for the whole block: t, 8 state rows, x, y, costs
-        f = Frenet()
-        f.index = int(eng.result[0][result_field])
-        f.t, f.d, f.dot_d, f.ddot_d, f.dddot_d, f.s, f.dot_s, f.ddot_s, f.dddot_s = rows[:9]
-        if eng.has_xy:
-            f.x, f.y = rows[9], rows[10]
-        f.cd, f.cv, f.ct, f.ctot = eng.winner[0, 11, :4].tolist()
-        return f
+        # a private copy of the block (the pinned one is rewritten by the next launch); its rows become lists on first use
+        rows = block[0, :11, :n].copy()
+        return WinnerFrenet(rows, 11 if eng.has_xy else 9, block[0, 11, :4].tolist(), int(eng.result[0][result_field]))
 
     def _winner(self, key: str):
         """`min(self.paths, key=attrgetter(key))` of the CURRENT lattice (first minimal element wins)."""
@@ -305,17 +327,23 @@ class _LatticePlanner(Planner):
 
     def optimal_at_time(self, time, opt_path, type_path):
         """trajectory_planner.py:183-195 (the reference prints a warning at both clamps; logged here)."""
-        if time <= opt_path.t[0]:
+        if isinstance(opt_path, WinnerFrenet):
+            val = opt_path._value          # reads the winner block directly unless the field was turned into a list already
+        else:
+            def val(name, i):
+                return getattr(opt_path, name)[i]
+        t_first = val("t", 0)
+        if time <= t_first:
             logger.debug('requested time %s is before the optimal path interval', time)
             index = 0
-        elif time >= opt_path.t[-1]:
+        elif time >= val("t", -1):
             logger.debug('requested time %s is after the optimal path interval', time)
             index = -1
         else:
-            index = round((time - opt_path.t[0]) / self._sample_period_for_lookup())
+            index = round((time - t_first) / self._sample_period_for_lookup())
         if type_path == "s":
-            return (opt_path.s[index], opt_path.dot_s[index], opt_path.ddot_s[index])
-        return (opt_path.d[index], opt_path.dot_d[index], opt_path.ddot_d[index])
+            return (val("s", index), val("dot_s", index), val("ddot_s", index))
+        return (val("d", index), val("dot_d", index), val("ddot_d", index))
 
     def _sample_period_for_lookup(self):
         return self.delta_t

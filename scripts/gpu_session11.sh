@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x -k "one_launch" > gpurun_out/s11_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/s11_tests.log
+tail -30 gpurun_out/s11_tests.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/s11_tests_all.log 2>&1
+echo "rc=$?" >> gpurun_out/s11_tests_all.log
+tail -5 gpurun_out/s11_tests_all.log
+timeout 300 python scripts/latency_modes.py > gpurun_out/s11_latency_modes.txt 2>&1
+tail -4 gpurun_out/s11_latency_modes.txt

@@ -26,7 +26,7 @@ def planner_attrs(prm: fo.OracleParams) -> Attr:
 
 def run_batch(prm: fo.OracleParams, p0, s0, t0, dd=None, desired=None, targets=None, trajectory=None, obstacles=None,
               active=None, use_mask=0, di_interval=None, t_interval=None, gather_sel=nat.SEL_CTOT, curvature=False,
-              engine=None, no_fuse=False, projection=None, radius_sq=0.7 ** 2):
+              engine=None, no_fuse=False, projection=None, radius_sq=0.7 ** 2, one_launch=False, repeat=1):
     """Runs B scenarios through K1..K5 (+K3/K4 when a path / obstacles are given).  Returns the engine."""
     a = planner_attrs(prm)
     p0 = np.atleast_2d(np.asarray(p0, dtype=np.float64))
@@ -70,8 +70,11 @@ def run_batch(prm: fo.OracleParams, p0, s0, t0, dd=None, desired=None, targets=N
         use_mask |= nat.MASK_COLLISION
     if no_fuse:
         stages |= nat.STAGE_NO_FUSE
+    if one_launch:
+        stages |= nat.STAGE_ONE_LAUNCH
     P = make_params(a, lat.VARIANTS[prm.variant]["rule"], lat.sample_period(a, prm.variant), follow, radius_sq=radius_sq)
-    eng.run(P, path, stages, use_mask, gather_sel)
+    for _ in range(repeat):
+        eng.run(P, path, stages, use_mask, gather_sel)
     return eng
 
 

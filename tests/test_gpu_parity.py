@@ -1354,10 +1354,142 @@ def test_pipelined_launch_equals_the_plain_one():
         got = bp.pipeline_wait()
         assert np.array_equal(np.asarray(got), rec)
         for i, m in enumerate(bp.engine.winner_steps):     # the blocks' padding beyond a winner's samples is whatever that block held before
-            assert np.array_equal(bp.engine.winner[i, :11, :m], win[i, :11, :m]) and np.array_equal(bp.engine.winner[i, 11, :4], win[i, 11, :4])
+            assert np.array_equal(bp.engine.winner[i, :11, :m], win[i, :11, :m]) and (m == 0 or np.array_equal(bp.engine.winner[i, 11, :4], win[i, 11, :4]))
     slots = set()
     for _ in range(4):                   # back to back without waiting: the blocks alternate
         bp.launch_pipelined()
         slots.add(bp.engine.out_slot)
     assert slots == {0, 1}
     assert np.array_equal(np.asarray(bp.pipeline_wait()), want[-1][1])
+
+
+def _all_outputs(eng, nat):
+    """Everything a pipeline run leaves behind, in a form that ignores never-written padding: per-scenario padded fields, the K1
+    arrays of existing rows, the result records and the winner blocks up to their step counts."""
+    out = {"result": eng.result.copy(), "steps": eng.winner_steps.copy()}
+    for b in range(eng.n_scen):
+        sc = eng.fetch_scenario(b)
+        f = eng.padded_fields(sc)
+        nv = sc["n_v"]
+        R, C_ = nv * eng.geom.n_t, nv * eng.geom.n_t * eng.geom.n_d
+        out[b] = dict(f, coef_lon=sc["coef_lon"][:R], coef_lat=sc["coef_lat"][:C_], row_S=sc["row_S"][:R], row_flags=sc["row_flags"][:R])
+        m = int(eng.winner_steps[b])
+        out[b]["winner"] = eng.winner[b, :, :m].copy()
+        out[b]["winner_costs"] = eng.winner[b, 11, :4].copy() if m else None
+    return out
+
+
+def _assert_same_outputs(a, b, what):
+    assert np.array_equal(a["result"], b["result"]), what
+    assert np.array_equal(a["steps"], b["steps"]), what
+    for k in (k for k in a if isinstance(k, int)):
+        for name, va in a[k].items():
+            vb = b[k][name]
+            if va is None:
+                assert vb is None
+                continue
+            assert np.array_equal(np.asarray(va), np.asarray(vb), equal_nan=np.asarray(va).dtype.kind == "f"), (what, k, name)
+
+
+@pytest.mark.parametrize("case", ["default", "default_batch_obstacles", "follow", "optimal_dropped_rows", "limits", "dense_spline_obstacles"])
+def test_one_launch_replan_equals_the_separate_launches(case):
+    """FRENET_STAGE_ONE_LAUNCH: K1 by every CTA for its own rows, the evaluate kernel, and K5 + winner gather by the scenario's
+    last CTA, as ONE kernel.  Every output - K1's coefficients, the sampled lattice, costs, masks, first blockers, records, winner
+    blocks - must be bit-identical to the separate launches, for short and long horizons, split rows, batches (a ticket per
+    scenario), follow mode, dropped rows and the limits variant; launching twice checks that the tickets are left at zero."""
+    _gpu, nat, Circle, Spline = _imports()
+    from otg_b200 import workloads as w
+    rng = np.random.default_rng(7)
+    kw = {}
+    if case == "default":
+        prm = fo.OracleParams.defaults("v1")
+        kw = dict(p0=(0.3, 0.1, 0.0), s0=(1.0, 2.5, 0.1), t0=0.4)
+    elif case == "default_batch_obstacles":
+        prm = fo.OracleParams.defaults("v1")
+        B = 5
+        p0 = np.c_[rng.uniform(-1, 1, B), rng.uniform(-0.3, 0.3, B), np.zeros(B)]
+        s0 = np.c_[rng.uniform(0, 20, B), [0.5, 1.9, 2.0, 2.6, 3.2], rng.uniform(-0.2, 0.2, B)]     # low- and high-speed rows
+        obs = np.stack([np.c_[rng.uniform(0, 12, 6), rng.uniform(-2, 3, 6)] for _ in range(B)])
+        kw = dict(p0=p0, s0=s0, t0=rng.uniform(0, 3, B), dd=rng.uniform(-1, 1, B), trajectory=Circle(8, 5, 2), obstacles=obs,
+                  gather_sel=nat.SEL_MASKED)
+    elif case == "follow":
+        prm = fo.OracleParams.defaults("v1")
+        trip = np.tile(np.array([[6.0, 1.5, 0.0]]), (len(np.arange(*prm.t_interval())), 1)) + rng.uniform(-0.1, 0.1, (len(np.arange(*prm.t_interval())), 3))
+        kw = dict(p0=(0.0, 0.0, 0.0), s0=(2.0, 2.2, 0.0), t0=1.0, targets=trip[None], gather_sel=nat.SEL_CT)
+    elif case == "optimal_dropped_rows":
+        prm = fo.OracleParams.defaults("optimal")
+        kw = dict(p0=np.array([[0.2, 0.0, 0.0], [0.1, 0.0, 0.0]]), s0=np.array([[0.0, 0.4, 0.0], [3.0, 2.4, 0.0]]), t0=np.array([0.0, 0.5]),
+                  trajectory=Circle(8, 5, 2))
+    elif case == "limits":
+        prm = fo.OracleParams.defaults("v1").with_(v_max=3.2, a_max=1.5)
+        kw = dict(p0=(0.3, 0.1, 0.0), s0=(1.0, 2.5, 0.1), t0=0.4, trajectory=Circle(8, 5, 2), use_mask=nat.MASK_KINEMATIC)
+    else:
+        prm = _dense_prm()
+        sc = w.config5_scenarios()
+        idx = np.r_[3:5]
+        fs, fd = w.moving_obstacle_frenet(sc["obs_s"][idx], sc["obs_d"][idx], sc["obs_speed"][idx], sc["obs_offset"][idx], sc["t0"][idx, None])
+        ox, oy = fo.frenet_to_cartesian(fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY), fs, fd)
+        kw = dict(p0=sc["p0"][idx], s0=sc["s0"][idx], t0=sc["t0"][idx], dd=sc["dd"][idx], trajectory=Spline(w.SPLINE_WX, w.SPLINE_WY),
+                  obstacles=np.stack([ox, oy], 2)[:, :64], gather_sel=nat.SEL_MASKED)
+    ref = _all_outputs(_gpu.run_batch(prm, **kw), nat)
+    one = _gpu.run_batch(prm, one_launch=True, repeat=2, **kw)
+    assert int(one.tickets.abs().sum()) == 0
+    _assert_same_outputs(ref, _all_outputs(one, nat), case)
+    assert int((ref["result"]["n_valid"] > 0).sum()) >= 1
+
+
+def test_one_launch_rejects_what_it_does_not_cover():
+    _gpu, nat, Circle, _ = _imports()
+    import ctypes as C
+    eng = _gpu.run_batch(fo.OracleParams.defaults("v1"), (0.0, 0.0, 0.0), (0.0, 2.5, 0.0), 0.0, trajectory=Circle(8, 5, 2))
+    from otg_b200.engine import make_params
+    P = make_params(_gpu.planner_attrs(fo.OracleParams.defaults("v1")), 0, 0.1, False)
+    full = nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER | nat.STAGE_ONE_LAUNCH
+    for stages, mask in ((full & ~nat.STAGE_K1, 0), (full | nat.STAGE_NO_FUSE, 0), (full | nat.STAGE_CURVATURE | nat.STAGE_K3, 0),
+                         (full | nat.STAGE_K4, 0), (full, nat.MASK_COLLISION)):
+        rc = nat.lib.frenet_plan(C.byref(eng.L), C.byref(P), C.byref(eng.path_handle(Circle(8, 5, 2)).desc), C.byref(eng.B), stages, mask, 0, None)
+        assert rc == nat.ERR_BAD_ARG, (stages, mask)
+    tk, eng.B.tickets = eng.B.tickets, None
+    assert nat.lib.frenet_plan(C.byref(eng.L), C.byref(P), None, C.byref(eng.B), full, 0, 0, None) == nat.ERR_BAD_ARG
+    eng.B.tickets = tk
+
+
+def test_collision_only_one_launch_equals_standalone_k4():
+    """Second form of FRENET_STAGE_ONE_LAUNCH: K4 | K5 | GATHER on a lattice that is already sampled - the collision stage from the
+    row-level table without reading a stored sample back, then the masked argmin + gather in the same kernel.  Masks, first
+    blockers, the record and the winner must equal the standalone K4 sweep followed by K5 + gather; the lattice itself (samples,
+    costs, flags) must be left untouched."""
+    _gpu, nat, _, Spline = _imports()
+    from otg_b200 import workloads as w
+    prm = _dense_prm()
+    sc = w.config5_scenarios()
+    idx = np.r_[3:6]
+    fs, fd = w.moving_obstacle_frenet(sc["obs_s"][idx], sc["obs_d"][idx], sc["obs_speed"][idx], sc["obs_offset"][idx], sc["t0"][idx, None])
+    ox, oy = fo.frenet_to_cartesian(fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY), fs, fd)
+    obs = np.stack([ox, oy], 2)[:, :64]
+    tr = Spline(w.SPLINE_WX, w.SPLINE_WY)
+    kw = dict(p0=sc["p0"][idx], s0=sc["s0"][idx], t0=sc["t0"][idx], dd=sc["dd"][idx], trajectory=tr)
+    ref = _all_outputs(_gpu.run_batch(prm, obstacles=obs, gather_sel=nat.SEL_MASKED, no_fuse=True, **kw), nat)
+    eng = _gpu.run_batch(prm, **kw)                       # K1, fused K2 + K3, K5: no obstacles yet
+    before = _all_outputs(eng, nat)
+    # an engine sampled with room for 64 obstacles, its collision outputs wiped, then the collision-only launch (twice: tickets)
+    from otg_b200.engine import FrenetEngine
+    e = FrenetEngine(len(idx))
+    _gpu.run_batch(prm, engine=e, obstacles=obs, **kw)
+    e.coll_free.zero_()
+    e.first_blocker.fill_(-7)
+    P = _gpu.make_params(_gpu.planner_attrs(prm), 0, prm.delta_t, False)
+    for _ in range(2):
+        e.run(P, e.path_handle(tr), nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER | nat.STAGE_ONE_LAUNCH, nat.MASK_COLLISION, nat.SEL_MASKED)
+    assert int(e.tickets.abs().sum()) == 0
+    e.has_xy = e.has_collision = True
+    got = _all_outputs(e, nat)
+    valid = [ref[b]["valid"] for b in range(len(idx))]
+    assert np.array_equal(got["result"], ref["result"]) and np.array_equal(got["steps"], ref["steps"])
+    for b in range(len(idx)):
+        for name in ("coll_free", "first_blocker"):
+            assert np.array_equal(got[b][name][valid[b]], ref[b][name][valid[b]]), (b, name)
+        for name in ("d", "x", "y", "s", "ctot", "cd", "valid", "winner"):
+            assert np.array_equal(got[b][name], ref[b][name], equal_nan=True), (b, name)
+        assert np.array_equal(before[b]["x"], got[b]["x"], equal_nan=True)
+    assert 0 < sum(int((ref[b]["coll_free"][valid[b]] == 0).sum()) for b in range(len(idx))) < sum(int(v.sum()) for v in valid)

@@ -478,3 +478,71 @@ def test_duckietown_lane_reference_style_trajectory_and_step():
     assert fo.check_collisions(x, y, n, pts, fo.AGENT_SAFETY_RAD ** 2)[0][0]
     assert not fo.offroad(x, y, n, (0.32, 0.05, -0.29), "right")[0] and not fo.offroad(x, y, n, (0.28, 0.05, 0.33), "left")[0]
     assert pl.opt_path_tot.ctot == min(f.ctot for f in kept)
+
+
+@pytest.mark.parametrize("lattice", ["default", "dense"])
+def test_speculative_replan_equals_the_plain_call_sequence(lattice):
+    """A planner remembers the path frenet_to_glob was given and - once check_paths has seen the same obstacle set twice - the
+    obstacles, and its next replan runs transform, collision stage and the masked pick in the same launch (one kernel:
+    FRENET_STAGE_ONE_LAUNCH); frenet_to_glob / check_paths then only validate.  Every call of the sequence must return what a
+    planner without any of this returns (separate launches, device-side I/O blocks, no speculation), on a static scene (hits),
+    after the scene changes (a miss, then hits again) and when nothing is sensed."""
+    import otg_b200  # noqa: F401
+    from otg_b200 import drivers, workloads as w
+    from otg_b200.drivers import moving_obstacle_planner as mv
+    from otg_b200.planner import TrajectoryPlannerV1, TrajectoryPlannerParams
+    from otg_b200.sensor import StaticObstacle
+    from otg_b200.trajectory import CircleTrajectory2D, SplineTrajectory2D
+    if lattice == "dense":
+        sc = w.config4_scenario()
+        tr = SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY)
+        prm = dict(w.DENSE_PARAMS)
+        init = dict(t0=sc["t0"], p0=sc["p0"], s0=sc["s0"], dd=sc["dd"])
+        xy = np.stack(fo.frenet_to_cartesian(fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY), sc["obs_s"], sc["obs_d"]), 1)[:40]
+    else:
+        tr = CircleTrajectory2D(8, 5, 2)
+        prm = {}
+        init = dict(t0=0.1, p0=(0.0, 0.0, 0.0), s0=(3.0, 2.0, 0.0))
+        xy = np.array([[5.0, 0.3], [6.0, -1.0], [4.5, 2.5], [9.0, 1.0]])
+
+    class Sees:
+        def __init__(self):
+            self.obstacles = [StaticObstacle(p.copy()) for p in xy]
+
+        def sense(self, *a, **k):
+            return list(self.obstacles)
+
+    planners = [TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64),
+                TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _speculate=False, _one_launch=False, _zero_copy=False)]
+    sensors = [Sees(), Sees()]
+    for pl in planners:
+        pl.initialize(**init)
+    hits = 0
+    for step in range(12):
+        t = init["t0"] + 0.1 * (step + 1)
+        if step == 6:                      # the scene changes: one obstacle moves, one disappears
+            for s in sensors:
+                s.obstacles[0].position = s.obstacles[0].position + np.array([0.4, -0.2])
+                s.obstacles.pop()
+        if step == 10:                     # nothing in sight
+            for s in sensors:
+                s.obstacles = []
+        out = []
+        for pl, s in zip(planners, sensors):
+            pos = pl.replanner(t)
+            if pl is planners[0] and getattr(pl._engine, "spec_pos", None) is not None:
+                hits += 1
+            paths = drivers.frenet_to_glob(pl, tr, pl.paths)
+            kept, leading = mv.check_paths(paths, s, None)
+            pl.paths = kept
+            best = drivers.best_path(kept)
+            pl.opt_path_tot = best
+            out.append((pos, len(kept), len(leading), best, [leading[i].position.tolist() for i in range(min(3, len(leading)))]))
+        (pa, na, la, fa, ba), (pb, nb, lb, fb, bb) = out
+        assert pa == pb and na == nb and la == lb and ba == bb, step
+        assert fa.index == fb.index and (fa.cd, fa.cv, fa.ct, fa.ctot) == (fb.cd, fb.cv, fb.ct, fb.ctot), step
+        for name in NAMES9 + ("x", "y"):
+            assert getattr(fa, name) == getattr(fb, name), (step, name)
+        if step in (3, 8):                 # and element access through the lazy views
+            assert [f.index for f in planners[0].paths[:5]] == [f.index for f in planners[1].paths[:5]]
+    assert hits >= 5          # replans 3..6 and 9.. ran with the obstacles on board
