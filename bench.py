@@ -859,7 +859,7 @@ def run_gpu(args):
                 "gpu_launches": bp.launches_per_plan * args.steps,
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity_spot_check": spot, "clocks": clk,
                 "candidate_timesteps_per_step": cts_step,
-                "replan_latency": replan_latency() if (world == 1 and not args.kernels_only) else None,
+                "replan_latency": None,
                 "literal_obstacle_fields": None, "fp32_fast_path": None,
                 "predicted_obstacles": None, "all_feasibility_checks": None, "default_lattice_batch": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))},
@@ -868,6 +868,14 @@ def run_gpu(args):
         if world == 1 and not args.kernels_only:
             del bp
             torch.cuda.empty_cache()
+            # single-replan latency through the drop-in API: the default planner (one kernel per replan with its inputs as the
+            # kernel argument, results written to mapped pinned memory, transform / collision stage riding along once the driver
+            # has shown its path and a repeating obstacle set), the same without the speculation (what a scene of MOVING obstacles
+            # gets), and with every round-2 latency feature off (separate launches in a graph, copy nodes: round 1's path)
+            lat = replan_latency()
+            lat["no_speculation"] = replan_latency(_speculate=False)
+            lat["separate_launches_copy_nodes_no_speculation"] = replan_latency(_zero_copy=False, _one_launch=False, _speculate=False)
+            line["replan_latency"] = lat
             line["literal_obstacle_fields"] = literal_field_legs(dev, lo, hi, max(3, args.steps // 3))
             line["fp32_fast_path"] = fp32_fast_path(wl, max(3, args.steps // 3), dev, peak, rec_f64)
             line["predicted_obstacles"] = predicted_mode(wl, max(3, args.steps // 3), dev)

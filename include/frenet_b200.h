@@ -212,6 +212,18 @@ typedef struct FrenetBuffers {
                                   argmin record (frenet_workspace_bytes reports the size as `partials`) */
 } FrenetBuffers;
 
+/* Inline inputs of frenet_replan_inline: ONE planner's per-replan inputs, passed to the kernel as an argument (no copy node). */
+#define FRENET_INLINE_MAX_V 16   /* longitudinal targets */
+#define FRENET_INLINE_MAX_T 24   /* horizons (follow-mode target triples) */
+typedef struct FrenetInline {
+    int32_t present;           /* 0: not used; 1: state, scal, axis_v, n_v; 2: + target */
+    int32_t n_v;
+    double state[6];
+    double scal[3];
+    double axis_v[FRENET_INLINE_MAX_V];
+    double target[FRENET_INLINE_MAX_T * 3];
+} FrenetInline;
+
 /* Lane boundaries for frenet_k3_offroad: each a parabola in vertex form (h, k, a) =
  * get_vertex_and_focus_distance(fit) (lib/tests/test_mapper_planner_obstacles.py:105-109). */
 typedef struct FrenetRoad {
@@ -297,6 +309,18 @@ int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetP
  * Point i is written to x[i * out_stride], y[i * out_stride] (out_stride 2 with y = x + 1 fills an [n][2] table). */
 int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
                                int64_t out_stride, frenet_stream_t stream);
+
+/* frenet_plan with FRENET_STAGE_ONE_LAUNCH (first form: K1 | K2 ... ) for ONE planner (n_scen == 1) whose per-replan inputs are read
+ * from HOST memory at call time and handed to the kernel as an argument: h_state[6], h_scal[3], h_axis_v[n_v_cap], *h_n_v and - in
+ * follow mode - h_target[n_t][3] (NULL otherwise).  The kernel spills them into buf->state / scal / target and lat->axis_v / n_v
+ * (which must be device-writable), so later launches on the same buffers (check_paths' collision stage, a gather) see them.  No
+ * host-to-device copy, no graph: a replan is this one launch.  n_v_cap <= FRENET_INLINE_MAX_V, n_t <= FRENET_INLINE_MAX_T in
+ * follow mode (FRENET_ERR_CAPACITY otherwise - use frenet_plan).  wait != 0: the call returns after the stream has drained (the
+ * results are then in buf->result / winner).  Replaces the same reference code as frenet_plan
+ * (lib/planner/trajectory_planner.py:108-181, 206-212). */
+int frenet_replan_inline(const FrenetLattice* lat, const FrenetParams* prm, const FrenetPath* path, const FrenetBuffers* buf, int32_t stages,
+                         int32_t use_mask, int32_t gather_sel, const double* h_state, const double* h_scal, const double* h_axis_v,
+                         const int32_t* h_n_v, const double* h_target, int32_t wait, frenet_stream_t stream);
 
 /* EXTENSION - device-side obstacle prediction: fills a predicted table [n_scen][n_obs][n_steps][2] from the moving-obstacle
  * time law of the reference (lib/sensor/dynamic_obstacle.py:43-56): at step k obstacle o of scenario b sits at arc length

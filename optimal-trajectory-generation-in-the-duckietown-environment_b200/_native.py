@@ -26,6 +26,7 @@ STAGE_K1, STAGE_K2, STAGE_K3, STAGE_K4, STAGE_K5, STAGE_GATHER, STAGE_CURVATURE,
 STAGE_OFFROAD = 256
 STAGE_ONE_LAUNCH = 512
 PARTIAL_BYTES, MAX_ROW_PARTS = 72, 8
+INLINE_MAX_V, INLINE_MAX_T = 16, 24
 FUSE_COLLISION, FUSE_CURVATURE = 1, 2
 MASK_KINEMATIC, MASK_CURVATURE, MASK_COLLISION, MASK_ROAD = 1, 2, 4, 8
 
@@ -123,6 +124,8 @@ def _load():
         "frenet_gather_winner": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_int32, C.c_int32, C.c_void_p]),
         "frenet_plan": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
+        "frenet_replan_inline": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
         "frenet_predict_obstacles": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                                C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
         "frenet_advance_state": (C.c_int, [P(FrenetLattice), P(FrenetBuffers), C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32,

@@ -96,6 +96,30 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     return code;
 }
 
+// Debug build only (-DFRENET_PHASE_TIMING=1): the latest arrival of any CTA's thread 0 at each phase mark of the one-launch
+// replan, in globaltimer nanoseconds (mark 0: the earliest) - scripts/phase_times.py reads them through frenet_debug_phase_times.
+// 1: after the table's resolve passes only the candidates with an uncertain obstacle go through the exact-test pass (compacted
+// list); 0: all of them walk through it (A/B, profiles/r2_history.md)
+#ifndef FRENET_POST_COMPACT
+#define FRENET_POST_COMPACT 1
+#endif
+#ifndef FRENET_PHASE_TIMING
+#define FRENET_PHASE_TIMING 0
+#endif
+#if FRENET_PHASE_TIMING
+__device__ unsigned long long g_phase_ts[16];
+#define FRENET_PHASE(i)                                                                     \
+    do {                                                                                    \
+        if (threadIdx.x == 0) {                                                             \
+            unsigned long long t_;                                                          \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                          \
+            if ((i) == 0) atomicMin(&g_phase_ts[0], t_); else atomicMax(&g_phase_ts[(i)], t_); \
+        }                                                                                   \
+    } while (0)
+#else
+#define FRENET_PHASE(i) do { } while (0)
+#endif
+
 #define FRENET_CHECK_LAUNCH(name)                                        \
     do {                                                                 \
         cudaError_t e_ = cudaGetLastError();                             \
@@ -331,6 +355,26 @@ __global__ void __launch_bounds__(256) k1_coefficients(FrenetLattice L, FrenetPa
 // first solves the boundary-value systems of its own rows (the K1 cells it is about to sample), and the CTA that finishes LAST
 // (a ticket per scenario, taken after a device-wide fence) runs the argmin and the winner gather for the scenario.
 // ------------------------------------------------------------------------------------------------
+// Inline inputs (frenet_replan_inline): ONE planner's per-replan inputs - a few hundred bytes - travel as a kernel ARGUMENT, so a
+// replan needs no host-to-device copy in front of its only kernel.  Every CTA spills them to the buffers' input arrays first
+// (identical values: the duplicate stores are harmless), which is where K1 and every later launch read them.
+__device__ __forceinline__ void spill_inline(const FrenetInline& in, const FrenetLattice& L, const FrenetBuffers& B) {
+    if (!in.present) return;
+    double* st = const_cast<double*>(B.state);
+    double* sc = const_cast<double*>(B.scal);
+    double* av = const_cast<double*>(L.axis_v);
+    const int t = threadIdx.x;
+    if (t < 6) st[t] = in.state[t];
+    if (t < 3) sc[t] = in.scal[t];
+    if (t < L.n_v_cap) av[t] = t < FRENET_INLINE_MAX_V ? in.axis_v[t] : 0.0;
+    if (t == 0) const_cast<int32_t*>(L.n_v)[0] = in.n_v;
+    if (in.present > 1 && B.target) {
+        double* tg = const_cast<double*>(B.target);
+        for (int i = t; i < L.n_t * 3; i += blockDim.x) tg[i] = in.target[i];
+    }
+    __syncthreads();
+}
+
 // Partial argmin records: each CTA reduces the candidates it produced itself (they are still in its L1 / L2), so the scenario's
 // last CTA combines a few hundred records instead of sweeping every candidate (a single K5 CTA over the 9600 candidates of a dense
 // lattice takes longer than the evaluate kernel).  The lexicographic (cost, index) minimum is associative: same result as K5.
@@ -387,7 +431,7 @@ __device__ __forceinline__ void block_best(Best (&best)[kKeys], int& nvalid, int
 
 template <bool kCg>
 __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int c, int has_xy,
-                                           double* winner_out = nullptr, int32_t* steps_out = nullptr);
+                                           double* winner_out = nullptr, int32_t* steps_out = nullptr, int tid = -1, int nthreads = 0);
 __device__ __forceinline__ int winner_index(const FrenetResult& res, int sel);
 
 // The CTA's own candidates: `count` of them, the i-th at scenario-relative index first + i * stride.  Then the ticket; the holder of
@@ -422,6 +466,7 @@ __device__ __forceinline__ void mono_tail(const FrenetLattice& L, const FrenetPa
         }
     }
     block_best(best, nvalid, nsurv);
+    FRENET_PHASE(7);
     Partial* part_rec = reinterpret_cast<Partial*>(B.partials) + (int64_t)b * ctas_per_scen;
     if (threadIdx.x == 0) {
         Partial pr;
@@ -438,6 +483,7 @@ __device__ __forceinline__ void mono_tail(const FrenetLattice& L, const FrenetPa
         if (sh_last) B.tickets[b] = 0;      // ready for the next launch (stream order)
     }
     __syncthreads();
+    FRENET_PHASE(8);
     if (!sh_last) return;
     __threadfence();
 #pragma unroll
@@ -451,6 +497,7 @@ __device__ __forceinline__ void mono_tail(const FrenetLattice& L, const FrenetPa
         nsurv += __ldcg(&pr->nsurv);
     }
     block_best(best, nvalid, nsurv);
+    FRENET_PHASE(9);
     if (threadIdx.x == 0) {
         FrenetResult res;
         auto idx = [](const Best& x) { return x.i == 0x7fffffff ? -1 : x.i; };
@@ -471,11 +518,18 @@ __device__ __forceinline__ void mono_tail(const FrenetLattice& L, const FrenetPa
     }
     if (gather_sel >= 0) {
         __syncthreads();
-        gather_one<true>(L, P, B, b, sh_winner, has_xy);
-        // the masked pick as well, in its own block: a replan launched with the obstacles the driver will most likely present to
-        // check_paths next leaves BOTH answers behind (the planner's unmasked winner and the driver's masked one)
-        if (B.winner_masked && B.winner_masked_steps) gather_one<true>(L, P, B, b, sh_winner2, has_xy, B.winner_masked, B.winner_masked_steps);
+        // With a mask in use the masked pick is gathered as well, into its own block: a replan launched with the obstacles the driver
+        // will most likely present to check_paths next leaves BOTH answers behind (the planner's unmasked winner and the driver's
+        // masked one).  The two copies are independent: one half of the CTA's warps takes each.
+        if (use_mask && B.winner_masked && B.winner_masked_steps) {
+            const int half = blockDim.x / 2;
+            if ((int)threadIdx.x < half) gather_one<true>(L, P, B, b, sh_winner, has_xy, nullptr, nullptr, threadIdx.x, half);
+            else gather_one<true>(L, P, B, b, sh_winner2, has_xy, B.winner_masked, B.winner_masked_steps, threadIdx.x - half, blockDim.x - half);
+        } else {
+            gather_one<true>(L, P, B, b, sh_winner, has_xy);
+        }
     }
+    FRENET_PHASE(10);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1088,9 +1142,11 @@ __device__ __forceinline__ void row_table_chunk(const RowTable& T, int ch, int s
 // Per candidate: lowest certain blocker, and the obstacles below it that only `maybe` block.  All threads of the CTA take part:
 // work item (chunk, candidate) scans that chunk's list; the candidates' results are combined with shared-memory atomics.
 // Pass 1 (T.first preset to kNoBlocker): lowest obstacle whose inner interval contains the candidate.
-__device__ __forceinline__ void row_table_resolve_first(const RowTable& T, int n_d, int O, int nch) {
-    for (int w = threadIdx.x; w < n_d * nch; w += blockDim.x) {
-        const int ch = w / n_d, id = w - ch * n_d;
+// (a CTA that owns only every n_parts-th candidate of a split row resolves only those)
+__device__ __forceinline__ void row_table_resolve_first(const RowTable& T, int n_d, int O, int nch, int n_parts = 1, int my_part = 0) {
+    const int n_own = (n_d - my_part + n_parts - 1) / n_parts;
+    for (int w = threadIdx.x; w < n_own * nch; w += blockDim.x) {
+        const int ch = w / n_own, id = my_part + (w - ch * n_own) * n_parts;
         const unsigned* ivl = T.ivl + ch * O;
         const unsigned short* ids = T.id + ch * O;
         const int cnt = T.cnt[ch];
@@ -1105,9 +1161,10 @@ __device__ __forceinline__ void row_table_resolve_first(const RowTable& T, int n
 }
 // Pass 2 (T.n_maybe preset to 0): obstacles below it that contain the candidate only in their outer interval.  The same obstacle can
 // be listed by several chunks; it is then re-tested more than once, which is harmless.
-__device__ __forceinline__ void row_table_resolve_maybe(const RowTable& T, int n_d, int O, int nch) {
-    for (int w = threadIdx.x; w < n_d * nch; w += blockDim.x) {
-        const int ch = w / n_d, id = w - ch * n_d;
+__device__ __forceinline__ void row_table_resolve_maybe(const RowTable& T, int n_d, int O, int nch, int n_parts = 1, int my_part = 0) {
+    const int n_own = (n_d - my_part + n_parts - 1) / n_parts;
+    for (int w = threadIdx.x; w < n_own * nch; w += blockDim.x) {
+        const int ch = w / n_own, id = my_part + (w - ch * n_own) * n_parts;
         const unsigned* ivl = T.ivl + ch * O;
         const unsigned short* ids = T.id + ch * O;
         const int cnt = T.cnt[ch];
@@ -1269,6 +1326,7 @@ __device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const F
             __syncthreads();   // phase A reads the spline table and the first / last candidate's coefficients
         }
     }
+    FRENET_PHASE(3);
     // Row table: usable only if the lateral axis is a uniform ascending grid and the staged coefficients are affine in the target
     // (what K1 produces; anything else - a caller's own coefficients - takes the per-candidate sweep).
     bool table_bad = false;
@@ -1387,6 +1445,7 @@ __device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const F
         }
         __syncthreads();
     }
+    FRENET_PHASE(4);
     const double clong = sh_clong;
     const bool rowfeas = sh_rowfeas;
     // Row table (see row_table_chunk): built by all warps once per row, then resolved per candidate.
@@ -1404,6 +1463,7 @@ __device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const F
             row_table_chunk(RT, item / nsub, item % nsub, nsub, A.N, fpx, fpy, fnx, fny, obs, B.n_obs, D0, D1, L.n_d, Rf, R2f, cM,
                             RT.scratch + warp * B.n_obs, lane);
     }
+    FRENET_PHASE(11);     // (warp 0 has built its share of the row table)
     // row constants of the lateral cost, fetched once (not per candidate, where a global load would stall the warp's epilogue)
     const double horizon = low ? B.row_S[br] : L.axis_t[A.iT];
     const double dd_target = B.scal[(int64_t)A.b * 3];
@@ -1559,18 +1619,36 @@ __device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const F
             RT.n_maybe[tid] = 0;
         }
         __syncthreads();
+        FRENET_PHASE(5);
+        if (tid == 0) sh_next = 0;          // every warp has left the hand-out loop: the counter now counts the candidates left for the exact test
+        // A_k / B_k are not needed any more: their storage ([2 n_pad_max] floats >= 132 shorts >= n_d) takes the list of candidates
+        // that still need the exact test - about one in a hundred; everybody else's answer is final after the resolve passes
+        unsigned short* todo = reinterpret_cast<unsigned short*>(RT.mA);
+        int n_todo = (L.n_d - part + parts - 1) / parts;       // rows the table does not cover: every own candidate
         if (table_ok) {
-            row_table_resolve_first(RT, L.n_d, B.n_obs, nch);
+            row_table_resolve_first(RT, L.n_d, B.n_obs, nch, parts, part);
             __syncthreads();
-            row_table_resolve_maybe(RT, L.n_d, B.n_obs, nch);
+            row_table_resolve_maybe(RT, L.n_d, B.n_obs, nch, parts, part);
             __syncthreads();
+#if FRENET_POST_COMPACT
+            if (tid < L.n_d && tid % parts == part) {
+                resi[tid * 2 + 1] = RT.first[tid];
+                if (RT.n_maybe[tid] > 0) todo[atomicAdd(&sh_next, 1)] = (unsigned short)tid;
+            }
+            __syncthreads();
+            n_todo = sh_next;
+#else
+            if (tid < n_todo) todo[tid] = (unsigned short)(tid * parts + part);     // A/B: every candidate walks through the post pass
+            __syncthreads();
+#endif
         }
+        FRENET_PHASE(12);
         // The few candidates with an uncertain obstacle below their first certain blocker - and every candidate of a row the table
         // does not cover - get the reference's fp64 test on their samples, recomputed from shared memory exactly as the sampling loop
         // formed them (same FMA sequence, same unfused pt + n * d), so that nothing is read back from HBM (and the fp32 fast path,
         // whose stored samples are rounded, tests the same fp64 points).
-        for (int q = warp; q * parts + part < L.n_d; q += nwarps) {
-            const int id = q * parts + part;
+        for (int q = warp; q < n_todo; q += nwarps) {
+            const int id = table_ok ? (int)todo[q] : q * parts + part;
             int best = kNoBlocker, nm = kMaybeCap + 1;
             if (table_ok) {
                 best = RT.first[id];
@@ -1619,6 +1697,7 @@ __device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const F
         }
     }
     __syncthreads();
+    FRENET_PHASE(13);
     for (int id = tid; id < L.n_d; id += blockDim.x) {
         if (id % parts != part) continue;   // another part's candidate
         const int64_t c = A.cand0 + id;
@@ -1639,14 +1718,20 @@ __device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const F
 // kMono: the one-launch replan (see mono_tail) - K1 of the row in front, K5 + gather by the scenario's last CTA behind.
 template <bool kXY, int kColl, bool kLimits, bool kSplit, bool kF32 = false, bool kMono = false, bool kCollOnly = false>
 __global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl))      // (kMono too: a dense single planner is hundreds of CTAs, occupancy matters)
-k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts, float radius_up, int use_mask, int gather_sel, int has_xy) {
+k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts, float radius_up, int use_mask, int gather_sel, int has_xy,
+            FrenetInline inl) {
+    FRENET_PHASE(0);
     if (kMono && !kCollOnly) {
+        spill_inline(inl, L, B);
+        FRENET_PHASE(1);
         // every part of a split row solves the row's n_d cells itself (identical values: the duplicate stores are harmless)
         const int64_t cand0 = (int64_t)blockIdx.x * L.n_d;
         for (int id = threadIdx.x; id < L.n_d; id += blockDim.x) k1_cell(L, P, B, cand0 + id);
         __syncthreads();
     }
+    FRENET_PHASE(2);
     k2_evaluate_body<kXY, kColl, kLimits, kSplit, kF32, kCollOnly>(L, P, path, B, opts, radius_up);
+    FRENET_PHASE(6);
     if (kMono) {
         const int R = L.n_v_cap * L.n_t;
         const int b = (int)(blockIdx.x / R), r = (int)(blockIdx.x % R);
@@ -1724,6 +1809,7 @@ __device__ __forceinline__ void k2_short_body(const FrenetLattice& L, const Fren
         }
     }
 
+    FRENET_PHASE(3);
     // Phase A: a warp per row.
     for (int g = warp; g < Ga; g += nwarps) {
         const int64_t br = br0 + g;
@@ -1790,6 +1876,7 @@ __device__ __forceinline__ void k2_short_body(const FrenetLattice& L, const Fren
         }
     }
     __syncthreads();
+    FRENET_PHASE(4);
 
     const double dd_target = B.scal[(int64_t)b * 3];
     const float Rf = kColl ? __double2float_ru(sqrt(P.radius_sq)) : 0.0f;
@@ -1901,6 +1988,7 @@ __device__ __forceinline__ void k2_short_body(const FrenetLattice& L, const Fren
         }
     }
     __syncthreads();
+    FRENET_PHASE(5);
     // per-candidate results of the whole group, written coalesced; candidates of rows that do not exist get the neutral record
     for (int c = tid; c < Ga * nd; c += blockDim.x) {
         const bool usable = rowi[4 * (c / nd) + 2];
@@ -1919,17 +2007,22 @@ __device__ __forceinline__ void k2_short_body(const FrenetLattice& L, const Fren
 
 template <bool kXY, int kColl, bool kLimits, bool kMono = false>
 __global__ void __launch_bounds__(kRowThreads, kMono ? 1 : (kColl ? FRENET_K2_MIN_CTAS_COLL : FRENET_K2_MIN_CTAS))
-k2_short(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int G, int opts, int use_mask, int gather_sel, int has_xy) {
+k2_short(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int G, int opts, int use_mask, int gather_sel, int has_xy, FrenetInline inl) {
     const int R = L.n_v_cap * L.n_t;
     const int groups = (R + G - 1) / G;
+    FRENET_PHASE(0);
     if (kMono) {
+        spill_inline(inl, L, B);
+        FRENET_PHASE(1);
         const int b = blockIdx.x / groups, row0 = (blockIdx.x % groups) * G;
         const int cells = min(G, R - row0) * L.n_d;
         const int64_t cand0 = ((int64_t)b * R + row0) * L.n_d;
         for (int i = threadIdx.x; i < cells; i += blockDim.x) k1_cell(L, P, B, cand0 + i);
         __syncthreads();
     }
+    FRENET_PHASE(2);
     k2_short_body<kXY, kColl, kLimits>(L, P, path, B, G, opts);
+    FRENET_PHASE(6);
     if (kMono) {
         const int b = blockIdx.x / groups, g = blockIdx.x % groups;
         if (skipped(B, b)) return;
@@ -2633,12 +2726,13 @@ __device__ __forceinline__ T ld_res(const T* p) {
 
 template <bool kCg>
 __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int c, int has_xy,
-                                           double* winner_out, int32_t* steps_out) {
+                                           double* winner_out, int32_t* steps_out, int tid, int nthreads) {
+    if (tid < 0) { tid = threadIdx.x; nthreads = blockDim.x; }     // default: the whole CTA copies
     // (default: the buffers' winner block; the one-launch replan also fills buf->winner_masked through the explicit form)
     double* const wbase = winner_out ? winner_out : B.winner;
     int32_t* const steps = steps_out ? steps_out : B.winner_steps;
     if (c < 0) {
-        if (threadIdx.x == 0) steps[b] = 0;
+        if (tid == 0) steps[b] = 0;
         return;
     }
     const int r = c / L.n_d, id = c % L.n_d;
@@ -2655,7 +2749,7 @@ __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetP
         pq.load(B.coef_lat + ((int64_t)b * L.n_v_cap * L.n_t * L.n_d + c) * 6);
         const bool low = B.row_flags[(int64_t)b * L.n_v_cap * L.n_t + r] & FRENET_ROW_LOWSPEED;
         const double s0 = B.state[(int64_t)b * 6 + 3];
-        for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
+        for (int k = tid; k < A.N; k += nthreads) {
             w[k] = __dadd_rn(__dmul_rn((double)k, P.sample_period), t0);   // two roundings, like the reference's arange()[k] + t_initial
             const double u = low ? fabs(lon[k] - s0) : (double)k * P.sample_period;
             double v0, v1, v2, v3;
@@ -2669,7 +2763,7 @@ __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetP
             }
         }
     } else
-    for (int k = threadIdx.x; k < A.N; k += blockDim.x) {
+    for (int k = tid; k < A.N; k += nthreads) {
         w[k] = __dadd_rn(__dmul_rn((double)k, P.sample_period), t0);   // f.t[i] += t_initial (:178-179): product and sum rounded separately
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
@@ -2681,8 +2775,8 @@ __device__ __forceinline__ void gather_one(const FrenetLattice& L, const FrenetP
             w[10 * L.n_pad_max + k] = ld_res<kCg>(cand + 5 * A.npad + k);
         }
     }
-    if (threadIdx.x < 4) w[11 * L.n_pad_max + threadIdx.x] = ld_res<kCg>(B.cost + threadIdx.x * A.candF + A.cand0 + id);
-    if (threadIdx.x == 0) steps[b] = A.N;
+    if (tid < 4) w[11 * L.n_pad_max + tid] = ld_res<kCg>(B.cost + tid * A.candF + A.cand0 + id);
+    if (tid == 0) steps[b] = A.N;
 }
 
 constexpr int kArgminThreads = 512;
@@ -2895,15 +2989,18 @@ K2Shape k2_shape(const FrenetLattice* L, bool xy, int coll, int n_knots_spline, 
     // second wave would pay again (config 4: 120 rows x 8 parts = 960 CTAs in two waves took 34 us, x 4 in one wave less)
     S.parts = 1;
     const int64_t slots = (int64_t)k2_min_ctas(coll) * 148;
-    while (S.parts < FRENET_MAX_ROW_PARTS && (int64_t)n_rows(L) * S.parts * 2 <= slots && S.parts * (kRowThreads / kWarp) < L->n_d) S.parts *= 2;
+    while (S.parts < FRENET_MAX_ROW_PARTS && (int64_t)n_rows(L) * (S.parts + 1) <= slots && S.parts * (kRowThreads / kWarp) < L->n_d) ++S.parts;
     S.grid = n_rows(L);
     return S;
 }
 
 // mono != nullptr: the one-launch replan - {use_mask, gather_sel, has_xy} of the K5 + gather tail (see mono_tail)
+const FrenetInline kNoInline = {};
+
 template <bool kXY, int kColl>
 int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int opts, cudaStream_t stream,
-              const int* mono = nullptr) {
+              const int* mono = nullptr, const FrenetInline* inl_in = nullptr) {
+    const FrenetInline& inl = inl_in ? *inl_in : kNoInline;
     // opts bit 0: also test the curvature limit in the kernel (needs kXY; selects the limits variant)
     const bool limits = !(isinf(P->v_max) && P->v_max > 0 && isinf(P->a_max) && P->a_max > 0) || (kXY && (opts & 1));
     const bool spline = kXY && path->kind == FRENET_PATH_SPLINE;
@@ -2921,7 +3018,7 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     do {                                                                                                                            \
         if (int rc = set_smem(k2_short<kXY, kColl, LIM, MONO>, S.smem, "k2: row group does not fit shared memory")) return rc;      \
         k2_short<kXY, kColl, LIM, MONO><<<S.grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, S.rows_per_cta, opts,              \
-                                                                                 mono ? mono[0] : 0, mono ? mono[1] : -1, mono ? mono[2] : 0); \
+                                                                                 mono ? mono[0] : 0, mono ? mono[1] : -1, mono ? mono[2] : 0, inl); \
     } while (0)
         if constexpr (kColl != 2) {
             if (mono && mono[3]) return fail(FRENET_ERR_BAD_ARG, "one launch: the collision-only form needs a long-horizon lattice (more than 32 padded samples)");
@@ -2945,10 +3042,10 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
             const dim3 grid1(S.grid, 1);
             if (limits) {
                 if (int rc = set_smem(k2_evaluate<true, kColl, true, false, true>, S.smem, "k2: row does not fit shared memory")) return rc;
-                k2_evaluate<true, kColl, true, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, 0, -1, 0);
+                k2_evaluate<true, kColl, true, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, 0, -1, 0, kNoInline);
             } else {
                 if (int rc = set_smem(k2_evaluate<true, kColl, false, false, true>, S.smem, "k2: row does not fit shared memory")) return rc;
-                k2_evaluate<true, kColl, false, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, 0, -1, 0);
+                k2_evaluate<true, kColl, false, false, true><<<grid1, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, 0, -1, 0, kNoInline);
             }
             FRENET_CHECK_LAUNCH("k2_evaluate (fp32 fast path)");
         }
@@ -2959,13 +3056,13 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     do {                                                                                                                                    \
         if (int rc = set_smem(k2_evaluate<kXY, kColl, LIM, SPLIT, false, MONO>, S.smem, "k2: row does not fit shared memory")) return rc;   \
         k2_evaluate<kXY, kColl, LIM, SPLIT, false, MONO><<<grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up,            \
-                                                                                                mono ? mono[0] : 0, mono ? mono[1] : -1, mono ? mono[2] : 0); \
+                                                                                                mono ? mono[0] : 0, mono ? mono[1] : -1, mono ? mono[2] : 0, inl); \
     } while (0)
     if constexpr (kColl != 2) {
         if constexpr (kXY && kColl == 1 && kRowTable) {
             if (mono && mono[3]) {   // collision stage alone on an existing lattice + the K5 / gather tail
                 if (int rc = set_smem(k2_evaluate<true, 1, false, true, false, true, true>, S.smem, "k2: row does not fit shared memory")) return rc;
-                k2_evaluate<true, 1, false, true, false, true, true><<<grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, mono[0], mono[1], mono[2]);
+                k2_evaluate<true, 1, false, true, false, true, true><<<grid, kRowThreads, S.smem, stream>>>(*L, *P, pd, *B, opts, radius_up, mono[0], mono[1], mono[2], inl);
                 FRENET_CHECK_LAUNCH("k2_evaluate (collision only, one launch)");
                 return FRENET_OK;
             }
@@ -3142,44 +3239,49 @@ int frenet_gather_winner(const FrenetLattice* L, const FrenetParams* P, const Fr
     return FRENET_OK;
 }
 
+// FRENET_STAGE_ONE_LAUNCH (both forms); inl: inline inputs of frenet_replan_inline, or NULL
+static int plan_one_launch(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int32_t stages,
+                           int32_t use_mask, int32_t gather_sel, frenet_stream_t stream, const FrenetInline* inl) {
+    int rc = FRENET_OK;
+    const int need = FRENET_STAGE_K1 | FRENET_STAGE_K2 | FRENET_STAGE_K5 | FRENET_STAGE_GATHER;
+    if ((stages & ~FRENET_STAGE_ONE_LAUNCH) == (FRENET_STAGE_K4 | FRENET_STAGE_K5 | FRENET_STAGE_GATHER)) {
+        // the collision stage alone on a lattice that is already sampled, through the row table (no stored sample is read back),
+        // with the argmin + gather tail: what check_paths needs when the obstacles arrive after the replan
+        if ((rc = check_k2(L, P, B))) return rc;
+        if ((rc = check_path(path))) return rc;
+        if (!B->tickets || !B->partials) return fail(FRENET_ERR_BAD_ARG, "one launch: buf->tickets / buf->partials is NULL");
+        if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "one launch: not available on the fp32 fast path");
+        if (!B->result || !B->winner || !B->winner_steps || !B->coll_free || !B->first_blocker)
+            return fail(FRENET_ERR_BAD_ARG, "one launch: NULL result / winner / collision buffer");
+        if ((use_mask & 2) || (use_mask & 8)) return fail(FRENET_ERR_BAD_ARG, "one launch: curvature / road masks are not produced by this launch");
+        if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "one launch: obstacle table missing");
+        if (B->n_obs_steps > 0 && B->n_obs > 0) return fail(FRENET_ERR_BAD_ARG, "one launch: predicted obstacles are not supported");
+        const int mono[4] = {use_mask, gather_sel, 1, 1};
+        return launch_k2<true, 1>(L, P, path, B, 0, (cudaStream_t)stream, mono, inl);
+    }
+    if ((stages & need) != need || (stages & (FRENET_STAGE_CURVATURE | FRENET_STAGE_NO_FUSE | FRENET_STAGE_OFFROAD)) ||
+        ((stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_K3)))
+        return fail(FRENET_ERR_BAD_ARG, "one launch: needs K1 | K2 | K5 | GATHER (K3, K3 | K4 optional) and none of CURVATURE / NO_FUSE / OFFROAD");
+    if ((rc = check_k2(L, P, B))) return rc;
+    if (!B->tickets || !B->partials) return fail(FRENET_ERR_BAD_ARG, "one launch: buf->tickets / buf->partials is NULL");
+    if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "one launch: not available on the fp32 fast path");
+    if (!B->result || !B->winner || !B->winner_steps) return fail(FRENET_ERR_BAD_ARG, "one launch: NULL result / winner buffer");
+    if ((use_mask & 2) || (use_mask & 8)) return fail(FRENET_ERR_BAD_ARG, "one launch: curvature / road masks are not produced by this launch");
+    if ((use_mask & 4) && !(stages & FRENET_STAGE_K4)) return fail(FRENET_ERR_BAD_ARG, "one launch: collision mask without K4");
+    const int mono[4] = {use_mask, gather_sel, (stages & FRENET_STAGE_K3) ? 1 : 0, 0};
+    if (!(stages & FRENET_STAGE_K3)) return launch_k2<false, 0>(L, P, nullptr, B, 0, (cudaStream_t)stream, mono, inl);
+    if ((rc = check_path(path))) return rc;
+    if (!(stages & FRENET_STAGE_K4)) return launch_k2<true, 0>(L, P, path, B, 0, (cudaStream_t)stream, mono, inl);
+    if (!B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "one launch: collision output is NULL");
+    if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "one launch: obstacle table missing");
+    if (B->n_obs_steps > 0 && B->n_obs > 0) return fail(FRENET_ERR_BAD_ARG, "one launch: predicted obstacles are not supported");
+    return launch_k2<true, 1>(L, P, path, B, 0, (cudaStream_t)stream, mono, inl);
+}
+
 int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int32_t stages,
                 int32_t use_mask, int32_t gather_sel, frenet_stream_t stream) {
     int rc = FRENET_OK;
-    if (stages & FRENET_STAGE_ONE_LAUNCH) {
-        const int need = FRENET_STAGE_K1 | FRENET_STAGE_K2 | FRENET_STAGE_K5 | FRENET_STAGE_GATHER;
-        if ((stages & ~FRENET_STAGE_ONE_LAUNCH) == (FRENET_STAGE_K4 | FRENET_STAGE_K5 | FRENET_STAGE_GATHER)) {
-            // the collision stage alone on a lattice that is already sampled, through the row table (no stored sample is read back),
-            // with the argmin + gather tail: what check_paths needs when the obstacles arrive after the replan
-            if ((rc = check_k2(L, P, B))) return rc;
-            if ((rc = check_path(path))) return rc;
-            if (!B->tickets || !B->partials) return fail(FRENET_ERR_BAD_ARG, "one launch: buf->tickets / buf->partials is NULL");
-            if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "one launch: not available on the fp32 fast path");
-            if (!B->result || !B->winner || !B->winner_steps || !B->coll_free || !B->first_blocker)
-                return fail(FRENET_ERR_BAD_ARG, "one launch: NULL result / winner / collision buffer");
-            if ((use_mask & 2) || (use_mask & 8)) return fail(FRENET_ERR_BAD_ARG, "one launch: curvature / road masks are not produced by this launch");
-            if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "one launch: obstacle table missing");
-            if (B->n_obs_steps > 0 && B->n_obs > 0) return fail(FRENET_ERR_BAD_ARG, "one launch: predicted obstacles are not supported");
-            const int mono[4] = {use_mask, gather_sel, 1, 1};
-            return launch_k2<true, 1>(L, P, path, B, 0, (cudaStream_t)stream, mono);
-        }
-        if ((stages & need) != need || (stages & (FRENET_STAGE_CURVATURE | FRENET_STAGE_NO_FUSE | FRENET_STAGE_OFFROAD)) ||
-            ((stages & FRENET_STAGE_K4) && !(stages & FRENET_STAGE_K3)))
-            return fail(FRENET_ERR_BAD_ARG, "one launch: needs K1 | K2 | K5 | GATHER (K3, K3 | K4 optional) and none of CURVATURE / NO_FUSE / OFFROAD");
-        if ((rc = check_k2(L, P, B))) return rc;
-        if (!B->tickets || !B->partials) return fail(FRENET_ERR_BAD_ARG, "one launch: buf->tickets / buf->partials is NULL");
-        if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "one launch: not available on the fp32 fast path");
-        if (!B->result || !B->winner || !B->winner_steps) return fail(FRENET_ERR_BAD_ARG, "one launch: NULL result / winner buffer");
-        if ((use_mask & 2) || (use_mask & 8)) return fail(FRENET_ERR_BAD_ARG, "one launch: curvature / road masks are not produced by this launch");
-        if ((use_mask & 4) && !(stages & FRENET_STAGE_K4)) return fail(FRENET_ERR_BAD_ARG, "one launch: collision mask without K4");
-        const int mono[4] = {use_mask, gather_sel, (stages & FRENET_STAGE_K3) ? 1 : 0, 0};
-        if (!(stages & FRENET_STAGE_K3)) return launch_k2<false, 0>(L, P, nullptr, B, 0, (cudaStream_t)stream, mono);
-        if ((rc = check_path(path))) return rc;
-        if (!(stages & FRENET_STAGE_K4)) return launch_k2<true, 0>(L, P, path, B, 0, (cudaStream_t)stream, mono);
-        if (!B->coll_free || !B->first_blocker) return fail(FRENET_ERR_BAD_ARG, "one launch: collision output is NULL");
-        if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "one launch: obstacle table missing");
-        if (B->n_obs_steps > 0 && B->n_obs > 0) return fail(FRENET_ERR_BAD_ARG, "one launch: predicted obstacles are not supported");
-        return launch_k2<true, 1>(L, P, path, B, 0, (cudaStream_t)stream, mono);
-    }
+    if (stages & FRENET_STAGE_ONE_LAUNCH) return plan_one_launch(L, P, path, B, stages, use_mask, gather_sel, stream, nullptr);
     if ((stages & FRENET_STAGE_K1) && (rc = frenet_k1_coefficients(L, P, B, stream))) return rc;
     // K2 and K3 (and K4 when nothing sits between them) run as ONE kernel unless the caller asks for separate launches:
     // same arithmetic, same outputs, but every sample is written once instead of being re-read by K3 and K4.
@@ -3205,6 +3307,49 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
         return rc;
     return rc;
 }
+
+int frenet_replan_inline(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int32_t stages,
+                         int32_t use_mask, int32_t gather_sel, const double* h_state, const double* h_scal, const double* h_axis_v,
+                         const int32_t* h_n_v, const double* h_target, int32_t wait, frenet_stream_t stream) {
+    if (!L || !h_state || !h_scal || !h_axis_v || !h_n_v) return fail(FRENET_ERR_BAD_ARG, "replan inline: NULL host input");
+    if (L->n_scen != 1) return fail(FRENET_ERR_BAD_ARG, "replan inline: one planner only (n_scen == 1)");
+    if (L->n_v_cap > FRENET_INLINE_MAX_V || *h_n_v > FRENET_INLINE_MAX_V || *h_n_v < 0)
+        return fail(FRENET_ERR_CAPACITY, "replan inline: longitudinal axis longer than FRENET_INLINE_MAX_V");
+    if (!(stages & FRENET_STAGE_ONE_LAUNCH) || !(stages & FRENET_STAGE_K1))
+        return fail(FRENET_ERR_BAD_ARG, "replan inline: needs FRENET_STAGE_ONE_LAUNCH with K1");
+    FrenetInline in;
+    in.present = 1;
+    in.n_v = *h_n_v;
+    for (int i = 0; i < 6; ++i) in.state[i] = h_state[i];
+    for (int i = 0; i < 3; ++i) in.scal[i] = h_scal[i];
+    for (int i = 0; i < FRENET_INLINE_MAX_V; ++i) in.axis_v[i] = i < L->n_v_cap ? h_axis_v[i] : 0.0;
+    const bool follow = P && (P->follow || (B && B->follow));
+    if (follow) {
+        if (!h_target) return fail(FRENET_ERR_BAD_ARG, "replan inline: follow mode needs target triples");
+        if (L->n_t * 3 > FRENET_INLINE_MAX_T * 3) return fail(FRENET_ERR_CAPACITY, "replan inline: more horizons than FRENET_INLINE_MAX_T");
+        in.present = 2;
+        for (int i = 0; i < L->n_t * 3; ++i) in.target[i] = h_target[i];
+    }
+    if (int rc = plan_one_launch(L, P, path, B, stages, use_mask, gather_sel, stream, &in)) return rc;
+    if (wait) {
+        const cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(FRENET_ERR_CUDA, "replan inline: stream synchronize", e);
+    }
+    return FRENET_OK;
+}
+
+#if FRENET_PHASE_TIMING
+// out[16]; reset != 0 re-arms the marks (0 -> max, the others -> 0)
+int frenet_debug_phase_times(unsigned long long* out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_phase_ts, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {};
+        z[0] = ~0ull;
+        cudaMemcpyToSymbol(g_phase_ts, z, sizeof(z));
+    }
+    return FRENET_OK;
+}
+#endif
 
 int frenet_predict_obstacles(const FrenetPath* path, const double* obs_s, const double* obs_d, const double* obs_speed,
                              const double* t0, int64_t t0_stride, int32_t n_scen, int32_t n_obs, int32_t n_steps, double period,

@@ -221,6 +221,7 @@ class FrenetEngine:
         self._in_host = torch.empty(tot, dtype=torch.uint8, pin_memory=True)
         self._in_dev = self._in_host if self._zc_in else torch.empty(tot, dtype=torch.uint8, device=dev)
         hv = self._in_host.numpy()
+        self._in_host_bytes = hv          # writable byte view of the staging block (struct.pack_into target of the planner's fast path)
         self.state = hv[offs["state"]:offs["state"] + Bn * 48].view(np.float64).reshape(Bn, 6)
         self.scal = hv[offs["scal"]:offs["scal"] + Bn * 24].view(np.float64).reshape(Bn, 3)
         self.axis_v = hv[offs["axis_v"]:offs["axis_v"] + Bn * self.n_v_cap * 8].view(np.float64).reshape(Bn, self.n_v_cap)
@@ -634,6 +635,30 @@ class FrenetEngine:
             return                      # the warm-up run already produced this call's results
         g.replay()
         torch.cuda.current_stream(self._dev_index).synchronize()
+        self._pending = False
+        if stages & nat.STAGE_K2:
+            self.generation += 1
+            self.has_xy = bool(stages & nat.STAGE_K3)
+            self.has_collision = bool(stages & nat.STAGE_K4)
+
+    @_on_device
+    def run_inline(self, params, path, stages, use_mask=0, gather_sel=nat.SEL_CTOT, n_obs=None, follow: bool = False):
+        """ONE planner's replan as one kernel launch and nothing else (frenet_replan_inline): the library reads state / scalars /
+        V axis (/ targets) from the pinned staging block at call time and hands them to the kernel as an ARGUMENT - no copy node,
+        no graph - and returns when the stream has drained.  Falls back to `run_graph` when the shape exceeds the inline
+        capacities.  The obstacle table is NOT part of the inline inputs: a launch that includes K4 tests the table that is on
+        the device (the planner only does that with the obstacles its last check_paths uploaded)."""
+        if self.n_scen != 1 or self.n_v_cap > nat.INLINE_MAX_V or (follow and self.geom.n_t > nat.INLINE_MAX_T) or self._zc_in:
+            return self.run_graph(params, path, stages, use_mask, gather_sel, n_obs)
+        if n_obs is not None:
+            if n_obs > self.n_obs:
+                raise ValueError(f"{n_obs} obstacles exceed the configured capacity {self.n_obs}")
+            self.B.n_obs = int(n_obs)
+        hp, o = self._in_host.data_ptr(), self._in_offs
+        stream = torch._C._cuda_getCurrentRawStream(self._dev_index)
+        nat.check(nat.lib.frenet_replan_inline(C.byref(self.L), C.byref(params), C.byref(path.desc) if path is not None else None,
+                                               C.byref(self.B), int(stages), int(use_mask), int(gather_sel), hp + o["state"], hp + o["scal"],
+                                               hp + o["axis_v"], hp + o["n_v"], hp + o["target"] if follow else None, 1, stream))
         self._pending = False
         if stages & nat.STAGE_K2:
             self.generation += 1

@@ -37,10 +37,19 @@ class WinnerFrenet(Frenet):
 
     def __init__(self, rows, n_rows_valid, costs, index):
         # (no Frenet.__init__: the list slots stay unset until they are asked for)
-        self._rows = rows
-        self._n_valid = n_rows_valid          # 9 without Cartesian samples, 11 with
-        self.cd, self.cv, self.ct, self.ctot = costs
-        self.index = index
+        d = self.__dict__
+        d["_rows"] = rows
+        d["_item"] = rows.item                # (row, index) -> Python float
+        d["_n_valid"] = n_rows_valid          # 9 without Cartesian samples, 11 with
+        d["_touched"] = False                 # True once any list field exists as a list (made on demand or assigned by the caller)
+        put = object.__setattr__
+        put(self, "cd", costs[0]); put(self, "cv", costs[1]); put(self, "ct", costs[2]); put(self, "ctot", costs[3])
+        put(self, "index", index)
+
+    def __setattr__(self, name, value):
+        if name in _ROW_OF:
+            self.__dict__["_touched"] = True
+        object.__setattr__(self, name, value)
 
     def __getattr__(self, name):              # only reached when normal lookup fails, i.e. for a list slot that is still unset
         i = _ROW_OF.get(name)
@@ -61,10 +70,13 @@ class WinnerFrenet(Frenet):
 
     def _value(self, name, index):
         """field[index] as a Python float without materialising the list (a list that already exists is used instead)."""
-        try:
-            return object.__getattribute__(self, name)[index]
-        except AttributeError:
-            return float(self._rows[_ROW_OF[name]][index])
+        d = self.__dict__
+        if d["_touched"]:
+            try:
+                return object.__getattribute__(self, name)[index]
+            except AttributeError:
+                pass
+        return d["_item"](_ROW_OF[name], index)
 
     def __repr__(self):
         return f"Frenet(index={self.index}, steps={self._rows.shape[1]}, ctot={self.ctot:.6g})"

@@ -16,6 +16,8 @@ from operator import attrgetter
 
 import numpy as np
 
+import struct
+
 from .. import _native as nat
 from .. import lattice as lat
 from ..engine import FrenetEngine, LatticeGeometry, make_params
@@ -164,6 +166,11 @@ class LatticePaths:
         return self._build(int(pos[int(np.argmin(vals))]))
 
 
+_pack_state = struct.Struct("<6d").pack_into
+_pack_scal = struct.Struct("<3d").pack_into
+_pack_int = struct.Struct("<i").pack_into
+
+
 class _LatticePlanner(Planner):
     """Shared implementation; subclasses pick the variant rules (variant table)."""
     _variant = "v1"
@@ -251,13 +258,17 @@ class _LatticePlanner(Planner):
             self._geom_cache[gkey] = geom
         if len(V) > self._n_v_cap or self._n_v_cap == 0:      # an empty axis (no candidates at all) still needs a valid layout
             self.__dict__["_n_v_cap"] = max(1, len(V), lat.max_long_axis_len(self))
-        eng.configure(geom, self._n_v_cap, self._n_obs_cap)
+        sig = (geom, self._n_v_cap, self._n_obs_cap)
+        if self.__dict__.get("_conf_sig") != sig:            # (configure compares the same things, a few microseconds slower)
+            eng.configure(geom, self._n_v_cap, self._n_obs_cap)
+            self.__dict__["_conf_sig"] = sig
         eng.host_block_free()
-        eng.state[0, :3] = self.p0
-        eng.state[0, 3:] = self.s0
-        eng.scal[0] = (self.dd, self.desired_speed, self.t_initial)
+        # state (p0, s0), scalars and the axis length straight into the pinned staging block
+        hv, offs = eng._in_host_bytes, eng._in_offs
+        _pack_state(hv, offs["state"], *self.p0, *self.s0)
+        _pack_scal(hv, offs["scal"], self.dd, self.desired_speed, self.t_initial)
+        _pack_int(hv, offs["n_v"], len(V))
         eng.axis_v[0, :len(V)] = V
-        eng.n_v[0] = len(V)
         if follow:
             eng.target[0] = self._target_triples(geom.T)
         # the parameter block is rebuilt only when one of the attributes it is made from changed (callers may mutate them)
@@ -290,7 +301,10 @@ class _LatticePlanner(Planner):
             stages |= nat.STAGE_K4
             use_mask = nat.MASK_COLLISION
             eng.spec_pos = spec_obs
-        eng.run_graph(P, handle, stages, use_mask, nat.SEL_CTOT, n_obs=n_obs)
+        if (stages & nat.STAGE_ONE_LAUNCH) and self.__dict__.get("_inline", True):
+            eng.run_inline(P, handle, stages, use_mask, nat.SEL_CTOT, n_obs=n_obs, follow=follow)    # one launch, inputs as its argument
+        else:
+            eng.run_graph(P, handle, stages, use_mask, nat.SEL_CTOT, n_obs=n_obs)
         eng.xy_path = spec if handle is not None else None
         self.__dict__["_winner_cache"] = {"ctot": self._frenet_from_winner("argmin_ctot")}
         paths = LatticePaths(self, len(V), follow)

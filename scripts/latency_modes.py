@@ -6,10 +6,13 @@ sys.path.insert(0, ROOT)
 import bench
 out = {}
 modes = [("device_blocks,separate", dict(_zero_copy=False, _one_launch=False)),
-         ("device_blocks,one_launch", dict(_zero_copy=False, _one_launch=True)),
+         ("device_blocks,one_launch", dict(_zero_copy=False, _one_launch=True, _inline=False)),
          ("out_mapped,separate", dict(_zero_copy="out", _one_launch=False)),
-         ("out_mapped,one_launch", dict(_zero_copy="out", _one_launch=True)),
-         ("all_mapped,one_launch", dict(_zero_copy=True, _one_launch=True))]
+         ("out_mapped,one_launch,graph", dict(_zero_copy="out", _one_launch=True, _inline=False)),
+         ("out_mapped,one_launch,inline", dict(_zero_copy="out", _one_launch=True)),
+         ("out_mapped,one_launch,inline,no_speculation", dict(_zero_copy="out", _one_launch=True, _speculate=False)),
+         ("all_mapped,one_launch", dict(_zero_copy=True, _one_launch=True)),
+         ("round1", dict(_zero_copy=False, _one_launch=False, _speculate=False))]
 for name, kw in modes:
     bench.replan_latency(40, **kw)
     out[name] = bench.replan_latency(400, **kw)

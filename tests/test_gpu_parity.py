@@ -1493,3 +1493,52 @@ def test_collision_only_one_launch_equals_standalone_k4():
             assert np.array_equal(got[b][name], ref[b][name], equal_nan=True), (b, name)
         assert np.array_equal(before[b]["x"], got[b]["x"], equal_nan=True)
     assert 0 < sum(int((ref[b]["coll_free"][valid[b]] == 0).sum()) for b in range(len(idx))) < sum(int(v.sum()) for v in valid)
+
+
+def test_replan_inline_equals_frenet_plan_and_checks_its_limits():
+    """frenet_replan_inline: the per-replan inputs of ONE planner travel as a kernel argument (read from host memory at call time)
+    and the kernel spills them into the input buffers.  Same outputs as the staged path; the device-side input arrays hold the
+    inline values afterwards; shapes beyond the inline capacities and batches are refused."""
+    _gpu, nat, Circle, _ = _imports()
+    import ctypes as C
+    import torch
+    from otg_b200.engine import make_params
+    prm = fo.OracleParams.defaults("v1")
+    tr = Circle(8, 5, 2)
+    trip = np.tile(np.array([[6.0, 1.5, 0.0]]), (len(np.arange(*prm.t_interval())), 1))
+    for follow in (False, True):
+        kw = dict(p0=(0.3, 0.1, 0.0), s0=(1.0, 2.5, 0.1), t0=0.4, trajectory=tr, targets=trip[None] if follow else None)
+        ref = _all_outputs(_gpu.run_batch(prm, **kw), nat)
+        eng = _gpu.run_batch(prm, **kw)
+        from otg_b200 import lattice as lat
+        P = make_params(_gpu.planner_attrs(prm), lat.VARIANTS["v1"]["rule"], prm.delta_t, follow)
+        st = np.array(eng.state[0]), np.array(eng.scal[0]), np.array(eng.axis_v[0]), np.array(eng.n_v[:1]), np.array(eng.target[0])
+        eng._in_dev.zero_()                   # the device copies of the inputs are gone: only the inline argument carries them
+        stages = nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K3 | nat.STAGE_K5 | nat.STAGE_GATHER | nat.STAGE_ONE_LAUNCH
+        args = [a.ctypes.data for a in st]
+        rc = nat.lib.frenet_replan_inline(C.byref(eng.L), C.byref(P), C.byref(eng.path_handle(tr).desc), C.byref(eng.B), stages, 0, nat.SEL_CTOT,
+                                          args[0], args[1], args[2], args[3], args[4] if follow else None, 1, None)
+        assert rc == nat.OK, nat.lib.frenet_last_error()
+        eng.download(sync=True)
+        _assert_same_outputs(ref, _all_outputs(eng, nat), f"inline follow={follow}")
+        dst, dsc, dnv = eng.device_state()
+        assert np.array_equal(dst[0], st[0]) and np.array_equal(dsc[0], st[1]) and dnv[0] == st[3][0]
+    # limits
+    rc = nat.lib.frenet_replan_inline(C.byref(eng.L), C.byref(P), None, C.byref(eng.B), stages & ~nat.STAGE_ONE_LAUNCH, 0, 0, args[0], args[1], args[2],
+                                      args[3], args[4], 1, None)
+    assert rc == nat.ERR_BAD_ARG
+    rc = nat.lib.frenet_replan_inline(C.byref(eng.L), C.byref(P), C.byref(eng.path_handle(tr).desc), C.byref(eng.B), stages, 0, 0, args[0], args[1],
+                                      args[2], args[3], None, 1, None)
+    assert rc == nat.ERR_BAD_ARG                                   # follow mode without targets
+    two = _gpu.run_batch(prm, p0=np.zeros((2, 3)), s0=np.array([[0, 2.5, 0], [1, 2.5, 0]]), t0=0.0)
+    P0 = make_params(_gpu.planner_attrs(prm), lat.VARIANTS["v1"]["rule"], prm.delta_t, False)
+    rc = nat.lib.frenet_replan_inline(C.byref(two.L), C.byref(P0), None, C.byref(two.B), stages & ~nat.STAGE_K3, 0, 0, args[0], args[1], args[2],
+                                      args[3], None, 1, None)
+    assert rc == nat.ERR_BAD_ARG                                   # a batch
+    wide = prm.with_(num_sample=9)                                 # 19 longitudinal targets > FRENET_INLINE_MAX_V
+    e3 = _gpu.run_batch(wide, p0=(0.0, 0.0, 0.0), s0=(0.0, 2.5, 0.0), t0=0.0)
+    assert e3.n_v_cap > nat.INLINE_MAX_V
+    big = np.zeros(e3.n_v_cap)
+    rc = nat.lib.frenet_replan_inline(C.byref(e3.L), C.byref(P0), None, C.byref(e3.B), stages & ~nat.STAGE_K3, 0, 0, args[0], args[1], big.ctypes.data,
+                                      args[3], None, 1, None)
+    assert rc == nat.ERR_CAPACITY
