@@ -481,6 +481,7 @@ def default_lattice_batch(dev, n_scen=32768, steps=10):
     p0 = np.stack([rng.uniform(-1, 1, B), rng.uniform(-.3, .3, B), rng.uniform(-.3, .3, B)], 1)
     s0 = np.stack([rng.uniform(0, 30, B), rng.uniform(0, 4, B), rng.uniform(-.3, .3, B)], 1)
     bp = BatchPlanner(TrajectoryPlannerParams(), CircleTrajectory2D(8, 5, 2), B, O, "v1", dev)
+    bp.pipeline_slots = 2          # 90 MB per output block here: two are enough on one GPU (no other rank to run ahead of)
     bp.stage_inputs(p0=p0, s0=s0, t0=np.full(B, 0.1), obs_s=s0[:, 0:1] + rng.uniform(2, 12, (B, O)), obs_d=rng.uniform(-3, 3, (B, O)))
     bp.engine.upload()
     for _ in range(3):
@@ -494,7 +495,7 @@ def default_lattice_batch(dev, n_scen=32768, steps=10):
     b.record()
     torch.cuda.synchronize()
     ms_serial = a.elapsed_time(b) / steps
-    # the same with the 90 MB of winner trajectories leaving on a side stream under the next step's kernels (two output blocks)
+    # the same with the 90 MB of winner trajectories leaving on a side stream under the next step's kernels (output blocks rotate)
     for _ in range(2):
         bp.launch_pipelined()
     bp.pipeline_wait()
@@ -690,7 +691,7 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     # Every step: the kernels on the compute stream; the D2H copy of its records + winners and (N > 1) the one collective of the
-    # path - the all-gather of the records - on a side stream, under the next step's kernels (two output blocks alternate).  The
+    # path - the all-gather of the records - on a side stream, under the next step's kernels (four output blocks rotate).  The
     # host does not wait per step (the e2e arm below is the one that hands every step's results to the host); the timed region
     # ends when the last step's results have arrived too.
     for _ in range(args.steps):

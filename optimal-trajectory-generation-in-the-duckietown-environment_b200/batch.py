@@ -87,6 +87,7 @@ class BatchPlanner:
                  robot_radius: float = 0.7, predict_steps: int = 0, lat_f32: bool = False):
         self.p = params
         self.variant = variant
+        self.pipeline_slots = 4          # output blocks of launch_pipelined (set before its first call)
         self.n_scen = int(n_scen)
         self.n_obs = int(n_obs)
         self.engine = FrenetEngine(self.n_scen, device)
@@ -222,16 +223,18 @@ class BatchPlanner:
     def launch_pipelined(self, n_total: int | None = None, group=None, gather: bool = True):
         """One resident step whose results leave the device on a SIDE stream: the D2H copy of records + winners and - with a
         process group - the one collective of the path (all-gather of the 64-byte records over NCCL) run under the next step's
-        kernels instead of in front of them.  Two output blocks alternate, so a rank may run one step ahead of the slowest one;
+        kernels instead of in front of them.  `pipeline_slots` output blocks rotate (default 4), so a rank may run that many steps
+        minus one ahead of the slowest one before it has to wait for a block - enough to absorb the step-to-step jitter between GPUs;
         `pipeline_wait()` returns the records of the last step enqueued.  gather=False leaves the collective out (this rank's
         records only) - bench.py uses it to separate the collective's cost from the ranks' own spread."""
         import torch.distributed as dist
         e = self.engine
         if not hasattr(self, "_pipe"):
-            e.enable_out_slots(2)
-            self._pipe = dict(side=torch.cuda.Stream(device=e.device), done=[None, None], gbuf=[None, None], ghost=[None, None], last=1)
+            n = self.pipeline_slots
+            e.enable_out_slots(n)
+            self._pipe = dict(side=torch.cuda.Stream(device=e.device), done=[None] * n, gbuf=[None] * n, ghost=[None] * n, last=n - 1)
         P = self._pipe
-        slot = P["last"] ^ 1
+        slot = (P["last"] + 1) % len(P["done"])
         compute = torch.cuda.current_stream(e.device)
         if P["done"][slot] is not None:
             compute.wait_event(P["done"][slot])       # the side-stream work of the step that used this block two steps ago
@@ -243,7 +246,8 @@ class BatchPlanner:
         side = P["side"]
         side.wait_event(ready)
         with torch.cuda.stream(side):
-            e._out_host.copy_(e._out_dev, non_blocking=True)
+            # the collective FIRST (it needs only the 64-byte records): the ranks' handshake must not queue behind this rank's own
+            # multi-megabyte download of winner trajectories
             if world > 1:
                 if n_total is None or n_total != world * self.n_scen:
                     raise ValueError("launch_pipelined needs equal shards: n_total = world size x scenarios of this planner")
@@ -254,6 +258,7 @@ class BatchPlanner:
                     P["ghost"][slot] = torch.empty(world * local.numel(), dtype=torch.uint8, pin_memory=True)
                 dist.all_gather_into_tensor(P["gbuf"][slot], local, group=group)
                 P["ghost"][slot].copy_(P["gbuf"][slot], non_blocking=True)
+            e._out_host.copy_(e._out_dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record(side)
         P["done"][slot] = done

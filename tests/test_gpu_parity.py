@@ -1356,10 +1356,10 @@ def test_pipelined_launch_equals_the_plain_one():
         for i, m in enumerate(bp.engine.winner_steps):     # the blocks' padding beyond a winner's samples is whatever that block held before
             assert np.array_equal(bp.engine.winner[i, :11, :m], win[i, :11, :m]) and (m == 0 or np.array_equal(bp.engine.winner[i, 11, :4], win[i, 11, :4]))
     slots = set()
-    for _ in range(4):                   # back to back without waiting: the blocks alternate
+    for _ in range(2 * bp.pipeline_slots):      # back to back without waiting: the blocks rotate
         bp.launch_pipelined()
         slots.add(bp.engine.out_slot)
-    assert slots == {0, 1}
+    assert slots == set(range(bp.pipeline_slots))
     assert np.array_equal(np.asarray(bp.pipeline_wait()), want[-1][1])
 
 

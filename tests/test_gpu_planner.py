@@ -513,8 +513,10 @@ def test_speculative_replan_equals_the_plain_call_sequence(lattice):
             return list(self.obstacles)
 
     planners = [TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64),
-                TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _speculate=False, _one_launch=False, _zero_copy=False)]
-    sensors = [Sees(), Sees()]
+                TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _speculate=False, _one_launch=False, _zero_copy=False),
+                # inputs AND outputs in mapped pinned memory, one launch replayed from a graph (no inline argument)
+                TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _zero_copy=True, _inline=False)]
+    sensors = [Sees(), Sees(), Sees()]
     for pl in planners:
         pl.initialize(**init)
     hits = 0
@@ -538,11 +540,12 @@ def test_speculative_replan_equals_the_plain_call_sequence(lattice):
             best = drivers.best_path(kept)
             pl.opt_path_tot = best
             out.append((pos, len(kept), len(leading), best, [leading[i].position.tolist() for i in range(min(3, len(leading)))]))
-        (pa, na, la, fa, ba), (pb, nb, lb, fb, bb) = out
-        assert pa == pb and na == nb and la == lb and ba == bb, step
-        assert fa.index == fb.index and (fa.cd, fa.cv, fa.ct, fa.ctot) == (fb.cd, fb.cv, fb.ct, fb.ctot), step
-        for name in NAMES9 + ("x", "y"):
-            assert getattr(fa, name) == getattr(fb, name), (step, name)
+        (pb, nb, lb, fb, bb) = out[1]
+        for which, (pa, na, la, fa, ba) in enumerate((out[0], out[2])):
+            assert pa == pb and na == nb and la == lb and ba == bb, (step, which)
+            assert fa.index == fb.index and (fa.cd, fa.cv, fa.ct, fa.ctot) == (fb.cd, fb.cv, fb.ct, fb.ctot), (step, which)
+            for name in NAMES9 + ("x", "y"):
+                assert getattr(fa, name) == getattr(fb, name), (step, which, name)
         if step in (3, 8):                 # and element access through the lazy views
             assert [f.index for f in planners[0].paths[:5]] == [f.index for f in planners[1].paths[:5]]
     assert hits >= 5          # replans 3..6 and 9.. ran with the obstacles on board
