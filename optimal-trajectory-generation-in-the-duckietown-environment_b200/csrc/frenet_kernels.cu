@@ -1209,8 +1209,11 @@ __device__ __forceinline__ void stage_obstacles(const FrenetBuffers& B, int b, d
 // Every lane owns two consecutive time steps per iteration (16-byte stores, half the per-step overhead): the mapping for long
 // horizons.  Lattices of at most 32 padded samples go through k2_short below instead.
 constexpr bool kRowTable = FRENET_ROW_TABLE != 0;
-constexpr int k2_min_ctas(int coll) {
+constexpr int k2_min_ctas(int coll, bool f32 = false) {
     if (FRENET_BULK_STORE) return 2;
+    // (fp32 fast path without collisions: half the store bytes leave the kernel latency-bound, a fourth resident CTA is worth 4 %;
+    //  the fp64 form is store-bound and loses 5 % at 64 registers - same-box A/B in profiles/r2_history.md)
+    if (f32 && coll == 0) return 4;
     return coll == 0 ? FRENET_K2_MIN_CTAS : (coll == 1 && kRowTable) ? FRENET_K2_MIN_CTAS_TABLE : FRENET_K2_MIN_CTAS_COLL;
 }
 // shared memory of the row table, in doubles (after the spline table)
@@ -1717,7 +1720,7 @@ __device__ __forceinline__ void k2_evaluate_body(const FrenetLattice& L, const F
 
 // kMono: the one-launch replan (see mono_tail) - K1 of the row in front, K5 + gather by the scenario's last CTA behind.
 template <bool kXY, int kColl, bool kLimits, bool kSplit, bool kF32 = false, bool kMono = false, bool kCollOnly = false>
-__global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl))      // (kMono too: a dense single planner is hundreds of CTAs, occupancy matters)
+__global__ void __launch_bounds__(kRowThreads, k2_min_ctas(kColl, kF32))      // (kMono too: a dense single planner is hundreds of CTAs, occupancy matters)
 k2_evaluate(FrenetLattice L, FrenetParams P, FrenetPath path, FrenetBuffers B, int opts, float radius_up, int use_mask, int gather_sel, int has_xy,
             FrenetInline inl) {
     FRENET_PHASE(0);
