@@ -1542,3 +1542,4 @@ def test_replan_inline_equals_frenet_plan_and_checks_its_limits():
     rc = nat.lib.frenet_replan_inline(C.byref(e3.L), C.byref(P0), None, C.byref(e3.B), stages & ~nat.STAGE_K3, 0, 0, args[0], args[1], big.ctypes.data,
                                       args[3], None, 1, None)
     assert rc == nat.ERR_CAPACITY
+

@@ -284,3 +284,35 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_winner_frenet_lists_are_made_on_first_use():
+    """The planner's picks are `WinnerFrenet` objects: a private copy of the winner block whose rows become plain lists the first
+    time a field is read (the reference's `Frenet` holds lists).  Values, list semantics, assignment, copies and the direct look-up
+    `optimal_at_time` uses must agree with an eagerly built `Frenet`."""
+    import copy
+    import pickle
+    from otg_b200.planner.frenet import Frenet, WinnerFrenet, LIST_FIELDS
+    rows = np.arange(11 * 7, dtype=np.float64).reshape(11, 7) / 3.0
+    f = WinnerFrenet(rows.copy(), 9, [1.5, 2.5, 3.5, 7.5], 42)
+    assert isinstance(f, Frenet) and (f.cd, f.cv, f.ct, f.ctot, f.index) == (1.5, 2.5, 3.5, 7.5, 42)
+    assert f._value("s", 2) == rows[5, 2] and f._value("t", -1) == rows[0, -1] and isinstance(f._value("d", 0), float)
+    assert f.x == [] and f.y == []                                   # gathered before the transform ran: no Cartesian samples
+    for i, name in enumerate(LIST_FIELDS[:9]):
+        got = getattr(f, name)
+        assert isinstance(got, list) and got == rows[i].tolist() and getattr(f, name) is got
+    f.t.append(99.0)                                                 # a list like any other from now on ...
+    assert f._value("t", -1) == 99.0                                 # ... and a list that exists wins over the block
+    f.s = [1.0, 2.0]
+    assert f._value("s", -1) == 2.0 and f.s == [1.0, 2.0]
+    g = WinnerFrenet(rows.copy(), 11, [0.0, 0.0, 0.0, 0.0], 3)
+    assert g.x == rows[9].tolist() and g.y == rows[10].tolist()
+    h = copy.deepcopy(g)
+    assert h.d == g.d and h.index == 3 and h._value("dot_s", 1) == rows[6, 1]
+    k = pickle.loads(pickle.dumps(g))
+    assert k.ddot_d == rows[3].tolist()
+    with pytest.raises(AttributeError):
+        g.no_such_field
+    lazy = WinnerFrenet(rows.copy(), 9, [0.0] * 4, 0)
+    lazy._xy_source = lambda name: [1.0, 2.0] if name == "x" else [3.0, 4.0]      # what frenet_to_glob leaves behind
+    assert lazy.x == [1.0, 2.0] and lazy.y == [3.0, 4.0]
