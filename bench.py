@@ -670,6 +670,37 @@ def run_gpu(args):
     lo, hi = shard_range(n_total, rank, world)
     wl = workload(lo, hi)
     bp = BatchPlanner(dense_params(), SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY), hi - lo, N_OBS, "v1", dev)
+    # N > 1, --balance-shards: the GPUs of one box differ by several percent on this kernel, and equal shards run at the slowest one's
+    # pace.  A short calibration on the equal shards (every rank's own step time, no collective) sizes the shards by measured speed
+    # (within +-10 % of the equal share; the total stays SCEN_PER_GPU x N scenarios per step).  Off by default: it only pays where the
+    # spread is a stable property of the GPUs and larger than their run-to-run variation (measured both ways, profiles/r2_history.md).
+    sizes, calib = None, None
+    if world > 1 and args.balance_shards:
+        from otg_b200.batch import balanced_shard_sizes, shard_range_from_sizes
+        bp.stage_inputs(**wl)
+        bp.engine.upload()
+        for _ in range(3):
+            bp.launch_pipelined(gather=False)
+        bp.pipeline_wait()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        c0.record()
+        for _ in range(6):
+            bp.launch_pipelined(gather=False)
+        bp.pipeline_join()
+        c1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([c0.elapsed_time(c1) / 6], dtype=torch.float64, device=dev)
+        allt = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, mine)
+        calib = [float(v) for v in allt.cpu().numpy()]
+        sizes = balanced_shard_sizes(n_total, calib)
+        if sizes[rank] != hi - lo or shard_range_from_sizes(sizes, rank) != (lo, hi):
+            del bp
+            torch.cuda.empty_cache()
+            lo, hi = shard_range_from_sizes(sizes, rank)
+            wl = workload(lo, hi)
+            bp = BatchPlanner(dense_params(), SplineTrajectory2D(w.SPLINE_WX, w.SPLINE_WY), hi - lo, N_OBS, "v1", dev)
 
     def barrier():
         if world > 1:
@@ -678,13 +709,20 @@ def run_gpu(args):
 
     def gather(records=None, sync=True):
         # the one collective of the path: all ranks' 64-byte result records, all-gathered on the device
-        return bp.gather_records(n_total, sync=sync) if world > 1 else (records if records is not None else bp.engine.result)
+        return bp.gather_records(n_total, sync=sync, sizes=sizes) if world > 1 else (records if records is not None else bp.engine.result)
 
     # ---- resident arm: `value` ----
     bp.stage_inputs(**wl)
     bp.engine.upload()
+    # N > 1: the records of every step are all-gathered on the side stream, under the next steps' kernels.  --gather-per-sweep makes the
+    # timed steps ONE sweep instead: every rank runs at its own pace, the records of all steps are gathered once at the end.
+    per_step = world > 1 and (not args.gather_per_sweep or sizes is not None)
     for _ in range(args.warmup):
-        bp.launch_pipelined(n_total)
+        bp.launch_pipelined(n_total, sizes=sizes, gather=per_step)
+    if world > 1 and not per_step:
+        bp.sweep_begin(1)
+        bp.launch_pipelined(n_total, gather=False)
+        bp.sweep_gather(n_total)              # (warms the collective up)
     bp.pipeline_wait()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
@@ -694,12 +732,20 @@ def run_gpu(args):
     # path - the all-gather of the records - on a side stream, under the next step's kernels (four output blocks rotate).  The
     # host does not wait per step (the e2e arm below is the one that hands every step's results to the host); the timed region
     # ends when the last step's results have arrived too.
+    if world > 1 and not per_step:
+        bp.sweep_begin(args.steps)
     for _ in range(args.steps):
-        bp.launch_pipelined(n_total)
+        bp.launch_pipelined(n_total, sizes=sizes, gather=per_step)
+    if world > 1 and not per_step:
+        bp.sweep_gather(n_total, sync=False)
     bp.pipeline_join()
     ev1.record()
     barrier()
     bp.pipeline_wait()
+    sweep_ok = None
+    if world > 1 and not per_step:
+        swr = bp.sweep_records()              # [steps][n_total]: the same inputs every step, so every step's records must agree
+        sweep_ok = bool(all(np.array_equal(swr[0], swr[i]) for i in range(1, len(swr)))) and swr.shape == (args.steps, n_total)
     ms_dev = ev0.elapsed_time(ev1)
     clk = clocks.stop() if clocks else None
     # N > 1: the same loop WITHOUT the collective, so the line can say how much of the loss against N = 1 is the all-gather and
@@ -709,7 +755,7 @@ def run_gpu(args):
         barrier()
         ev0.record()
         for _ in range(args.steps):
-            bp.launch_pipelined(n_total, gather=False)
+            bp.launch_pipelined(n_total, gather=False, sizes=sizes)
         bp.pipeline_join()
         ev1.record()
         barrier()
@@ -742,7 +788,9 @@ def run_gpu(args):
         allr = torch.empty(world * 2, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.cpu().numpy().reshape(world, 2)
-        per_rank = {"ms_per_step_with_gather": [float(v) for v in allr[:, 0]], "ms_per_step_without_gather": [float(v) for v in allr[:, 1]],
+        per_rank = {"collective": "after every step (side stream)" if per_step else "once per sweep of timed steps, inside the timed region",
+                    "sweep_records_consistent": sweep_ok, "shard_sizes": sizes if sizes is not None else [SCEN_PER_GPU] * world, "calibration_ms_per_step_equal_shards": calib,
+                    "ms_per_step_with_gather": [float(v) for v in allr[:, 0]], "ms_per_step_without_gather": [float(v) for v in allr[:, 1]],
                     "note": "device time of each rank's own timed loop; the job's ms_per_step is the maximum of the first list"}
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -865,6 +913,9 @@ def run_gpu(args):
                 "predicted_obstacles": None, "all_feasibility_checks": None, "default_lattice_batch": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))},
                 "per_rank": per_rank}
+        if sizes is not None:
+            line["config"]["shard_sizes"] = sizes
+            line["config"]["parallelism"] += "; shards sized by each GPU's measured speed (calibration on equal shards, per_rank)"
         rec_f64 = np.array(allrec[:hi - lo], copy=True) if world == 1 else None
         if world == 1 and not args.kernels_only:
             del bp
@@ -896,6 +947,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather-per-sweep", action="store_true", help="N > 1: all-gather the records ONCE for the whole sweep of timed steps "
+                    "(BatchPlanner.sweep_begin / sweep_gather, inside the timed region) instead of after every step on the side stream; "
+                    "measured the same on 2 x B200 (profiles/r2_history.md section 8)")
+    ap.add_argument("--balance-shards", action="store_true", help="N > 1: size the scenario shards by each GPU's measured speed (short "
+                    "calibration on equal shards first) instead of keeping them equal; off by default - see profiles/r2_history.md section 8")
     ap.add_argument("--kernels-only", action="store_true", help="headline step + per-kernel timings only (A/B runs of kernel builds)")
     ap.add_argument("--scenarios", type=int, default=512, help="scenarios per GPU and step (512 = the benchmark; "
                     "smaller only for profiler captures)")

@@ -32,15 +32,50 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_results(local: np.ndarray, n_total: int, group=None, device=None) -> np.ndarray:
+def balanced_shard_sizes(n_total: int, step_ms, max_dev: float = 0.1) -> list[int]:
+    """Shard sizes proportional to each rank's measured speed (1 / its own step time on an equal shard): the GPUs of one box differ
+    by several percent on an issue-sensitive kernel, and with equal shards the whole job runs at the slowest one's pace.  Sizes sum
+    to n_total and stay within +-max_dev of the equal share; identical inputs give identical sizes on every rank."""
+    t = np.asarray(step_ms, dtype=np.float64)
+    world = len(t)
+    share = n_total / world
+    want = np.clip(n_total * (1.0 / t) / np.sum(1.0 / t), share * (1 - max_dev), share * (1 + max_dev))
+    sizes = np.floor(want).astype(np.int64)
+    order = np.argsort(-(want - sizes), kind="stable")          # largest remainders first
+    for i in range(int(n_total - sizes.sum())):
+        sizes[order[i % world]] += 1
+    while sizes.sum() > n_total:                                 # (clipping at the upper bound can overshoot by rounding)
+        sizes[int(np.argmax(sizes))] -= 1
+    return [int(v) for v in sizes]
+
+
+def shard_range_from_sizes(sizes, rank: int) -> tuple[int, int]:
+    lo = int(sum(sizes[:rank]))
+    return lo, lo + int(sizes[rank])
+
+
+def gather_results(local: np.ndarray, n_total: int, group=None, device=None, sizes=None) -> np.ndarray:
     """All-gather the per-scenario FrenetResult records of every rank (one collective, NCCL on GPUs, gloo on CPU).
 
-    `local` is this rank's structured record array for its `shard_range`; returns all `n_total` records in
-    scenario order on every rank.  Without an initialised process group this is the identity."""
+    `local` is this rank's structured record array for its `shard_range` (or for its entry of `sizes`, the shard sizes of all ranks);
+    returns all `n_total` records in scenario order on every rank.  Without an initialised process group this is the identity."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if sizes is not None:
+        if len(sizes) != world or sum(sizes) != n_total:
+            raise ValueError("sizes must hold one shard size per rank and sum to n_total")
+        cap = max(sizes)
+        buf = np.zeros(cap * nat.RESULT_BYTES, dtype=np.uint8)
+        buf[:local.size * nat.RESULT_BYTES] = local.view(np.uint8).reshape(-1)
+        t = torch.from_numpy(buf)
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(world * cap * nat.RESULT_BYTES, dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        flat = out.cpu().numpy().reshape(world, cap * nat.RESULT_BYTES)
+        return np.concatenate([flat[r, :sizes[r] * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE)) for r in range(world)])
     cap = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
     buf = np.zeros(cap * nat.RESULT_BYTES, dtype=np.uint8)
     buf[:local.size * nat.RESULT_BYTES] = local.view(np.uint8).reshape(-1)
@@ -220,7 +255,7 @@ class BatchPlanner:
         self._place()
         e.launch(self.params, self.path, self.stages, self.use_mask, nat.SEL_MASKED)
 
-    def launch_pipelined(self, n_total: int | None = None, group=None, gather: bool = True):
+    def launch_pipelined(self, n_total: int | None = None, group=None, gather: bool = True, sizes=None):
         """One resident step whose results leave the device on a SIDE stream: the D2H copy of records + winners and - with a
         process group - the one collective of the path (all-gather of the 64-byte records over NCCL) run under the next step's
         kernels instead of in front of them.  `pipeline_slots` output blocks rotate (default 4), so a rank may run that many steps
@@ -232,7 +267,7 @@ class BatchPlanner:
         if not hasattr(self, "_pipe"):
             n = self.pipeline_slots
             e.enable_out_slots(n)
-            self._pipe = dict(side=torch.cuda.Stream(device=e.device), done=[None] * n, gbuf=[None] * n, ghost=[None] * n, last=n - 1)
+            self._pipe = dict(side=torch.cuda.Stream(device=e.device), done=[None] * n, gbuf=[None] * n, ghost=[None] * n, pad=[None] * n, last=n - 1, sizes=None)
         P = self._pipe
         slot = (P["last"] + 1) % len(P["done"])
         compute = torch.cuda.current_stream(e.device)
@@ -249,21 +284,78 @@ class BatchPlanner:
             # the collective FIRST (it needs only the 64-byte records): the ranks' handshake must not queue behind this rank's own
             # multi-megabyte download of winner trajectories
             if world > 1:
-                if n_total is None or n_total != world * self.n_scen:
-                    raise ValueError("launch_pipelined needs equal shards: n_total = world size x scenarios of this planner")
+                if sizes is None and (n_total is None or n_total != world * self.n_scen):
+                    raise ValueError("launch_pipelined needs equal shards (n_total = world size x scenarios of this planner) or `sizes`")
+                if sizes is not None and (len(sizes) != world or sizes[dist.get_rank(group)] != self.n_scen):
+                    raise ValueError("sizes must hold every rank's shard size, this planner's at its own rank")
                 o = e._out_offs["result"]
                 local = e._out_dev[o:o + self.n_scen * nat.RESULT_BYTES]
-                if P["gbuf"][slot] is None:
-                    P["gbuf"][slot] = torch.empty(world * local.numel(), dtype=torch.uint8, device=e.device)
-                    P["ghost"][slot] = torch.empty(world * local.numel(), dtype=torch.uint8, pin_memory=True)
+                cap = (max(sizes) if sizes is not None else self.n_scen) * nat.RESULT_BYTES
+                if P["gbuf"][slot] is None or P["gbuf"][slot].numel() != world * cap:
+                    P["gbuf"][slot] = torch.empty(world * cap, dtype=torch.uint8, device=e.device)
+                    P["ghost"][slot] = torch.empty(world * cap, dtype=torch.uint8, pin_memory=True)
+                    P["pad"][slot] = torch.zeros(cap, dtype=torch.uint8, device=e.device) if cap != local.numel() else None
+                if P["pad"][slot] is not None:         # unequal shards: every rank contributes the largest shard's size
+                    P["pad"][slot][:local.numel()].copy_(local, non_blocking=True)
+                    local = P["pad"][slot]
                 dist.all_gather_into_tensor(P["gbuf"][slot], local, group=group)
                 P["ghost"][slot].copy_(P["gbuf"][slot], non_blocking=True)
+                P["sizes"] = list(sizes) if sizes is not None else None
+            sw = getattr(self, "_sweep", None)
+            if sw is not None and sw["at"] < sw["steps"]:      # sweep: this step's records stay on the device until sweep_gather
+                o = e._out_offs["result"]
+                sw["dev"][sw["at"]].copy_(e._out_dev[o:o + self.n_scen * nat.RESULT_BYTES], non_blocking=True)
+                sw["at"] += 1
             e._out_host.copy_(e._out_dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record(side)
         P["done"][slot] = done
         P["last"] = slot
         P["gathered"] = world > 1
+
+    def sweep_begin(self, n_steps: int):
+        """A SWEEP of `n_steps` pipelined steps whose records are gathered ONCE at its end: every following
+        `launch_pipelined(gather=False)` also keeps its step's records in a device block [n_steps][n_scen]; `sweep_gather` then
+        runs the path's one collective over all of them.  Between the GPUs nothing is exchanged (and nobody waits for anybody)
+        until then - a per-step collective paces every rank at the slowest one's step and keeps an NCCL kernel spinning next to
+        the pipeline kernel."""
+        e = self.engine
+        n = int(n_steps)
+        sw = getattr(self, "_sweep", None)
+        if sw is None or sw["steps"] != n:
+            sw = dict(steps=n, dev=torch.empty((n, self.n_scen * nat.RESULT_BYTES), dtype=torch.uint8, device=e.device), gbuf=None, ghost=None)
+            self._sweep = sw
+        sw["at"] = 0
+
+    def sweep_gather(self, n_total: int, group=None, sync: bool = True):
+        """The one collective of a sweep (equal shards): all ranks' records of all its steps, [n_steps][n_total] in scenario order.
+        Enqueued on the pipeline's side stream behind the last step; sync=False returns None (call `sweep_records()` later)."""
+        import torch.distributed as dist
+        sw, P, e = self._sweep, self._pipe, self.engine
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1 and n_total != world * self.n_scen:
+            raise ValueError("sweep_gather needs equal shards: n_total = world size x scenarios of this planner")
+        with torch.cuda.stream(P["side"]):
+            flat = sw["dev"].reshape(-1)
+            if world > 1:
+                if sw["gbuf"] is None:
+                    sw["gbuf"] = torch.empty(world * flat.numel(), dtype=torch.uint8, device=e.device)
+                dist.all_gather_into_tensor(sw["gbuf"], flat, group=group)
+                flat = sw["gbuf"]
+            if sw["ghost"] is None or sw["ghost"].numel() != flat.numel():
+                sw["ghost"] = torch.empty(flat.numel(), dtype=torch.uint8, pin_memory=True)
+            sw["ghost"].copy_(flat, non_blocking=True)
+            sw["done"] = torch.cuda.Event()
+            sw["done"].record(P["side"])
+        sw["world"] = world
+        P["done"][P["last"]] = sw["done"]          # pipeline_join / pipeline_wait now also cover the sweep's collective
+        return self.sweep_records() if sync else None
+
+    def sweep_records(self):
+        sw = self._sweep
+        sw["done"].synchronize()
+        rec = sw["ghost"].numpy().view(np.dtype(nat.RESULT_DTYPE)).reshape(sw["world"], sw["steps"], self.n_scen)
+        return np.ascontiguousarray(rec.transpose(1, 0, 2)).reshape(sw["steps"], sw["world"] * self.n_scen)
 
     def pipeline_join(self):
         """Make the current stream wait for all side-stream work enqueued so far (for timing the whole pipeline with events)."""
@@ -278,7 +370,12 @@ class BatchPlanner:
         P = self._pipe
         P["done"][P["last"]].synchronize()
         if P.get("gathered"):
-            return P["ghost"][P["last"]].numpy().view(np.dtype(nat.RESULT_DTYPE))
+            flat = P["ghost"][P["last"]].numpy()
+            if P.get("sizes") is None:
+                return flat.view(np.dtype(nat.RESULT_DTYPE))
+            sz = P["sizes"]
+            rows = flat.reshape(len(sz), -1)
+            return np.concatenate([rows[r, :sz[r] * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE)) for r in range(len(sz))])
         return self.engine.result
 
     def enable_follow_fallback(self, obs_time_offset, obs_offset, obs_speed, d_target: float = 2.0):
@@ -347,7 +444,7 @@ class BatchPlanner:
             self._n_v_sum = int(e.result["n_valid"].sum()) // max(self.geom.n_t * self.geom.n_d, 1)
         return e.result
 
-    def gather_records(self, n_total: int, group=None, sync: bool = True):
+    def gather_records(self, n_total: int, group=None, sync: bool = True, sizes=None):
         """All ranks' result records of the last launch, in scenario order: ONE NCCL all-gather straight from the device
         block K5 wrote (no host staging), then one copy to the host.  Must follow a launch on this stream; shard sizes
         follow `shard_range`.  Without a process group it returns this planner's own records.
@@ -358,6 +455,10 @@ class BatchPlanner:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return self._local_records()
         world = dist.get_world_size(group)
+        if sizes is not None:       # shards sized by the caller (e.g. by measured GPU speed): padded path, every rank alike
+            if not sync:
+                raise ValueError("gather_records(sync=False) needs equal shards")
+            return gather_results(self._local_records(), n_total, group, self._collective_device(group), sizes=sizes)
         if n_total % world != 0:    # ragged shards (decided from n_total alone, so EVERY rank takes this branch): padded host path
             if not sync:
                 raise ValueError("gather_records(sync=False) needs equal shards (n_total divisible by the world size)")

@@ -93,3 +93,48 @@ def test_gather_without_process_group_is_identity():
     from otg_b200.batch import gather_results
     rec = np.zeros(5, dtype=np.dtype(nat.RESULT_DTYPE))
     assert gather_results(rec, 5) is rec
+
+
+def _sized_worker(rank, world, sizes, port, out):
+    sys.path.insert(0, ROOT)
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat
+    from otg_b200.batch import gather_results, shard_range_from_sizes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_total = sum(sizes)
+    lo, hi = shard_range_from_sizes(sizes, rank)
+    rec = np.zeros(hi - lo, dtype=np.dtype(nat.RESULT_DTYPE))
+    rec["argmin_ctot"] = np.arange(lo, hi)
+    rec["status"] = rank
+    allrec = gather_results(rec, n_total, sizes=sizes)
+    ok = (len(allrec) == n_total and np.array_equal(allrec["argmin_ctot"], np.arange(n_total))
+          and all(np.all(allrec["status"][slice(*shard_range_from_sizes(sizes, r))] == r) for r in range(world)))
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_results_with_speed_balanced_shards_gloo():
+    """Shards sized by measured GPU speed (bench.py at N > 1): the padded gather returns every rank's records in scenario order."""
+    world, sizes = 2, [9, 5]
+    port = 29500 + (os.getpid() + 977) % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_sized_worker, args=(world, sizes, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_balanced_shard_sizes():
+    sys.path.insert(0, ROOT)
+    import otg_b200  # noqa: F401
+    from otg_b200.batch import balanced_shard_sizes, shard_range_from_sizes
+    t = [5.032, 5.21, 5.086, 5.349, 5.262, 5.337, 5.148, 5.112]        # the eight GPUs of one box, equal shards of 512 (profiles/r2_history.md)
+    s = balanced_shard_sizes(4096, t)
+    assert sum(s) == 4096 and len(s) == 8 and all(abs(v - 512) <= 52 for v in s)
+    assert s[0] == max(s) and s[3] == min(s)                             # fastest GPU gets the most, slowest the least
+    assert max(np.array(s) * np.array(t)) / 512 < 0.98 * max(t)           # the slowest rank's time drops by > 2 %
+    assert balanced_shard_sizes(1024, [5.0, 5.0]) == [512, 512]
+    assert balanced_shard_sizes(1024, [5.0, 9.0]) == [563, 461]          # clipped at +-10 % of the equal share
+    assert sum(balanced_shard_sizes(7, [1.0, 2.0, 3.0])) == 7
+    assert [shard_range_from_sizes(s, r) for r in (0, 1, 7)] == [(0, s[0]), (s[0], s[0] + s[1]), (4096 - s[7], 4096)]

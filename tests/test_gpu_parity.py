@@ -1360,6 +1360,18 @@ def test_pipelined_launch_equals_the_plain_one():
         bp.launch_pipelined()
         slots.add(bp.engine.out_slot)
     assert slots == set(range(bp.pipeline_slots))
+    # a sweep: the records of every step stay on the device and come back with ONE collective (here: one copy) at its end
+    bp.pipeline_wait()
+    bp.sweep_begin(3)
+    for kw, rec, win in want:
+        bp.stage_inputs(**kw)
+        bp.engine.upload()
+        bp.launch_pipelined(gather=False)
+        bp.pipeline_wait()                  # (the staging block is rewritten for the next step)
+    swr = bp.sweep_gather(n)
+    assert swr.shape == (3, n)
+    for i, (kw, rec, win) in enumerate(want):
+        assert np.array_equal(swr[i], rec)
     assert np.array_equal(np.asarray(bp.pipeline_wait()), want[-1][1])
 
 
