@@ -193,37 +193,58 @@ def config_dict(n_gpus, field="spread"):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi sampling of SM clock and throttle reasons every 20 ms.  Started BEFORE the warm-up (nvidia-smi needs a few hundred
+    milliseconds to come up on an 8-GPU box - longer than a 20-step timed region); `mark()` brackets the timed region and `stop()`
+    reports the samples inside it, or - if the region was too short to catch one - the samples since the start of the warm-up,
+    which ran the same kernels (`window` says which)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
+    def mark(self):
+        """First call: the timed region starts; second call: it ended."""
+        if self.t0 is None:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        import datetime
         self.proc.terminate()
         out = self.proc.communicate()[0]
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[4:8]]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
+        t0, t1 = self.t0 or 0.0, self.t1 or time.time()
+        inside = [r for r in rows if t0 - 0.01 <= r[0] <= t1 + 0.01]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (no sample fell inside the timed region)"
+        reasons = set()
+        for r in inside:
+            for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if on:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def time_kernels(bp, reps):
@@ -717,6 +738,7 @@ def run_gpu(args):
     # N > 1: the records of every step are all-gathered on the side stream, under the next steps' kernels.  --gather-per-sweep makes the
     # timed steps ONE sweep instead: every rank runs at its own pace, the records of all steps are gathered once at the end.
     per_step = world > 1 and (not args.gather_per_sweep or sizes is not None)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         bp.launch_pipelined(n_total, sizes=sizes, gather=per_step)
     if world > 1 and not per_step:
@@ -724,8 +746,9 @@ def run_gpu(args):
         bp.launch_pipelined(n_total, gather=False)
         bp.sweep_gather(n_total)              # (warms the collective up)
     bp.pipeline_wait()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
+    if clocks:
+        clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     # Every step: the kernels on the compute stream; the D2H copy of its records + winners and (N > 1) the one collective of the
@@ -747,6 +770,8 @@ def run_gpu(args):
         swr = bp.sweep_records()              # [steps][n_total]: the same inputs every step, so every step's records must agree
         sweep_ok = bool(all(np.array_equal(swr[0], swr[i]) for i in range(1, len(swr)))) and swr.shape == (args.steps, n_total)
     ms_dev = ev0.elapsed_time(ev1)
+    if clocks:
+        clocks.mark()
     clk = clocks.stop() if clocks else None
     # N > 1: the same loop WITHOUT the collective, so the line can say how much of the loss against N = 1 is the all-gather and
     # how much is the spread between the ranks' own GPUs (the job's time is the slowest rank's)
