@@ -257,10 +257,13 @@ struct RowAddr {
 __device__ __forceinline__ RowAddr row_addr(const FrenetLattice& L, int64_t br) {
     RowAddr A;
     const int R = L.n_v_cap * L.n_t;
-    A.b = (int)(br / R);
-    A.r = (int)(br % R);
-    A.iv = A.r / L.n_t;
-    A.iT = A.r % L.n_t;
+    // (row indices are grid indices, < 2^31: 32-bit unsigned divisions - a 64-bit division is ~100 instructions, and every thread
+    //  of every row CTA does this)
+    const unsigned ubr = (unsigned)br;
+    A.b = (int)(ubr / (unsigned)R);
+    A.r = (int)(ubr - (unsigned)A.b * (unsigned)R);
+    A.iv = (int)((unsigned)A.r / (unsigned)L.n_t);
+    A.iT = A.r - A.iv * L.n_t;
     A.N = L.n_steps[A.iT];
     const int off = L.t_offset[A.iT];
     A.npad = L.t_offset[A.iT + 1] - off;

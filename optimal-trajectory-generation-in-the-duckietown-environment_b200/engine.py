@@ -166,6 +166,8 @@ class FrenetEngine:
         self.generation = 0
         self.has_xy = False
         self.has_collision = False
+        self.xy_path = None           # the trajectory object the lattice's x, y were computed against (drivers.frenet_to_glob / planner)
+        self.spec_pos = None          # obstacle positions the last replan tested speculatively (drivers.collision_filter validates)
         self.relative_s = False       # Duckietown lane runs: the transform evaluates the path at path_origin + (s - s0[0])
         self.per_scenario_lanes = False   # every scenario has its own lane-centre parabola and lane boundaries (lane_params, road_params)
 
@@ -185,6 +187,10 @@ class FrenetEngine:
             return
         dev, Bn = self.device, self.n_scen
         self._graphs.clear()          # captured graphs point into the buffers that are about to be replaced
+        # ... and so do views of the previous lattice: they go stale now, not at the next launch
+        self.generation += 1
+        self.has_xy = self.has_collision = False
+        self.xy_path = self.spec_pos = None
         self.geom, self.n_v_cap, self.n_obs = geom, int(n_v_cap), n_obs
         nT, nD = geom.n_t, geom.n_d
         R = self.n_v_cap * nT
