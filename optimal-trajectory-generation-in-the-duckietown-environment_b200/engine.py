@@ -327,6 +327,7 @@ class FrenetEngine:
         ov = self._out_host.numpy()
         self.winner = ov[:Bn * 12 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 12, geom.n_pad_max)
         self.result = ov[ooffs["result"]:ooffs["result"] + Bn * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE))
+        self.result_i32 = ov[ooffs["result"]:ooffs["result"] + Bn * nat.RESULT_BYTES].view(np.int32)     # (the planner's fast look-up of scenario 0's indices)
         self.winner_steps = ov[ooffs["winner_steps"]:ooffs["winner_steps"] + Bn * 4].view(np.int32)
         op = self._out_dev.data_ptr()
         self.B.result = op + ooffs["result"]

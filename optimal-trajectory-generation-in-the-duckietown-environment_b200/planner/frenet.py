@@ -78,5 +78,21 @@ class WinnerFrenet(Frenet):
                 pass
         return d["_item"](_ROW_OF[name], index)
 
+    def state_at(self, time, period):
+        """((d, d', d''), (s, s', s'')) at `time` - both `optimal_at_time` look-ups of a replan in one go (trajectory_planner.py:183-195,
+        207-208), straight from the winner block; None if a list field has been materialised (the caller then takes the list path)."""
+        d = self.__dict__
+        if d["_touched"]:
+            return None
+        item = d["_item"]
+        t_first = item(0, 0)
+        if time <= t_first:
+            k = 0
+        elif time >= item(0, -1):
+            k = -1
+        else:
+            k = round((time - t_first) / period)
+        return (item(1, k), item(2, k), item(3, k)), (item(5, k), item(6, k), item(7, k))
+
     def __repr__(self):
         return f"Frenet(index={self.index}, steps={self._rows.shape[1]}, ctot={self.ctot:.6g})"

@@ -42,9 +42,9 @@ class LatticePaths:
     been materialised after a newer replan raises RuntimeError (call `materialize()` first to keep it).
     """
 
-    def __init__(self, planner, n_v: int, follow: bool):
+    def __init__(self, planner, n_v: int, follow: bool, engine=None):
         self._planner = planner
-        self._engine = planner._engine
+        self._engine = engine if engine is not None else planner._engine
         self._generation = self._engine.generation
         self._n_v = n_v
         self._follow = follow
@@ -166,6 +166,7 @@ class LatticePaths:
         return self._build(int(pos[int(np.argmin(vals))]))
 
 
+_RESULT_I32 = {name: i for i, (name, *_rest) in enumerate(nat.RESULT_DTYPE[:8])}     # the int32 fields lead the 64-byte record
 _pack_state = struct.Struct("<6d").pack_into
 _pack_scal = struct.Struct("<3d").pack_into
 _pack_int = struct.Struct("<i").pack_into
@@ -243,7 +244,8 @@ class _LatticePlanner(Planner):
         """The lattice of one replan (trajectory_planner.py:108-181): K1 + K2 + K5 on the device.
 
         Returns the candidate list as a lazy `LatticePaths` view."""
-        eng = self._engine
+        d = self.__dict__
+        eng = d.get("_engine_obj") or self._engine
         ds0 = self.s0[1]
         self.si_interval = lat.si_interval(self)
         self.dsi_interval = lat.dsi_interval(self, ds0)
@@ -257,11 +259,11 @@ class _LatticePlanner(Planner):
             geom = LatticeGeometry.from_intervals(self.di_interval, self.t_interval, period)
             self._geom_cache[gkey] = geom
         if len(V) > self._n_v_cap or self._n_v_cap == 0:      # an empty axis (no candidates at all) still needs a valid layout
-            self.__dict__["_n_v_cap"] = max(1, len(V), lat.max_long_axis_len(self))
+            d["_n_v_cap"] = max(1, len(V), lat.max_long_axis_len(self))
         sig = (geom, self._n_v_cap, self._n_obs_cap)
-        if self.__dict__.get("_conf_sig") != sig:            # (configure compares the same things, a few microseconds slower)
+        if d.get("_conf_sig") != sig:            # (configure compares the same things, a few microseconds slower)
             eng.configure(geom, self._n_v_cap, self._n_obs_cap)
-            self.__dict__["_conf_sig"] = sig
+            d["_conf_sig"] = sig
         eng.host_block_free()
         # state (p0, s0), scalars and the axis length straight into the pinned staging block
         hv, offs = eng._in_host_bytes, eng._in_offs
@@ -273,17 +275,17 @@ class _LatticePlanner(Planner):
             eng.target[0] = self._target_triples(geom.T)
         # the parameter block is rebuilt only when one of the attributes it is made from changed (callers may mutate them)
         pkey = (self.kj, self.kt, self.kd, self.ks, self.kdots, self.klat, self.klong, self.low_speed_threshold, period, follow,
-                self.__dict__.get("S_thresh"), self.__dict__.get("v_max"), self.__dict__.get("a_max"), self.__dict__.get("kappa_max"))
-        if self.__dict__.get("_params_key") != pkey:
-            self.__dict__["_params"] = make_params(self, self._rule, period, follow)
-            self.__dict__["_params_key"] = pkey
+                d.get("S_thresh"), d.get("v_max"), d.get("a_max"), d.get("kappa_max"))
+        if d.get("_params_key") != pkey:
+            d["_params"] = make_params(self, self._rule, period, follow)
+            d["_params_key"] = pkey
         P = self._params
         stages = nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K5 | nat.STAGE_GATHER
-        if self.__dict__.get("_one_launch", True):
+        if d.get("_one_launch", True):
             stages |= nat.STAGE_ONE_LAUNCH     # K1, the evaluate kernel and K5 + gather as ONE kernel (a replan is launch-bound)
         # the driver's next call is frenet_to_glob on the path it used last time (drivers.frenet_to_glob remembers it here): the
         # transform is fused into this launch and that call finds x, y already there
-        spec = self.__dict__.get("_spec_path")
+        spec = d.get("_spec_path")
         handle = None
         if spec is not None and not eng.relative_s:
             stages |= nat.STAGE_K3
@@ -291,7 +293,7 @@ class _LatticePlanner(Planner):
         # ... and if the driver presented the SAME obstacles to check_paths twice in a row (a static scene), it will most likely do
         # so again: the collision stage (nearly free inside the fused kernel) and the masked pick ride along, and check_paths only
         # has to compare its obstacle list with the one that was tested (drivers.collision_filter)
-        spec_obs = self.__dict__.get("_spec_obs")
+        spec_obs = d.get("_spec_obs")
         use_mask, n_obs, eng.spec_pos = 0, None, None
         if (handle is not None and spec_obs is not None and (stages & nat.STAGE_ONE_LAUNCH) and eng.masked_winner
                 and eng.partials is not None and 0 < len(spec_obs) <= eng.n_obs):
@@ -301,27 +303,31 @@ class _LatticePlanner(Planner):
             stages |= nat.STAGE_K4
             use_mask = nat.MASK_COLLISION
             eng.spec_pos = spec_obs
-        if (stages & nat.STAGE_ONE_LAUNCH) and self.__dict__.get("_inline", True):
-            eng.run_inline(P, handle, stages, use_mask, nat.SEL_CTOT, n_obs=n_obs, follow=follow)    # one launch, inputs as its argument
+        if (stages & nat.STAGE_ONE_LAUNCH) and d.get("_inline", False):
+            # one launch with its inputs as the kernel argument (frenet_replan_inline): no graph, no copy node.  Measured 1-1.5 us
+            # SLOWER per replan than replaying the two-node graph below (the 14-argument foreign call and a plain launch cost more
+            # than cudaGraphLaunch), so it is an option, not the default; it is the form a host without graphs would use.
+            eng.run_inline(P, handle, stages, use_mask, nat.SEL_CTOT, n_obs=n_obs, follow=follow)
         else:
             eng.run_graph(P, handle, stages, use_mask, nat.SEL_CTOT, n_obs=n_obs)
         eng.xy_path = spec if handle is not None else None
-        self.__dict__["_winner_cache"] = {"ctot": self._frenet_from_winner("argmin_ctot")}
-        paths = LatticePaths(self, len(V), follow)
-        paths._best["ctot"] = self._winner_cache["ctot"]     # None when the lattice is empty
+        best = self._frenet_from_winner("argmin_ctot")
+        d["_winner_cache"] = {"ctot": best}
+        paths = LatticePaths(self, len(V), follow, eng)
+        paths._best["ctot"] = best     # None when the lattice is empty
         return paths
 
     def _frenet_from_winner(self, result_field: str, masked_block: bool = False):
         """Frenet object from the engine's winner block (None if the selection is empty); masked_block: from the second block,
         which a replan launched with obstacles fills with the masked pick."""
-        eng = self._engine
+        eng = self.__dict__.get("_engine_obj") or self._engine
         block, steps = (eng.winner_masked, eng.winner_masked_steps) if masked_block else (eng.winner, eng.winner_steps)
         n = int(steps[0])
         if n == 0:
             return None
         # a private copy of the block (the pinned one is rewritten by the next launch); its rows become lists on first use
         rows = block[0, :11, :n].copy()
-        return WinnerFrenet(rows, 11 if eng.has_xy else 9, block[0, 11, :4].tolist(), int(eng.result[0][result_field]))
+        return WinnerFrenet(rows, 11 if eng.has_xy else 9, block[0, 11, :4].tolist(), eng.result_i32.item(_RESULT_I32[result_field]))
 
     def _winner(self, key: str):
         """`min(self.paths, key=attrgetter(key))` of the CURRENT lattice (first minimal element wins)."""
@@ -372,8 +378,13 @@ class _LatticePlanner(Planner):
         self.opt_path_ct = self._winner("ct")
 
     def replan_ctot(self, time: float):
-        self.p0 = self.optimal_at_time(time, self.opt_path_tot, "d")
-        self.s0 = self.optimal_at_time(time, self.opt_path_tot, "s")
+        path = self.opt_path_tot
+        both = path.state_at(time, self._sample_period_for_lookup()) if type(path) is WinnerFrenet else None
+        if both is not None:           # the pick of the last replan, untouched: both look-ups straight from its block
+            self.p0, self.s0 = both
+        else:
+            self.p0 = self.optimal_at_time(time, path, "d")
+            self.s0 = self.optimal_at_time(time, path, "s")
         self.t_initial = time
         self.paths = self.generate_range_polynomials()
         self.opt_path_tot = self._winner("ctot")

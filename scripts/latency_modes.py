@@ -8,9 +8,9 @@ out = {}
 modes = [("device_blocks,separate", dict(_zero_copy=False, _one_launch=False)),
          ("device_blocks,one_launch", dict(_zero_copy=False, _one_launch=True, _inline=False)),
          ("out_mapped,separate", dict(_zero_copy="out", _one_launch=False)),
-         ("out_mapped,one_launch,graph", dict(_zero_copy="out", _one_launch=True, _inline=False)),
-         ("out_mapped,one_launch,inline", dict(_zero_copy="out", _one_launch=True)),
-         ("out_mapped,one_launch,inline,no_speculation", dict(_zero_copy="out", _one_launch=True, _speculate=False)),
+         ("out_mapped,one_launch,graph (default)", dict(_zero_copy="out", _one_launch=True)),
+         ("out_mapped,one_launch,inline", dict(_zero_copy="out", _one_launch=True, _inline=True)),
+         ("out_mapped,one_launch,graph,no_speculation", dict(_zero_copy="out", _one_launch=True, _speculate=False)),
          ("all_mapped,one_launch", dict(_zero_copy=True, _one_launch=True)),
          ("round1", dict(_zero_copy=False, _one_launch=False, _speculate=False))]
 for name, kw in modes:

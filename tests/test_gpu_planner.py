@@ -515,8 +515,10 @@ def test_speculative_replan_equals_the_plain_call_sequence(lattice):
     planners = [TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64),
                 TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _speculate=False, _one_launch=False, _zero_copy=False),
                 # inputs AND outputs in mapped pinned memory, one launch replayed from a graph (no inline argument)
-                TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _zero_copy=True, _inline=False)]
-    sensors = [Sees(), Sees(), Sees()]
+                TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _zero_copy=True),
+                # the inputs as the kernel's argument (frenet_replan_inline) instead of a copy node
+                TrajectoryPlannerV1(TrajectoryPlannerParams(**prm), _n_obs_cap=64, _inline=True)]
+    sensors = [Sees(), Sees(), Sees(), Sees()]
     for pl in planners:
         pl.initialize(**init)
     hits = 0
@@ -541,7 +543,7 @@ def test_speculative_replan_equals_the_plain_call_sequence(lattice):
             pl.opt_path_tot = best
             out.append((pos, len(kept), len(leading), best, [leading[i].position.tolist() for i in range(min(3, len(leading)))]))
         (pb, nb, lb, fb, bb) = out[1]
-        for which, (pa, na, la, fa, ba) in enumerate((out[0], out[2])):
+        for which, (pa, na, la, fa, ba) in enumerate((out[0], out[2], out[3])):
             assert pa == pb and na == nb and la == lb and ba == bb, (step, which)
             assert fa.index == fb.index and (fa.cd, fa.cv, fa.ct, fa.ctot) == (fb.cd, fb.cv, fb.ct, fb.ctot), (step, which)
             for name in NAMES9 + ("x", "y"):

@@ -297,7 +297,10 @@ def test_winner_frenet_lists_are_made_on_first_use():
     f = WinnerFrenet(rows.copy(), 9, [1.5, 2.5, 3.5, 7.5], 42)
     assert isinstance(f, Frenet) and (f.cd, f.cv, f.ct, f.ctot, f.index) == (1.5, 2.5, 3.5, 7.5, 42)
     assert f._value("s", 2) == rows[5, 2] and f._value("t", -1) == rows[0, -1] and isinstance(f._value("d", 0), float)
+    assert f.state_at(rows[0, 3], 1.0 / 3.0) == ((rows[1, 3], rows[2, 3], rows[3, 3]), (rows[5, 3], rows[6, 3], rows[7, 3]))
+    assert f.state_at(-1.0, 1.0 / 3.0)[1][0] == rows[5, 0] and f.state_at(1e9, 1.0 / 3.0)[0][0] == rows[1, -1]       # both clamps
     assert f.x == [] and f.y == []                                   # gathered before the transform ran: no Cartesian samples
+    assert f.state_at(0.0, 1.0) is None                               # a list exists now: the caller takes the list path
     for i, name in enumerate(LIST_FIELDS[:9]):
         got = getattr(f, name)
         assert isinstance(got, list) and got == rows[i].tolist() and getattr(f, name) is got
