@@ -310,6 +310,10 @@ int frenet_plan(const FrenetLattice* lat, const FrenetParams* prm, const FrenetP
 int frenet_points_to_cartesian(const FrenetPath* path, const double* s, const double* d, int64_t n, double* x, double* y,
                                int64_t out_stride, frenet_stream_t stream);
 
+/* cudaStreamSynchronize behind the same error convention (a host that holds only the raw stream handle - e.g. a Python binding, where
+ * fetching a stream OBJECT to wait on costs more than the wait - calls this after the asynchronous entry points). */
+int frenet_stream_synchronize(frenet_stream_t stream);
+
 /* frenet_plan with FRENET_STAGE_ONE_LAUNCH (first form: K1 | K2 ... ) for ONE planner (n_scen == 1) whose per-replan inputs are read
  * from HOST memory at call time and handed to the kernel as an argument: h_state[6], h_scal[3], h_axis_v[n_v_cap], *h_n_v and - in
  * follow mode - h_target[n_t][3] (NULL otherwise).  The kernel spills them into buf->state / scal / target and lat->axis_v / n_v

@@ -124,6 +124,7 @@ def _load():
         "frenet_gather_winner": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetBuffers), C.c_int32, C.c_int32, C.c_void_p]),
         "frenet_plan": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p]),
+        "frenet_stream_synchronize": (C.c_int, [C.c_void_p]),
         "frenet_replan_inline": (C.c_int, [P(FrenetLattice), P(FrenetParams), P(FrenetPath), P(FrenetBuffers), C.c_int32, C.c_int32,
                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
         "frenet_predict_obstacles": (C.c_int, [P(FrenetPath), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

@@ -3314,6 +3314,12 @@ int frenet_plan(const FrenetLattice* L, const FrenetParams* P, const FrenetPath*
     return rc;
 }
 
+int frenet_stream_synchronize(frenet_stream_t stream) {
+    const cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FRENET_ERR_CUDA, "stream synchronize", e);
+    return FRENET_OK;
+}
+
 int frenet_replan_inline(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* path, const FrenetBuffers* B, int32_t stages,
                          int32_t use_mask, int32_t gather_sel, const double* h_state, const double* h_scal, const double* h_axis_v,
                          const int32_t* h_n_v, const double* h_target, int32_t wait, frenet_stream_t stream) {

@@ -623,8 +623,9 @@ class FrenetEngine:
         path.  The graph bakes in the kernel arguments (parameters, sizes, pointers), so it is keyed by them and
         re-captured when any of them changes; the per-replan inputs travel through the pinned block, which the graph's
         copy node reads at replay time."""
-        key = (bytes(params), id(path), int(stages), int(use_mask), int(gather_sel), self.B.n_obs if n_obs is None else int(n_obs),
-               self._cap_key, self.out_slot)
+        # (configure() clears the graphs, so the capacities need not be part of the key; the parameter block is keyed by its bytes:
+        #  callers may mutate it in place)
+        key = (bytes(params), id(path), stages, use_mask, gather_sel, self.B.n_obs if n_obs is None else n_obs, self.out_slot)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) > 16:
@@ -641,7 +642,8 @@ class FrenetEngine:
             self._pending = False
             return                      # the warm-up run already produced this call's results
         g.replay()
-        torch.cuda.current_stream(self._dev_index).synchronize()
+        # (the raw handle + one foreign call: building a torch Stream object just to wait on it costs ~4 us of a ~30 us replan)
+        nat.check(nat.lib.frenet_stream_synchronize(torch._C._cuda_getCurrentRawStream(self._dev_index)))
         self._pending = False
         if stages & nat.STAGE_K2:
             self.generation += 1
