@@ -503,7 +503,8 @@ def default_lattice_batch(dev, n_scen=32768, steps=10):
     s0 = np.stack([rng.uniform(0, 30, B), rng.uniform(0, 4, B), rng.uniform(-.3, .3, B)], 1)
     bp = BatchPlanner(TrajectoryPlannerParams(), CircleTrajectory2D(8, 5, 2), B, O, "v1", dev)
     bp.pipeline_slots = 2          # 90 MB per output block here: two are enough on one GPU (no other rank to run ahead of)
-    bp.stage_inputs(p0=p0, s0=s0, t0=np.full(B, 0.1), obs_s=s0[:, 0:1] + rng.uniform(2, 12, (B, O)), obs_d=rng.uniform(-3, 3, (B, O)))
+    inputs = dict(p0=p0, s0=s0, t0=np.full(B, 0.1), obs_s=s0[:, 0:1] + rng.uniform(2, 12, (B, O)), obs_d=rng.uniform(-3, 3, (B, O)))
+    bp.stage_inputs(**inputs)
     bp.engine.upload()
     for _ in range(3):
         bp.launch_resident()

@@ -119,7 +119,7 @@ class BatchPlanner:
     """
 
     def __init__(self, params, trajectory, n_scen: int, n_obs: int = 0, variant: str = "v1", device=None,
-                 robot_radius: float = 0.7, predict_steps: int = 0, lat_f32: bool = False):
+                 robot_radius: float = 0.7, predict_steps: int = 0, lat_f32: bool = False, one_launch: bool = False):
         self.p = params
         self.variant = variant
         self.pipeline_slots = 4          # output blocks of launch_pipelined (set before its first call)
@@ -142,12 +142,21 @@ class BatchPlanner:
         self.params = make_params(params, lat.VARIANTS[variant]["rule"], self.period, False, self.radius_sq)
         self.stages = nat.STAGE_K1 | nat.STAGE_K2 | nat.STAGE_K3 | nat.STAGE_K5 | nat.STAGE_GATHER
         self.use_mask = 0
+        # one_launch: K1 and K5 + gather folded into the evaluate kernel (FRENET_STAGE_ONE_LAUNCH: every CTA solves its own rows'
+        # boundary-value systems and reduces its own candidates, the scenario's last CTA finishes) - one kernel per step instead of three
+        self.one_launch = bool(one_launch)
+        if self.one_launch:
+            if self.predict_steps or self.lat_f32:
+                raise ValueError("one_launch is not available with predicted obstacles or the fp32 fast path")
+            self.stages |= nat.STAGE_ONE_LAUNCH
         if self.n_obs > 0:
             self.stages |= nat.STAGE_K4
             self.use_mask |= nat.MASK_COLLISION
         if np.isfinite(self.params.v_max) or np.isfinite(self.params.a_max):
             self.use_mask |= nat.MASK_KINEMATIC
         if np.isfinite(self.params.kappa_max):
+            if self.one_launch:
+                raise ValueError("one_launch is not available with the curvature limit")
             self.stages |= nat.STAGE_CURVATURE
             self.use_mask |= nat.MASK_CURVATURE
         self._n_v_sum = 0
@@ -497,6 +506,8 @@ class BatchPlanner:
                 n -= 1 + (1 if st & nat.STAGE_K4 else 0) + (1 if st & nat.STAGE_CURVATURE else 0)
             if (st & nat.STAGE_K5) and (st & nat.STAGE_GATHER):  # argmin + winner gather
                 n -= 1
+        if st & nat.STAGE_ONE_LAUNCH:
+            n = 1                                                # K1, evaluate (+ K3, K4), K5 + gather: one kernel
         if self.predict_steps and (st & nat.STAGE_K4):
             n += 1                                               # per-chunk obstacle bounds
         return n + (1 if (self.n_obs and getattr(self, "_obs_frenet", False)) else 0)

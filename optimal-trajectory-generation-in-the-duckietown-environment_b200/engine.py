@@ -277,10 +277,12 @@ class FrenetEngine:
         self.coll_free = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
         self.first_blocker = torch.empty((Bn, Cc), dtype=torch.int32, device=dev)
         self.road_ok = torch.empty((Bn, Cc), dtype=torch.uint8, device=dev)
-        # FRENET_STAGE_ONE_LAUNCH scratch: completion tickets per scenario, a partial argmin record per CTA (small batches only -
-        # the mode exists for launch-bound replans)
+        # FRENET_STAGE_ONE_LAUNCH scratch: completion tickets per scenario, a partial argmin record per CTA
         self.tickets = torch.zeros(Bn, dtype=torch.int32, device=dev)
-        self.partials = torch.empty(Bn * R * nat.MAX_ROW_PARTS * nat.PARTIAL_BYTES, dtype=torch.uint8, device=dev) if Bn * R <= 65536 else None
+        # (a row is split over several CTAs only while all of them fit the GPU at once - a handful of scenarios; beyond that one
+        #  record per row is the most a scenario's CTAs can need)
+        parts_cap = nat.MAX_ROW_PARTS if Bn * R <= 4 * 148 else 1
+        self.partials = torch.empty(Bn * R * parts_cap * nat.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
         self.n_obs_steps = n_obs_steps
         self.obs_xy_t = self.obs_bounds = None
         if n_obs_steps > 0 and n_obs > 0:

@@ -1376,12 +1376,17 @@ def test_pipelined_launch_equals_the_plain_one():
 
 
 def _all_outputs(eng, nat):
+    return _all_outputs_of(eng, nat, range(eng.n_scen))
+
+
+def _all_outputs_of(eng, nat, scenarios):
     """Everything a pipeline run leaves behind, in a form that ignores never-written padding: per-scenario padded fields, the K1
     arrays of existing rows, the result records and the winner blocks up to their step counts."""
     out = {"result": eng.result.copy(), "steps": eng.winner_steps.copy()}
-    for b in range(eng.n_scen):
+    for b in scenarios:
         sc = eng.fetch_scenario(b)
-        f = eng.padded_fields(sc)
+        import _gpu
+        f = _gpu.compact(eng.padded_fields(sc))       # candidates of dropped rows are never sampled: their storage is whatever it held
         nv = sc["n_v"]
         R, C_ = nv * eng.geom.n_t, nv * eng.geom.n_t * eng.geom.n_d
         out[b] = dict(f, coef_lon=sc["coef_lon"][:R], coef_lat=sc["coef_lat"][:C_], row_S=sc["row_S"][:R], row_flags=sc["row_flags"][:R])
@@ -1403,7 +1408,8 @@ def _assert_same_outputs(a, b, what):
             assert np.array_equal(np.asarray(va), np.asarray(vb), equal_nan=np.asarray(va).dtype.kind == "f"), (what, k, name)
 
 
-@pytest.mark.parametrize("case", ["default", "default_batch_obstacles", "follow", "optimal_dropped_rows", "limits", "dense_spline_obstacles"])
+@pytest.mark.parametrize("case", ["default", "default_batch_obstacles", "default_large_batch", "follow", "optimal_dropped_rows", "limits",
+                                  "dense_spline_obstacles"])
 def test_one_launch_replan_equals_the_separate_launches(case):
     """FRENET_STAGE_ONE_LAUNCH: K1 by every CTA for its own rows, the evaluate kernel, and K5 + winner gather by the scenario's
     last CTA, as ONE kernel.  Every output - K1's coefficients, the sampled lattice, costs, masks, first blockers, records, winner
@@ -1422,6 +1428,14 @@ def test_one_launch_replan_equals_the_separate_launches(case):
         p0 = np.c_[rng.uniform(-1, 1, B), rng.uniform(-0.3, 0.3, B), np.zeros(B)]
         s0 = np.c_[rng.uniform(0, 20, B), [0.5, 1.9, 2.0, 2.6, 3.2], rng.uniform(-0.2, 0.2, B)]     # low- and high-speed rows
         obs = np.stack([np.c_[rng.uniform(0, 12, 6), rng.uniform(-2, 3, 6)] for _ in range(B)])
+        kw = dict(p0=p0, s0=s0, t0=rng.uniform(0, 3, B), dd=rng.uniform(-1, 1, B), trajectory=Circle(8, 5, 2), obstacles=obs,
+                  gather_sel=nat.SEL_MASKED)
+    elif case == "default_large_batch":       # enough planners for SEVERAL rows per CTA and several CTAs per scenario in k2_short
+        prm = fo.OracleParams.defaults("v1")
+        B = 700
+        p0 = np.c_[rng.uniform(-1, 1, B), rng.uniform(-0.3, 0.3, B), rng.uniform(-0.3, 0.3, B)]
+        s0 = np.c_[rng.uniform(0, 20, B), rng.uniform(0.2, 4.0, B), rng.uniform(-0.2, 0.2, B)]
+        obs = np.stack([np.c_[rng.uniform(0, 12, 4), rng.uniform(-2, 3, 4)] for _ in range(B)])
         kw = dict(p0=p0, s0=s0, t0=rng.uniform(0, 3, B), dd=rng.uniform(-1, 1, B), trajectory=Circle(8, 5, 2), obstacles=obs,
                   gather_sel=nat.SEL_MASKED)
     elif case == "follow":
@@ -1443,9 +1457,27 @@ def test_one_launch_replan_equals_the_separate_launches(case):
         ox, oy = fo.frenet_to_cartesian(fo.SplinePath(w.SPLINE_WX, w.SPLINE_WY), fs, fd)
         kw = dict(p0=sc["p0"][idx], s0=sc["s0"][idx], t0=sc["t0"][idx], dd=sc["dd"][idx], trajectory=Spline(w.SPLINE_WX, w.SPLINE_WY),
                   obstacles=np.stack([ox, oy], 2)[:, :64], gather_sel=nat.SEL_MASKED)
-    ref = _all_outputs(_gpu.run_batch(prm, **kw), nat)
+    ref_eng = _gpu.run_batch(prm, **kw)
     one = _gpu.run_batch(prm, one_launch=True, repeat=2, **kw)
     assert int(one.tickets.abs().sum()) == 0
+    if case == "default_large_batch":
+        shape = one.launch_shape(one.path_handle(kw["trajectory"]), 1)
+        assert shape["rows_per_cta"] > 1
+        assert np.array_equal(one.result, ref_eng.result) and np.array_equal(one.winner_steps, ref_eng.winner_steps)
+        for name in ("cost", "cand_flags", "coll_free", "first_blocker", "coef_lat", "coef_lon", "row_S", "row_flags"):
+            a, b = getattr(one, name).cpu().numpy(), getattr(ref_eng, name).cpu().numpy()
+            if name in ("coll_free", "first_blocker"):
+                v = (ref_eng.cand_flags.cpu().numpy() & nat.CAND_VALID) != 0
+                a, b = a[v], b[v]
+            assert np.array_equal(a, b), name
+        for i in range(0, 700, 97):
+            m = int(ref_eng.winner_steps[i])
+            assert np.array_equal(one.winner[i, :11, :m], ref_eng.winner[i, :11, :m])
+        sub = [0, 350, 699]
+        ref = {k: v for k, v in _all_outputs_of(ref_eng, nat, sub).items()}
+        _assert_same_outputs(ref, _all_outputs_of(one, nat, sub), case)
+        return
+    ref = _all_outputs(ref_eng, nat)
     _assert_same_outputs(ref, _all_outputs(one, nat), case)
     assert int((ref["result"]["n_valid"] > 0).sum()) >= 1
 
