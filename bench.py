@@ -950,6 +950,9 @@ def run_gpu(args):
             # kernel argument, results written to mapped pinned memory, transform / collision stage riding along once the driver
             # has shown its path and a repeating obstacle set), the same without the speculation (what a scene of MOVING obstacles
             # gets), and with every round-2 latency feature off (separate launches in a graph, copy nodes: round 1's path)
+            # untimed pass first: single replans leave the GPU idle most of the time, and the first ~10 ms of them after the big legs
+            # run 20 % slower than the steady state (scripts/latency_order.py: 38 us for the first leg of a process, 30-32 us after)
+            replan_latency(1500)
             lat = replan_latency()
             lat["no_speculation"] = replan_latency(_speculate=False)
             lat["separate_launches_copy_nodes_no_speculation"] = replan_latency(_zero_copy=False, _one_launch=False, _speculate=False)
