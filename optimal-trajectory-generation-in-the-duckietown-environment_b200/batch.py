@@ -322,6 +322,34 @@ class BatchPlanner:
         P["last"] = slot
         P["gathered"] = world > 1
 
+    def launch_streamed(self, n_total: int | None = None, group=None, sizes=None) -> int:
+        """`launch()` whose results leave on the side stream: H2D of the staged inputs and the pipeline on the current stream, the
+        all-gather (with a process group) and the D2H of records + winners behind an event on the pipeline's side stream, into the
+        next of the rotating output blocks.  Returns the block's slot for `collect(slot)`.  A host loop that stages step i + 1 and
+        collects step i - 1 while step i runs keeps PCIe, host and kernels busy at the same time:
+
+            slot = bp.launch_streamed(); bp.stage_inputs(next...); res = bp.collect(previous_slot); previous_slot = slot"""
+        self.engine.upload()
+        self.launch_pipelined(n_total, group, True, sizes)
+        return self._pipe["last"]
+
+    def collect(self, slot: int) -> BatchResult:
+        """Wait for the side-stream work of the step that wrote output block `slot` and hand out its results (views of that block's
+        pinned host copy, valid until the block comes round again: `pipeline_slots` launches later).  With a process group `records`
+        are all ranks' (scenario order), winners this rank's."""
+        P, e = self._pipe, self.engine
+        P["done"][slot].synchronize()
+        rec, win, steps = e.out_views(slot)
+        if P["ghost"][slot] is not None and P.get("gathered"):
+            flat = P["ghost"][slot].numpy()
+            if P.get("sizes") is None:
+                rec = flat.view(np.dtype(nat.RESULT_DTYPE))
+            else:
+                sz = P["sizes"]
+                rows = flat.reshape(len(sz), -1)
+                rec = np.concatenate([rows[r, :sz[r] * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE)) for r in range(len(sz))])
+        return BatchResult(rec, win, steps, self.cand_timesteps())
+
     def sweep_begin(self, n_steps: int):
         """A SWEEP of `n_steps` pipelined steps whose records are gathered ONCE at its end: every following
         `launch_pipelined(gather=False)` also keeps its step's records in a device block [n_steps][n_scen]; `sweep_gather` then

@@ -341,6 +341,14 @@ class FrenetEngine:
             self.winner_masked_steps = ov[o:o + Bn * 4].view(np.int32)
             self.B.winner_masked, self.B.winner_masked_steps = op + ooffs["winner_masked"], op + ooffs["winner_masked_steps"]
 
+    def out_views(self, slot: int):
+        """(result records, winner blocks, winner step counts) as NumPy views of output block `slot`'s pinned host copy."""
+        Bn, geom, ooffs = self.n_scen, self.geom, self._out_offs
+        ov = self._out_blocks[slot][0].numpy()
+        return (ov[ooffs["result"]:ooffs["result"] + Bn * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE)),
+                ov[:Bn * 12 * geom.n_pad_max * 8].view(np.float64).reshape(Bn, 12, geom.n_pad_max),
+                ov[ooffs["winner_steps"]:ooffs["winner_steps"] + Bn * 4].view(np.int32))
+
     def enable_out_slots(self, n: int = 2):
         """A second output block (result records + winner trajectories), so that step i's results can leave the device on a
         side stream while step i + 1 already writes the other block (BatchPlanner.launch_pipelined)."""

@@ -1360,6 +1360,26 @@ def test_pipelined_launch_equals_the_plain_one():
         bp.launch_pipelined()
         slots.add(bp.engine.out_slot)
     assert slots == set(range(bp.pipeline_slots))
+    # launch_streamed / collect: stage the next step while this one runs, collect the previous one (what bench.py's e2e arm does)
+    bp.pipeline_wait()
+    slots_used, prev, got = [], None, []
+    bp.stage_inputs(**want[0][0])
+    for i in range(3):
+        slot = bp.launch_streamed()
+        if i + 1 < 3:
+            bp.stage_inputs(**want[i + 1][0])
+        if prev is not None:
+            r = bp.collect(prev)
+            got.append((r.records.copy(), r.winner.copy(), r.winner_steps.copy()))
+        prev = slot
+        slots_used.append(slot)
+    r = bp.collect(prev)
+    got.append((r.records.copy(), r.winner.copy(), r.winner_steps.copy()))
+    assert len(set(slots_used)) == 3
+    for (kw, rec, win), (grec, gwin, gsteps) in zip(want, got):
+        assert np.array_equal(grec, rec)
+        for i, m in enumerate(gsteps):
+            assert np.array_equal(gwin[i, :11, :m], win[i, :11, :m])
     # a sweep: the records of every step stay on the device and come back with ONE collective (here: one copy) at its end
     bp.pipeline_wait()
     bp.sweep_begin(3)
