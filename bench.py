@@ -736,9 +736,12 @@ def run_gpu(args):
     # ---- resident arm: `value` ----
     bp.stage_inputs(**wl)
     bp.engine.upload()
-    # N > 1: the records of every step are all-gathered on the side stream, under the next steps' kernels.  --gather-per-sweep makes the
-    # timed steps ONE sweep instead: every rank runs at its own pace, the records of all steps are gathered once at the end.
-    per_step = world > 1 and (not args.gather_per_sweep or sizes is not None)
+    # N > 1: the timed steps are ONE sweep - every rank runs its steps at its own pace, every step's records stay on the device, and
+    # the path's one collective gathers the records of all steps at the end of the sweep, inside the timed region
+    # (BatchPlanner.sweep_begin / sweep_gather).  --gather-per-step runs the collective after every step on the side stream instead
+    # (what the e2e arm below always does): on 4 and 8 GPUs the NCCL kernel spinning next to the pipeline kernel while it waits
+    # for the slowest rank costs 1-2.5 % per step.
+    per_step = world > 1 and (args.gather_per_step or sizes is not None)
     clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         bp.launch_pipelined(n_total, sizes=sizes, gather=per_step)
@@ -943,6 +946,10 @@ def run_gpu(args):
                 "predicted_obstacles": None, "all_feasibility_checks": None, "default_lattice_batch": None, "closed_loop": None,
                 "survivors": {"scenarios_with_feasible": int((allrec["status"] == 0).sum()), "scenarios": int(len(allrec))},
                 "per_rank": per_rank}
+        if world > 1:
+            line["config"]["parallelism"] += ("; resident arm: the records of all timed steps all-gathered once at the end of the sweep (inside the "
+                                              "timed region)" if not per_step else "; resident arm: all-gather after every step on a side stream")
+            line["config"]["parallelism"] += "; e2e arm: all-gather after every step"
         if sizes is not None:
             line["config"]["shard_sizes"] = sizes
             line["config"]["parallelism"] += "; shards sized by each GPU's measured speed (calibration on equal shards, per_rank)"
@@ -980,9 +987,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather-per-sweep", action="store_true", help="N > 1: all-gather the records ONCE for the whole sweep of timed steps "
-                    "(BatchPlanner.sweep_begin / sweep_gather, inside the timed region) instead of after every step on the side stream; "
-                    "measured the same on 2 x B200 (profiles/r2_history.md section 8)")
+    ap.add_argument("--gather-per-step", action="store_true", help="N > 1, resident arm: all-gather the records after EVERY step (on the side "
+                    "stream) instead of once for the whole sweep of timed steps (BatchPlanner.sweep_begin / sweep_gather, inside the timed "
+                    "region): the same on 2 GPUs, 1-2.5 %% slower on 4 and 8 (profiles/r2_history.md section 8).  The e2e arm always "
+                    "gathers per step.")
     ap.add_argument("--balance-shards", action="store_true", help="N > 1: size the scenario shards by each GPU's measured speed (short "
                     "calibration on equal shards first) instead of keeping them equal; off by default - see profiles/r2_history.md section 8")
     ap.add_argument("--kernels-only", action="store_true", help="headline step + per-kernel timings only (A/B runs of kernel builds)")
