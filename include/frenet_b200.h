@@ -243,9 +243,10 @@ enum {
                                      and the winner gather (needs buf->tickets).  Same results as the separate launches; meant for a
                                      single planner, whose replan is a chain of launch latencies.  Not combined with the curvature /
                                      off-road stages, predicted obstacles, FRENET_STAGE_NO_FUSE or the fp32 fast path.
-                                     Second form: K4 | K5 | GATHER | ONE_LAUNCH (long-horizon lattices, path required) - the collision
-                                     stage alone on a lattice that is already sampled, from the row-level table (no stored sample is
-                                     read back), plus the argmin / gather tail: check_paths on obstacles that arrive after the replan. */
+                                     Second form: K4 | K5 | GATHER | ONE_LAUNCH - the collision stage alone on a lattice that is already
+                                     sampled (x, y present), plus the argmin / gather tail: check_paths on obstacles that arrive after
+                                     the replan.  Long horizons (path required): from the row-level table, no stored sample is read
+                                     back; lattices of at most 32 padded samples: the sweep over the stored x, y (path may be NULL). */
 };
 
 int frenet_abi_version(void);

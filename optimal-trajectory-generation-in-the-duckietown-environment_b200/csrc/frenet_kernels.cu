@@ -439,8 +439,9 @@ __device__ __forceinline__ int winner_index(const FrenetResult& res, int sel);
 
 // The CTA's own candidates: `count` of them, the i-th at scenario-relative index first + i * stride.  Then the ticket; the holder of
 // the scenario's last one combines the partial records, writes the result record and gathers the winner.
+// (run > 1: the CTA's candidates come in runs of `run` consecutive indices, `stride` apart - the standalone K4's warp-major split)
 __device__ __forceinline__ void mono_tail(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int b, int cta, int ctas_per_scen,
-                                          int first, int count, int stride, int use_mask, int gather_sel, int has_xy) {
+                                          int first, int count, int stride, int use_mask, int gather_sel, int has_xy, int run = 1) {
     __shared__ int sh_last, sh_winner, sh_winner2;
     const int C = L.n_v_cap * L.n_t * L.n_d;
     const int64_t base = (int64_t)b * C, candF = (int64_t)L.n_scen * C;
@@ -450,7 +451,7 @@ __device__ __forceinline__ void mono_tail(const FrenetLattice& L, const FrenetPa
     int nvalid = 0, nsurv = 0;
     __syncthreads();          // the CTA's per-candidate results are in global memory (written by other threads of this CTA)
     for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const int c = first + i * stride;
+        const int c = run == 1 ? first + i * stride : first + (i / run) * stride + (i % run);
         const int64_t g = base + c;
         const int fl = B.cand_flags[g];
         if (!(fl & FRENET_CAND_VALID)) continue;
@@ -2190,7 +2191,10 @@ __global__ void __launch_bounds__(kRowThreads) k3_offroad(FrenetLattice L, Frene
 // ------------------------------------------------------------------------------------------------
 // K4: collision, one CTA per row; obstacles staged in shared memory
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, FrenetParams P, FrenetBuffers B, int parts) {
+// kMono: FRENET_STAGE_ONE_LAUNCH's second form for SHORT-horizon lattices - the sweep over the stored x, y as below, then the
+// partial-argmin / ticket / gather tail of the one-launch replan (mono_tail), so that check_paths is one kernel for every lattice.
+template <bool kMono>
+__device__ __forceinline__ void k4_collision_row(const FrenetLattice& L, const FrenetParams& P, const FrenetBuffers& B, int parts) {
     extern __shared__ __align__(16) double sm[];
     const int O = B.n_obs;
     double2* obs = reinterpret_cast<double2*>(sm);
@@ -2242,6 +2246,22 @@ __global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, Fre
             B.coll_free[A.cand0 + id] = best == kNoBlocker ? 1 : 0;
             B.first_blocker[A.cand0 + id] = best == kNoBlocker ? -1 : best;
         }
+    }
+}
+
+template <bool kMono>
+__global__ void __launch_bounds__(kRowThreads) k4_collision(FrenetLattice L, FrenetParams P, FrenetBuffers B, int parts, int use_mask, int gather_sel,
+                                                            int has_xy) {
+    k4_collision_row<kMono>(L, P, B, parts);
+    if (kMono) {
+        const int R = L.n_v_cap * L.n_t, nwarps = blockDim.x >> 5, part = blockIdx.y;
+        const int b = (int)(blockIdx.x / R), r = (int)(blockIdx.x % R);
+        if (skipped(B, b)) return;
+        // this CTA's candidates of row r: runs of nwarps consecutive indices starting at nwarps * part, nwarps * parts apart
+        int count = 0;
+        for (int id0 = nwarps * part; id0 < L.n_d; id0 += nwarps * parts) count += min(nwarps, L.n_d - id0);
+        // (the runs are complete except possibly the last one, which mono_tail's index formula covers: i / run, i % run)
+        mono_tail(L, P, B, b, r * parts + part, R * parts, r * L.n_d + nwarps * part, count, nwarps * parts, use_mask, gather_sel, has_xy, nwarps);
     }
 }
 
@@ -3090,6 +3110,22 @@ int launch_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetPath* p
     return FRENET_OK;
 }
 
+// The standalone K4 sweep over the stored x, y; mono = {use_mask, gather_sel, has_xy}: with the one-launch tail (short-horizon lattices)
+int launch_k4(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B, const int* mono, cudaStream_t stream) {
+    const size_t smem = (size_t)3 * B->n_obs * sizeof(double);
+    int parts = 1;
+    while (parts < FRENET_MAX_ROW_PARTS && (int64_t)n_rows(L) * parts < 4 * 148 && parts * (kRowThreads / kWarp) < L->n_d) parts *= 2;
+    if (mono) {
+        if (int rc = set_smem(k4_collision<true>, smem, "k4: too many obstacles for shared memory")) return rc;
+        k4_collision<true><<<dim3(n_rows(L), parts), kRowThreads, smem, stream>>>(*L, *P, *B, parts, mono[0], mono[1], mono[2]);
+    } else {
+        if (int rc = set_smem(k4_collision<false>, smem, "k4: too many obstacles for shared memory")) return rc;
+        k4_collision<false><<<dim3(n_rows(L), parts), kRowThreads, smem, stream>>>(*L, *P, *B, parts, 0, -1, 0);
+    }
+    FRENET_CHECK_LAUNCH("k4_collision");
+    return FRENET_OK;
+}
+
 int check_k2(const FrenetLattice* L, const FrenetParams* P, const FrenetBuffers* B) {
     if (int rc = check_lattice(L)) return rc;
     if (!P || !B || !B->state || !B->scal || !B->coef_lon || !B->coef_lat || !B->row_S || !B->row_flags || !B->lon || !B->lat ||
@@ -3208,13 +3244,7 @@ int frenet_k4_collision(const FrenetLattice* L, const FrenetParams* P, const Fre
         return FRENET_OK;
     }
     if (B->n_obs > 0 && !B->obs_xy) return fail(FRENET_ERR_BAD_ARG, "k4: obstacle table missing");
-    const size_t smem = (size_t)3 * B->n_obs * sizeof(double);
-    if (int rc = set_smem(k4_collision, smem, "k4: too many obstacles for shared memory")) return rc;
-    int parts = 1;
-    while (parts < 8 && (int64_t)n_rows(L) * parts < 4 * 148 && parts * (kRowThreads / kWarp) < L->n_d) parts *= 2;
-    k4_collision<<<dim3(n_rows(L), parts), kRowThreads, smem, (cudaStream_t)stream>>>(*L, *P, *B, parts);
-    FRENET_CHECK_LAUNCH("k4_collision");
-    return FRENET_OK;
+    return launch_k4(L, P, B, nullptr, (cudaStream_t)stream);
 }
 
 int frenet_k3_offroad(const FrenetLattice* L, const FrenetRoad* road, const FrenetBuffers* B, frenet_stream_t stream) {
@@ -3254,7 +3284,6 @@ static int plan_one_launch(const FrenetLattice* L, const FrenetParams* P, const 
         // the collision stage alone on a lattice that is already sampled, through the row table (no stored sample is read back),
         // with the argmin + gather tail: what check_paths needs when the obstacles arrive after the replan
         if ((rc = check_k2(L, P, B))) return rc;
-        if ((rc = check_path(path))) return rc;
         if (!B->tickets || !B->partials) return fail(FRENET_ERR_BAD_ARG, "one launch: buf->tickets / buf->partials is NULL");
         if (L->lat_f32) return fail(FRENET_ERR_BAD_ARG, "one launch: not available on the fp32 fast path");
         if (!B->result || !B->winner || !B->winner_steps || !B->coll_free || !B->first_blocker)
@@ -3262,6 +3291,12 @@ static int plan_one_launch(const FrenetLattice* L, const FrenetParams* P, const 
         if ((use_mask & 2) || (use_mask & 8)) return fail(FRENET_ERR_BAD_ARG, "one launch: curvature / road masks are not produced by this launch");
         if (B->n_obs < 0 || (B->n_obs > 0 && !B->obs_xy)) return fail(FRENET_ERR_BAD_ARG, "one launch: obstacle table missing");
         if (B->n_obs_steps > 0 && B->n_obs > 0) return fail(FRENET_ERR_BAD_ARG, "one launch: predicted obstacles are not supported");
+        if (L->n_pad_max <= kWarp) {
+            // short horizons: the sweep over the stored x, y (a few KB per row) with the same tail; no path needed
+            const int mono3[3] = {use_mask, gather_sel, 1};
+            return launch_k4(L, P, B, mono3, (cudaStream_t)stream);
+        }
+        if ((rc = check_path(path))) return rc;
         const int mono[4] = {use_mask, gather_sel, 1, 1};
         return launch_k2<true, 1>(L, P, path, B, 0, (cudaStream_t)stream, mono, inl);
     }

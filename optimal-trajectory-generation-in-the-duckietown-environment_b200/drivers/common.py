@@ -173,12 +173,14 @@ def collision_filter(frenet_paths, sensor, rpose, want_blockers: bool = False):
         xy_path = getattr(eng, "xy_path", None)
         if hit:
             pass
-        elif (xy_path is not None and eng.geom.n_pad_max > 32 and not eng.relative_s and eng.partials is not None
-                and planner.__dict__.get("_one_launch", True)):
-            # long horizons: the collision stage from the row-level table (nothing is read back from the lattice) with the masked
-            # argmin + gather in its tail - ONE kernel instead of K4 sweeping every stored sample, then K5
-            eng.run_graph(planner._params, eng.path_handle(xy_path), nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER | nat.STAGE_ONE_LAUNCH,
-                          nat.MASK_COLLISION, nat.SEL_MASKED, n_obs=n)
+        elif (eng.partials is not None and planner.__dict__.get("_one_launch", True) and eng.has_xy
+              and (eng.geom.n_pad_max <= 32 or (xy_path is not None and not eng.relative_s))):
+            # the collision stage with the masked argmin + gather in its tail - ONE kernel instead of K4, then K5.  Long horizons: from
+            # the row-level table (nothing is read back from the lattice; needs the path the x, y were computed against); short ones:
+            # the sweep over the stored x, y
+            long_h = eng.geom.n_pad_max > 32
+            eng.run_graph(planner._params, eng.path_handle(xy_path) if long_h else None,
+                          nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER | nat.STAGE_ONE_LAUNCH, nat.MASK_COLLISION, nat.SEL_MASKED, n_obs=n)
         else:
             eng.run_graph(planner._params, None, nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER, nat.MASK_COLLISION,
                           nat.SEL_MASKED, n_obs=n)

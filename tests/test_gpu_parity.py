@@ -1607,3 +1607,40 @@ def test_replan_inline_equals_frenet_plan_and_checks_its_limits():
                                       args[3], None, 1, None)
     assert rc == nat.ERR_CAPACITY
 
+
+
+def test_collision_only_one_launch_on_short_lattices():
+    """The second form of FRENET_STAGE_ONE_LAUNCH on the reference's default lattice (at most 32 padded samples): the standalone K4 sweep
+    with the partial-argmin / ticket / gather tail in ONE kernel, no path needed.  Same masks, first blockers, record and winner as
+    K4 followed by K5 + gather - for one planner (rows split over several CTAs) and for a batch."""
+    _gpu, nat, Circle, _ = _imports()
+    from otg_b200 import lattice as lat
+    from otg_b200.engine import make_params
+    prm = fo.OracleParams.defaults("v1")
+    rng = np.random.default_rng(3)
+    tr = Circle(8, 5, 2)
+    blocked = total = 0
+    for B in (1, 40):
+        p0 = np.c_[rng.uniform(-1, 1, B), rng.uniform(-0.3, 0.3, B), np.zeros(B)]
+        s0 = np.c_[rng.uniform(0, 3, B), rng.uniform(0.5, 3.5, B), rng.uniform(-0.2, 0.2, B)]
+        obs = np.stack([np.c_[rng.uniform(1, 8, 5), rng.uniform(-1.5, 1.5, 5)] for _ in range(B)])      # on the path's first straight
+        kw = dict(p0=p0, s0=s0, t0=rng.uniform(0, 3, B), dd=rng.uniform(-1, 1, B), trajectory=tr)
+        ref = _gpu.run_batch(prm, obstacles=obs, gather_sel=nat.SEL_MASKED, no_fuse=True, **kw)
+        e = _gpu.run_batch(prm, obstacles=obs, **kw)                      # allocates for 5 obstacles; its collision outputs are wiped below
+        e.coll_free.zero_()
+        e.first_blocker.fill_(-7)
+        P = make_params(_gpu.planner_attrs(prm), lat.VARIANTS["v1"]["rule"], prm.delta_t, False)
+        for _ in range(2):
+            e.run(P, None, nat.STAGE_K4 | nat.STAGE_K5 | nat.STAGE_GATHER | nat.STAGE_ONE_LAUNCH, nat.MASK_COLLISION, nat.SEL_MASKED)
+        assert int(e.tickets.abs().sum()) == 0
+        assert np.array_equal(e.result, ref.result) and np.array_equal(e.winner_steps, ref.winner_steps)
+        valid = (ref.cand_flags.cpu().numpy() & nat.CAND_VALID) != 0
+        assert np.array_equal(e.coll_free.cpu().numpy()[valid], ref.coll_free.cpu().numpy()[valid])
+        assert np.array_equal(e.first_blocker.cpu().numpy()[valid], ref.first_blocker.cpu().numpy()[valid])
+        for i in range(B):
+            m = int(ref.winner_steps[i])
+            assert np.array_equal(e.winner[i, :11, :m], ref.winner[i, :11, :m])
+            assert m == 0 or np.array_equal(e.winner[i, 11, :4], ref.winner[i, 11, :4])
+        blocked += int((ref.coll_free.cpu().numpy()[valid] == 0).sum())
+        total += int(valid.sum())
+    assert 0 < blocked < total
