@@ -551,3 +551,34 @@ def test_speculative_replan_equals_the_plain_call_sequence(lattice):
         if step in (3, 8):                 # and element access through the lazy views
             assert [f.index for f in planners[0].paths[:5]] == [f.index for f in planners[1].paths[:5]]
     assert hits >= 5          # replans 3..6 and 9.. ran with the obstacles on board
+
+
+def test_c_host_example_matches_the_python_planner(tmp_path):
+    """examples/replan_c_host.c: a host without Python or PyTorch - buffers sized by frenet_workspace_bytes, one replan through
+    frenet_replan_inline, results read from mapped host memory.  Built with nvcc against the in-tree library and compared with the
+    drop-in planner on the same inputs: candidate count, the pick, its cost (bit for bit) and the state the next replan starts from."""
+    import os
+    import shutil
+    import subprocess
+    import otg_b200  # noqa: F401
+    from otg_b200 import _native as nat
+    from otg_b200.planner import TrajectoryPlannerV1, TrajectoryPlannerParams
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(nat.LIB_PATH)
+    exe = str(tmp_path / "replan_c_host")
+    subprocess.run([nvcc, "-o", exe, os.path.join(root, "examples", "replan_c_host.c"), "-I", os.path.join(root, "include"), "-L", libdir,
+                    "-lfrenet_b200", "-Xlinker", "-rpath", "-Xlinker", libdir], check=True, capture_output=True)
+    for p0, s0, t0 in (((0.2, 0.1, 0.0), (3.0, 2.2, 0.1), 0.1), ((-0.7, 0.0, 0.05), (11.0, 0.6, -0.1), 2.0)):       # high- and low-speed rows
+        out = subprocess.run([exe] + [repr(float(v)) for v in (*p0, *s0, t0)], check=True, capture_output=True, text=True).stdout.split("\n")
+        head = dict(zip(out[0].split()[0::2], out[0].split()[1::2]))
+        nxt = [float(v) for v in out[1].split()[1:]]
+        pl = TrajectoryPlannerV1(TrajectoryPlannerParams())
+        pl.initialize(t0=t0, p0=p0, s0=s0)
+        best = pl.opt_path_tot
+        assert int(head["abi"]) == nat.ABI_VERSION
+        assert int(head["n_valid"]) == len(pl.paths) and int(head["argmin_ctot"]) == best.index and int(head["steps"]) == len(best.t)
+        assert float(head["min_ctot"]) == best.ctot
+        assert nxt == [best.d[1], best.dot_d[1], best.ddot_d[1], best.s[1], best.dot_s[1], best.ddot_s[1]]

@@ -319,3 +319,17 @@ def test_winner_frenet_lists_are_made_on_first_use():
     lazy = WinnerFrenet(rows.copy(), 9, [0.0] * 4, 0)
     lazy._xy_source = lambda name: [1.0, 2.0] if name == "x" else [3.0, 4.0]      # what frenet_to_glob leaves behind
     assert lazy.x == [1.0, 2.0] and lazy.y == [3.0, 4.0]
+
+
+def test_c_host_example_compiles_against_the_header():
+    """examples/replan_c_host.c (a host that uses nothing but the C ABI) must keep compiling against include/frenet_b200.h; the GPU
+    suite builds, runs and compares it with the Python planner."""
+    import shutil
+    import tempfile
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    with tempfile.TemporaryDirectory() as tmp:
+        res = subprocess.run([nvcc, "-c", os.path.join(ROOT, "examples", "replan_c_host.c"), "-I", os.path.join(ROOT, "include"), "-o",
+                              os.path.join(tmp, "replan_c_host.o")], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
