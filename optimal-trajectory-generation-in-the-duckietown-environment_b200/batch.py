@@ -276,7 +276,8 @@ class BatchPlanner:
         if not hasattr(self, "_pipe"):
             n = self.pipeline_slots
             e.enable_out_slots(n)
-            self._pipe = dict(side=torch.cuda.Stream(device=e.device), done=[None] * n, gbuf=[None] * n, ghost=[None] * n, pad=[None] * n, last=n - 1, sizes=None)
+            self._pipe = dict(side=torch.cuda.Stream(device=e.device), done=[None] * n, gbuf=[None] * n, ghost=[None] * n, pad=[None] * n, last=n - 1, sizes=None,
+                              slot_mode=[(False, None)] * n)
         P = self._pipe
         slot = (P["last"] + 1) % len(P["done"])
         compute = torch.cuda.current_stream(e.device)
@@ -321,6 +322,7 @@ class BatchPlanner:
         P["done"][slot] = done
         P["last"] = slot
         P["gathered"] = world > 1
+        P["slot_mode"][slot] = (world > 1, list(sizes) if (sizes is not None and world > 1) else None)     # what THIS block's step did
 
     def launch_streamed(self, n_total: int | None = None, group=None, sizes=None) -> int:
         """`launch()` whose results leave on the side stream: H2D of the staged inputs and the pipeline on the current stream, the
@@ -340,12 +342,12 @@ class BatchPlanner:
         P, e = self._pipe, self.engine
         P["done"][slot].synchronize()
         rec, win, steps = e.out_views(slot)
-        if P["ghost"][slot] is not None and P.get("gathered"):
+        gathered, sz = P["slot_mode"][slot]
+        if gathered:
             flat = P["ghost"][slot].numpy()
-            if P.get("sizes") is None:
+            if sz is None:
                 rec = flat.view(np.dtype(nat.RESULT_DTYPE))
             else:
-                sz = P["sizes"]
                 rows = flat.reshape(len(sz), -1)
                 rec = np.concatenate([rows[r, :sz[r] * nat.RESULT_BYTES].view(np.dtype(nat.RESULT_DTYPE)) for r in range(len(sz))])
         return BatchResult(rec, win, steps, self.cand_timesteps())
